@@ -1,0 +1,29 @@
+# Build of libsarw_b200.so (CUDA kernels + C ABI), the sarw CLI host, and the test oracles.
+# sm_100a only. -fmad=false / -ffp-contract=off: accept/reject arithmetic must not contract multiply-adds.
+NVCC ?= /usr/local/cuda/bin/nvcc
+CXX ?= g++
+PKG := polymer-sarw_b200
+ARCH := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -fmad=false -Xcompiler -fPIC,-ffp-contract=off,-Wall -Iinclude -I$(PKG)/csrc
+LIB := $(PKG)/lib/libsarw_b200.so
+CLI := $(PKG)/bin/sarw
+
+all: lib oracle
+
+lib: $(LIB)
+$(LIB): $(PKG)/csrc/sarw_kernels.cu $(PKG)/csrc/sarw_abi.cu $(PKG)/csrc/sarw_device.cuh $(PKG)/csrc/sarw_host.h include/sarw_abi.h
+	mkdir -p $(PKG)/lib
+	$(NVCC) $(NVFLAGS) -Xptxas -v -shared -o $@ $(PKG)/csrc/sarw_kernels.cu $(PKG)/csrc/sarw_abi.cu 2> $(PKG)/lib/ptxas.log || (cat $(PKG)/lib/ptxas.log; exit 1)
+
+cli: $(CLI)
+$(CLI): $(wildcard $(PKG)/host/*.cpp) $(wildcard $(PKG)/host/*.h) include/sarw_abi.h $(LIB)
+	mkdir -p $(PKG)/bin
+	$(CXX) -O2 -g -std=c++17 -Wall -ffp-contract=off -Iinclude -I$(PKG)/host -o $@ $(wildcard $(PKG)/host/*.cpp) -L$(PKG)/lib -lsarw_b200 -Wl,-rpath,'$$ORIGIN/../lib' -lpthread
+
+oracle:
+	$(MAKE) -C oracle all
+
+clean:
+	rm -rf $(PKG)/lib $(PKG)/bin
+	$(MAKE) -C oracle clean
+.PHONY: all lib cli oracle clean

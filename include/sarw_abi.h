@@ -1,0 +1,117 @@
+/* sarw_abi.h — C ABI of libsarw_b200.so: the chain-growth hot path of polymer-sarw on one B200 (sm_100a).
+ *
+ * This is the drop-in boundary. The reference has no plugin/FFI layer; the seam is the two C++
+ * classes its main() drives, so each entry point names the reference interface it replaces
+ * (file:line under /root/reference):
+ *
+ *   PeriodicLookup{ctor, addPoint, find}                PeriodicLookup.h:26,37,51
+ *   SARW{ctor, initiateChain, propagateChain, terminateChain, addAtom, public state vectors}
+ *                                                       sarw.h:77-94,116-126; sarw.cpp:220-368
+ *   main()'s growth loop                                sarw.cpp:66-79
+ *
+ * Conventions: every function returns 0 on success, non-zero on error (sarw_last_error gives the text).
+ * "Jammed" (no chain progressed) is NOT an error; it is reported in sarw_stats like the reference's early
+ * loop exit (sarw.cpp:69). The handle owns all device memory; the caller owns every host buffer. There is no
+ * CPU fallback: without a CUDA device every call fails. One host thread per context.
+ */
+#ifndef SARW_ABI_H
+#define SARW_ABI_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sarw_ctx sarw_ctx;
+
+enum { SARW_GRAFT_FILE = 0, SARW_GRAFT_Z = 1, SARW_GRAFT_ZCENTER = 2, SARW_GRAFT_OTHER = 3 };   /* sarw.cpp:342-347 */
+enum { SARW_ORDER_ROUNDROBIN = 0, SARW_ORDER_GRAFTED = 1 };                                   /* sarw.cpp:230-249 */
+enum { SARW_BOUNDARY_PPP = 0, SARW_BOUNDARY_PPF = 1, SARW_BOUNDARY_PFP = 2, SARW_BOUNDARY_FPP = 3 }; /* sarw.cpp:201-203 */
+
+/* The fields main() reads from the input file (sarw.cpp:22-38) plus the extensions of this build. */
+typedef struct sarw_params {
+	int64_t nChains;            /* sarw.cpp:22 */
+	double boxSize[3];          /* sarw.cpp:23, Angstrom */
+	double minDist;             /* sarw.cpp:24 */
+	double targetMassDensity;   /* sarw.cpp:30, g/cc */
+	int64_t nGraftChains;       /* sarw.cpp:31 */
+	int32_t maxTrials;          /* sarw.cpp:35 */
+	int32_t graftLoc;           /* sarw.cpp:32, SARW_GRAFT_* */
+	int32_t growthOrder;        /* sarw.cpp:33, SARW_ORDER_* */
+	int32_t boundary;           /* sarw.cpp:34, SARW_BOUNDARY_* */
+	double growthBias[3];       /* README.md:33 only (no reference code): a trial whose step has bias.step < 0 fails */
+	uint64_t seed;              /* extension: Philox key; the reference is unseeded (sarw.cpp:16) */
+	int32_t device;             /* CUDA device ordinal; < 0 = current device */
+	int32_t cellCapacity;       /* 0 = default (7 beads inline per cell); 1..7 = test hook forcing overflow handling */
+	double cellEdge;            /* 0 = default; minimum cell edge in Angstrom (>= 2.002*minDist is always enforced) */
+	int64_t reserveRounds;      /* 0 = auto; growth rounds to pre-allocate bead storage for */
+} sarw_params;
+
+typedef struct sarw_stats {
+	int64_t nBeads;             /* SARW::actualCount(), sarw.h:102 */
+	int64_t nBonds;             /* SARW::nBonds(), sarw.h:98 */
+	int64_t target;             /* SARW::targetCount(), sarw.h:104 */
+	int64_t rounds;             /* propagateChain() calls made so far */
+	int32_t initiated;          /* return value of initiateChain(), sarw.cpp:290 */
+	int32_t lastProgressed;     /* return value of the last propagateChain(), sarw.cpp:282 */
+	uint64_t trials;            /* growth trials evaluated in reference terms (what sarw.cpp:259 would have looped) */
+	uint64_t seedTrials;        /* seeding trials in reference terms (sarw.cpp:333) */
+	uint64_t queries;           /* overlap queries the device actually evaluated (candidates tested against the cell list) */
+	uint64_t conflicts;         /* same-round conflicts re-resolved in chain order */
+	uint64_t overflowBeads;     /* beads held in the overflow list because their cell was full */
+	double seedMs;              /* device time of seeding (CUDA events on the context's stream) */
+	double growMs;              /* device time of all growth launches so far */
+	int64_t growLaunches;       /* kernel launches made by growth so far */
+	int64_t seedLaunches;
+} sarw_stats;
+
+/* SARW::SARW + PeriodicLookup::PeriodicLookup (sarw.h:88-94, PeriodicLookup.h:26-34): allocates the device cell list. */
+int sarw_create(const sarw_params* params, sarw_ctx** out);
+void sarw_destroy(sarw_ctx* ctx);
+/* text of the last error on this context (or of the last failed sarw_create when ctx == NULL) */
+const char* sarw_last_error(const sarw_ctx* ctx);
+/* run on a caller-provided CUDA stream (cudaStream_t passed as void*); default is a stream owned by the context */
+int sarw_set_stream(sarw_ctx* ctx, void* cudaStream);
+
+/* SARW::addObstacle's effect (sarw.cpp:135-142): points enter the lookup before any bead; host xyz[3*n]. */
+int sarw_add_obstacles(sarw_ctx* ctx, const double* xyz, int64_t n);
+/* SARW::readGrafts' effect (sarw.cpp:110-119): graft seed positions for chains [0, nGraftChains); host xyz[3*n]. */
+int sarw_set_grafts(sarw_ctx* ctx, const double* xyz, int64_t n);
+
+/* SARW::initiateChain (sarw.cpp:290-319): seed two beads per chain, chain i seeing chains < i. */
+int sarw_initiate(sarw_ctx* ctx, int32_t* ok);
+/* SARW::propagateChain (sarw.cpp:220-283): ONE round. */
+int sarw_propagate_round(sarw_ctx* ctx, int32_t* progressed);
+/* main()'s loop (sarw.cpp:67-78) on the device: rounds until actualCount >= target, a round makes no progress, or
+ * maxRounds more rounds were run (maxRounds < 0: unbounded). target <= 0 means SARW::targetCount(). */
+int sarw_grow(sarw_ctx* ctx, int64_t target, int64_t maxRounds, sarw_stats* stats);
+/* SARW::terminateChain (sarw.cpp:359-368) */
+int sarw_terminate(sarw_ctx* ctx);
+
+int sarw_get_stats(sarw_ctx* ctx, sarw_stats* stats);
+/* SARW::targetCount (sarw.h:103-104) with a 64-bit volume */
+int64_t sarw_target_count(const double boxSize[3], double targetMassDensity);
+
+/* The public state vectors main()'s exporters read (sarw.h:77-83), in the reference's acceptance order:
+ * xyz[3*nBeads] (polymerChains[i].pos), chainID[nBeads], type[nBeads], bonds[2*nBonds] (1-based species, listBonds).
+ * Any pointer may be NULL. */
+int sarw_download(sarw_ctx* ctx, double* xyz, int32_t* chainID, int32_t* type, int64_t* bonds);
+/* chainLengths (sarw.h:83): lengths[nChains] */
+int sarw_chain_lengths(sarw_ctx* ctx, int32_t* lengths);
+/* actualCount() after each completed round, for the PROGRESS log of sarw.cpp:70-76: counts[min(n, rounds)] */
+int sarw_round_counts(sarw_ctx* ctx, int64_t* counts, int64_t n);
+
+/* PeriodicLookup::addPoint (PeriodicLookup.h:37-47) for n points; they take the next n lookup indices. */
+int sarw_lookup_add_points(sarw_ctx* ctx, const double* xyz, int64_t n);
+/* PeriodicLookup::find (PeriodicLookup.h:51-75) for n candidates: hit[i] = any stored point other than ignore[i]
+ * (ignored only when >= 0; ignore may be NULL) within minDist under the minimum-image convention. Host buffers. */
+int sarw_lookup_find_batch(sarw_ctx* ctx, const double* xyz, const int64_t* ignore, int64_t n, uint8_t* hit);
+/* same with DEVICE pointers (inputs already resident in HBM); runs on the context's stream, does not synchronise */
+int sarw_lookup_find_batch_device(sarw_ctx* ctx, const double* d_xyz, const int64_t* d_ignore, int64_t n, uint8_t* d_hit);
+/* number of points currently in the lookup (obstacles + beads + added points) */
+int64_t sarw_lookup_size(sarw_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SARW_ABI_H */

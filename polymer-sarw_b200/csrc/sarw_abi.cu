@@ -1,0 +1,516 @@
+// sarw_abi.cu — host side of the C ABI declared in include/sarw_abi.h: context, device memory, launches.
+// No CPU fallback anywhere: every entry point needs a CUDA device and fails with an error text otherwise.
+#include "sarw_abi.h"
+#include "sarw_host.h"
+#include <cmath>
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+using namespace sarw;
+
+namespace {
+thread_local std::string g_createError;
+
+constexpr double AVOGADRO = 6.022e23;   // sarw.h:4
+constexpr double BOND_LENGTH = 1.54;    // sarw.h:5
+constexpr double ATOM_MASS = 14.0;      // sarw.h:6
+}
+
+struct sarw_ctx {
+	sarw_params p{};
+	Geom g{};
+	Tables T{};
+	int device = 0, numSMs = 0, growBlocksMax = 0;
+	cudaStream_t stream = nullptr; bool ownStream = false;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	std::string err;
+
+	// lookup index space: [0, nObstacles) obstacles / added points, then atom slots
+	uint32_t nextId = 0;          // next lookup index for add_points / obstacles
+	uint64_t idCapacity = 0;      // lookup indices lpos is allocated for
+	bool initiated = false, initiateCalled = false, terminated = false;
+	uint32_t nSeeded = 0;
+	uint32_t roundCap = 0;        // growth rounds storage is allocated for
+
+	Control* ctl = nullptr;
+	ChainState* chains = nullptr;
+	uint32_t* resTrial = nullptr; double* resPos = nullptr;
+	uint32_t* prev = nullptr; uint64_t prevCap = 0;
+	uint32_t *roundAcc = nullptr, *roundProg = nullptr, *dirtyCount = nullptr, *dirtyList = nullptr;
+	double* grafts = nullptr; int64_t nGrafts = 0;
+
+	double seedMs = 0, growMs = 0; int64_t growLaunches = 0, seedLaunches = 0;
+};
+
+namespace {
+
+int fail(sarw_ctx* c, const char* fmt, ...)
+{
+	char buf[1024];
+	va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+	if (c) c->err = buf; else g_createError = buf;
+	return 1;
+}
+#define CU(c, x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(c, "%s: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+uint64_t slots_for_rounds(const sarw_ctx* c, uint64_t rounds) { return 2ull * c->g.nChains + rounds * c->g.nChains; }
+
+// grow (or create) lpos to hold `cap` lookup indices; new entries get the all-ones "never accepted" pattern
+int ensure_ids(sarw_ctx* c, uint64_t cap)
+{
+	if (cap <= c->idCapacity) return 0;
+	if (cap >= 0xFFFFFFF0ull) return fail(c, "lookup index space exhausted (%llu indices needed, 32-bit ids)", (unsigned long long)cap);
+	uint64_t newCap = std::max<uint64_t>(cap, c->idCapacity + c->idCapacity / 2);
+	if (newCap >= 0xFFFFFFF0ull) newCap = 0xFFFFFFEFull;
+	double* np = nullptr;
+	CU(c, cudaMalloc(&np, newCap * 3 * sizeof(double)));
+	if (c->idCapacity) CU(c, cudaMemcpyAsync(np, c->T.lpos, c->idCapacity * 3 * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+	CU(c, cudaMemsetAsync(np + 3 * c->idCapacity, 0xFF, (newCap - c->idCapacity) * 3 * sizeof(double), c->stream));
+	CU(c, cudaStreamSynchronize(c->stream));
+	if (c->T.lpos) cudaFree(c->T.lpos);
+	c->T.lpos = np; c->idCapacity = newCap;
+	return 0;
+}
+
+int ensure_rounds(sarw_ctx* c, uint32_t rounds)
+{
+	if (rounds <= c->roundCap) return 0;
+	uint32_t newCap = std::max<uint32_t>(rounds, c->roundCap + c->roundCap / 2 + 16);
+	uint64_t slots = slots_for_rounds(c, newCap);
+	if ((uint64_t)c->g.idAtomBase + slots >= 0xFFFFFFF0ull) {
+		newCap = rounds; slots = slots_for_rounds(c, newCap);
+		if ((uint64_t)c->g.idAtomBase + slots >= 0xFFFFFFF0ull) return fail(c, "bead index space exhausted (32-bit lookup ids)");
+	}
+	if (ensure_ids(c, c->g.idAtomBase + slots)) return 1;
+	// prev[] per slot
+	uint32_t* np = nullptr;
+	CU(c, cudaMalloc(&np, slots * sizeof(uint32_t)));
+	if (c->prevCap) CU(c, cudaMemcpyAsync(np, c->prev, c->prevCap * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
+	// per-round counters
+	uint32_t* arrs[3]; uint32_t** olds[3] = { &c->roundAcc, &c->roundProg, &c->dirtyCount };
+	for (int k = 0; k < 3; k++) {
+		CU(c, cudaMalloc(&arrs[k], (size_t)newCap * sizeof(uint32_t)));
+		CU(c, cudaMemsetAsync(arrs[k], 0, (size_t)newCap * sizeof(uint32_t), c->stream));
+		if (c->roundCap) CU(c, cudaMemcpyAsync(arrs[k], *olds[k], (size_t)c->roundCap * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
+	}
+	CU(c, cudaStreamSynchronize(c->stream));
+	if (c->prev) cudaFree(c->prev);
+	for (int k = 0; k < 3; k++) { if (*olds[k]) cudaFree(*olds[k]); *olds[k] = arrs[k]; }
+	c->prev = np; c->prevCap = slots; c->roundCap = newCap;
+	return 0;
+}
+
+int read_control(sarw_ctx* c, Control* h)
+{
+	CU(c, cudaMemcpyAsync(h, c->ctl, sizeof(Control), cudaMemcpyDeviceToHost, c->stream));
+	CU(c, cudaStreamSynchronize(c->stream));
+	return 0;
+}
+
+int check_overflow(sarw_ctx* c)
+{
+	uint32_t n = 0;
+	CU(c, cudaMemcpyAsync(&n, c->T.ovfCount, sizeof n, cudaMemcpyDeviceToHost, c->stream));
+	CU(c, cudaStreamSynchronize(c->stream));
+	if (n > c->T.ovfCap) return fail(c, "cell overflow list exhausted (%u beads did not fit their cells; raise cellEdge or lower density)", n);
+	return 0;
+}
+
+void fill_stats(sarw_ctx* c, const Control& h, sarw_stats* s)
+{
+	memset(s, 0, sizeof *s);
+	s->nBeads = (int64_t)h.nBeads;
+	s->nBonds = (int64_t)h.nBeads - (int64_t)c->nSeeded;
+	if (s->nBonds < 0) s->nBonds = 0;
+	s->target = c->g.target;
+	s->rounds = h.round;
+	s->initiated = (int32_t)h.initiated;
+	s->lastProgressed = (int32_t)h.lastProgressed;
+	s->trials = h.trials; s->seedTrials = h.seedTrials; s->queries = h.queries; s->conflicts = h.conflicts;
+	s->seedMs = c->seedMs; s->growMs = c->growMs; s->growLaunches = c->growLaunches; s->seedLaunches = c->seedLaunches;
+}
+
+} // namespace
+
+extern "C" {
+
+int64_t sarw_target_count(const double boxSize[3], double targetMassDensity)
+{
+	// sarw.h:103-104: int vol() truncates; kept, but in 64 bits
+	int64_t vol = (int64_t)(boxSize[0] * boxSize[1] * boxSize[2]);
+	return (int64_t)nearbyint((vol * targetMassDensity * AVOGADRO * 1e-24) / ATOM_MASS);
+}
+
+const char* sarw_last_error(const sarw_ctx* ctx) { return ctx ? ctx->err.c_str() : g_createError.c_str(); }
+
+int sarw_create(const sarw_params* p, sarw_ctx** out)
+{
+	if (!p || !out) return fail(nullptr, "sarw_create: null argument");
+	*out = nullptr;
+	if (p->nChains < 1 || p->nChains > 0x7FFFFFFF) return fail(nullptr, "nChains must be in [1, 2^31)");
+	if (!(p->minDist > 0)) return fail(nullptr, "minDist must be positive");
+	if (p->maxTrials < 1) return fail(nullptr, "maxTrials must be at least 1");
+	for (int k = 0; k < 3; k++)
+		if (!(p->boxSize[k] >= 2 * p->minDist))   // the reference needs S = floor(L/minDist) >= 2 (PeriodicLookup.h:16-22,29)
+			return fail(nullptr, "boxSize[%d] = %g must be at least 2*minDist = %g", k, p->boxSize[k], 2 * p->minDist);
+	if (p->nGraftChains < 0 || p->nGraftChains > p->nChains) return fail(nullptr, "nGraftChains must be in [0, nChains]");
+
+	int nDev = 0;
+	cudaError_t e = cudaGetDeviceCount(&nDev);
+	if (e != cudaSuccess || nDev == 0) return fail(nullptr, "no CUDA device available (%s); libsarw_b200 has no CPU fallback", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+	sarw_ctx* c = new sarw_ctx();
+	c->p = *p;
+	auto bail = [&](int rc) { g_createError = c->err; sarw_destroy(c); return rc; };
+	if (p->device >= 0) { if (cudaSetDevice(p->device) != cudaSuccess) { fail(c, "cudaSetDevice(%d) failed", p->device); return bail(1); } }
+	cudaGetDevice(&c->device);
+	cudaDeviceProp prop;
+	if (cudaGetDeviceProperties(&prop, c->device) != cudaSuccess) { fail(c, "cudaGetDeviceProperties failed"); return bail(1); }
+	if (prop.major < 10) { fail(c, "device %d is sm_%d%d; libsarw_b200 is built for sm_100a only", c->device, prop.major, prop.minor); return bail(1); }
+	c->numSMs = prop.multiProcessorCount;
+	if (!prop.cooperativeLaunch) { fail(c, "device lacks cooperative launch"); return bail(1); }
+
+	Geom& g = c->g;
+	g.thresh = p->minDist;
+	double edgeMin = std::max(2.002 * p->minDist, p->cellEdge > 0 ? p->cellEdge : 2.5);
+	double amax = 0;
+	for (int k = 0; k < 3; k++) {
+		g.L[k] = p->boxSize[k]; g.Linv[k] = 1. / p->boxSize[k];
+		int S = (int)floor(p->boxSize[k] / edgeMin); if (S < 1) S = 1;
+		g.S[k] = S; g.a[k] = p->boxSize[k] / S; g.ainv[k] = S / p->boxSize[k]; g.sOverL[k] = (double)S;
+		g.reachCells[k] = (p->minDist / g.a[k]) * (1 + 1e-9) + 1e-7;
+		amax = std::max(amax, g.a[k]);
+	}
+	g.cap = (p->cellCapacity >= 1 && p->cellCapacity <= MAX_CAP) ? p->cellCapacity : MAX_CAP;
+	{	// fp32 pre-filter bounds; the undecided band covers fp32 storage + arithmetic error with a wide margin
+		double band = 4e-6 * (p->minDist + amax + 2 * BOND_LENGTH);
+		double lo = std::max(0.0, p->minDist - band), hi = p->minDist + band;
+		g.lo2 = nextafterf((float)(lo * lo * (1 - 1e-6)), 0.f);
+		g.hi2 = nextafterf((float)(hi * hi * (1 + 1e-6)), INFINITY);
+		g.regionReach = p->minDist * (1 + 1e-9) + 1e-6 * amax + band;
+	}
+	{	double phi = (180 - 109.5) * M_PI / 180, sp, cp;   // sarw.cpp:165
+		sincos_portable(phi, sp, cp);
+		g.dSinPhi = BOND_LENGTH * sp; g.dCosPhi = BOND_LENGTH * cp;
+	}
+	for (int k = 0; k < 3; k++) g.bias[k] = p->growthBias[k];
+	g.biased = (p->growthBias[0] != 0 || p->growthBias[1] != 0 || p->growthBias[2] != 0) ? 1 : 0;
+	g.boundary = p->boundary; g.graftLoc = p->graftLoc; g.growthOrder = p->growthOrder;
+	g.maxTrials = p->maxTrials;
+	g.key0 = (uint32_t)p->seed; g.key1 = (uint32_t)(p->seed >> 32);
+	g.nChains = (uint32_t)p->nChains; g.nGraft = (uint32_t)p->nGraftChains;
+	g.idAtomBase = 0; g.seedIgnoreId = ID_NONE;
+	g.target = sarw_target_count(p->boxSize, p->targetMassDensity);
+	g.nGraftAtoms = (p->nGraftChains * g.target / p->nChains) + (p->nChains - p->nGraftChains) * 2;   // sarw.cpp:232
+
+	if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { fail(c, "cudaStreamCreate failed"); return bail(1); }
+	c->ownStream = true;
+	cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
+
+	const size_t nCells = (size_t)g.S[0] * g.S[1] * g.S[2];
+#define CUB_(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fail(c, "%s: %s", #x, cudaGetErrorString(e_)); return bail(1); } } while (0)
+	CUB_(cudaMalloc(&c->T.cells, nCells * sizeof(Cell)));
+	CUB_(cudaMemsetAsync(c->T.cells, 0xFF, nCells * sizeof(Cell), c->stream));
+	c->T.ovfCap = 1u << 16;
+	CUB_(cudaMalloc(&c->T.ovf, c->T.ovfCap * sizeof(uint32_t)));
+	CUB_(cudaMalloc(&c->T.ovfCount, sizeof(uint32_t)));
+	CUB_(cudaMemsetAsync(c->T.ovfCount, 0, sizeof(uint32_t), c->stream));
+	CUB_(cudaMalloc(&c->ctl, sizeof(Control)));
+	CUB_(cudaMemsetAsync(c->ctl, 0, sizeof(Control), c->stream));
+	CUB_(cudaMalloc(&c->chains, (size_t)g.nChains * sizeof(ChainState)));
+	CUB_(cudaMemsetAsync(c->chains, 0, (size_t)g.nChains * sizeof(ChainState), c->stream));
+	CUB_(cudaMalloc(&c->resTrial, (size_t)g.nChains * sizeof(uint32_t)));
+	CUB_(cudaMemsetAsync(c->resTrial, 0, (size_t)g.nChains * sizeof(uint32_t), c->stream));
+	CUB_(cudaMalloc(&c->resPos, (size_t)g.nChains * 3 * sizeof(double)));
+	CUB_(cudaMalloc(&c->dirtyList, (size_t)g.nChains * sizeof(uint32_t)));
+	CUB_(grow_max_blocks(c->numSMs, &c->growBlocksMax));
+	CUB_(cudaStreamSynchronize(c->stream));
+#undef CUB_
+	if (c->growBlocksMax < 1) { fail(c, "growth kernel does not fit on the device"); return bail(1); }
+	*out = c;
+	return 0;
+}
+
+void sarw_destroy(sarw_ctx* c)
+{
+	if (!c) return;
+	cudaSetDevice(c->device);
+	if (c->stream) cudaStreamSynchronize(c->stream);
+	cudaFree(c->T.cells); cudaFree(c->T.lpos); cudaFree(c->T.ovf); cudaFree(c->T.ovfCount);
+	cudaFree(c->ctl); cudaFree(c->chains); cudaFree(c->resTrial); cudaFree(c->resPos); cudaFree(c->prev);
+	cudaFree(c->roundAcc); cudaFree(c->roundProg); cudaFree(c->dirtyCount); cudaFree(c->dirtyList); cudaFree(c->grafts);
+	if (c->ev0) cudaEventDestroy(c->ev0);
+	if (c->ev1) cudaEventDestroy(c->ev1);
+	if (c->ownStream && c->stream) cudaStreamDestroy(c->stream);
+	delete c;
+}
+
+int sarw_set_stream(sarw_ctx* c, void* s)
+{
+	if (!c) return 1;
+	cudaStreamSynchronize(c->stream);
+	if (c->ownStream && c->stream) cudaStreamDestroy(c->stream);
+	c->stream = (cudaStream_t)s; c->ownStream = false;
+	return 0;
+}
+
+int sarw_lookup_add_points(sarw_ctx* c, const double* xyz, int64_t n)
+{
+	if (!c) return 1;
+	if (n < 0 || (n > 0 && !xyz)) return fail(c, "sarw_lookup_add_points: bad arguments");
+	if (c->initiateCalled) return fail(c, "points/obstacles must be added before sarw_initiate");
+	if (n == 0) return 0;
+	cudaSetDevice(c->device);
+	if (ensure_ids(c, (uint64_t)c->nextId + (uint64_t)n)) return 1;
+	double* d = nullptr;
+	CU(c, cudaMalloc(&d, (size_t)n * 3 * sizeof(double)));
+	CU(c, cudaMemcpyAsync(d, xyz, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	cudaError_t e = launch_add_points(c->g, c->T, d, n, c->nextId, c->stream);
+	cudaError_t e2 = cudaStreamSynchronize(c->stream);
+	cudaFree(d);
+	if (e != cudaSuccess || e2 != cudaSuccess) return fail(c, "add_points failed: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+	c->nextId += (uint32_t)n;
+	return check_overflow(c);
+}
+
+int sarw_add_obstacles(sarw_ctx* c, const double* xyz, int64_t n) { return sarw_lookup_add_points(c, xyz, n); }
+
+int64_t sarw_lookup_size(sarw_ctx* c)
+{
+	if (!c) return -1;
+	if (!c->initiateCalled) return c->nextId;
+	Control h; if (read_control(c, &h)) return -1;
+	return (int64_t)c->g.idAtomBase + (int64_t)h.nBeads;
+}
+
+int sarw_set_grafts(sarw_ctx* c, const double* xyz, int64_t n)
+{
+	if (!c) return 1;
+	if (n < 0 || (n > 0 && !xyz)) return fail(c, "sarw_set_grafts: bad arguments");
+	cudaSetDevice(c->device);
+	if (c->grafts) { cudaFree(c->grafts); c->grafts = nullptr; }
+	c->nGrafts = n;
+	if (n == 0) return 0;
+	CU(c, cudaMalloc(&c->grafts, (size_t)n * 3 * sizeof(double)));
+	CU(c, cudaMemcpyAsync(c->grafts, xyz, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	CU(c, cudaStreamSynchronize(c->stream));
+	return 0;
+}
+
+int sarw_lookup_find_batch_device(sarw_ctx* c, const double* d_xyz, const int64_t* d_ignore, int64_t n, uint8_t* d_hit)
+{
+	if (!c) return 1;
+	if (n < 0 || (n > 0 && (!d_xyz || !d_hit))) return fail(c, "sarw_lookup_find_batch_device: bad arguments");
+	cudaSetDevice(c->device);
+	CU(c, launch_find_batch(c->g, c->T, d_xyz, d_ignore, n, d_hit, c->numSMs, c->stream));
+	return 0;
+}
+
+int sarw_lookup_find_batch(sarw_ctx* c, const double* xyz, const int64_t* ignore, int64_t n, uint8_t* hit)
+{
+	if (!c) return 1;
+	if (n < 0 || (n > 0 && (!xyz || !hit))) return fail(c, "sarw_lookup_find_batch: bad arguments");
+	if (n == 0) return 0;
+	cudaSetDevice(c->device);
+	double* dx = nullptr; int64_t* di = nullptr; uint8_t* dh = nullptr;
+	int rc = 0;
+	auto cleanup = [&]() { cudaFree(dx); cudaFree(di); cudaFree(dh); };
+#define CUF(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { rc = fail(c, "%s: %s", #x, cudaGetErrorString(e_)); cleanup(); return rc; } } while (0)
+	CUF(cudaMalloc(&dx, (size_t)n * 3 * sizeof(double)));
+	CUF(cudaMalloc(&dh, (size_t)n));
+	CUF(cudaMemcpyAsync(dx, xyz, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	if (ignore) {
+		CUF(cudaMalloc(&di, (size_t)n * sizeof(int64_t)));
+		CUF(cudaMemcpyAsync(di, ignore, (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+	}
+	CUF(launch_find_batch(c->g, c->T, dx, di, n, dh, c->numSMs, c->stream));
+	CUF(cudaMemcpyAsync(hit, dh, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+	CUF(cudaStreamSynchronize(c->stream));
+#undef CUF
+	cleanup();
+	return 0;
+}
+
+int sarw_initiate(sarw_ctx* c, int32_t* ok)
+{
+	if (!c) return 1;
+	if (c->initiateCalled) return fail(c, "sarw_initiate was already called on this context");
+	cudaSetDevice(c->device);
+	Geom& g = c->g;
+	if (g.graftLoc == SARW_GRAFT_FILE && g.nGraft > 0 && c->nGrafts < (int64_t)g.nGraft)
+		// the reference only logs "Inadequate number of seeds" and then reads out of bounds (sarw.cpp:114-115,343)
+		return fail(c, "Inadequate number of graft seeds: %lld given, %u grafted chains", (long long)c->nGrafts, g.nGraft);
+	g.idAtomBase = c->nextId;                                  // = nObstacles
+	g.seedIgnoreId = c->nextId > 0 ? c->nextId - 1 : ID_NONE;  // sarw.cpp:198,353: find(pos, -1 + nObstacles)
+	uint64_t wantRounds = c->p.reserveRounds > 0 ? (uint64_t)c->p.reserveRounds
+		: (uint64_t)std::max<int64_t>(0, (g.target - 2 * (int64_t)g.nChains) / (int64_t)g.nChains) * 9 / 8 + 32;
+	if (wantRounds > 0xFFFFFFFFull) wantRounds = 0xFFFFFFFFull;
+	if ((uint64_t)g.idAtomBase + slots_for_rounds(c, wantRounds) >= 0xFFFFFFF0ull) wantRounds = 0;
+	if (ensure_rounds(c, (uint32_t)std::max<uint64_t>(wantRounds, 1))) return 1;
+
+	Control h0; memset(&h0, 0, sizeof h0);
+	h0.seedFailChain = ID_NONE; h0.lastProgressed = 1;
+	CU(c, cudaMemcpyAsync(c->ctl, &h0, sizeof h0, cudaMemcpyHostToDevice, c->stream));
+	CU(c, cudaEventRecord(c->ev0, c->stream));
+	int launches = 0;
+	CU(c, launch_seed(g, c->T, c->chains, c->resTrial, c->prev, c->grafts, c->ctl, c->dirtyList, c->numSMs, c->stream, &launches));
+	CU(c, cudaEventRecord(c->ev1, c->stream));
+	Control h; if (read_control(c, &h)) return 1;
+	float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+	c->seedMs += ms; c->seedLaunches += launches;
+	c->initiateCalled = true;
+	c->initiated = h.initiated != 0;
+	c->nSeeded = (uint32_t)(h.nBeads / 2);
+	if (ok) *ok = c->initiated ? 1 : 0;
+	return check_overflow(c);
+}
+
+static int grow_impl(sarw_ctx* c, int64_t target, int64_t maxRounds, sarw_stats* stats)
+{
+	if (!c->initiateCalled) return fail(c, "sarw_initiate must be called before growing");
+	cudaSetDevice(c->device);
+	Geom g = c->g;
+	if (target > 0) g.target = target;
+	Control h; if (read_control(c, &h)) return 1;
+	int64_t roundsLeft = maxRounds < 0 ? INT64_MAX : maxRounds;
+	// main() only enters the loop when initiateChain succeeded (sarw.cpp:66)
+	while (c->initiated && roundsLeft > 0 && (int64_t)h.nBeads < g.target && h.lastProgressed) {
+		if (h.round >= c->roundCap && ensure_rounds(c, h.round + 1)) return 1;
+		uint32_t roundEnd = c->roundCap;
+		if ((int64_t)(roundEnd - h.round) > roundsLeft) roundEnd = h.round + (uint32_t)roundsLeft;
+		int blocks = (int)std::min<int64_t>(c->growBlocksMax, ((int64_t)g.nChains + 7) / 8);
+		if (blocks < 1) blocks = 1;
+		CU(c, cudaEventRecord(c->ev0, c->stream));
+		CU(c, launch_grow(g, c->T, c->chains, c->resTrial, c->resPos, c->prev, c->ctl, c->roundAcc, c->roundProg, c->dirtyCount,
+			c->dirtyList, roundEnd, blocks, c->stream));
+		CU(c, cudaEventRecord(c->ev1, c->stream));
+		uint32_t before = h.round;
+		if (read_control(c, &h)) return 1;
+		float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+		c->growMs += ms; c->growLaunches += 1;
+		roundsLeft -= (int64_t)(h.round - before);
+		if (check_overflow(c)) return 1;
+		if (h.round == before) break;
+	}
+	if (stats) fill_stats(c, h, stats);
+	return 0;
+}
+
+int sarw_grow(sarw_ctx* c, int64_t target, int64_t maxRounds, sarw_stats* stats)
+{
+	if (!c) return 1;
+	return grow_impl(c, target, maxRounds, stats);
+}
+
+int sarw_propagate_round(sarw_ctx* c, int32_t* progressed)
+{
+	if (!c) return 1;
+	if (!c->initiateCalled) return fail(c, "sarw_initiate must be called before sarw_propagate_round");
+	if (!c->initiated) return fail(c, "initiateChain failed; the reference never propagates in that case (sarw.cpp:66)");
+	// one unconditional round, like a direct call of SARW::propagateChain
+	cudaSetDevice(c->device);
+	Control h; if (read_control(c, &h)) return 1;
+	if (h.round >= c->roundCap && ensure_rounds(c, h.round + 1)) return 1;
+	Geom g = c->g;
+	g.target = INT64_MAX;
+	unsigned one = 1;
+	CU(c, cudaMemcpyAsync(&c->ctl->lastProgressed, &one, sizeof one, cudaMemcpyHostToDevice, c->stream));
+	int blocks = (int)std::min<int64_t>(c->growBlocksMax, ((int64_t)g.nChains + 7) / 8);
+	CU(c, cudaEventRecord(c->ev0, c->stream));
+	CU(c, launch_grow(g, c->T, c->chains, c->resTrial, c->resPos, c->prev, c->ctl, c->roundAcc, c->roundProg, c->dirtyCount,
+		c->dirtyList, h.round + 1, blocks, c->stream));
+	CU(c, cudaEventRecord(c->ev1, c->stream));
+	if (read_control(c, &h)) return 1;
+	float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+	c->growMs += ms; c->growLaunches += 1;
+	if (progressed) *progressed = (int32_t)h.lastProgressed;
+	return check_overflow(c);
+}
+
+int sarw_terminate(sarw_ctx* c)
+{
+	if (!c) return 1;
+	if (!c->initiateCalled) return fail(c, "sarw_initiate must be called before sarw_terminate");
+	c->terminated = true;   // applied when atoms are gathered: type of each chain's last bead := 1 (sarw.cpp:365)
+	return 0;
+}
+
+int sarw_get_stats(sarw_ctx* c, sarw_stats* s)
+{
+	if (!c || !s) return 1;
+	cudaSetDevice(c->device);
+	Control h; if (read_control(c, &h)) return 1;
+	fill_stats(c, h, s);
+	uint32_t n = 0;
+	cudaMemcpy(&n, c->T.ovfCount, sizeof n, cudaMemcpyDeviceToHost);
+	s->overflowBeads = n;
+	return 0;
+}
+
+int sarw_download(sarw_ctx* c, double* xyz, int32_t* chainID, int32_t* type, int64_t* bonds)
+{
+	if (!c) return 1;
+	if (!c->initiateCalled) return fail(c, "nothing to download before sarw_initiate");
+	cudaSetDevice(c->device);
+	Control h; if (read_control(c, &h)) return 1;
+	const uint64_t N = h.nBeads, nBonds = N > c->nSeeded ? N - c->nSeeded : 0;
+	if (N == 0) return 0;
+	const uint64_t nSlots = slots_for_rounds(c, h.round);
+	uint32_t *flags = nullptr, *scan = nullptr; void* tmp = nullptr; size_t tmpBytes = 0;
+	double* dx = nullptr; int32_t *dc = nullptr, *dt = nullptr; int64_t* db = nullptr;
+	int rc = 0;
+	auto cleanup = [&]() { cudaFree(flags); cudaFree(scan); cudaFree(tmp); cudaFree(dx); cudaFree(dc); cudaFree(dt); cudaFree(db); };
+#define CUF(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { rc = fail(c, "%s: %s", #x, cudaGetErrorString(e_)); cleanup(); return rc; } } while (0)
+	CUF(cudaMalloc(&flags, nSlots * sizeof(uint32_t)));
+	CUF(cudaMalloc(&scan, nSlots * sizeof(uint32_t)));
+	CUF(download_scan_bytes(nSlots, &tmpBytes));
+	CUF(cudaMalloc(&tmp, tmpBytes ? tmpBytes : 16));
+	if (xyz) CUF(cudaMalloc(&dx, N * 3 * sizeof(double)));
+	if (chainID) CUF(cudaMalloc(&dc, N * sizeof(int32_t)));
+	if (type) CUF(cudaMalloc(&dt, N * sizeof(int32_t)));
+	if (bonds && nBonds) CUF(cudaMalloc(&db, nBonds * 2 * sizeof(int64_t)));
+	CUF(launch_download(c->g, c->T, c->prev, c->chains, nSlots, c->nSeeded, c->terminated ? 1 : 0, flags, scan, tmp, tmpBytes, dx, dc, dt, db, c->stream));
+	if (dx) CUF(cudaMemcpyAsync(xyz, dx, N * 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	if (dc) CUF(cudaMemcpyAsync(chainID, dc, N * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+	if (dt) CUF(cudaMemcpyAsync(type, dt, N * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+	if (db) CUF(cudaMemcpyAsync(bonds, db, nBonds * 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+	CUF(cudaStreamSynchronize(c->stream));
+#undef CUF
+	cleanup();
+	return 0;
+}
+
+int sarw_chain_lengths(sarw_ctx* c, int32_t* lengths)
+{
+	if (!c || !lengths) return 1;
+	cudaSetDevice(c->device);
+	int32_t* d = nullptr;
+	CU(c, cudaMalloc(&d, (size_t)c->g.nChains * sizeof(int32_t)));
+	cudaError_t e = launch_chain_lengths(c->chains, c->g.nChains, d, c->stream);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(lengths, d, (size_t)c->g.nChains * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+	cudaFree(d);
+	if (e != cudaSuccess) return fail(c, "sarw_chain_lengths: %s", cudaGetErrorString(e));
+	return 0;
+}
+
+int sarw_round_counts(sarw_ctx* c, int64_t* counts, int64_t n)
+{
+	if (!c || (n > 0 && !counts)) return 1;
+	if (!c->initiateCalled) return fail(c, "sarw_initiate must be called first");
+	cudaSetDevice(c->device);
+	Control h; if (read_control(c, &h)) return 1;
+	int64_t m = std::min<int64_t>(n, h.round);
+	if (m <= 0) return 0;
+	std::vector<uint32_t> acc((size_t)m);
+	CU(c, cudaMemcpyAsync(acc.data(), c->roundAcc, (size_t)m * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+	CU(c, cudaStreamSynchronize(c->stream));
+	int64_t run = 2ll * c->nSeeded;
+	for (int64_t r = 0; r < m; r++) { run += acc[(size_t)r]; counts[r] = run; }
+	return 0;
+}
+
+} // extern "C"

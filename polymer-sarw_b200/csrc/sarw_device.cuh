@@ -1,0 +1,351 @@
+// sarw_device.cuh — device-side building blocks of libsarw_b200 (sm_100a).
+//
+// Everything that decides accept/reject is IEEE-754 double arithmetic in the reference's operation order
+// (file:line citations are into /root/reference); the translation unit is compiled with -fmad=false so that no
+// multiply-add is contracted. fp32 is used only as a conservative pre-filter whose undecided band falls back
+// to the exact test.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace sarw {
+
+// ------------------------------------------------------------------ data layout in HBM
+// One 128-byte line per cell: header + up to 7 beads inline. slot = (ox, oy, oz, id): Cartesian offset of the
+// bead from the cell's low corner in fp32 (|error| <= edge * 2^-24) and the bead's lookup index (bit-cast).
+// The header word holds count-1 (so that a memset to 0xFF yields "empty cell, all ids invalid").
+struct __align__(16) Cell {
+	uint32_t countMinus1;
+	uint32_t pad[3];
+	float4 slot[7];
+};
+static_assert(sizeof(Cell) == 128, "cell record must be one 128-byte line");
+
+constexpr uint32_t ID_NONE = 0xFFFFFFFFu;
+constexpr int MAX_CAP = 7;
+
+// Per-chain growth state (sarw.h:81-83 lastIndices / penultimateIndices / chainLengths, plus the two tip
+// positions so that a round needs one 64-byte read per chain).
+struct __align__(16) ChainState {
+	double last[3];
+	double pen[3];
+	uint32_t lastId;
+	uint32_t penId;
+	uint32_t length;
+	uint32_t flags;
+};
+static_assert(sizeof(ChainState) == 64, "chain state is 64 bytes");
+
+// Immutable per-context parameters, passed to kernels by value.
+struct Geom {
+	double L[3], Linv[3];     // boxSize, 1./boxSize (PeriodicLookup.h:10-11,30)
+	double thresh;            // minDist
+	double a[3], ainv[3];     // cell edge L/S and its inverse
+	double sOverL[3];         // S as double (cell-space scale for fractional coordinates)
+	double reachCells[3];     // conservative query half-width in cell units (< 0.5)
+	int S[3];
+	int cap;                  // inline capacity in use (<= 7)
+	float lo2, hi2;           // fp32 pre-filter: d2 < lo2 => certainly within thresh, d2 > hi2 => certainly outside
+	double regionReach;       // thresh + margin, Angstrom: halo around the cone circle when staging
+	double dSinPhi, dCosPhi;  // BondLength*sin(phi), BondLength*cos(phi)   (sarw.cpp:165,178-180)
+	double bias[3];
+	int biased;
+	int boundary, graftLoc, growthOrder;
+	int maxTrials;
+	uint32_t key0, key1;
+	uint32_t nChains, nGraft;
+	uint32_t idAtomBase;      // lookup index of atom slot 0 (= nObstacles, sarw.cpp:198)
+	uint32_t seedIgnoreId;    // nObstacles-1 or ID_NONE: the reference's "ignoreIndex=-1 + nObstacles" quirk (sarw.cpp:198,353)
+	int64_t target;
+	int64_t nGraftAtoms;      // threshold of sarw.cpp:232
+};
+
+struct Tables {
+	Cell* cells;
+	double* lpos;             // Cartesian position by lookup index, 3 doubles each; all-ones bit pattern = never accepted
+	uint32_t* ovf;            // overflow list: lookup indices of beads whose cell was full
+	uint32_t* ovfCount;
+	uint32_t ovfCap;
+};
+
+// ------------------------------------------------------------------ Philox4x32-10 (independent of oracle/philox.h)
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1)
+{
+#pragma unroll
+	for (int r = 0; r < 10; ++r) {
+		const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+		uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+		uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+		c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
+		k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+	}
+	return c;
+}
+__device__ __forceinline__ uint32_t pick(uint4 w, uint32_t i)
+{	return i == 0 ? w.x : (i == 1 ? w.y : (i == 2 ? w.z : w.w));
+}
+// U[0,1) of growth trial t (1-based): counter (chain, round, (t-1)>>2, 0), word (t-1)&3
+__device__ __forceinline__ double u_grow(const Geom& g, uint32_t chain, uint32_t round, uint32_t trial)
+{	uint4 w = philox4x32_10(make_uint4(chain, round, (trial - 1u) >> 2, 0u), g.key0, g.key1);
+	return (double)pick(w, (trial - 1u) & 3u) * (1.0 / 4294967296.0);
+}
+
+// ------------------------------------------------------------------ portable sin/cos
+// Fixed sequence of double +,-,* (valid for 0 <= x < 2*pi + small): identical bits on CPU and GPU.
+__host__ __device__ __forceinline__ void sincos_portable(double x, double& s, double& c)
+{
+	const double PIO2_HI = 1.57079632673412561417e+00, PIO2_LO = 6.07710050650619224932e-11;
+	const double TWO_OVER_PI = 6.36619772367581382433e-01;
+	const double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03, S3 = -1.98412698298579493134e-04,
+		S4 = 2.75573137070700676789e-06, S5 = -2.50507602534068634195e-08, S6 = 1.58969099521155010221e-10;
+	const double C1 = 4.16666666666666019037e-02, C2 = -1.38888888888741095749e-03, C3 = 2.48015872894767294178e-05,
+		C4 = -2.75573143513906633035e-07, C5 = 2.08757232129817482790e-09, C6 = -1.13596475577881948265e-11;
+	int k = (int)(x * TWO_OVER_PI + 0.5);
+	double kd = (double)k;
+	double r = (x - kd * PIO2_HI) - kd * PIO2_LO;
+	double z = r * r;
+	double ps = S2 + z * (S3 + z * (S4 + z * (S5 + z * S6)));
+	double sr = r + (z * r) * (S1 + z * ps);
+	double pc = z * (C1 + z * (C2 + z * (C3 + z * (C4 + z * (C5 + z * C6)))));
+	double cr = 1.0 - (0.5 * z - z * pc);
+	switch (k & 3) {
+	case 0: s = sr; c = cr; break;
+	case 1: s = cr; c = 0.0 - sr; break;
+	case 2: s = 0.0 - sr; c = 0.0 - cr; break;
+	default: s = 0.0 - cr; c = sr; break;
+	}
+}
+
+// ------------------------------------------------------------------ geometry in the reference's operation order
+__device__ __forceinline__ void normalize3(double v[3])   // v * (1.0 / sqrt(v0*v0 + v1*v1 + v2*v2))
+{	double inv = 1.0 / sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+	v[0] = v[0] * inv; v[1] = v[1] * inv; v[2] = v[2] * inv;
+}
+
+struct Frame { double X[3], Y[3], Z[3]; };
+
+// local frame of the cone, sarw.cpp:168-173
+__device__ __forceinline__ void cone_frame(const double last[3], const double pen[3], Frame& f)
+{
+	f.Z[0] = last[0] - pen[0]; f.Z[1] = last[1] - pen[1]; f.Z[2] = last[2] - pen[2];
+	normalize3(f.Z);
+	if (abs((int)f.Z[0]) > 0) {     // sarw.cpp:170: abs() there is int abs(int)
+		f.X[0] = 1.0 - f.Z[0] * f.Z[0]; f.X[1] = 0.0 - f.Z[1] * f.Z[0]; f.X[2] = 0.0 - f.Z[2] * f.Z[0];
+	} else {                        // sarw.cpp:171
+		f.X[0] = 0.0 - f.Z[0] * f.Z[1]; f.X[1] = 1.0 - f.Z[1] * f.Z[1]; f.X[2] = 0.0 - f.Z[2] * f.Z[1];
+	}
+	normalize3(f.X);
+	f.Y[0] = f.Z[1] * f.X[2] - f.Z[2] * f.X[1];
+	f.Y[1] = f.Z[2] * f.X[0] - f.Z[0] * f.X[2];
+	f.Y[2] = f.Z[0] * f.X[1] - f.Z[1] * f.X[0];
+	normalize3(f.Y);
+}
+
+// candidate of sarw.cpp:177-184 for u01 = U[0,1)
+__device__ __forceinline__ void cone_candidate(const Geom& g, const Frame& f, const double last[3], double u01, double out[3])
+{
+	double theta = (0.0 + (359.0 - 0.0) * u01) * 3.14159265358979323846 / 180;
+	double st, ct;
+	sincos_portable(theta, st, ct);
+	double a = g.dSinPhi * ct, b = g.dSinPhi * st, c = g.dCosPhi;
+#pragma unroll
+	for (int k = 0; k < 3; k++) {
+		double np = (f.X[k] * a + f.Y[k] * b) + f.Z[k] * c;
+		out[k] = np + last[k];
+	}
+}
+
+// fractional coordinates of PeriodicLookup.h:38-41 / :53-55
+__device__ __forceinline__ void to_frac(const Geom& g, const double pos[3], double v[3])
+{
+#pragma unroll
+	for (int k = 0; k < 3; k++) { double t = pos[k] * g.Linv[k]; v[k] = t - floor(t); }
+}
+
+// the per-pair decision of PeriodicLookup.h:67-71 between candidate (fractional v) and stored bead (Cartesian p)
+__device__ __forceinline__ bool exact_pair(const Geom& g, const double v[3], const double* __restrict__ p)
+{
+	double c[3];
+#pragma unroll
+	for (int k = 0; k < 3; k++) {
+		double t = __ldcg(p + k) * g.Linv[k];
+		double vp = t - floor(t);
+		double dv = v[k] - vp;
+		dv = dv - floor(0.5 + dv);
+		c[k] = g.L[k] * dv;
+	}
+	double dist = sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+	return dist <= g.thresh;
+}
+
+// fixed walls (sarw.cpp:201-203), zCenter half-space rule (:206-211) and the growthBias extension
+__device__ __forceinline__ bool walls_reject(const Geom& g, const double pos[3])
+{
+	if (g.boundary == 1) return pos[2] < 0 || pos[2] > g.L[2];
+	if (g.boundary == 2) return pos[1] < 0 || pos[1] > g.L[1];
+	if (g.boundary == 3) return pos[0] < 0 || pos[0] > g.L[0];
+	return false;
+}
+__device__ __forceinline__ bool growth_rules_reject(const Geom& g, const double pos[3], const double last[3])
+{
+	if (g.biased) {
+		double sx = pos[0] - last[0], sy = pos[1] - last[1], sz = pos[2] - last[2];
+		if ((g.bias[0] * sx + g.bias[1] * sy) + g.bias[2] * sz < 0) return true;
+	}
+	if (walls_reject(g, pos)) return true;
+	if (g.graftLoc == 2) {
+		double lastPos = last[2] - 0.5 * g.L[2];
+		double newPos = pos[2] - 0.5 * g.L[2];
+		if (lastPos * newPos < 0) return true;
+	}
+	return false;
+}
+
+// ------------------------------------------------------------------ cell addressing
+__device__ __forceinline__ int wrap_cell(int c, int S)
+{	c %= S; return c < 0 ? c + S : c;
+}
+__device__ __forceinline__ int64_t cell_index(const Geom& g, int wx, int wy, int wz)
+{	return wx + (int64_t)g.S[0] * (wy + (int64_t)g.S[1] * wz);
+}
+
+// cell + in-cell offset of a bead from its fractional coordinates
+__device__ __forceinline__ int64_t bead_cell(const Geom& g, const double v[3], float o[3])
+{
+	int c[3];
+#pragma unroll
+	for (int k = 0; k < 3; k++) {
+		double s = v[k] * g.sOverL[k];
+		int ci = (int)floor(s);
+		if (ci >= g.S[k]) ci = g.S[k] - 1;
+		if (ci < 0) ci = 0;
+		c[k] = ci;
+		o[k] = (float)((s - (double)ci) * g.a[k]);
+	}
+	return cell_index(g, c[0], c[1], c[2]);
+}
+
+// ------------------------------------------------------------------ overlap query against the cell list
+// Does any stored bead with lookup index in [idLo, idHi) and != ignoreId lie within thresh of the candidate?
+// GROUP lanes share the (<= 8) cells of the query: lane `sub` takes cells sub, sub+GROUP, ... ; the caller ORs
+// the per-lane results. The overflow list is scanned by the same striding.
+template <int GROUP>
+__device__ __forceinline__ bool probe_cells(const Geom& g, const Tables& T, const double v[3],
+	uint32_t idLo, uint32_t idHi, uint32_t ignoreId, int sub)
+{
+	int c0[3], n[3];
+	float q[3][2];
+#pragma unroll
+	for (int k = 0; k < 3; k++) {
+		double s = v[k] * g.sOverL[k];
+		int lo = (int)floor(s - g.reachCells[k]);
+		int hi = (int)floor(s + g.reachCells[k]);
+		c0[k] = lo; n[k] = hi - lo + 1;   // 1 or 2
+		q[k][0] = (float)(((double)lo - s) * g.a[k]);
+		q[k][1] = (float)(((double)(lo + 1) - s) * g.a[k]);
+	}
+	bool hit = false;
+	const int total = n[0] * n[1] * n[2];
+	for (int ci = sub; ci < total && !hit; ci += GROUP) {
+		int ix = ci % n[0], rest = ci / n[0];
+		int iy = rest % n[1], iz = rest / n[1];
+		const Cell* cell = T.cells + cell_index(g, wrap_cell(c0[0] + ix, g.S[0]), wrap_cell(c0[1] + iy, g.S[1]), wrap_cell(c0[2] + iz, g.S[2]));
+		uint32_t cnt = __ldcg(&cell->countMinus1) + 1u;
+		if (cnt > (uint32_t)g.cap) cnt = (uint32_t)g.cap;
+		for (uint32_t s = 0; s < cnt; ++s) {
+			float4 b = __ldcg(&cell->slot[s]);
+			uint32_t id = __float_as_uint(b.w);
+			if (id < idLo || id >= idHi || id == ignoreId) continue;
+			float dx = q[0][ix] + b.x, dy = q[1][iy] + b.y, dz = q[2][iz] + b.z;
+			float d2 = dx * dx + dy * dy + dz * dz;
+			if (d2 < g.lo2) { hit = true; break; }
+			if (d2 <= g.hi2 && exact_pair(g, v, T.lpos + 3 * (size_t)id)) { hit = true; break; }
+		}
+	}
+	if (!hit) {
+		uint32_t novf = __ldcg(T.ovfCount);
+		if (novf > T.ovfCap) novf = T.ovfCap;
+		for (uint32_t j = sub; j < novf && !hit; j += GROUP) {
+			uint32_t id = __ldcg(T.ovf + j);
+			if (id < idLo || id >= idHi || id == ignoreId) continue;
+			hit = exact_pair(g, v, T.lpos + 3 * (size_t)id);
+		}
+	}
+	return hit;
+}
+
+// insert a bead (PeriodicLookup.h:37-47 + the atom store of sarw.h:123-126); any number of threads may insert concurrently
+__device__ __forceinline__ void insert_bead(const Geom& g, const Tables& T, const double pos[3], uint32_t id)
+{
+	double v[3]; float o[3];
+	to_frac(g, pos, v);
+	int64_t ci = bead_cell(g, v, o);
+	double* lp = T.lpos + 3 * (size_t)id;
+	lp[0] = pos[0]; lp[1] = pos[1]; lp[2] = pos[2];
+	Cell* cell = T.cells + ci;
+	uint32_t k = atomicAdd(&cell->countMinus1, 1u) + 1u;
+	if (k < (uint32_t)g.cap) {
+		__stcg(&cell->slot[k], make_float4(o[0], o[1], o[2], __uint_as_float(id)));
+	} else {
+		atomicSub(&cell->countMinus1, 1u);
+		uint32_t j = atomicAdd(T.ovfCount, 1u);
+		if (j < T.ovfCap) T.ovf[j] = id;   // beyond ovfCap the host sees ovfCount > ovfCap and fails the call
+	}
+}
+
+// remove a bead again (only ever called from the single-threaded conflict clean-up, nobody else is touching cells)
+__device__ inline void remove_bead(const Geom& g, const Tables& T, uint32_t id)
+{
+	double* lp = T.lpos + 3 * (size_t)id;
+	double pos[3] = { __ldcg(lp), __ldcg(lp + 1), __ldcg(lp + 2) };
+	double v[3]; float o[3];
+	to_frac(g, pos, v);
+	Cell* cell = T.cells + bead_cell(g, v, o);
+	uint32_t cnt = __ldcg(&cell->countMinus1) + 1u;
+	uint32_t cc = cnt > (uint32_t)g.cap ? (uint32_t)g.cap : cnt;
+	bool found = false;
+	for (uint32_t s = 0; s < cc; ++s) {
+		float4 b = __ldcg(&cell->slot[s]);
+		if (__float_as_uint(b.w) == id) {
+			float4 lastSlot = __ldcg(&cell->slot[cc - 1]);
+			__stcg(&cell->slot[s], lastSlot);
+			__stcg(&cell->slot[cc - 1], make_float4(0.f, 0.f, 0.f, __uint_as_float(ID_NONE)));
+			cell->countMinus1 = cc - 2u;   // (cc-1) beads remain
+			found = true;
+			break;
+		}
+	}
+	if (!found) {
+		uint32_t novf = __ldcg(T.ovfCount);
+		if (novf > T.ovfCap) novf = T.ovfCap;
+		for (uint32_t j = 0; j < novf; ++j)
+			if (__ldcg(T.ovf + j) == id) { T.ovf[j] = __ldcg(T.ovf + novf - 1); *T.ovfCount = novf - 1; break; }
+	}
+	unsigned long long ones = ~0ull;
+	lp[0] = __longlong_as_double((long long)ones); lp[1] = lp[0]; lp[2] = lp[0];
+	__threadfence();
+}
+
+// ------------------------------------------------------------------ grid-wide barrier for the persistent kernel
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p)
+{	unsigned v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void grid_barrier(unsigned* count, unsigned* gen, unsigned nBlocks)
+{
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		unsigned my = ld_acquire_u32(gen);
+		__threadfence();
+		if (atomicAdd(count, 1u) == nBlocks - 1u) {
+			atomicExch(count, 0u);
+			__threadfence();
+			atomicAdd(gen, 1u);
+		} else {
+			while (ld_acquire_u32(gen) == my) { }
+		}
+		__threadfence();
+	}
+	__syncthreads();
+}
+
+} // namespace sarw

@@ -1,0 +1,34 @@
+// sarw_host.h — what the C-ABI host layer (sarw_abi.cu) and the kernels (sarw_kernels.cu) share.
+#pragma once
+#include "sarw_device.cuh"
+
+namespace sarw {
+
+// device-resident control block of one context
+struct Control {
+	unsigned barCount, barGen;        // grid barrier of the persistent growth kernel
+	unsigned round;                   // next growth round (= propagateChain() calls made)
+	unsigned lastProgressed;          // return value of the last propagateChain(), sarw.cpp:282
+	unsigned initiated;               // return value of initiateChain(), sarw.cpp:290
+	unsigned seedFailChain;           // first chain whose seeding failed, ID_NONE if none
+	unsigned seedDirtyCount;
+	unsigned pad0;
+	unsigned long long nBeads;        // SARW::actualCount()
+	unsigned long long trials, queries, conflicts, seedTrials;
+};
+
+cudaError_t launch_find_batch(const Geom& g, const Tables& T, const double* xyz, const int64_t* ignore, int64_t n, uint8_t* hit, int numSMs, cudaStream_t st);
+cudaError_t launch_add_points(const Geom& g, const Tables& T, const double* xyz, int64_t n, uint32_t baseId, cudaStream_t st);
+cudaError_t launch_seed(const Geom& g, const Tables& T, ChainState* chains, uint32_t* resTrial, uint32_t* prev, const double* grafts,
+	Control* ctl, uint32_t* dirtyList, int numSMs, cudaStream_t st, int* launches);
+cudaError_t grow_max_blocks(int numSMs, int* maxBlocks);
+cudaError_t launch_grow(const Geom& g, const Tables& T, ChainState* chains, uint32_t* resTrial, double* resPos, uint32_t* prev, Control* ctl,
+	uint32_t* roundAcc, uint32_t* roundProg, uint32_t* dirtyCount, uint32_t* dirtyList, uint32_t roundEnd, int blocks, cudaStream_t st);
+cudaError_t download_scan_bytes(uint64_t nSlots, size_t* bytes);
+cudaError_t launch_download(const Geom& g, const Tables& T, const uint32_t* prev, const ChainState* chains, uint64_t nSlots, uint32_t nSeeded,
+	int terminated, uint32_t* flags, uint32_t* scan, void* cubTemp, size_t cubBytes,
+	double* xyz, int32_t* chainID, int32_t* type, int64_t* bonds, cudaStream_t st);
+cudaError_t launch_chain_lengths(const ChainState* chains, uint32_t n, int32_t* out, cudaStream_t st);
+cudaError_t launch_fill_u32(uint32_t* p, uint64_t n, uint32_t v, cudaStream_t st);
+
+} // namespace sarw

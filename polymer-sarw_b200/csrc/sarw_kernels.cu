@@ -1,0 +1,684 @@
+// sarw_kernels.cu — the CUDA kernels of libsarw_b200 (sm_100a) and their launch wrappers.
+//
+//   K1  seed_*            SARW::initiateChain / randomSeed / randomUnitStep     sarw.cpp:290-357, 147-152
+//   K2-K4 grow_kernel     SARW::propagateChain / randomConePos / checkCollision sarw.cpp:220-283, 159-214
+//                         + PeriodicLookup::find / addPoint                     PeriodicLookup.h:37-75
+//                         + main()'s while loop                                 sarw.cpp:67-78
+//   K5  find_batch_kernel PeriodicLookup::find on caller-supplied candidates    PeriodicLookup.h:51-75
+//       add_points_kernel PeriodicLookup::addPoint                              PeriodicLookup.h:37-47
+//   K7  download kernels  terminateChain's type flip (sarw.cpp:359-368) + compaction into acceptance order
+//
+// Exact sequential semantics in a parallel round (DESIGN.md "Round protocol"): every chain of the round proposes
+// against the beads present at round start and inserts its first passing candidate tentatively (phase A); after a
+// grid barrier each chain re-checks its bead against the tentative beads of LOWER-indexed chains (phase V); the
+// (rare) chains that conflict are re-resolved one by one in chain order against the true state (clean-up), which
+// is exactly what the serial loop of sarw.cpp:251-281 would have produced.
+#include "sarw_device.cuh"
+#include "sarw_host.h"
+#include <cub/device/device_scan.cuh>
+
+namespace sarw {
+
+constexpr int GROW_WARPS = 8;
+constexpr int GROW_THREADS = GROW_WARPS * 32;
+constexpr int NBMAX = 128;          // staged neighbour beads per chain (shared memory, 16 B each)
+constexpr unsigned FULL = 0xFFFFFFFFu;
+constexpr uint32_t DONE_BIT = 0x80000000u;
+
+// ------------------------------------------------------------------ K5: overlap query on caller-supplied candidates
+__global__ void __launch_bounds__(256) find_batch_kernel(Geom g, Tables T, const double* __restrict__ xyz,
+	const int64_t* __restrict__ ignore, int64_t n, uint8_t* __restrict__ hit)
+{
+	const int sub = threadIdx.x & 7;
+	const int grp = (threadIdx.x & 31) >> 3;
+	int64_t q0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+	const int64_t stride = ((int64_t)gridDim.x * blockDim.x) >> 3;
+	// all 32 lanes of a warp iterate together (q0 - grp is warp-uniform)
+	for (int64_t qb = q0 - grp; qb < n; qb += stride) {
+		int64_t q = qb + grp;
+		bool h = false;
+		if (q < n) {
+			double pos[3] = { xyz[3 * q], xyz[3 * q + 1], xyz[3 * q + 2] }, v[3];
+			to_frac(g, pos, v);
+			int64_t ig = ignore ? ignore[q] : -1;
+			// PeriodicLookup.h:65: ignoreIndex<0 || int(index)!=ignoreIndex
+			h = probe_cells<8>(g, T, v, 0u, ID_NONE, ig < 0 ? ID_NONE : (uint32_t)ig, sub);
+		}
+		unsigned b = __ballot_sync(FULL, h);
+		if (sub == 0 && q < n) hit[q] = ((b >> (grp * 8)) & 0xFFu) ? 1 : 0;
+	}
+}
+
+__global__ void add_points_kernel(Geom g, Tables T, const double* __restrict__ xyz, int64_t n, uint32_t baseId)
+{
+	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	double pos[3] = { xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2] };
+	insert_bead(g, T, pos, baseId + (uint32_t)i);
+}
+
+// enumerate beads with id in (idLo, idHi) within thresh of the candidate (single thread; clean-up only)
+template <typename F>
+__device__ void enumerate_hits(const Geom& g, const Tables& T, const double v[3], uint32_t idLoExcl, uint32_t idHi, F&& fn)
+{
+	int c0[3], n[3];
+	float q[3][2];
+	for (int k = 0; k < 3; k++) {
+		double s = v[k] * g.sOverL[k];
+		int lo = (int)floor(s - g.reachCells[k]), hi = (int)floor(s + g.reachCells[k]);
+		c0[k] = lo; n[k] = hi - lo + 1;
+		q[k][0] = (float)(((double)lo - s) * g.a[k]);
+		q[k][1] = (float)(((double)(lo + 1) - s) * g.a[k]);
+	}
+	for (int iz = 0; iz < n[2]; iz++) for (int iy = 0; iy < n[1]; iy++) for (int ix = 0; ix < n[0]; ix++) {
+		const Cell* cell = T.cells + cell_index(g, wrap_cell(c0[0] + ix, g.S[0]), wrap_cell(c0[1] + iy, g.S[1]), wrap_cell(c0[2] + iz, g.S[2]));
+		uint32_t cnt = __ldcg(&cell->countMinus1) + 1u;
+		if (cnt > (uint32_t)g.cap) cnt = (uint32_t)g.cap;
+		for (uint32_t s = 0; s < cnt; ++s) {
+			float4 b = __ldcg(&cell->slot[s]);
+			uint32_t id = __float_as_uint(b.w);
+			if (id <= idLoExcl || id >= idHi) continue;
+			float dx = q[0][ix] + b.x, dy = q[1][iy] + b.y, dz = q[2][iz] + b.z;
+			float d2 = dx * dx + dy * dy + dz * dz;
+			if (d2 < g.lo2 || (d2 <= g.hi2 && exact_pair(g, v, T.lpos + 3 * (size_t)id))) fn(id);
+		}
+	}
+	uint32_t novf = __ldcg(T.ovfCount);
+	if (novf > T.ovfCap) novf = T.ovfCap;
+	for (uint32_t j = 0; j < novf; ++j) {
+		uint32_t id = __ldcg(T.ovf + j);
+		if (id <= idLoExcl || id >= idHi) continue;
+		if (exact_pair(g, v, T.lpos + 3 * (size_t)id)) fn(id);
+	}
+}
+
+// dirty-list helpers (single thread)
+__device__ void dirty_push_unique(volatile uint32_t* list, volatile uint32_t* count, uint32_t chain)
+{
+	uint32_t n = *count;
+	for (uint32_t j = 0; j < n; ++j) if ((list[j] & ~DONE_BIT) == chain) return;
+	list[n] = chain; *count = n + 1;
+}
+__device__ int dirty_pop_min(volatile uint32_t* list, volatile const uint32_t* count, uint32_t& chain)
+{
+	uint32_t n = *count, best = ID_NONE; int at = -1;
+	for (uint32_t j = 0; j < n; ++j) { uint32_t e = list[j]; if (!(e & DONE_BIT) && e < best) { best = e; at = (int)j; } }
+	if (at < 0) return 0;
+	list[at] |= DONE_BIT; chain = best;
+	return 1;
+}
+
+// ------------------------------------------------------------------ K1: seeding (sarw.cpp:290-357)
+// six draws of seeding trial t: counter (chain, t, block, 1); see oracle/philox.h for the word -> coordinate map
+__device__ __forceinline__ void seed_candidate(const Geom& g, const double* __restrict__ grafts, uint32_t chain, uint32_t trial, double p0[3], double p1[3])
+{
+	uint4 w0 = philox4x32_10(make_uint4(chain, trial, 0u, 1u), g.key0, g.key1);
+	uint4 w1 = philox4x32_10(make_uint4(chain, trial, 1u, 1u), g.key0, g.key1);
+	const double sc = 1.0 / 4294967296.0;
+	double u[6] = { w0.x * sc, w0.y * sc, w0.z * sc, w0.w * sc, w1.x * sc, w1.y * sc };
+	for (int k = 0; k < 3; k++) p0[k] = 0.0 + (g.L[k] - 0.0) * u[2 - k];            // sarw.cpp:336-339 (right-to-left draws)
+	if (g.graftLoc == 0 && chain < g.nGraft) { for (int k = 0; k < 3; k++) p0[k] = grafts[3 * (size_t)chain + k]; }   // :342-343
+	else if (g.graftLoc == 1 && chain < g.nGraft && g.boundary == 1) p0[2] = (chain % 2) ? 0 : g.L[2];               // :344-345
+	else if (g.graftLoc == 2 && chain < g.nGraft && g.boundary == 1) p0[2] = 0.5 * g.L[2];                           // :346-347
+	double step[3] = { -.5 + (.5 - -.5) * u[5], -.5 + (.5 - -.5) * u[4], -.5 + (.5 - -.5) * u[3] };   // sarw.cpp:150
+	normalize3(step);                                                                                // :151
+	for (int k = 0; k < 3; k++) p1[k] = p0[k] + step[k] * 1.54;                                       // :350,352
+}
+
+struct SeedArgs {
+	Geom g; Tables T;
+	ChainState* chains;
+	uint32_t* resTrial;
+	uint32_t* prev;
+	const double* grafts;
+	Control* ctl;
+	uint32_t* dirtyList;
+};
+
+// does the seed pair pass checkCollision (sarw.cpp:353,193-204) against beads with id < idHi?
+__device__ __forceinline__ bool seed_pair_ok(const Geom& g, const Tables& T, const double p0[3], const double p1[3], uint32_t idHi)
+{
+	if (walls_reject(g, p0) || walls_reject(g, p1)) return false;
+	double v[3];
+	to_frac(g, p0, v);
+	if (probe_cells<1>(g, T, v, 0u, idHi, g.seedIgnoreId, 0)) return false;
+	to_frac(g, p1, v);
+	if (probe_cells<1>(g, T, v, 0u, idHi, g.seedIgnoreId, 0)) return false;
+	return true;
+}
+
+__global__ void __launch_bounds__(256) seed_propose_kernel(SeedArgs A)
+{
+	const Geom& g = A.g;
+	const int lane = threadIdx.x & 31;
+	const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nW = (gridDim.x * blockDim.x) >> 5;
+	const uint32_t usable = g.maxTrials > 0 ? (uint32_t)g.maxTrials - 1u : 0u;   // sarw.cpp:355: success on trial maxTrials counts as failure
+	for (uint32_t i = gw; i < g.nChains; i += nW) {
+		uint32_t accepted = 0;
+		double p0[3], p1[3];
+		for (uint32_t base = 0; base < usable && !accepted; base += 32) {
+			uint32_t t = base + lane + 1;
+			bool ok = t <= usable;
+			if (ok) { seed_candidate(g, A.grafts, i, t, p0, p1); ok = seed_pair_ok(g, A.T, p0, p1, g.idAtomBase); }
+			unsigned m = __ballot_sync(FULL, ok);
+			if (m) {
+				int first = __ffs(m) - 1;
+				accepted = base + first + 1;
+				if (lane == first) {
+					insert_bead(g, A.T, p0, g.idAtomBase + 2 * i);
+					insert_bead(g, A.T, p1, g.idAtomBase + 2 * i + 1);
+				}
+			}
+		}
+		if (lane == 0) {
+			A.resTrial[i] = accepted ? accepted : (uint32_t)g.maxTrials + 1u;
+			if (!accepted) atomicMin(&A.ctl->seedFailChain, i);
+		}
+	}
+}
+
+__global__ void __launch_bounds__(256) seed_verify_kernel(SeedArgs A)
+{
+	const Geom& g = A.g;
+	const int sub = threadIdx.x & 7, grp = (threadIdx.x & 31) >> 3;
+	const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nW = (gridDim.x * blockDim.x) >> 5;
+	for (uint32_t base = gw * 4; base < g.nChains; base += nW * 4) {
+		uint32_t i = base + grp;
+		bool h = false;
+		if (i < g.nChains && __ldcg(&A.resTrial[i]) <= (uint32_t)g.maxTrials && i > 0) {
+			for (int b = 0; b < 2 && !h; b++) {
+				const double* lp = A.T.lpos + 3 * (size_t)(g.idAtomBase + 2 * i + b);
+				double pos[3] = { __ldcg(lp), __ldcg(lp + 1), __ldcg(lp + 2) }, v[3];
+				to_frac(g, pos, v);
+				h = probe_cells<8>(g, A.T, v, g.idAtomBase, g.idAtomBase + 2 * i, ID_NONE, sub);
+			}
+		}
+		unsigned bal = __ballot_sync(FULL, h);
+		if (sub == 0 && ((bal >> (grp * 8)) & 0xFFu)) {
+			uint32_t at = atomicAdd(&A.ctl->seedDirtyCount, 1u);
+			A.dirtyList[at] = i;
+		}
+	}
+}
+
+// single thread: re-resolve conflicting seeds in chain order; then discard everything from the first failing chain on
+__global__ void seed_cleanup_kernel(SeedArgs A)
+{
+	const Geom& g = A.g;
+	const uint32_t T_ = (uint32_t)g.maxTrials, usable = T_ > 0 ? T_ - 1u : 0u;
+	uint32_t chain;
+	while (dirty_pop_min(A.dirtyList, &A.ctl->seedDirtyCount, chain)) {
+		if (chain >= A.ctl->seedFailChain) break;
+		const uint32_t id0 = g.idAtomBase + 2 * chain, id1 = id0 + 1;
+		uint32_t t0 = A.resTrial[chain];
+		remove_bead(g, A.T, id0); remove_bead(g, A.T, id1);
+		uint32_t found = 0; double p0[3], p1[3];
+		for (uint32_t t = t0; t <= usable; ++t) {
+			seed_candidate(g, A.grafts, chain, t, p0, p1);
+			if (seed_pair_ok(g, A.T, p0, p1, id0)) { found = t; break; }
+		}
+		A.ctl->conflicts++;
+		if (!found) { A.resTrial[chain] = T_ + 1u; if (chain < A.ctl->seedFailChain) A.ctl->seedFailChain = chain; continue; }
+		A.resTrial[chain] = found;
+		insert_bead(g, A.T, p0, id0); insert_bead(g, A.T, p1, id1);
+		__threadfence();
+		const uint32_t idEnd = g.idAtomBase + 2 * g.nChains;
+		auto mark = [&](uint32_t id) { dirty_push_unique(A.dirtyList, &A.ctl->seedDirtyCount, (id - g.idAtomBase) >> 1); };
+		double v[3];
+		to_frac(g, p0, v); enumerate_hits(g, A.T, v, id1, idEnd, mark);
+		to_frac(g, p1, v); enumerate_hits(g, A.T, v, id1, idEnd, mark);
+	}
+	const uint32_t fail = A.ctl->seedFailChain;
+	if (fail != ID_NONE)   // sarw.cpp:313-314: initiateChain returns at the first failing chain; later chains are never seeded
+		for (uint32_t i = fail; i < g.nChains; ++i)
+			if (A.resTrial[i] <= T_) { remove_bead(g, A.T, g.idAtomBase + 2 * i); remove_bead(g, A.T, g.idAtomBase + 2 * i + 1); A.resTrial[i] = T_ + 1u; }
+}
+
+__global__ void seed_commit_kernel(SeedArgs A)
+{
+	const Geom& g = A.g;
+	const uint32_t fail = A.ctl->seedFailChain;
+	const uint32_t nSeeded = fail == ID_NONE ? g.nChains : fail;
+	unsigned long long myTrials = 0;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < g.nChains; i += gridDim.x * blockDim.x) {
+		ChainState cs;
+		memset(&cs, 0, sizeof cs);
+		cs.lastId = cs.penId = ID_NONE;
+		if (i < nSeeded) {
+			const uint32_t id0 = g.idAtomBase + 2 * i, id1 = id0 + 1;
+			for (int k = 0; k < 3; k++) { cs.pen[k] = A.T.lpos[3 * (size_t)id0 + k]; cs.last[k] = A.T.lpos[3 * (size_t)id1 + k]; }
+			cs.penId = id0; cs.lastId = id1; cs.length = 2;   // sarw.cpp:306-310
+			A.prev[2 * i] = ID_NONE; A.prev[2 * i + 1] = id0;
+			myTrials += A.resTrial[i];
+		} else if (i == nSeeded) myTrials += (unsigned)g.maxTrials;
+		A.chains[i] = cs;
+		A.resTrial[i] = 0;
+	}
+	if (myTrials) atomicAdd(&A.ctl->seedTrials, myTrials);
+	if (blockIdx.x == 0 && threadIdx.x == 0) {
+		A.ctl->nBeads = 2ull * nSeeded;
+		A.ctl->initiated = fail == ID_NONE ? 1u : 0u;
+	}
+}
+
+// ------------------------------------------------------------------ K2-K4: persistent growth kernel
+struct GrowArgs {
+	Geom g; Tables T;
+	ChainState* chains;
+	uint32_t* resTrial;     // per chain: 0 nothing pending, 1..T accepted trial of the running round, T+1 failed
+	double* resPos;         // per chain: tentative / accepted bead of the running round
+	uint32_t* prev;         // per atom slot: lookup index of the previous bead of its chain (bond partner, sarw.cpp:272)
+	Control* ctl;
+	uint32_t* roundAcc;     // per round: beads accepted
+	uint32_t* roundProg;    // per round: chains accepted before their last trial (sarw.cpp:277)
+	uint32_t* dirtyCount;   // per round
+	uint32_t* dirtyList;
+	uint32_t roundEnd;      // run rounds [ctl->round, roundEnd)
+};
+
+__device__ __forceinline__ uint32_t round_id_base(const Geom& g, uint32_t round)
+{	return g.idAtomBase + 2u * g.nChains + round * g.nChains;
+}
+
+// chain range of a round, sarw.cpp:230-249
+__device__ __forceinline__ void round_range(const Geom& g, unsigned long long nBeads, uint32_t& start, uint32_t& end)
+{
+	start = 0; end = g.nChains;
+	if (g.growthOrder == 1 && g.nGraft > 0) {
+		if ((long long)nBeads < g.nGraftAtoms) end = g.nGraft; else start = g.nGraft;
+	}
+}
+
+// stage every bead that can be within thresh of any point of the cone circle into shared memory, as positions
+// relative to the (wrapped) last bead; returns the number staged or -1 when NBMAX does not suffice
+__device__ __forceinline__ int stage_region(const Geom& g, const Tables& T, const double lw[3], const Frame& f,
+	uint32_t idLimit, uint32_t ignoreId, float4* nb, int lane)
+{
+	int lo[3], nn[3];
+#pragma unroll
+	for (int k = 0; k < 3; k++) {
+		double cen = lw[k] + g.dCosPhi * f.Z[k];
+		double w = 1.0 - f.Z[k] * f.Z[k];
+		double e = g.dSinPhi * sqrt(w > 0 ? w : 0.0) + g.regionReach;
+		lo[k] = (int)floor((cen - e) * g.ainv[k]);
+		nn[k] = (int)floor((cen + e) * g.ainv[k]) - lo[k] + 1;
+	}
+	const int ncell = nn[0] * nn[1] * nn[2];
+	int total = 0;
+	for (int cbase = 0; cbase < ncell; cbase += 32) {
+		const int ci = cbase + lane;
+		uint32_t cnt = 0; float4 s0 = make_float4(0, 0, 0, 0); const Cell* cell = nullptr; float sh[3] = { 0, 0, 0 };
+		if (ci < ncell) {
+			int ix = ci % nn[0], rest = ci / nn[0];
+			int iy = rest % nn[1], iz = rest / nn[1];
+			int cx = lo[0] + ix, cy = lo[1] + iy, cz = lo[2] + iz;
+			cell = T.cells + cell_index(g, wrap_cell(cx, g.S[0]), wrap_cell(cy, g.S[1]), wrap_cell(cz, g.S[2]));
+			uint32_t h = __ldcg(&cell->countMinus1);
+			s0 = __ldcg(&cell->slot[0]);
+			cnt = h + 1u; if (cnt > (uint32_t)g.cap) cnt = (uint32_t)g.cap;
+			sh[0] = (float)((double)cx * g.a[0] - lw[0]); sh[1] = (float)((double)cy * g.a[1] - lw[1]); sh[2] = (float)((double)cz * g.a[2] - lw[2]);
+		}
+		uint32_t incl = cnt;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += y; }
+		const int sum = (int)__shfl_sync(FULL, incl, 31);
+		if (total + sum > NBMAX) return -1;
+		int at = total + (int)(incl - cnt);
+		for (uint32_t s = 0; s < cnt; ++s) {
+			float4 b = s == 0 ? s0 : __ldcg(&cell->slot[s]);
+			uint32_t id = __float_as_uint(b.w);
+			if (id >= idLimit || id == ignoreId) nb[at + s] = make_float4(1e30f, 1e30f, 1e30f, __uint_as_float(ID_NONE));
+			else nb[at + s] = make_float4(sh[0] + b.x, sh[1] + b.y, sh[2] + b.z, b.w);
+		}
+		total += sum;
+	}
+	__syncwarp();
+	return total;
+}
+
+// apply the result of the previous round to the chain state (sarw.cpp:270-273); all lanes compute, lane 0 stores
+__device__ __forceinline__ void commit_pending(const GrowArgs& A, uint32_t i, uint32_t pendingRound, ChainState& cs, int lane)
+{
+	const Geom& g = A.g;
+	uint32_t t = __ldcg(&A.resTrial[i]);
+	if (t >= 1u && t <= (uint32_t)g.maxTrials) {
+		const uint32_t id = round_id_base(g, pendingRound) + i;
+		for (int k = 0; k < 3; k++) { cs.pen[k] = cs.last[k]; cs.last[k] = __ldcg(&A.resPos[3 * (size_t)i + k]); }
+		if (lane == 0) A.prev[id - g.idAtomBase] = cs.lastId;
+		cs.penId = cs.lastId; cs.lastId = id; cs.length += 1;
+		if (lane == 0) A.chains[i] = cs;
+	}
+	if (t != 0 && lane == 0) A.resTrial[i] = 0;
+}
+
+__device__ __forceinline__ ChainState load_chain(const ChainState* p)
+{
+	ChainState cs;
+	const double2* q = reinterpret_cast<const double2*>(p);   // 64 B = 4 x 16 B, L2 (cache-global) loads
+	double2 a = __ldcg(q), b = __ldcg(q + 1), c = __ldcg(q + 2), d = __ldcg(q + 3);
+	cs.last[0] = a.x; cs.last[1] = a.y; cs.last[2] = b.x; cs.pen[0] = b.y; cs.pen[1] = c.x; cs.pen[2] = c.y;
+	unsigned long long u = (unsigned long long)__double_as_longlong(d.x), w = (unsigned long long)__double_as_longlong(d.y);
+	cs.lastId = (uint32_t)u; cs.penId = (uint32_t)(u >> 32); cs.length = (uint32_t)w; cs.flags = (uint32_t)(w >> 32);
+	return cs;
+}
+
+// single thread: re-resolve the conflicting chains of a round in chain order (what sarw.cpp:251-281 does serially)
+__device__ void cleanup_round(const GrowArgs& A, uint32_t round)
+{
+	const Geom& g = A.g;
+	const uint32_t T_ = (uint32_t)g.maxTrials;
+	const uint32_t idRound = round_id_base(g, round), idEnd = idRound + g.nChains;
+	uint32_t chain;
+	while (dirty_pop_min(A.dirtyList, &A.dirtyCount[round], chain)) {
+		const uint32_t myId = idRound + chain;
+		ChainState cs = load_chain(A.chains + chain);
+		Frame f; cone_frame(cs.last, cs.pen, f);
+		const uint32_t t0 = __ldcg(&A.resTrial[chain]);
+		remove_bead(g, A.T, myId);
+		uint32_t found = 0; double cand[3], v[3];
+		for (uint32_t t = t0; t <= T_; ++t) {
+			cone_candidate(g, f, cs.last, u_grow(g, chain, round, t), cand);
+			if (growth_rules_reject(g, cand, cs.last)) continue;
+			to_frac(g, cand, v);
+			if (probe_cells<1>(g, A.T, v, 0u, myId, cs.lastId, 0)) continue;
+			found = t; break;
+		}
+		atomicAdd(&A.ctl->conflicts, 1ull);
+		const unsigned long long before = t0, after = found ? found : T_;
+		atomicAdd(&A.ctl->trials, after - before);
+		atomicAdd(&A.ctl->queries, after - before + 1ull);
+		if (!found) {
+			A.resTrial[chain] = T_ + 1u;
+			atomicSub(&A.roundAcc[round], 1u);
+			if (t0 < T_) atomicSub(&A.roundProg[round], 1u);
+			continue;
+		}
+		if (t0 < T_ && !(found < T_)) atomicSub(&A.roundProg[round], 1u);
+		A.resTrial[chain] = found;
+		for (int k = 0; k < 3; k++) A.resPos[3 * (size_t)chain + k] = cand[k];
+		insert_bead(g, A.T, cand, myId);
+		__threadfence();
+		enumerate_hits(g, A.T, v, myId, idEnd, [&](uint32_t id) { dirty_push_unique(A.dirtyList, &A.dirtyCount[round], id - idRound); });
+	}
+}
+
+__global__ void __launch_bounds__(GROW_THREADS) grow_kernel(GrowArgs A)
+{
+	__shared__ float4 nbShared[GROW_WARPS][NBMAX];
+	const Geom& g = A.g;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint32_t gw = blockIdx.x * GROW_WARPS + warp, nW = gridDim.x * GROW_WARPS;
+	float4* nb = nbShared[warp];
+	const uint32_t T_ = (uint32_t)g.maxTrials;
+
+	uint32_t round = __ldcg(&A.ctl->round);
+	unsigned long long nBeads = __ldcg(&A.ctl->nBeads);
+	uint32_t lastProg = __ldcg(&A.ctl->lastProgressed);
+	unsigned long long myTrials = 0, myQueries = 0;
+	bool pendingValid = false;   // is there a round of this launch whose results are not yet committed?
+
+	while (round < A.roundEnd && (long long)nBeads < g.target && lastProg) {
+		uint32_t start, end;
+		round_range(g, nBeads, start, end);
+		const uint32_t idRound = round_id_base(g, round);
+
+		// ---------------- phase A: commit last round, then propose + tentatively insert
+		for (uint32_t i = gw; i < g.nChains; i += nW) {
+			ChainState cs = load_chain(A.chains + i);
+			if (pendingValid) commit_pending(A, i, round - 1, cs, lane);
+			if (i < start || i >= end) continue;
+			Frame f; cone_frame(cs.last, cs.pen, f);
+			double lw[3];
+			{ double vl[3]; to_frac(g, cs.last, vl); for (int k = 0; k < 3; k++) lw[k] = vl[k] * g.L[k]; }
+			const int nnb = stage_region(g, A.T, lw, f, idRound, cs.lastId, nb, lane);
+			const uint32_t novf = __ldcg(A.T.ovfCount);
+
+			uint32_t accepted = 0; double cand[3] = { 0, 0, 0 };
+			for (uint32_t base = 0; base < T_ && !accepted; base += 32) {
+				const uint32_t t = base + lane + 1;
+				bool ok = t <= T_;
+				double v[3];
+				if (ok) {
+					cone_candidate(g, f, cs.last, u_grow(g, i, round, t), cand);
+					ok = !growth_rules_reject(g, cand, cs.last);
+				}
+				if (ok) {
+					if (nnb >= 0) {
+						const float rx = (float)(cand[0] - cs.last[0]), ry = (float)(cand[1] - cs.last[1]), rz = (float)(cand[2] - cs.last[2]);
+						bool haveV = false;
+						for (int j = 0; j < nnb; ++j) {
+							const float4 b = nb[j];
+							const float dx = rx - b.x, dy = ry - b.y, dz = rz - b.z;
+							const float d2 = dx * dx + dy * dy + dz * dz;
+							if (d2 < g.lo2) { ok = false; break; }
+							if (d2 <= g.hi2) {
+								if (!haveV) { to_frac(g, cand, v); haveV = true; }
+								if (exact_pair(g, v, A.T.lpos + 3 * (size_t)__float_as_uint(b.w))) { ok = false; break; }
+							}
+						}
+					} else {   // region too crowded for the staging buffer: query the cell list directly
+						to_frac(g, cand, v);
+						ok = !probe_cells<1>(g, A.T, v, 0u, idRound, cs.lastId, 0);
+					}
+					if (ok && novf && nnb >= 0) {   // beads that did not fit their cell live in the overflow list
+						to_frac(g, cand, v);
+						uint32_t m = novf > A.T.ovfCap ? A.T.ovfCap : novf;
+						for (uint32_t j = 0; j < m && ok; ++j) {
+							uint32_t id = __ldcg(A.T.ovf + j);
+							if (id < idRound && id != cs.lastId && exact_pair(g, v, A.T.lpos + 3 * (size_t)id)) ok = false;
+						}
+					}
+				}
+				const unsigned m = __ballot_sync(FULL, ok);
+				const uint32_t evaluated = (T_ - base) < 32u ? (T_ - base) : 32u;
+				myQueries += (lane == 0) ? evaluated : 0;
+				if (m) {
+					const int first = __ffs(m) - 1;
+					accepted = base + first + 1;
+					for (int k = 0; k < 3; k++) cand[k] = __shfl_sync(FULL, cand[k], first);
+				}
+			}
+			if (lane == 0) {
+				if (accepted) {
+					insert_bead(g, A.T, cand, idRound + i);
+					for (int k = 0; k < 3; k++) A.resPos[3 * (size_t)i + k] = cand[k];
+				}
+				A.resTrial[i] = accepted ? accepted : T_ + 1u;
+			}
+		}
+		pendingValid = true;
+		grid_barrier(&A.ctl->barCount, &A.ctl->barGen, gridDim.x);
+
+		// ---------------- phase V: conflicts with tentative beads of lower-indexed chains of this round
+		{
+			const int sub = lane & 7, grp = lane >> 3;
+			uint32_t acc = 0, prog = 0; unsigned long long tr = 0;
+			for (uint32_t base = start + gw * 4; base < end; base += nW * 4) {
+				const uint32_t i = base + grp;
+				bool h = false; uint32_t t = 0;
+				if (i < end) {
+					t = __ldcg(&A.resTrial[i]);
+					if (t <= T_ && i > start) {
+						double pos[3] = { __ldcg(&A.resPos[3 * (size_t)i]), __ldcg(&A.resPos[3 * (size_t)i + 1]), __ldcg(&A.resPos[3 * (size_t)i + 2]) }, v[3];
+						to_frac(g, pos, v);
+						h = probe_cells<8>(g, A.T, v, idRound, idRound + i, ID_NONE, sub);
+					}
+				}
+				const unsigned bal = __ballot_sync(FULL, h);
+				if (sub == 0 && i < end) {
+					if (t <= T_) { acc++; tr += t; if (t < T_) prog++; } else tr += T_;
+					if ((bal >> (grp * 8)) & 0xFFu) {
+						uint32_t at = atomicAdd(&A.dirtyCount[round], 1u);
+						A.dirtyList[at] = i;
+					}
+				}
+			}
+#pragma unroll
+			for (int d = 16; d > 0; d >>= 1) {
+				acc += __shfl_xor_sync(FULL, acc, d); prog += __shfl_xor_sync(FULL, prog, d); tr += __shfl_xor_sync(FULL, tr, d);
+			}
+			if (lane == 0) {
+				if (acc) atomicAdd(&A.roundAcc[round], acc);
+				if (prog) atomicAdd(&A.roundProg[round], prog);
+				myTrials += tr;
+			}
+		}
+		grid_barrier(&A.ctl->barCount, &A.ctl->barGen, gridDim.x);
+
+		// ---------------- clean-up (rare): serial re-resolution in chain order
+		if (__ldcg(&A.dirtyCount[round]) != 0u) {
+			if (gw == 0 && lane == 0) cleanup_round(A, round);
+			grid_barrier(&A.ctl->barCount, &A.ctl->barGen, gridDim.x);
+		}
+		nBeads += __ldcg(&A.roundAcc[round]);
+		lastProg = __ldcg(&A.roundProg[round]) != 0u;
+		round++;
+	}
+
+	// commit the last round of this launch
+	if (pendingValid)
+		for (uint32_t i = gw; i < g.nChains; i += nW) {
+			ChainState cs = load_chain(A.chains + i);
+			commit_pending(A, i, round - 1, cs, lane);
+		}
+	if (lane == 0) {
+		if (myTrials) atomicAdd(&A.ctl->trials, myTrials);
+		if (myQueries) atomicAdd(&A.ctl->queries, myQueries);
+	}
+	if (gw == 0 && lane == 0) {
+		A.ctl->round = round; A.ctl->nBeads = nBeads; A.ctl->lastProgressed = lastProg ? 1u : 0u;
+	}
+}
+
+// ------------------------------------------------------------------ K7: compaction into acceptance order
+__global__ void flag_slots_kernel(const double* __restrict__ lpos, uint32_t idAtomBase, uint64_t nSlots, uint32_t* __restrict__ flags)
+{
+	uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= nSlots) return;
+	flags[s] = (__double_as_longlong(lpos[3 * (size_t)(idAtomBase + s)]) != -1ll) ? 1u : 0u;
+}
+
+__global__ void gather_atoms_kernel(Geom g, const double* __restrict__ lpos, const uint32_t* __restrict__ flags, const uint32_t* __restrict__ scan,
+	const uint32_t* __restrict__ prev, const ChainState* __restrict__ chains, uint64_t nSlots, uint32_t nSeeded, int terminated,
+	double* __restrict__ xyz, int32_t* __restrict__ chainID, int32_t* __restrict__ type, int64_t* __restrict__ bonds)
+{
+	uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= nSlots || !flags[s]) return;
+	const uint32_t gidx = scan[s];
+	const uint32_t id = g.idAtomBase + (uint32_t)s;
+	const uint64_t nSeedSlots = 2ull * g.nChains;
+	const uint32_t chain = s < nSeedSlots ? (uint32_t)(s >> 1) : (uint32_t)((s - nSeedSlots) % g.nChains);
+	const bool first = s < nSeedSlots && !(s & 1);
+	if (xyz) for (int k = 0; k < 3; k++) xyz[3 * (size_t)gidx + k] = lpos[3 * (size_t)id + k];
+	if (chainID) chainID[gidx] = (int32_t)chain + 1;
+	if (type) type[gidx] = (first || (terminated && chains[chain].lastId == id)) ? 1 : 2;   // sarw.cpp:351-352,262,365
+	if (bonds && !first) {
+		const uint64_t b = s < nSeedSlots ? chain : (uint64_t)gidx - nSeeded;              // listBonds order, sarw.cpp:309,272
+		bonds[2 * b] = (int64_t)scan[prev[s] - g.idAtomBase] + 1;
+		bonds[2 * b + 1] = (int64_t)gidx + 1;
+	}
+}
+
+__global__ void chain_lengths_kernel(const ChainState* __restrict__ chains, uint32_t n, int32_t* __restrict__ out)
+{
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) out[i] = (int32_t)chains[i].length;
+}
+
+__global__ void fill_u32_kernel(uint32_t* p, uint64_t n, uint32_t v)
+{
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// ------------------------------------------------------------------ launch wrappers (called from sarw_abi.cpp)
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
+
+cudaError_t launch_find_batch(const Geom& g, const Tables& T, const double* xyz, const int64_t* ignore, int64_t n, uint8_t* hit, int numSMs, cudaStream_t st)
+{
+	if (n <= 0) return cudaSuccess;
+	int64_t blocks = (n * 8 + 255) / 256;
+	int64_t maxBlocks = (int64_t)numSMs * 8 * 4;
+	if (blocks > maxBlocks) blocks = maxBlocks;
+	find_batch_kernel<<<(unsigned)blocks, 256, 0, st>>>(g, T, xyz, ignore, n, hit);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_add_points(const Geom& g, const Tables& T, const double* xyz, int64_t n, uint32_t baseId, cudaStream_t st)
+{
+	if (n <= 0) return cudaSuccess;
+	add_points_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g, T, xyz, n, baseId);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_seed(const Geom& g, const Tables& T, ChainState* chains, uint32_t* resTrial, uint32_t* prev, const double* grafts,
+	Control* ctl, uint32_t* dirtyList, int numSMs, cudaStream_t st, int* launches)
+{
+	SeedArgs A{ g, T, chains, resTrial, prev, grafts, ctl, dirtyList };
+	unsigned wblocks = (unsigned)((g.nChains + 7) / 8);
+	unsigned cap = (unsigned)numSMs * 8;
+	if (wblocks > cap) wblocks = cap;
+	if (wblocks == 0) wblocks = 1;
+	seed_propose_kernel<<<wblocks, 256, 0, st>>>(A);
+	unsigned vblocks = (unsigned)((g.nChains + 31) / 32);
+	if (vblocks > cap) vblocks = cap;
+	if (vblocks == 0) vblocks = 1;
+	seed_verify_kernel<<<vblocks, 256, 0, st>>>(A);
+	seed_cleanup_kernel<<<1, 1, 0, st>>>(A);
+	unsigned cblocks = (unsigned)((g.nChains + 255) / 256);
+	if (cblocks > cap) cblocks = cap;
+	if (cblocks == 0) cblocks = 1;
+	seed_commit_kernel<<<cblocks, 256, 0, st>>>(A);
+	*launches += 4;
+	return cudaGetLastError();
+}
+
+cudaError_t grow_max_blocks(int numSMs, int* maxBlocks)
+{
+	int perSM = 0;
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, grow_kernel, GROW_THREADS, 0));
+	*maxBlocks = perSM * numSMs;
+	return cudaSuccess;
+}
+
+cudaError_t launch_grow(const Geom& g, const Tables& T, ChainState* chains, uint32_t* resTrial, double* resPos, uint32_t* prev, Control* ctl,
+	uint32_t* roundAcc, uint32_t* roundProg, uint32_t* dirtyCount, uint32_t* dirtyList, uint32_t roundEnd, int blocks, cudaStream_t st)
+{
+	GrowArgs A{ g, T, chains, resTrial, resPos, prev, ctl, roundAcc, roundProg, dirtyCount, dirtyList, roundEnd };
+	void* args[] = { &A };
+	return cudaLaunchCooperativeKernel((const void*)grow_kernel, dim3((unsigned)blocks), dim3(GROW_THREADS), args, 0, st);
+}
+
+cudaError_t launch_download(const Geom& g, const Tables& T, const uint32_t* prev, const ChainState* chains, uint64_t nSlots, uint32_t nSeeded,
+	int terminated, uint32_t* flags, uint32_t* scan, void* cubTemp, size_t cubBytes,
+	double* xyz, int32_t* chainID, int32_t* type, int64_t* bonds, cudaStream_t st)
+{
+	if (nSlots == 0) return cudaSuccess;
+	unsigned blocks = (unsigned)((nSlots + 255) / 256);
+	flag_slots_kernel<<<blocks, 256, 0, st>>>(T.lpos, g.idAtomBase, nSlots, flags);
+	CK(cub::DeviceScan::ExclusiveSum(cubTemp, cubBytes, flags, scan, (int64_t)nSlots, st));
+	gather_atoms_kernel<<<blocks, 256, 0, st>>>(g, T.lpos, flags, scan, prev, chains, nSlots, nSeeded, terminated, xyz, chainID, type, bonds);
+	return cudaGetLastError();
+}
+
+cudaError_t download_scan_bytes(uint64_t nSlots, size_t* bytes)
+{
+	*bytes = 0;
+	return cub::DeviceScan::ExclusiveSum(nullptr, *bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int64_t)nSlots, 0);
+}
+
+cudaError_t launch_chain_lengths(const ChainState* chains, uint32_t n, int32_t* out, cudaStream_t st)
+{
+	if (!n) return cudaSuccess;
+	chain_lengths_kernel<<<(n + 255) / 256, 256, 0, st>>>(chains, n, out);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_fill_u32(uint32_t* p, uint64_t n, uint32_t v, cudaStream_t st)
+{
+	if (!n) return cudaSuccess;
+	uint64_t blocks = (n + 255) / 256; if (blocks > 65535) blocks = 65535;
+	fill_u32_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, n, v);
+	return cudaGetLastError();
+}
+
+} // namespace sarw

@@ -1,0 +1,264 @@
+"""ctypes binding of libsarw_b200.so — the same C ABI (include/sarw_abi.h) the C++ `sarw` host links against.
+
+Mirrors the reference's two classes for the hot path so parity tests read like the reference's own calls:
+
+    PeriodicLookup(boxSize, thresh).addPoint / .find        PeriodicLookup.h:26,37,51   (batched here)
+    SARW(nChains, boxSize, minDist) .initiateChain() .propagateChain() .terminateChain()   sarw.h:88-118
+
+There is NO fallback: if the shared library is missing or no CUDA device is present, construction raises.
+The oracle under oracle/ is never imported from here.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libsarw_b200.so")
+
+GRAFT = {"file": 0, "z": 1, "zCenter": 2}
+ORDER = {"roundRobin": 0, "grafted": 1}
+BOUNDARY = {"ppp": 0, "ppf": 1, "pfp": 2, "fpp": 3}
+
+ABI_SYMBOLS = [
+    "sarw_create", "sarw_destroy", "sarw_last_error", "sarw_set_stream", "sarw_add_obstacles", "sarw_set_grafts",
+    "sarw_initiate", "sarw_propagate_round", "sarw_grow", "sarw_terminate", "sarw_get_stats", "sarw_target_count",
+    "sarw_download", "sarw_chain_lengths", "sarw_round_counts", "sarw_lookup_add_points", "sarw_lookup_find_batch",
+    "sarw_lookup_find_batch_device", "sarw_lookup_size",
+]
+
+
+class SarwError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    _fields_ = [("nChains", C.c_int64), ("boxSize", C.c_double * 3), ("minDist", C.c_double),
+                ("targetMassDensity", C.c_double), ("nGraftChains", C.c_int64), ("maxTrials", C.c_int32),
+                ("graftLoc", C.c_int32), ("growthOrder", C.c_int32), ("boundary", C.c_int32),
+                ("growthBias", C.c_double * 3), ("seed", C.c_uint64), ("device", C.c_int32),
+                ("cellCapacity", C.c_int32), ("cellEdge", C.c_double), ("reserveRounds", C.c_int64)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("nBeads", C.c_int64), ("nBonds", C.c_int64), ("target", C.c_int64), ("rounds", C.c_int64),
+                ("initiated", C.c_int32), ("lastProgressed", C.c_int32), ("trials", C.c_uint64),
+                ("seedTrials", C.c_uint64), ("queries", C.c_uint64), ("conflicts", C.c_uint64),
+                ("overflowBeads", C.c_uint64), ("seedMs", C.c_double), ("growMs", C.c_double),
+                ("growLaunches", C.c_int64), ("seedLaunches", C.c_int64)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+_lib = None
+
+
+def load_library(path=LIB_PATH):
+    """dlopen libsarw_b200.so and declare the ABI; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(path):
+        raise SarwError(f"{path} is missing: build it with `make lib` (python __graft_entry__.py); there is no CPU fallback")
+    lib = C.CDLL(path)
+    vp = C.c_void_p
+    lib.sarw_create.argtypes = [C.POINTER(Params), C.POINTER(vp)]
+    lib.sarw_destroy.argtypes = [vp]; lib.sarw_destroy.restype = None
+    lib.sarw_last_error.argtypes = [vp]; lib.sarw_last_error.restype = C.c_char_p
+    lib.sarw_set_stream.argtypes = [vp, vp]
+    lib.sarw_add_obstacles.argtypes = [vp, vp, C.c_int64]
+    lib.sarw_set_grafts.argtypes = [vp, vp, C.c_int64]
+    lib.sarw_initiate.argtypes = [vp, C.POINTER(C.c_int32)]
+    lib.sarw_propagate_round.argtypes = [vp, C.POINTER(C.c_int32)]
+    lib.sarw_grow.argtypes = [vp, C.c_int64, C.c_int64, C.POINTER(Stats)]
+    lib.sarw_terminate.argtypes = [vp]
+    lib.sarw_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    lib.sarw_target_count.argtypes = [C.POINTER(C.c_double), C.c_double]; lib.sarw_target_count.restype = C.c_int64
+    lib.sarw_download.argtypes = [vp, vp, vp, vp, vp]
+    lib.sarw_chain_lengths.argtypes = [vp, vp]
+    lib.sarw_round_counts.argtypes = [vp, vp, C.c_int64]
+    lib.sarw_lookup_add_points.argtypes = [vp, vp, C.c_int64]
+    lib.sarw_lookup_find_batch.argtypes = [vp, vp, vp, C.c_int64, vp]
+    lib.sarw_lookup_find_batch_device.argtypes = [vp, vp, vp, C.c_int64, vp]
+    lib.sarw_lookup_size.argtypes = [vp]; lib.sarw_lookup_size.restype = C.c_int64
+    _lib = lib
+    return lib
+
+
+def target_count(boxSize, targetMassDensity):
+    b = (C.c_double * 3)(*boxSize)
+    return load_library().sarw_target_count(b, targetMassDensity)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64).reshape(-1, 3)
+
+
+class Context:
+    """Owns one sarw_ctx (one GPU). Thin: every method is one ABI call."""
+
+    def __init__(self, nChains=1, boxSize=(10, 10, 10), minDist=2.0, targetMassDensity=0.92, maxTrials=100,
+                 boundary="ppp", nGraftChains=0, graftLoc="file", growthOrder="roundRobin", growthBias=(0, 0, 0),
+                 seed=1, device=-1, cellCapacity=0, cellEdge=0.0, reserveRounds=0):
+        self.lib = load_library()
+        p = Params()
+        p.nChains = nChains; p.boxSize = (C.c_double * 3)(*boxSize); p.minDist = minDist
+        p.targetMassDensity = targetMassDensity; p.nGraftChains = nGraftChains; p.maxTrials = maxTrials
+        p.graftLoc = GRAFT.get(graftLoc, 3); p.growthOrder = ORDER.get(growthOrder, 0)
+        p.boundary = BOUNDARY.get(boundary, 0)   # only exact ppf/pfp/fpp act, anything else == ppp (sarw.cpp:201-203)
+        p.growthBias = (C.c_double * 3)(*growthBias); p.seed = seed; p.device = device
+        p.cellCapacity = cellCapacity; p.cellEdge = cellEdge; p.reserveRounds = reserveRounds
+        self.params = p
+        self.nChains = nChains
+        h = C.c_void_p()
+        if self.lib.sarw_create(C.byref(p), C.byref(h)) != 0:
+            raise SarwError(self.lib.sarw_last_error(None).decode())
+        self.h = h
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise SarwError(self.lib.sarw_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.sarw_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- lookup (PeriodicLookup.h)
+    def add_points(self, xyz):
+        a = _f64(xyz)
+        self._ck(self.lib.sarw_lookup_add_points(self.h, a.ctypes.data, a.shape[0]))
+
+    def add_obstacles(self, xyz):
+        a = _f64(xyz)
+        self._ck(self.lib.sarw_add_obstacles(self.h, a.ctypes.data, a.shape[0]))
+
+    def find(self, xyz, ignore=None):
+        a = _f64(xyz)
+        ig = None if ignore is None else np.ascontiguousarray(ignore, dtype=np.int64)
+        out = np.zeros(a.shape[0], np.uint8)
+        self._ck(self.lib.sarw_lookup_find_batch(self.h, a.ctypes.data, ig.ctypes.data if ig is not None else None,
+                                                 a.shape[0], out.ctypes.data))
+        return out
+
+    def find_device(self, d_xyz_ptr, d_ignore_ptr, n, d_hit_ptr):
+        self._ck(self.lib.sarw_lookup_find_batch_device(self.h, d_xyz_ptr, d_ignore_ptr, n, d_hit_ptr))
+
+    def lookup_size(self):
+        return self.lib.sarw_lookup_size(self.h)
+
+    def set_stream(self, cuda_stream_ptr):
+        self._ck(self.lib.sarw_set_stream(self.h, cuda_stream_ptr))
+
+    # ---- walk (sarw.cpp)
+    def set_grafts(self, xyz):
+        a = _f64(xyz)
+        self._ck(self.lib.sarw_set_grafts(self.h, a.ctypes.data, a.shape[0]))
+
+    def initiate(self):
+        ok = C.c_int32()
+        self._ck(self.lib.sarw_initiate(self.h, C.byref(ok)))
+        return bool(ok.value)
+
+    def propagate_round(self):
+        pr = C.c_int32()
+        self._ck(self.lib.sarw_propagate_round(self.h, C.byref(pr)))
+        return bool(pr.value)
+
+    def grow(self, target=0, maxRounds=-1):
+        s = Stats()
+        self._ck(self.lib.sarw_grow(self.h, target, maxRounds, C.byref(s)))
+        return s
+
+    def terminate(self):
+        self._ck(self.lib.sarw_terminate(self.h))
+
+    def stats(self):
+        s = Stats()
+        self._ck(self.lib.sarw_get_stats(self.h, C.byref(s)))
+        return s
+
+    def download(self):
+        s = self.stats()
+        xyz = np.zeros((s.nBeads, 3), np.float64)
+        chainID = np.zeros(s.nBeads, np.int32)
+        typ = np.zeros(s.nBeads, np.int32)
+        bonds = np.zeros((s.nBonds, 2), np.int64)
+        self._ck(self.lib.sarw_download(self.h, xyz.ctypes.data, chainID.ctypes.data, typ.ctypes.data, bonds.ctypes.data))
+        return xyz, chainID, typ, bonds
+
+    def chain_lengths(self):
+        out = np.zeros(self.nChains, np.int32)
+        self._ck(self.lib.sarw_chain_lengths(self.h, out.ctypes.data))
+        return out
+
+    def round_counts(self):
+        s = self.stats()
+        out = np.zeros(s.rounds, np.int64)
+        self._ck(self.lib.sarw_round_counts(self.h, out.ctypes.data, s.rounds))
+        return out
+
+
+class PeriodicLookup:
+    """Mirror of the reference class (PeriodicLookup.h:9-76), batched: addPoint/find take (n,3) arrays."""
+
+    def __init__(self, boxSize, thresh, **kw):
+        self.ctx = Context(nChains=1, boxSize=boxSize, minDist=thresh, **kw)
+
+    def addPoint(self, pos):
+        self.ctx.add_points(pos)
+
+    def find(self, pos, ignoreIndex=None):
+        return self.ctx.find(pos, ignoreIndex)
+
+    def close(self):
+        self.ctx.close()
+
+
+class SARW:
+    """Mirror of the reference's SARW object for the hot path (sarw.h:59-136, sarw.cpp:220-368)."""
+
+    def __init__(self, nChains, boxSize, minDist, **kw):
+        self.ctx = Context(nChains=nChains, boxSize=boxSize, minDist=minDist, **kw)
+        self.nChains = nChains
+        self.boxSize = tuple(boxSize)
+
+    def readGrafts(self, xyz):
+        self.ctx.set_grafts(xyz)
+
+    def addObstacle(self, xyz):
+        self.ctx.add_obstacles(xyz)
+
+    def initiateChain(self):
+        return self.ctx.initiate()
+
+    def propagateChain(self):
+        return self.ctx.propagate_round()
+
+    def terminateChain(self):
+        self.ctx.terminate()
+
+    def actualCount(self):
+        return self.ctx.stats().nBeads
+
+    def targetCount(self):
+        return self.ctx.stats().target
+
+    def run(self, maxRounds=-1):
+        """main()'s sequence sarw.cpp:66-79: initiate, grow to the target, terminate. Returns the final stats."""
+        self.ctx.initiate()
+        st = self.ctx.grow(0, maxRounds)
+        self.ctx.terminate()
+        return st
+
+    def close(self):
+        self.ctx.close()

@@ -1,0 +1,24 @@
+"""Quick timing probe on a GPU box (not a bench line): growth ms, rounds, trials for a few configs."""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "polymer-sarw_b200")); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import sarw_b200, cases
+
+which = sys.argv[1:] or ["PE_IN", "C2", "C3"]
+for name in which:
+    cfg = getattr(cases, name)
+    for seed in (1, 2):
+        t0 = time.time()
+        s = sarw_b200.SARW(cfg["nChains"], cfg["boxSize"], cfg["minDist"], seed=seed,
+                           **{k: v for k, v in cfg.items() if k not in ("nChains", "boxSize", "minDist")})
+        t1 = time.time()
+        st = s.run()
+        t2 = time.time()
+        xyz, cid, typ, bonds = s.ctx.download()
+        t3 = time.time()
+        d = s.ctx.stats().as_dict()
+        s.close()
+        print(name, seed, f"create {t1-t0:.3f}s run {t2-t1:.3f}s download {t3-t2:.3f}s | beads {d['nBeads']} rounds {d['rounds']} "
+              f"trials {d['trials']} queries {d['queries']} conflicts {d['conflicts']} ovf {d['overflowBeads']} "
+              f"seedMs {d['seedMs']:.3f} growMs {d['growMs']:.3f} launches {d['growLaunches']} "
+              f"| {d['nBeads']/ (d['growMs']+d['seedMs']) * 1e3:.3e} beads/s, {d['growMs']*1e3/max(1,d['rounds']):.2f} us/round", flush=True)

@@ -1,0 +1,75 @@
+"""Shared test configurations (keyword sets understood by OracleLib.walk, RefLib.walk and sarw_b200.Context)."""
+import numpy as np
+
+PE_IN = dict(nChains=20, boxSize=(10.0, 10.0, 40.0), minDist=1.0, maxTrials=1000, boundary="ppf")   # test/pe.in as the code reads it
+C2 = dict(nChains=100, boxSize=(136.2, 136.2, 136.2), minDist=1.0, maxTrials=1000)                  # BASELINE configs[1]
+C3 = dict(nChains=10000, boxSize=(632.2, 632.2, 632.2), minDist=1.0, maxTrials=1000)                # BASELINE configs[2]
+SMALL_DEFAULTS = dict(nChains=30, boxSize=(30.0, 30.0, 30.0), minDist=2.0, maxTrials=100)            # the code's default minDist/maxTrials
+DENSE_TINY = dict(nChains=40, boxSize=(12.0, 12.0, 12.0), minDist=1.0, maxTrials=200)                # many same-round conflicts
+MID = dict(nChains=400, boxSize=(60.0, 60.0, 60.0), minDist=1.0, maxTrials=300)
+
+
+def oracle_kwargs(cfg):
+    d = dict(cfg)
+    d["box"] = d.pop("boxSize")
+    return d
+
+
+def make_grafts(n, box, seed=2024, zval=0.0, min_sep=1.0):
+    """BASELINE.md C4 recipe: x,y ~ U(0,L), z fixed, rejected if within min_sep (min-image in x,y) of an earlier point."""
+    rng = np.random.default_rng(seed)
+    pts = []
+    while len(pts) < n:
+        p = np.array([rng.uniform(0, box[0]), rng.uniform(0, box[1]), zval])
+        ok = True
+        for q in pts:
+            d = p - q
+            d[0] -= box[0] * np.round(d[0] / box[0]); d[1] -= box[1] * np.round(d[1] / box[1])
+            if np.dot(d, d) <= min_sep * min_sep:
+                ok = False; break
+        if ok:
+            pts.append(p)
+    return np.array(pts)
+
+
+def make_obstacles(n, box, seed=7):
+    rng = np.random.default_rng(seed)
+    return rng.uniform(0, 1, (n, 3)) * np.array(box)
+
+
+def verify_structure(xyz, chainID, typ, bonds, box, minDist, nChains, check_pairs=True):
+    """Brute-force verifier (north_star): bonds 1.54 A, 1-3 distance of the 109.5 degree angle, every non-bonded
+    pair farther than minDist under the minimum image in all three directions. Returns a dict of extrema."""
+    from scipy.spatial import cKDTree
+    xyz = np.asarray(xyz); box = np.asarray(box, float)
+    out = {}
+    a, b = bonds[:, 0] - 1, bonds[:, 1] - 1
+    bl = np.linalg.norm(xyz[a] - xyz[b], axis=1)
+    out["bond_min"], out["bond_max"] = bl.min(), bl.max()
+    assert np.all(chainID[a] == chainID[b])
+    # 1-3 distances: for each chain, consecutive beads in acceptance order
+    order = np.argsort(chainID, kind="stable")
+    cid = chainID[order]; p = xyz[order]
+    same2 = cid[2:] == cid[:-2]
+    d13 = np.linalg.norm(p[2:] - p[:-2], axis=1)[same2]
+    out["d13_min"], out["d13_max"] = (d13.min(), d13.max()) if d13.size else (np.nan, np.nan)
+    if check_pairs:
+        w = xyz - np.floor(xyz / box) * box
+        w = np.minimum(w, np.nextafter(box, 0))
+        tree = cKDTree(w, boxsize=box)
+        pairs = tree.query_pairs(minDist * 1.0000001, output_type="ndarray")
+        # bonded = consecutive beads of one chain
+        pos_in_order = np.empty(len(order), np.int64); pos_in_order[order] = np.arange(len(order))
+        i, j = pairs[:, 0], pairs[:, 1]
+        bonded = (chainID[i] == chainID[j]) & (np.abs(pos_in_order[i] - pos_in_order[j]) == 1)
+        nb = pairs[~bonded]
+        if len(nb):
+            d = w[nb[:, 0]] - w[nb[:, 1]]
+            d -= box * np.round(d / box)
+            dist = np.linalg.norm(d, axis=1)
+            out["closest_nonbonded"] = dist.min()
+            out["violations"] = int(np.sum(dist <= minDist))
+        else:
+            out["closest_nonbonded"] = np.inf
+            out["violations"] = 0
+    return out

@@ -1,0 +1,54 @@
+"""CPU tests of the drop-in boundary: libsarw_b200.so loads and exports every symbol include/sarw_abi.h declares;
+without a GPU every entry point fails loudly (there is no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "sarw_abi.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sarw_[a-z_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(sarw):
+    lib = sarw.load_library()
+    names = _declared_symbols()
+    assert len(names) >= 19
+    for n in names:
+        assert hasattr(lib, n), n
+    assert sorted(sarw.ABI_SYMBOLS) == names
+
+
+def test_target_count_needs_no_gpu(sarw):
+    assert sarw.target_count((10, 10, 40), 0.92) == 158
+    assert sarw.target_count((632.2, 632.2, 632.2), 0.92) == 9999171
+    assert sarw.target_count((2934.5, 2934.5, 2934.5), 0.92) > 2 ** 31 / 3   # 64-bit volume (sarw.h:103 overflows here)
+
+
+def test_parameter_validation_and_no_cpu_fallback(sarw):
+    with pytest.raises(sarw.SarwError):
+        sarw.Context(nChains=0)
+    with pytest.raises(sarw.SarwError):
+        sarw.Context(nChains=1, boxSize=(1.5, 10, 10), minDist=1.0)   # the reference needs floor(L/minDist) >= 2
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(sarw.SarwError, match="no CUDA device|CUDA"):
+            sarw.Context(nChains=4, boxSize=(10, 10, 10), minDist=1.0)
+
+
+def test_product_never_imports_oracle():
+    """The product package must not include, import or load anything under oracle/ (parity claims depend on it)."""
+    pkg = os.path.join(ROOT, "polymer-sarw_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if not f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                continue
+            for line in open(os.path.join(dirpath, f), errors="ignore").read().splitlines():
+                code = line.split("//")[0].split("#include")[-1] if "#include" in line else line.split("//")[0]
+                if re.search(r"#include|^\s*(import|from)\s|dlopen|CDLL", line):
+                    assert "oracle" not in code.lower(), (f, line)

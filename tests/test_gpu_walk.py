@@ -1,0 +1,189 @@
+"""GPU parity of the chain-growth path (K1-K4,K7) through the C ABI.
+
+Bar (north_star): bit-exact against the oracle's sequential walk for the same Philox key — same accepted trial of
+every chain in every round, same atom order, ids, types, bonds, and coordinates equal bit for bit (the oracle is run
+with the same portable sin/cos; its libm-trig twin is pinned bit-exactly to the unmodified reference in
+tests/test_oracle.py). Against fixtures written by the unmodified reference itself the decisions must be identical
+and coordinates equal to 1e-9 A (libm vs portable trig)."""
+import os
+import numpy as np
+import pytest
+
+import cases
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+def run_gpu(sarw, cfg, seed, maxRounds=-1, grafts=None, obstacles=None, **extra):
+    s = sarw.SARW(cfg["nChains"], cfg["boxSize"], cfg["minDist"], seed=seed,
+                  **{k: v for k, v in cfg.items() if k not in ("nChains", "boxSize", "minDist")}, **extra)
+    if obstacles is not None:
+        s.addObstacle(obstacles)
+    if grafts is not None:
+        s.readGrafts(grafts)
+    st = s.run(maxRounds)
+    xyz, chainID, typ, bonds = s.ctx.download()
+    out = dict(st=st.as_dict(), xyz=xyz, chainID=chainID, type=typ, bonds=bonds, chainLengths=s.ctx.chain_lengths(),
+               countAfterRound=s.ctx.round_counts(), stats=s.ctx.stats().as_dict())
+    s.close()
+    return out
+
+
+def assert_same_walk(g, o, exact=True):
+    st = g["st"]
+    assert (st["nBeads"], st["nBonds"], st["target"], st["rounds"], st["initiated"], st["lastProgressed"]) == \
+        (o.nAtoms, o.nBonds, o.target, o.rounds, o.initiated, o.lastProgressed)
+    assert (st["trials"], st["seedTrials"]) == (o.trials, o.seedTrials)
+    assert np.array_equal(g["chainID"], o.chainID)
+    assert np.array_equal(g["type"], o.type)
+    assert np.array_equal(g["bonds"], o.bonds)
+    assert np.array_equal(g["chainLengths"], o.chainLengths)
+    assert np.array_equal(g["countAfterRound"], o.countAfterRound)
+    if exact:
+        assert np.array_equal(g["xyz"], o.xyz), float(np.abs(g["xyz"] - o.xyz).max())
+    else:
+        assert np.abs(g["xyz"] - o.xyz).max() < 1e-9
+
+
+@pytest.mark.parametrize("name,cfg", [("pe_in", cases.PE_IN), ("small_defaults", cases.SMALL_DEFAULTS), ("dense_tiny", cases.DENSE_TINY)])
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_walk_bit_exact_vs_oracle_and_reference_fixture(sarw, oracle, name, cfg, seed):
+    g = run_gpu(sarw, cfg, seed)
+    o = oracle.walk(seed=seed, trig="portable", **cases.oracle_kwargs(cfg))
+    assert_same_walk(g, o, exact=True)
+    gold = np.load(os.path.join(GOLDEN, f"walk_{name}_seed{seed}.npz"))   # written by the unmodified reference
+    assert list(gold["meta"][:4]) == [g["st"]["nBeads"], g["st"]["nBonds"], g["st"]["target"], g["st"]["rounds"]]
+    assert np.array_equal(g["chainID"], gold["chainID"]) and np.array_equal(g["type"], gold["type"])
+    assert np.array_equal(g["bonds"], gold["bonds"]) and np.array_equal(g["countAfterRound"], gold["countAfterRound"])
+    assert np.abs(g["xyz"] - gold["xyz"]).max() < 1e-9
+
+
+@pytest.mark.parametrize("name", ["graft_file", "graft_z", "graft_zcenter", "graft_order", "obstacles", "pfp", "fpp"])
+def test_walk_variants_vs_oracle_and_reference_fixture(sarw, oracle, name):
+    gold = np.load(os.path.join(GOLDEN, f"walk_{name}.npz"))
+    cfg = dict(nChains=24, boxSize=(24.0, 24.0, 30.0), minDist=1.0, maxTrials=200)
+    if name.startswith("graft"):
+        cfg.update(boundary="ppf", nGraftChains=12, graftLoc={"graft_file": "file", "graft_z": "z", "graft_zcenter": "zCenter", "graft_order": "file"}[name])
+        if name == "graft_order":
+            cfg["growthOrder"] = "grafted"
+    if name in ("pfp", "fpp"):
+        cfg["boundary"] = name
+    grafts = gold["grafts"] if "grafts" in gold.files else None
+    obstacles = gold["obstacles"] if "obstacles" in gold.files else None
+    g = run_gpu(sarw, cfg, 11, grafts=grafts, obstacles=obstacles)
+    o = oracle.walk(seed=11, trig="portable", grafts=grafts, obstacles=obstacles, **cases.oracle_kwargs(cfg))
+    assert_same_walk(g, o, exact=True)
+    assert np.array_equal(g["bonds"], gold["bonds"]) and np.array_equal(g["type"], gold["type"])
+    assert np.abs(g["xyz"] - gold["xyz"]).max() < 1e-9
+
+
+@pytest.mark.parametrize("seed", [1, 4])
+def test_walk_c2_full_size_bit_exact(sarw, oracle, seed):
+    """BASELINE configs[1]: 100 chains x 1000 beads, 0.92 g/cc, ppp — every bead bit-exact against the oracle."""
+    g = run_gpu(sarw, cases.C2, seed)
+    o = oracle.walk(seed=seed, trig="portable", **cases.oracle_kwargs(cases.C2))
+    assert_same_walk(g, o, exact=True)
+    v = cases.verify_structure(g["xyz"], g["chainID"], g["type"], g["bonds"], cases.C2["boxSize"], 1.0, 100)
+    assert abs(v["bond_min"] - 1.54) < 1e-5 and abs(v["bond_max"] - 1.54) < 1e-5
+    assert abs(v["d13_min"] - 2.515256) < 1e-5 and abs(v["d13_max"] - 2.515256) < 1e-5
+    assert v["violations"] == 0 and v["closest_nonbonded"] > 1.0
+    assert g["st"]["target"] <= g["st"]["nBeads"] < g["st"]["target"] + 100
+
+
+def test_walk_mid_size_many_conflicts_bit_exact(sarw, oracle):
+    g = run_gpu(sarw, cases.MID, 9)
+    o = oracle.walk(seed=9, trig="portable", **cases.oracle_kwargs(cases.MID))
+    assert_same_walk(g, o, exact=True)
+    assert g["stats"]["conflicts"] > 0   # the same-round conflict path was exercised
+
+
+@pytest.mark.parametrize("cap", [1, 2])
+def test_walk_with_overflowing_cells_bit_exact(sarw, oracle, cap):
+    """cellCapacity forced small: most beads live in the overflow list; results must not change."""
+    g = run_gpu(sarw, cases.DENSE_TINY, 5, cellCapacity=cap)
+    o = oracle.walk(seed=5, trig="portable", **cases.oracle_kwargs(cases.DENSE_TINY))
+    assert_same_walk(g, o, exact=True)
+    assert g["stats"]["overflowBeads"] > 0
+
+
+def test_walk_growth_bias_extension_matches_oracle(sarw, oracle):
+    cfg = dict(nChains=24, boxSize=(24.0, 24.0, 60.0), minDist=1.0, maxTrials=200, boundary="ppf", nGraftChains=12,
+               graftLoc="file", growthBias=(0.0, 0.0, 1.0), targetMassDensity=0.3)
+    grafts = cases.make_grafts(12, cfg["boxSize"], seed=3)
+    g = run_gpu(sarw, cfg, 2, grafts=grafts)
+    o = oracle.walk(seed=2, trig="portable", grafts=grafts, **cases.oracle_kwargs(cfg))
+    assert_same_walk(g, o, exact=True)
+    # every bond of a biased chain points up (bias . step >= 0)
+    a, b = g["bonds"][:, 0] - 1, g["bonds"][:, 1] - 1
+    grown = b >= 2 * 24
+    assert np.all((g["xyz"][b] - g["xyz"][a])[grown, 2] >= 0)
+
+
+def test_round_by_round_api_equals_whole_loop(sarw, oracle):
+    """sarw_propagate_round (one SARW::propagateChain per call) gives the same walk as sarw_grow."""
+    cfg = cases.PE_IN
+    s = sarw.SARW(cfg["nChains"], cfg["boxSize"], cfg["minDist"], seed=3, maxTrials=cfg["maxTrials"], boundary=cfg["boundary"])
+    assert s.initiateChain()
+    rounds = 0
+    while s.actualCount() < s.targetCount():          # sarw.cpp:67-69
+        if not s.propagateChain():
+            break
+        rounds += 1
+    s.terminateChain()
+    xyz, chainID, typ, bonds = s.ctx.download()
+    s.close()
+    o = oracle.walk(seed=3, trig="portable", **cases.oracle_kwargs(cfg))
+    assert rounds == o.rounds
+    assert np.array_equal(xyz, o.xyz) and np.array_equal(typ, o.type) and np.array_equal(bonds, o.bonds)
+
+
+def test_partial_growth_and_resume(sarw, oracle):
+    """maxRounds stops early; a second sarw_grow continues the same walk (several kernel launches, same result)."""
+    cfg = cases.SMALL_DEFAULTS
+    s = sarw.SARW(cfg["nChains"], cfg["boxSize"], cfg["minDist"], seed=6, maxTrials=cfg["maxTrials"], reserveRounds=4)
+    s.ctx.initiate()
+    st = s.ctx.grow(0, 5)
+    assert st.rounds == 5
+    o5 = oracle.walk(seed=6, trig="portable", maxRounds=5, **cases.oracle_kwargs(cfg))
+    assert st.nBeads == o5.nAtoms
+    st = s.ctx.grow(0, -1)           # storage was reserved for 4 rounds only: exercises the re-allocation path
+    s.ctx.terminate()
+    xyz, chainID, typ, bonds = s.ctx.download()
+    s.close()
+    o = oracle.walk(seed=6, trig="portable", **cases.oracle_kwargs(cfg))
+    assert st.rounds == o.rounds and np.array_equal(xyz, o.xyz) and np.array_equal(bonds, o.bonds) and np.array_equal(typ, o.type)
+
+
+def test_determinism_same_seed_twice(sarw):
+    a = run_gpu(sarw, cases.MID, 21)
+    b = run_gpu(sarw, cases.MID, 21)
+    assert np.array_equal(a["xyz"], b["xyz"]) and np.array_equal(a["bonds"], b["bonds"])
+    c = run_gpu(sarw, cases.MID, 22)
+    assert not np.array_equal(a["xyz"][:100], c["xyz"][:100])
+
+
+def test_jammed_seeding_matches_oracle(sarw, oracle):
+    """Too many chains for the box: initiateChain fails at the same chain, growth is skipped (sarw.cpp:66,313-314)."""
+    cfg = dict(nChains=400, boxSize=(8.0, 8.0, 8.0), minDist=1.5, maxTrials=20)
+    g = run_gpu(sarw, cfg, 1)
+    o = oracle.walk(seed=1, trig="portable", **cases.oracle_kwargs(cfg))
+    assert o.initiated == 0
+    assert (g["st"]["initiated"], g["st"]["nBeads"], g["st"]["rounds"]) == (0, o.nAtoms, 0)
+    assert np.array_equal(g["xyz"], o.xyz) and np.array_equal(g["bonds"], o.bonds) and np.array_equal(g["type"], o.type)
+
+
+def test_c3_full_size_invariants(sarw):
+    """BASELINE configs[2] at full size (1e4 x 1000 = 1e7 beads): no CPU oracle in test time, so size-independent
+    properties: bead count window, bond/angle geometry, zero minDist violations, topology consistency."""
+    g = run_gpu(sarw, cases.C3, 1)
+    st = g["st"]
+    assert st["initiated"] == 1 and st["target"] == 9999171
+    assert st["target"] <= st["nBeads"] < st["target"] + 10000
+    assert st["nBonds"] == st["nBeads"] - 10000
+    assert g["chainLengths"].sum() == st["nBeads"] and np.array_equal(np.bincount(g["chainID"], minlength=10001)[1:], g["chainLengths"])
+    v = cases.verify_structure(g["xyz"], g["chainID"], g["type"], g["bonds"], cases.C3["boxSize"], 1.0, 10000)
+    assert abs(v["bond_min"] - 1.54) < 1e-5 and abs(v["bond_max"] - 1.54) < 1e-5
+    assert abs(v["d13_min"] - 2.515256) < 1e-5 and abs(v["d13_max"] - 2.515256) < 1e-5
+    assert v["violations"] == 0
+    assert np.sum(g["type"] == 1) == 2 * 10000
