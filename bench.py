@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py — accepted beads/s of the chain-growth hot path (BASELINE.json metric) on N B200s of one node.
+
+A step = one complete pass of the hot path over one synthetic melt: SARW::initiateChain + the growth loop of
+main() (sarw.cpp:66-78) for BASELINE.json configs[1] (PE melt, 100 chains x 1000 beads, 0.92 g/cc, ppp,
+minDist 1.0, maxTrials 1000). Every step uses a fresh Philox key, so no work is cached between steps.
+
+  value : device-resident throughput — contexts (cell tables) are created before the timed region; a step is
+          timed with CUDA events on the stream the kernels run on.
+  e2e   : the same metric through the public C ABI with host buffers: sarw_create (allocations + table init),
+          H2D of the inputs, seeding, growth, sarw_terminate and sarw_download of every bead/bond into host memory,
+          wall clock around the calls.
+  N > 1 : one process per GPU (torchrun). The melts of different ranks are independent (no data-path collective yet:
+          spatial decomposition with NCCL halo exchange is the next §8e row); "scaling": "weak".
+  --impl reference : the UNMODIFIED reference (oracle/_ref, built from /root/reference) timed on the host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "polymer-sarw_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOADS = {
+    # BASELINE.json configs[1] / SURVEY §8d C2
+    "C2": dict(name="PE melt 100 chains x 1000 beads, 0.92 g/cc, ppp, minDist 1.0, maxTrials 1000 (BASELINE configs[1])",
+               nChains=100, boxSize=(136.2, 136.2, 136.2), minDist=1.0, maxTrials=1000, boundary="ppp", targetMassDensity=0.92),
+    # BASELINE.json configs[2] / C3
+    "C3": dict(name="PE melt 1e4 chains x 1000 beads, 0.92 g/cc, ppp, minDist 1.0, maxTrials 1000 (BASELINE configs[2])",
+               nChains=10000, boxSize=(632.2, 632.2, 632.2), minDist=1.0, maxTrials=1000, boundary="ppp", targetMassDensity=0.92),
+}
+# algorithmic bytes per overlap query and per accepted bead
+B_QUERY = 121.0
+B_BEAD = 108.0
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return json.load(open(path)).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def ctx_kwargs(w, seed):
+    return dict(nChains=w["nChains"], boxSize=w["boxSize"], minDist=w["minDist"], targetMassDensity=w["targetMassDensity"],
+                maxTrials=w["maxTrials"], boundary=w["boundary"], seed=seed)
+
+
+# ------------------------------------------------------------------ reference on host cores (oracle/_ref)
+def _ref_one(args):
+    w, seed = args
+    import oracle_bindings as ob
+    R = ob.RefLib()
+    r = R.walk(nChains=w["nChains"], box=w["boxSize"], minDist=w["minDist"], targetMassDensity=w["targetMassDensity"],
+               maxTrials=w["maxTrials"], boundary=w["boundary"], rng="mt", seed=seed)
+    return r.nAtoms, r.seconds, r.trials, r.rounds
+
+
+def reference_throughput(w, instances, seed0):
+    """`instances` independent melts of the reference, one per host core, run concurrently (the reference itself is
+    strictly serial: 1 thread per instance). Returns (beads/s aggregate, wall seconds of the slowest, details)."""
+    import multiprocessing as mp
+    import oracle_bindings as ob
+    if not ob.RefLib.available():
+        if os.path.isdir("/root/reference"):
+            ob.build_oracles()
+    if not ob.RefLib.available():
+        return None
+    ctx = mp.get_context("fork")
+    with ctx.Pool(instances) as pool:
+        t0 = time.perf_counter()
+        res = pool.map(_ref_one, [(w, seed0 + i) for i in range(instances)])
+        wall = time.perf_counter() - t0
+    beads = sum(r[0] for r in res)
+    slowest = max(r[1] for r in res)
+    per_core = statistics.median(r[0] / r[1] for r in res)
+    return dict(value=beads / slowest, wall=wall, slowest=slowest, per_core=per_core, beads=beads,
+                trials_per_bead=sum(r[2] for r in res) / beads, rounds=[r[3] for r in res])
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = max(1, min(os.cpu_count() or 1, 32))
+    times, values = [], []
+    last = None
+    for s in range(args.warmup + args.steps):
+        r = reference_throughput(w, cores, 1000 + 100 * s)
+        if r is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref is not built (needs /root/reference at build time)"}))
+            return
+        if s >= args.warmup:
+            times.append(r["slowest"]); values.append(r["value"]); last = r
+    value = sum(values) / len(values)
+    sample = (f"{cores} concurrent instances (1 thread each; the reference is serial) of the full workload per step, unmodified reference "
+              f"sources (oracle/_ref) with mt19937_64 re-seeded per trial like upstream; seeding + growth loop timed (sarw.cpp:66-78)")
+    line = {"impl": "reference", "metric": "accepted beads/sec", "value": value, "unit": "beads/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": w["name"], "instances": cores},
+            "cpu_baseline": {"value": value, "unit": "beads/s", "cores": cores, "kind": "reference", "sample": sample,
+                             "per_core_beads_per_s": last["per_core"], "trials_per_bead": last["trials_per_bead"]},
+            "e2e": {"value": value, "unit": "beads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary C3 / find_batch measurements")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference(args, w)
+
+    import numpy as np
+    import torch
+    import sarw_b200
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libsarw_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    stream = torch.cuda.current_stream()
+    hbm_peak, peak_src = load_peaks()
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")   # > 126 MB L2
+
+    def one_step_device(ctx):
+        """initiate + grow + terminate on an existing context; device time from CUDA events on the kernels' stream"""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        ctx.initiate()
+        st = ctx.grow(0, -1)
+        ctx.terminate()
+        e1.record(stream)
+        e1.synchronize()
+        return e0.elapsed_time(e1), st
+
+    def make_ctx(seed):
+        c = sarw_b200.Context(device=local, **ctx_kwargs(w, seed))
+        c.set_stream(stream.cuda_stream)
+        return c
+
+    total = args.warmup + args.steps
+    seeds = [10_000 * (rank + 1) + s for s in range(total)]
+    # -------- device-resident arm
+    ctxs = [make_ctx(s) for s in seeds]
+    for i in range(args.warmup):
+        flush.fill_(float(i)); one_step_device(ctxs[i])
+    torch.cuda.synchronize()
+    if dist: dist.barrier()
+    sampler = ClockSampler(local); sampler.start()
+    step_ms, beads, queries, trials, rounds, launches, grow_ms, seed_ms, conflicts = [], 0, 0, 0, 0, 0, 0.0, 0.0, 0
+    for i in range(args.warmup, total):
+        flush.fill_(float(i))          # L2 flush between timed iterations (outside the event pair)
+        torch.cuda.synchronize()
+        ms, st = one_step_device(ctxs[i])
+        step_ms.append(ms)
+        beads += st.nBeads; queries += st.queries; trials += st.trials; rounds += st.rounds
+        launches += st.growLaunches + st.seedLaunches; grow_ms += st.growMs; seed_ms += st.seedMs; conflicts += st.conflicts
+    torch.cuda.synchronize()
+    if dist: dist.barrier()
+    clocks = sampler.stop()
+    for c in ctxs:
+        c.close()
+    t_dev = sum(step_ms) / 1e3
+
+    # -------- end-to-end arm through the C ABI with host buffers
+    e2e_times, e2e_beads, h2d, d2h, e2e_launch = [], 0, 0, 0, 0
+    for i in range(total):
+        flush.fill_(float(i)); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        c = sarw_b200.Context(device=local, **ctx_kwargs(w, seeds[i] + 5_000))
+        c.set_stream(stream.cuda_stream)
+        c.initiate(); st = c.grow(0, -1); c.terminate()
+        xyz, cid, typ, bonds = c.download()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        c.close()
+        if i >= args.warmup:
+            e2e_times.append(dt); e2e_beads += st.nBeads
+            h2d += sarw_b200.C.sizeof(sarw_b200.Params) + 64                      # parameters + control block
+            d2h += xyz.nbytes + cid.nbytes + typ.nbytes + bonds.nbytes + 3 * 64 + st.growLaunches * 64 + 8   # results + control/stat reads
+            e2e_launch += st.growLaunches + st.seedLaunches + 5                   # + flag, 2x cub scan, gather
+
+    # -------- aggregate over ranks (max time, summed work)
+    t_e2e = sum(e2e_times)
+    agg = torch.tensor([t_dev, t_e2e, float(beads), float(e2e_beads), float(queries), grow_ms, float(launches)], dtype=torch.float64, device="cuda")
+    if dist:
+        tmax = agg.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = agg.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        t_dev, t_e2e = tmax[0].item(), tmax[1].item()
+        beads_all, e2e_beads_all = tsum[2].item(), tsum[3].item()
+    else:
+        beads_all, e2e_beads_all = float(beads), float(e2e_beads)
+
+    if rank == 0:
+        value = beads_all / t_dev
+        # roofline of the dominant kernel (grow_kernel: ~all of the step): algorithmic bytes / its CUDA-event duration
+        alg_bytes = queries * B_QUERY + beads * B_BEAD
+        n_launch = max(1, sum(1 for _ in range(args.steps)))   # one growth launch per step unless storage had to grow
+        achieved = alg_bytes / (grow_ms / 1e3) / 1e9
+        line = {
+            "metric": "accepted beads/sec", "value": value, "unit": "beads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": w["name"], "seeds": "distinct Philox key per step and rank", "l2": "256 MB flush write between timed steps",
+                       "multi_gpu": "independent melts per rank, no data-path collective" if world > 1 else "single GPU",
+                       "rounds_per_step": rounds / args.steps, "trials_per_bead": trials / max(1, beads), "conflicts_per_step": conflicts / args.steps},
+            "e2e": {"value": e2e_beads_all / t_e2e, "unit": "beads/s", "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps,
+                    "ms_per_step": 1e3 * t_e2e / args.steps,
+                    "includes": "sarw_create (alloc + cell-table init), seeding, growth, terminate, sarw_download to host"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                         "kernel": "sarw::grow_kernel (persistent, one launch per step)", "peak_source": peak_src,
+                         "algorithmic_bytes": f"queries*{B_QUERY:.0f} + beads*{B_BEAD:.0f} (SURVEY §8d)", "queries_per_launch": queries / args.steps,
+                         "avg_launch_ms": grow_ms / args.steps, "note": "latency-bound: ~1e2 chains per round, ~1e3 dependent rounds"},
+        }
+        if not args.no_extra:
+            line["extra"] = extra_measurements(sarw_b200, torch, stream, flush, local)
+        if not args.no_cpu_baseline and world == 1:
+            cores = max(1, min(os.cpu_count() or 1, 32))
+            r = reference_throughput(w, cores, 777)
+            if r is not None:
+                line["cpu_baseline"] = {"value": r["value"], "unit": "beads/s", "cores": cores, "kind": "reference",
+                                        "sample": f"{cores} concurrent single-thread instances of the full workload, unmodified reference (oracle/_ref), "
+                                                  f"seeding + growth timed; slowest instance {r['slowest']:.2f} s", "per_core_beads_per_s": r["per_core"],
+                                        "trials_per_bead": r["trials_per_bead"]}
+            else:
+                line["cpu_baseline"] = {"value": None, "unit": "beads/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
+        print(json.dumps(line))
+    if dist:
+        dist.barrier(); dist.destroy_process_group()
+
+
+def extra_measurements(sarw_b200, torch, stream, flush, local):
+    """Secondary numbers (not the headline): BASELINE configs[2] growth and the overlap-query kernel on its melt."""
+    import numpy as np
+    out = {}
+    w = WORKLOADS["C3"]
+    try:
+        c = sarw_b200.Context(device=local, **ctx_kwargs(w, 4242))
+        c.set_stream(stream.cuda_stream)
+        c.initiate(); st = c.grow(0, -1); c.terminate()
+        out["C3_growth"] = {"workload": w["name"], "beads": st.nBeads, "rounds": st.rounds, "grow_ms": st.growMs, "seed_ms": st.seedMs,
+                            "beads_per_s": st.nBeads / ((st.growMs + st.seedMs) / 1e3), "trials_per_bead": st.trials / st.nBeads,
+                            "queries": st.queries, "conflicts": st.conflicts}
+        # K5 on the finished melt: 16 Mi random candidates resident in HBM
+        n = 1 << 24
+        g = torch.Generator(device="cuda"); g.manual_seed(5)
+        q = torch.rand((n, 3), dtype=torch.float64, device="cuda", generator=g) * w["boxSize"][0]
+        hit = torch.empty(n, dtype=torch.uint8, device="cuda")
+        for _ in range(3):
+            c.find_device(q.data_ptr(), None, n, hit.data_ptr())
+        torch.cuda.synchronize()
+        ms = []
+        for i in range(5):
+            flush.fill_(float(i)); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream); c.find_device(q.data_ptr(), None, n, hit.data_ptr()); e1.record(stream); e1.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        t = statistics.median(ms) / 1e3
+        hbm_peak, _ = load_peaks()
+        bq = 134.0 + 24 + 1   # SURVEY §8d B_q at full density + candidate read + result write
+        out["find_batch"] = {"queries": n, "ms": t * 1e3, "queries_per_s": n / t, "algorithmic_GBps": n * bq / t / 1e9,
+                             "frac_of_hbm_peak": n * bq / t / 1e9 / hbm_peak, "hit_fraction": float(hit.float().mean().item()),
+                             "bytes_per_query": bq}
+        c.close()
+    except Exception as e:   # secondary numbers must never take the headline down
+        out["error"] = repr(e)
+    return out
+
+
+if __name__ == "__main__":
+    main()

@@ -161,7 +161,7 @@ ref_walk* ref_walk_run(const ref_params* p, const double* grafts, int64_t nGraft
 	w->seconds = std::chrono::duration<double>(t1 - t0).count();
 	w->trials = standin_rng_seed_calls() - seedCallsAfterInit;
 	w->seedTrials = (p->rngMode == 1) ? K.seedTrials : seedCallsAfterInit;
-	if(s->actualCount() > 0 && w->initiated) s->terminateChain(); // sarw.cpp:79 (guarded: it indexes atom 0 of unseeded chains)
+	if(s->actualCount() > 0) s->terminateChain(); // sarw.cpp:79, unconditional in main(); guarded only against the empty-vector write it would do when chain 0 failed
 	standin_rng_set_hooks(0, 0);
 	return w;
 }

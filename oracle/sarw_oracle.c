@@ -369,8 +369,8 @@ oracle_walk* oracle_walk_run(const oracle_params* p, const double* grafts, int64
 	}
 	clock_gettime(CLOCK_MONOTONIC, &t1);
 	w->seconds = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
-	if (w->nAtoms > 0 && w->initiated)
-		for (int i = 0; i < p->nChains; ++i) w->type[w->lastIdx[i]] = 1;              /* sarw.cpp:359-368 */
+	if (w->nAtoms > 0)   /* sarw.cpp:79,359-368: unconditional in main(); unseeded chains have lastIndices = 0 (sarw.h:91) */
+		for (int i = 0; i < p->nChains; ++i) w->type[w->lastIdx[i]] = 1;
 	return w;
 }
 

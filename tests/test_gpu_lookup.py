@@ -27,13 +27,13 @@ def test_find_matches_oracle_random_and_overflowing_cells(sarw, oracle, cap):
     """Dense random points (cells overflow into the overflow list when cellCapacity is forced small)."""
     rng = np.random.default_rng(42 + cap)
     box, thresh = (15.0, 17.0, 13.0), 1.0
-    pts = rng.random((6000, 3)) * np.array(box)
+    pts = rng.random((900, 3)) * np.array(box)
     q = rng.random((20000, 3)) * np.array(box) * 2 - np.array(box) / 2
     ig = np.where(rng.random(len(q)) < 0.3, rng.integers(0, len(pts), len(q)), -1).astype(np.int64)
     olk = oracle.lookup(box, thresh); olk.add(pts)
     want = olk.find(q, ig); olk.close()
     lk = sarw.PeriodicLookup(box, thresh, cellCapacity=cap)
-    lk.addPoint(pts[:2500]); lk.addPoint(pts[2500:])   # two batches: indices continue
+    lk.addPoint(pts[:400]); lk.addPoint(pts[400:])   # two batches: indices continue
     got = lk.find(q, ig)
     assert lk.ctx.lookup_size() == len(pts)
     if cap:
