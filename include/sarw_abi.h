@@ -63,6 +63,11 @@ typedef struct sarw_stats {
 	double growMs;              /* device time of all growth launches so far */
 	int64_t growLaunches;       /* kernel launches made by growth so far */
 	int64_t seedLaunches;
+	uint64_t cycPropose;        /* SM cycles block 0 spent per phase of the growth kernel, closing barrier included: */
+	uint64_t cycVerify;         /*   propose+insert / verify / conflict clean-up (diagnostics for DESIGN.md) */
+	uint64_t cycCleanup;
+	int64_t cleanupRounds;      /* rounds that needed the serial conflict clean-up */
+	int64_t deadChains;         /* chains proven permanently blocked (skipped from then on; the reference retries them) */
 } sarw_stats;
 
 /* SARW::SARW + PeriodicLookup::PeriodicLookup (sarw.h:88-94, PeriodicLookup.h:26-34): allocates the device cell list. */

@@ -132,6 +132,8 @@ void fill_stats(sarw_ctx* c, const Control& h, sarw_stats* s)
 	s->lastProgressed = (int32_t)h.lastProgressed;
 	s->trials = h.trials; s->seedTrials = h.seedTrials; s->queries = h.queries; s->conflicts = h.conflicts;
 	s->seedMs = c->seedMs; s->growMs = c->growMs; s->growLaunches = c->growLaunches; s->seedLaunches = c->seedLaunches;
+	s->cycPropose = h.cycPropose; s->cycVerify = h.cycVerify; s->cycCleanup = h.cycCleanup;
+	s->cleanupRounds = h.cleanupRounds; s->deadChains = h.deadChains;
 }
 
 } // namespace
@@ -175,7 +177,7 @@ int sarw_create(const sarw_params* p, sarw_ctx** out)
 
 	Geom& g = c->g;
 	g.thresh = p->minDist;
-	double edgeMin = std::max(2.002 * p->minDist, p->cellEdge > 0 ? p->cellEdge : 2.5);
+	double edgeMin = std::max(2.002 * p->minDist, p->cellEdge > 0 ? p->cellEdge : 2.0);
 	double amax = 0;
 	for (int k = 0; k < 3; k++) {
 		g.L[k] = p->boxSize[k]; g.Linv[k] = 1. / p->boxSize[k];

@@ -13,10 +13,13 @@ namespace sarw {
 // ------------------------------------------------------------------ data layout in HBM
 // One 128-byte line per cell: header + up to 7 beads inline. slot = (ox, oy, oz, id): Cartesian offset of the
 // bead from the cell's low corner in fp32 (|error| <= edge * 2^-24) and the bead's lookup index (bit-cast).
-// The header word holds count-1 (so that a memset to 0xFF yields "empty cell, all ids invalid").
+// The header word holds count-1 (so that a memset to 0xFF yields "empty cell, all ids invalid, not overflowed").
+// Beads that do not fit (more than `cap` in one cell) go to a global overflow list and flag their cell; a query
+// scans that list only when one of the cells it visits is flagged.
 struct __align__(16) Cell {
 	uint32_t countMinus1;
-	uint32_t pad[3];
+	uint32_t ovfFlagInv;      // 0xFFFFFFFF = no bead of this cell lives in the overflow list (memset state); anything else = some do
+	uint32_t pad[2];
 	float4 slot[7];
 };
 static_assert(sizeof(Cell) == 128, "cell record must be one 128-byte line");
@@ -244,13 +247,15 @@ __device__ __forceinline__ bool probe_cells(const Geom& g, const Tables& T, cons
 		q[k][0] = (float)(((double)lo - s) * g.a[k]);
 		q[k][1] = (float)(((double)(lo + 1) - s) * g.a[k]);
 	}
-	bool hit = false;
+	bool hit = false, anyOvf = false;
 	const int total = n[0] * n[1] * n[2];
 	for (int ci = sub; ci < total && !hit; ci += GROUP) {
 		int ix = ci % n[0], rest = ci / n[0];
 		int iy = rest % n[1], iz = rest / n[1];
 		const Cell* cell = T.cells + cell_index(g, wrap_cell(c0[0] + ix, g.S[0]), wrap_cell(c0[1] + iy, g.S[1]), wrap_cell(c0[2] + iz, g.S[2]));
-		uint32_t cnt = __ldcg(&cell->countMinus1) + 1u;
+		const uint2 hdr = __ldcg(reinterpret_cast<const uint2*>(cell));
+		uint32_t cnt = hdr.x + 1u;
+		anyOvf |= (hdr.y != ID_NONE);
 		if (cnt > (uint32_t)g.cap) cnt = (uint32_t)g.cap;
 		for (uint32_t s = 0; s < cnt; ++s) {
 			float4 b = __ldcg(&cell->slot[s]);
@@ -262,10 +267,10 @@ __device__ __forceinline__ bool probe_cells(const Geom& g, const Tables& T, cons
 			if (d2 <= g.hi2 && exact_pair(g, v, T.lpos + 3 * (size_t)id)) { hit = true; break; }
 		}
 	}
-	if (!hit) {
+	if (!hit && anyOvf) {   // only lanes whose own cells overflowed scan the list: the overflowed beads of a cell are in range of it
 		uint32_t novf = __ldcg(T.ovfCount);
 		if (novf > T.ovfCap) novf = T.ovfCap;
-		for (uint32_t j = sub; j < novf && !hit; j += GROUP) {
+		for (uint32_t j = 0; j < novf && !hit; ++j) {
 			uint32_t id = __ldcg(T.ovf + j);
 			if (id < idLo || id >= idHi || id == ignoreId) continue;
 			hit = exact_pair(g, v, T.lpos + 3 * (size_t)id);
@@ -288,6 +293,7 @@ __device__ __forceinline__ void insert_bead(const Geom& g, const Tables& T, cons
 		__stcg(&cell->slot[k], make_float4(o[0], o[1], o[2], __uint_as_float(id)));
 	} else {
 		atomicSub(&cell->countMinus1, 1u);
+		atomicExch(&cell->ovfFlagInv, 0u);
 		uint32_t j = atomicAdd(T.ovfCount, 1u);
 		if (j < T.ovfCap) T.ovf[j] = id;   // beyond ovfCap the host sees ovfCount > ovfCap and fails the call
 	}

@@ -15,6 +15,8 @@ struct Control {
 	unsigned pad0;
 	unsigned long long nBeads;        // SARW::actualCount()
 	unsigned long long trials, queries, conflicts, seedTrials;
+	unsigned long long cycPropose, cycVerify, cycCleanup;   // SM cycles of block 0 per phase (incl. the closing barrier)
+	unsigned cleanupRounds, deadChains;
 };
 
 cudaError_t launch_find_batch(const Geom& g, const Tables& T, const double* xyz, const int64_t* ignore, int64_t n, uint8_t* hit, int numSMs, cudaStream_t st);

@@ -22,6 +22,8 @@ namespace sarw {
 constexpr int GROW_WARPS = 8;
 constexpr int GROW_THREADS = GROW_WARPS * 32;
 constexpr int NBMAX = 128;          // staged neighbour beads per chain (shared memory, 16 B each)
+constexpr int NARCMAX = 128;        // blocked torsion arcs per chain (shared memory, 8 B each)
+constexpr uint32_t CHAIN_DEAD = 1u; // ChainState.flags: every torsion angle is permanently blocked
 constexpr unsigned FULL = 0xFFFFFFFFu;
 constexpr uint32_t DONE_BIT = 0x80000000u;
 
@@ -57,12 +59,14 @@ __global__ void add_points_kernel(Geom g, Tables T, const double* __restrict__ x
 	insert_bead(g, T, pos, baseId + (uint32_t)i);
 }
 
-// enumerate beads with id in (idLo, idHi) within thresh of the candidate (single thread; clean-up only)
-template <typename F>
-__device__ void enumerate_hits(const Geom& g, const Tables& T, const double v[3], uint32_t idLoExcl, uint32_t idHi, F&& fn)
+// enumerate beads with id in (idLo, idHi) within thresh of the candidate (clean-up only); lane `sub` of GROUP takes
+// cells sub, sub+GROUP, ... and, when one of its cells is flagged, the overflow list
+template <int GROUP, typename F>
+__device__ void enumerate_hits(const Geom& g, const Tables& T, const double v[3], uint32_t idLoExcl, uint32_t idHi, int sub, F&& fn)
 {
 	int c0[3], n[3];
 	float q[3][2];
+	bool anyOvf = false;
 	for (int k = 0; k < 3; k++) {
 		double s = v[k] * g.sOverL[k];
 		int lo = (int)floor(s - g.reachCells[k]), hi = (int)floor(s + g.reachCells[k]);
@@ -70,9 +74,14 @@ __device__ void enumerate_hits(const Geom& g, const Tables& T, const double v[3]
 		q[k][0] = (float)(((double)lo - s) * g.a[k]);
 		q[k][1] = (float)(((double)(lo + 1) - s) * g.a[k]);
 	}
-	for (int iz = 0; iz < n[2]; iz++) for (int iy = 0; iy < n[1]; iy++) for (int ix = 0; ix < n[0]; ix++) {
+	const int total = n[0] * n[1] * n[2];
+	for (int ci = sub; ci < total; ci += GROUP) {
+		const int ix = ci % n[0], rest = ci / n[0];
+		const int iy = rest % n[1], iz = rest / n[1];
 		const Cell* cell = T.cells + cell_index(g, wrap_cell(c0[0] + ix, g.S[0]), wrap_cell(c0[1] + iy, g.S[1]), wrap_cell(c0[2] + iz, g.S[2]));
-		uint32_t cnt = __ldcg(&cell->countMinus1) + 1u;
+		const uint2 hdr = __ldcg(reinterpret_cast<const uint2*>(cell));
+		uint32_t cnt = hdr.x + 1u;
+		anyOvf |= (hdr.y != ID_NONE);
 		if (cnt > (uint32_t)g.cap) cnt = (uint32_t)g.cap;
 		for (uint32_t s = 0; s < cnt; ++s) {
 			float4 b = __ldcg(&cell->slot[s]);
@@ -83,6 +92,7 @@ __device__ void enumerate_hits(const Geom& g, const Tables& T, const double v[3]
 			if (d2 < g.lo2 || (d2 <= g.hi2 && exact_pair(g, v, T.lpos + 3 * (size_t)id))) fn(id);
 		}
 	}
+	if (!anyOvf) return;
 	uint32_t novf = __ldcg(T.ovfCount);
 	if (novf > T.ovfCap) novf = T.ovfCap;
 	for (uint32_t j = 0; j < novf; ++j) {
@@ -225,8 +235,8 @@ __global__ void seed_cleanup_kernel(SeedArgs A)
 		const uint32_t idEnd = g.idAtomBase + 2 * g.nChains;
 		auto mark = [&](uint32_t id) { dirty_push_unique(A.dirtyList, &A.ctl->seedDirtyCount, (id - g.idAtomBase) >> 1); };
 		double v[3];
-		to_frac(g, p0, v); enumerate_hits(g, A.T, v, id1, idEnd, mark);
-		to_frac(g, p1, v); enumerate_hits(g, A.T, v, id1, idEnd, mark);
+		to_frac(g, p0, v); enumerate_hits<1>(g, A.T, v, id1, idEnd, 0, mark);
+		to_frac(g, p1, v); enumerate_hits<1>(g, A.T, v, id1, idEnd, 0, mark);
 	}
 	const uint32_t fail = A.ctl->seedFailChain;
 	if (fail != ID_NONE)   // sarw.cpp:313-314: initiateChain returns at the first failing chain; later chains are never seeded
@@ -292,9 +302,10 @@ __device__ __forceinline__ void round_range(const Geom& g, unsigned long long nB
 // stage every bead that can be within thresh of any point of the cone circle into shared memory, as positions
 // relative to the (wrapped) last bead; returns the number staged or -1 when NBMAX does not suffice
 __device__ __forceinline__ int stage_region(const Geom& g, const Tables& T, const double lw[3], const Frame& f,
-	uint32_t idLimit, uint32_t ignoreId, float4* nb, int lane)
+	uint32_t idLimit, uint32_t ignoreId, float4* nb, int lane, bool& regionOvf)
 {
 	int lo[3], nn[3];
+	bool ovf = false;
 #pragma unroll
 	for (int k = 0; k < 3; k++) {
 		double cen = lw[k] + g.dCosPhi * f.Z[k];
@@ -313,16 +324,17 @@ __device__ __forceinline__ int stage_region(const Geom& g, const Tables& T, cons
 			int iy = rest % nn[1], iz = rest / nn[1];
 			int cx = lo[0] + ix, cy = lo[1] + iy, cz = lo[2] + iz;
 			cell = T.cells + cell_index(g, wrap_cell(cx, g.S[0]), wrap_cell(cy, g.S[1]), wrap_cell(cz, g.S[2]));
-			uint32_t h = __ldcg(&cell->countMinus1);
+			const uint2 hdr = __ldcg(reinterpret_cast<const uint2*>(cell));
 			s0 = __ldcg(&cell->slot[0]);
-			cnt = h + 1u; if (cnt > (uint32_t)g.cap) cnt = (uint32_t)g.cap;
+			ovf |= (hdr.y != ID_NONE);
+			cnt = hdr.x + 1u; if (cnt > (uint32_t)g.cap) cnt = (uint32_t)g.cap;
 			sh[0] = (float)((double)cx * g.a[0] - lw[0]); sh[1] = (float)((double)cy * g.a[1] - lw[1]); sh[2] = (float)((double)cz * g.a[2] - lw[2]);
 		}
 		uint32_t incl = cnt;
 #pragma unroll
 		for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += y; }
 		const int sum = (int)__shfl_sync(FULL, incl, 31);
-		if (total + sum > NBMAX) return -1;
+		if (total + sum > NBMAX) { regionOvf = true; return -1; }
 		int at = total + (int)(incl - cnt);
 		for (uint32_t s = 0; s < cnt; ++s) {
 			float4 b = s == 0 ? s0 : __ldcg(&cell->slot[s]);
@@ -332,8 +344,119 @@ __device__ __forceinline__ int stage_region(const Geom& g, const Tables& T, cons
 		}
 		total += sum;
 	}
+	regionOvf = __any_sync(FULL, ovf);
 	__syncwarp();
 	return total;
+}
+
+
+// ------------------------------------------------------------------ blocked torsion arcs
+// A candidate is last + rho*(cos(theta) X + sin(theta) Y) + h Z (sarw.cpp:178-184). For a staged bead at w (relative to
+// the circle centre) its distance satisfies d^2 = |w|^2 + rho^2 - 2 rho R cos(theta - alpha), so the bead blocks the arc
+// |theta - alpha| <= omega. Arcs are used ONLY to skip trials that are CERTAINLY rejected: they are shrunk by margins
+// that dominate every rounding error (1e-5 A in distance, 1e-9 in cos, 2e-5 rad in angle), and every trial that is not
+// certainly blocked still goes through the exact reference arithmetic. Decisions are therefore unchanged.
+__device__ __forceinline__ int build_arcs(const Geom& g, const Frame& f, const float4* nb, int nnb, float2* arcs, int lane)
+{
+	const double rho = g.dSinPhi, h = g.dCosPhi;
+	const double ts = g.thresh - 1e-5;
+	int narcs = 0;
+	for (int jb = 0; jb < nnb; jb += 32) {
+		const int j = jb + lane;
+		bool have = false; float2 arc = make_float2(0.f, 0.f);
+		if (j < nnb && ts > 0) {
+			const float4 b = nb[j];
+			if (b.x < 1e29f) {
+				const double wx = (double)b.x - h * f.Z[0], wy = (double)b.y - h * f.Z[1], wz = (double)b.z - h * f.Z[2];
+				const double px = wx * f.X[0] + wy * f.X[1] + wz * f.X[2];
+				const double py = wx * f.Y[0] + wy * f.Y[1] + wz * f.Y[2];
+				const double pz = wx * f.Z[0] + wy * f.Z[1] + wz * f.Z[2];
+				const double R2 = px * px + py * py, R = sqrt(R2);
+				if (R > 1e-6) {
+					const double kappa = (R2 + pz * pz + rho * rho - ts * ts) / (2.0 * rho * R) + 1e-9;
+					if (kappa < 1.0) {
+						const double omega = (kappa <= -1.0 ? 3.14159265358979323846 : acos(kappa)) - 2e-5;
+						if (omega > 0) { have = true; arc = make_float2((float)atan2(py, px), (float)omega); }
+					}
+				}
+			}
+		}
+		const unsigned m = __ballot_sync(FULL, have);
+		if (narcs + __popc(m) > NARCMAX) return -1;
+		if (have) arcs[narcs + __popc(m & ((1u << lane) - 1u))] = arc;
+		narcs += __popc(m);
+	}
+	__syncwarp();
+	return narcs;
+}
+
+__device__ __forceinline__ float wrap_pi(float d)
+{	return d - 6.28318530717958647692f * rintf(d * 0.15915494309189533577f);
+}
+__device__ __forceinline__ bool theta_blocked(float theta, const float2* arcs, int narcs)
+{
+	for (int a = 0; a < narcs; ++a) {
+		const float2 arc = arcs[a];
+		if (fabsf(wrap_pi(theta - arc.x)) <= arc.y) return true;
+	}
+	return false;
+}
+
+// do the (shrunk) arcs, together with the never-sampled gap [359 deg, 360 deg) of sarw.cpp:177, cover the whole circle?
+// Closed arcs cover the circle iff every arc's upper end lies strictly inside another arc.
+__device__ __forceinline__ bool arcs_cover_circle(const float2* arcs, int narcs, int lane)
+{
+	if (narcs <= 0) return false;
+	const float gapLo = (float)(359.0 * 3.14159265358979323846 / 180 - 1e-9), gapHi = 6.28318530717958647692f;
+	const float gapC = 0.5f * (gapLo + gapHi), gapW = 0.5f * (gapHi - gapLo) - 1e-6f;   // virtual arc, index narcs
+	bool allCovered = true;
+	for (int ib = 0; ib <= narcs; ib += 32) {
+		const int i = ib + lane;
+		bool covered = true;
+		if (i <= narcs) {
+			const float c = i < narcs ? arcs[i].x : gapC, w = i < narcs ? arcs[i].y : gapW;
+			const float e = c + w;
+			covered = false;
+			for (int j = 0; j <= narcs && !covered; ++j) {
+				const float cj = j < narcs ? arcs[j].x : gapC, wj = j < narcs ? arcs[j].y : gapW;
+				if (wj >= 3.1415f) covered = true;
+				else covered = fabsf(wrap_pi(e - cj)) < wj - 2e-6f;
+			}
+		}
+		allCovered = allCovered && __all_sync(FULL, covered);
+	}
+	return allCovered;
+}
+
+// exact evaluation of one trial by the whole warp (reference arithmetic; neighbours split across lanes)
+__device__ __forceinline__ bool eval_trial_coop(const Geom& g, const Tables& T, const Frame& f, const ChainState& cs, double u01,
+	const float4* nb, int nnb, uint32_t idRound, uint32_t novf, int lane, double cand[3])
+{
+	cone_candidate(g, f, cs.last, u01, cand);
+	if (growth_rules_reject(g, cand, cs.last)) return false;
+	double v[3];
+	to_frac(g, cand, v);
+	bool hit = false;
+	if (nnb >= 0) {
+		const float rx = (float)(cand[0] - cs.last[0]), ry = (float)(cand[1] - cs.last[1]), rz = (float)(cand[2] - cs.last[2]);
+		for (int j = lane; j < nnb && !hit; j += 32) {
+			const float4 b = nb[j];
+			const float dx = rx - b.x, dy = ry - b.y, dz = rz - b.z;
+			const float d2 = dx * dx + dy * dy + dz * dz;
+			if (d2 < g.lo2) hit = true;
+			else if (d2 <= g.hi2) hit = exact_pair(g, v, T.lpos + 3 * (size_t)__float_as_uint(b.w));
+		}
+		if (novf) {   // beads that did not fit their cell live in the overflow list
+			const uint32_t m = novf > T.ovfCap ? T.ovfCap : novf;
+			for (uint32_t j = lane; j < m && !hit; j += 32) {
+				const uint32_t id = __ldcg(T.ovf + j);
+				if (id < idRound && id != cs.lastId) hit = exact_pair(g, v, T.lpos + 3 * (size_t)id);
+			}
+		}
+	} else {   // region too crowded for the staging buffer: query the cell list directly (8 cells over 8 lanes)
+		if (lane < 8) hit = probe_cells<8>(g, T, v, 0u, idRound, cs.lastId, lane);
+	}
+	return !__any_sync(FULL, hit);
 }
 
 // apply the result of the previous round to the chain state (sarw.cpp:270-273); all lanes compute, lane 0 stores
@@ -362,53 +485,89 @@ __device__ __forceinline__ ChainState load_chain(const ChainState* p)
 	return cs;
 }
 
-// single thread: re-resolve the conflicting chains of a round in chain order (what sarw.cpp:251-281 does serially)
-__device__ void cleanup_round(const GrowArgs& A, uint32_t round)
+// one warp: re-resolve the conflicting chains of a round in chain order (what sarw.cpp:251-281 does serially).
+// Lanes 8g..8g+7 evaluate trial t0+g (one cell each), so four trials are in flight per pass.
+__device__ void cleanup_round(const GrowArgs& A, uint32_t round, int lane)
 {
 	const Geom& g = A.g;
 	const uint32_t T_ = (uint32_t)g.maxTrials;
 	const uint32_t idRound = round_id_base(g, round), idEnd = idRound + g.nChains;
-	uint32_t chain;
-	while (dirty_pop_min(A.dirtyList, &A.dirtyCount[round], chain)) {
+	const int sub = lane & 7, grp = lane >> 3;
+	for (;;) {
+		uint32_t chain = 0; int have = 0;
+		if (lane == 0) have = dirty_pop_min(A.dirtyList, &A.dirtyCount[round], chain);
+		have = __shfl_sync(FULL, have, 0); chain = __shfl_sync(FULL, chain, 0);
+		if (!have) break;
 		const uint32_t myId = idRound + chain;
-		ChainState cs = load_chain(A.chains + chain);
+		const ChainState cs = load_chain(A.chains + chain);
 		Frame f; cone_frame(cs.last, cs.pen, f);
 		const uint32_t t0 = __ldcg(&A.resTrial[chain]);
-		remove_bead(g, A.T, myId);
-		uint32_t found = 0; double cand[3], v[3];
-		for (uint32_t t = t0; t <= T_; ++t) {
-			cone_candidate(g, f, cs.last, u_grow(g, chain, round, t), cand);
-			if (growth_rules_reject(g, cand, cs.last)) continue;
-			to_frac(g, cand, v);
-			if (probe_cells<1>(g, A.T, v, 0u, myId, cs.lastId, 0)) continue;
-			found = t; break;
+		if (lane == 0) remove_bead(g, A.T, myId);
+		__syncwarp();
+		uint32_t found = 0; double cand[3] = { 0, 0, 0 }, v[3] = { 0, 0, 0 };
+		for (uint32_t tb = t0; tb <= T_ && !found; tb += 4) {
+			const uint32_t t = tb + grp;
+			bool rejected = t > T_, hit = false;
+			if (!rejected) {
+				cone_candidate(g, f, cs.last, u_grow(g, chain, round, t), cand);
+				rejected = growth_rules_reject(g, cand, cs.last);
+				if (!rejected) { to_frac(g, cand, v); hit = probe_cells<8>(g, A.T, v, 0u, myId, cs.lastId, sub); }
+			}
+			const unsigned hm = __ballot_sync(FULL, hit || rejected);
+			for (int q = 0; q < 4 && !found; ++q)
+				if (((hm >> (8 * q)) & 0xFFu) == 0u) {   // first group (lowest trial) whose 8 lanes all report "free"
+					found = tb + q;
+					for (int k2 = 0; k2 < 3; k2++) { cand[k2] = __shfl_sync(FULL, cand[k2], 8 * q); v[k2] = __shfl_sync(FULL, v[k2], 8 * q); }
+				}
 		}
-		atomicAdd(&A.ctl->conflicts, 1ull);
-		const unsigned long long before = t0, after = found ? found : T_;
-		atomicAdd(&A.ctl->trials, after - before);
-		atomicAdd(&A.ctl->queries, after - before + 1ull);
-		if (!found) {
-			A.resTrial[chain] = T_ + 1u;
-			atomicSub(&A.roundAcc[round], 1u);
-			if (t0 < T_) atomicSub(&A.roundProg[round], 1u);
-			continue;
+		if (lane == 0) {
+			atomicAdd(&A.ctl->conflicts, 1ull);
+			const unsigned long long before = t0, after = found ? found : T_;
+			atomicAdd(&A.ctl->trials, after - before);
+			atomicAdd(&A.ctl->queries, after - before + 1ull);
+			if (!found) {
+				A.resTrial[chain] = T_ + 1u;
+				atomicSub(&A.roundAcc[round], 1u);
+				if (t0 < T_) atomicSub(&A.roundProg[round], 1u);
+			} else {
+				if (t0 < T_ && !(found < T_)) atomicSub(&A.roundProg[round], 1u);
+				A.resTrial[chain] = found;
+				for (int k2 = 0; k2 < 3; k2++) A.resPos[3 * (size_t)chain + k2] = cand[k2];
+				insert_bead(g, A.T, cand, myId);
+				__threadfence();
+			}
 		}
-		if (t0 < T_ && !(found < T_)) atomicSub(&A.roundProg[round], 1u);
-		A.resTrial[chain] = found;
-		for (int k = 0; k < 3; k++) A.resPos[3 * (size_t)chain + k] = cand[k];
-		insert_bead(g, A.T, cand, myId);
-		__threadfence();
-		enumerate_hits(g, A.T, v, myId, idEnd, [&](uint32_t id) { dirty_push_unique(A.dirtyList, &A.dirtyCount[round], id - idRound); });
+		__syncwarp();
+		if (found) {   // higher-indexed chains of this round whose tentative bead now collides with the new position
+			uint32_t hits[8]; int nh = 0;
+			if (lane < 8) enumerate_hits<8>(g, A.T, v, myId, idEnd, lane, [&](uint32_t id) { if (nh < 8) hits[nh++] = id; });
+			unsigned pending = __ballot_sync(FULL, nh > 0);
+			while (pending) {
+				const int src = __ffs(pending) - 1;
+				const int cnt = __shfl_sync(FULL, nh, src);
+				for (int q = 0; q < cnt; ++q) {
+					uint32_t id = 0;
+#pragma unroll
+					for (int z = 0; z < 8; ++z) if (z == q) id = hits[z];
+					id = __shfl_sync(FULL, id, src);
+					if (lane == 0) dirty_push_unique(A.dirtyList, &A.dirtyCount[round], id - idRound);
+				}
+				pending &= pending - 1;
+			}
+			__syncwarp();
+		}
 	}
 }
 
 __global__ void __launch_bounds__(GROW_THREADS) grow_kernel(GrowArgs A)
 {
 	__shared__ float4 nbShared[GROW_WARPS][NBMAX];
+	__shared__ float2 arcShared[GROW_WARPS][NARCMAX];
 	const Geom& g = A.g;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const uint32_t gw = blockIdx.x * GROW_WARPS + warp, nW = gridDim.x * GROW_WARPS;
 	float4* nb = nbShared[warp];
+	float2* arcs = arcShared[warp];
 	const uint32_t T_ = (uint32_t)g.maxTrials;
 
 	uint32_t round = __ldcg(&A.ctl->round);
@@ -417,7 +576,10 @@ __global__ void __launch_bounds__(GROW_THREADS) grow_kernel(GrowArgs A)
 	unsigned long long myTrials = 0, myQueries = 0;
 	bool pendingValid = false;   // is there a round of this launch whose results are not yet committed?
 
+	const bool timer = (blockIdx.x == 0 && threadIdx.x == 0);
+	long long cycA = 0, cycV = 0, cycC = 0; uint32_t cleanRounds = 0;
 	while (round < A.roundEnd && (long long)nBeads < g.target && lastProg) {
+		const long long tk0 = clock64();
 		uint32_t start, end;
 		round_range(g, nBeads, start, end);
 		const uint32_t idRound = round_id_base(g, round);
@@ -427,56 +589,56 @@ __global__ void __launch_bounds__(GROW_THREADS) grow_kernel(GrowArgs A)
 			ChainState cs = load_chain(A.chains + i);
 			if (pendingValid) commit_pending(A, i, round - 1, cs, lane);
 			if (i < start || i >= end) continue;
+			if (cs.flags & CHAIN_DEAD) {   // permanently blocked: the reference burns maxTrials here every round
+				if (lane == 0) A.resTrial[i] = T_ + 1u;
+				continue;
+			}
 			Frame f; cone_frame(cs.last, cs.pen, f);
 			double lw[3];
 			{ double vl[3]; to_frac(g, cs.last, vl); for (int k = 0; k < 3; k++) lw[k] = vl[k] * g.L[k]; }
-			const int nnb = stage_region(g, A.T, lw, f, idRound, cs.lastId, nb, lane);
-			const uint32_t novf = __ldcg(A.T.ovfCount);
+			bool regionOvf = false;
+			const int nnb = stage_region(g, A.T, lw, f, idRound, cs.lastId, nb, lane, regionOvf);
+			const int narcs = nnb >= 0 ? build_arcs(g, f, nb, nnb, arcs, lane) : -1;
+			const uint32_t novf = regionOvf ? __ldcg(A.T.ovfCount) : 0u;   // overflowed beads near this chain? (rare)
 
+			// 128 trials per pass: lane l owns trials base+4l+1 .. base+4l+4 (one Philox block)
 			uint32_t accepted = 0; double cand[3] = { 0, 0, 0 };
-			for (uint32_t base = 0; base < T_ && !accepted; base += 32) {
-				const uint32_t t = base + lane + 1;
-				bool ok = t <= T_;
-				double v[3];
-				if (ok) {
-					cone_candidate(g, f, cs.last, u_grow(g, i, round, t), cand);
-					ok = !growth_rules_reject(g, cand, cs.last);
-				}
-				if (ok) {
-					if (nnb >= 0) {
-						const float rx = (float)(cand[0] - cs.last[0]), ry = (float)(cand[1] - cs.last[1]), rz = (float)(cand[2] - cs.last[2]);
-						bool haveV = false;
-						for (int j = 0; j < nnb; ++j) {
-							const float4 b = nb[j];
-							const float dx = rx - b.x, dy = ry - b.y, dz = rz - b.z;
-							const float d2 = dx * dx + dy * dy + dz * dz;
-							if (d2 < g.lo2) { ok = false; break; }
-							if (d2 <= g.hi2) {
-								if (!haveV) { to_frac(g, cand, v); haveV = true; }
-								if (exact_pair(g, v, A.T.lpos + 3 * (size_t)__float_as_uint(b.w))) { ok = false; break; }
-							}
-						}
-					} else {   // region too crowded for the staging buffer: query the cell list directly
-						to_frac(g, cand, v);
-						ok = !probe_cells<1>(g, A.T, v, 0u, idRound, cs.lastId, 0);
+			for (uint32_t base = 0; base < T_ && !accepted; base += 128) {
+				const uint32_t blk = (base >> 2) + lane;
+				const uint4 w = philox4x32_10(make_uint4(i, round, blk, 0u), g.key0, g.key1);
+				const uint32_t wj[4] = { w.x, w.y, w.z, w.w };
+				unsigned cm[4];
+#pragma unroll
+				for (int j = 0; j < 4; ++j) {
+					const uint32_t t = base + 4 * lane + j + 1;
+					bool candidate = t <= T_;
+					if (candidate && narcs > 0) {
+						const float theta = (float)wj[j] * (float)(359.0 * 3.14159265358979323846 / 180 / 4294967296.0);
+						candidate = !theta_blocked(theta, arcs, narcs);
 					}
-					if (ok && novf && nnb >= 0) {   // beads that did not fit their cell live in the overflow list
-						to_frac(g, cand, v);
-						uint32_t m = novf > A.T.ovfCap ? A.T.ovfCap : novf;
-						for (uint32_t j = 0; j < m && ok; ++j) {
-							uint32_t id = __ldcg(A.T.ovf + j);
-							if (id < idRound && id != cs.lastId && exact_pair(g, v, A.T.lpos + 3 * (size_t)id)) ok = false;
-						}
+					cm[j] = __ballot_sync(FULL, candidate);
+				}
+				unsigned any = cm[0] | cm[1] | cm[2] | cm[3];
+				while (any) {   // candidates in increasing trial order
+					const int l = __ffs(any) - 1;
+					int j = 0;
+#pragma unroll
+					for (int jj = 3; jj >= 0; --jj) if ((cm[jj] >> l) & 1u) j = jj;
+					const uint32_t word = __shfl_sync(FULL, wj[0], l) * (j == 0) + __shfl_sync(FULL, wj[1], l) * (j == 1)
+						+ __shfl_sync(FULL, wj[2], l) * (j == 2) + __shfl_sync(FULL, wj[3], l) * (j == 3);
+					myQueries += (lane == 0);
+					if (eval_trial_coop(g, A.T, f, cs, (double)word * (1.0 / 4294967296.0), nb, nnb, idRound, novf, lane, cand)) {
+						accepted = base + 4 * l + j + 1;
+						break;
 					}
+#pragma unroll
+					for (int jj = 0; jj < 4; ++jj) if (jj == j) cm[jj] &= ~(1u << l);
+					any = cm[0] | cm[1] | cm[2] | cm[3];
 				}
-				const unsigned m = __ballot_sync(FULL, ok);
-				const uint32_t evaluated = (T_ - base) < 32u ? (T_ - base) : 32u;
-				myQueries += (lane == 0) ? evaluated : 0;
-				if (m) {
-					const int first = __ffs(m) - 1;
-					accepted = base + first + 1;
-					for (int k = 0; k < 3; k++) cand[k] = __shfl_sync(FULL, cand[k], first);
-				}
+			}
+			if (!accepted && narcs > 0 && arcs_cover_circle(arcs, narcs, lane)) {
+				cs.flags |= CHAIN_DEAD;
+				if (lane == 0) { A.chains[i].flags = cs.flags; atomicAdd(&A.ctl->deadChains, 1u); }
 			}
 			if (lane == 0) {
 				if (accepted) {
@@ -488,6 +650,7 @@ __global__ void __launch_bounds__(GROW_THREADS) grow_kernel(GrowArgs A)
 		}
 		pendingValid = true;
 		grid_barrier(&A.ctl->barCount, &A.ctl->barGen, gridDim.x);
+		const long long tk1 = clock64();
 
 		// ---------------- phase V: conflicts with tentative beads of lower-indexed chains of this round
 		{
@@ -525,11 +688,14 @@ __global__ void __launch_bounds__(GROW_THREADS) grow_kernel(GrowArgs A)
 		}
 		grid_barrier(&A.ctl->barCount, &A.ctl->barGen, gridDim.x);
 
+		const long long tk2 = clock64();
 		// ---------------- clean-up (rare): serial re-resolution in chain order
 		if (__ldcg(&A.dirtyCount[round]) != 0u) {
-			if (gw == 0 && lane == 0) cleanup_round(A, round);
+			if (gw == 0) cleanup_round(A, round, lane);
 			grid_barrier(&A.ctl->barCount, &A.ctl->barGen, gridDim.x);
+			cleanRounds++;
 		}
+		cycA += tk1 - tk0; cycV += tk2 - tk1; cycC += clock64() - tk2;
 		nBeads += __ldcg(&A.roundAcc[round]);
 		lastProg = __ldcg(&A.roundProg[round]) != 0u;
 		round++;
@@ -548,6 +714,7 @@ __global__ void __launch_bounds__(GROW_THREADS) grow_kernel(GrowArgs A)
 	if (gw == 0 && lane == 0) {
 		A.ctl->round = round; A.ctl->nBeads = nBeads; A.ctl->lastProgressed = lastProg ? 1u : 0u;
 	}
+	if (timer) { A.ctl->cycPropose += cycA; A.ctl->cycVerify += cycV; A.ctl->cycCleanup += cycC; A.ctl->cleanupRounds += cleanRounds; }
 }
 
 // ------------------------------------------------------------------ K7: compaction into acceptance order

@@ -44,7 +44,9 @@ class Stats(C.Structure):
                 ("initiated", C.c_int32), ("lastProgressed", C.c_int32), ("trials", C.c_uint64),
                 ("seedTrials", C.c_uint64), ("queries", C.c_uint64), ("conflicts", C.c_uint64),
                 ("overflowBeads", C.c_uint64), ("seedMs", C.c_double), ("growMs", C.c_double),
-                ("growLaunches", C.c_int64), ("seedLaunches", C.c_int64)]
+                ("growLaunches", C.c_int64), ("seedLaunches", C.c_int64), ("cycPropose", C.c_uint64),
+                ("cycVerify", C.c_uint64), ("cycCleanup", C.c_uint64), ("cleanupRounds", C.c_int64),
+                ("deadChains", C.c_int64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
