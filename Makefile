@@ -8,17 +8,22 @@ NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -fmad=false -Xcompiler -fPIC,-ffp-co
 LIB := $(PKG)/lib/libsarw_b200.so
 CLI := $(PKG)/bin/sarw
 
-all: lib oracle
+all: lib cli oracle
 
 lib: $(LIB)
 $(LIB): $(PKG)/csrc/sarw_kernels.cu $(PKG)/csrc/sarw_abi.cu $(PKG)/csrc/sarw_device.cuh $(PKG)/csrc/sarw_host.h include/sarw_abi.h
 	mkdir -p $(PKG)/lib
 	$(NVCC) $(NVFLAGS) -Xptxas -v -shared -o $@ $(PKG)/csrc/sarw_kernels.cu $(PKG)/csrc/sarw_abi.cu 2> $(PKG)/lib/ptxas.log || (cat $(PKG)/lib/ptxas.log; exit 1)
 
-cli: $(CLI)
-$(CLI): $(wildcard $(PKG)/host/*.cpp) $(wildcard $(PKG)/host/*.h) include/sarw_abi.h $(LIB)
+HOSTSRC := $(PKG)/host/input_map.cpp $(PKG)/host/polymer_io.cpp
+cli: $(CLI) $(PKG)/bin/sarw_hosttest
+$(CLI): $(HOSTSRC) $(PKG)/host/main.cpp $(wildcard $(PKG)/host/*.h) include/sarw_abi.h $(LIB)
 	mkdir -p $(PKG)/bin
-	$(CXX) -O2 -g -std=c++17 -Wall -ffp-contract=off -Iinclude -I$(PKG)/host -o $@ $(wildcard $(PKG)/host/*.cpp) -L$(PKG)/lib -lsarw_b200 -Wl,-rpath,'$$ORIGIN/../lib' -lpthread
+	$(CXX) -O2 -g -std=c++17 -Wall -ffp-contract=off -Iinclude -I$(PKG)/host -o $@ $(HOSTSRC) $(PKG)/host/main.cpp -L$(PKG)/lib -lsarw_b200 -Wl,-rpath,'$$ORIGIN/../lib' -lpthread
+# host layer without the GPU library (CPU tests of parser / topology / exporters)
+$(PKG)/bin/sarw_hosttest: $(HOSTSRC) $(PKG)/host/hosttest.cpp $(wildcard $(PKG)/host/*.h)
+	mkdir -p $(PKG)/bin
+	$(CXX) -O2 -g -std=c++17 -Wall -DSARW_HOSTTEST -I$(PKG)/host -o $@ $(HOSTSRC) $(PKG)/host/hosttest.cpp -lpthread
 
 oracle:
 	$(MAKE) -C oracle all

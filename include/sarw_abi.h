@@ -45,6 +45,8 @@ typedef struct sarw_params {
 	int32_t cellCapacity;       /* 0 = default (7 beads inline per cell); 1..7 = test hook forcing overflow handling */
 	double cellEdge;            /* 0 = default; minimum cell edge in Angstrom (>= 2.002*minDist is always enforced) */
 	int64_t reserveRounds;      /* 0 = auto; growth rounds to pre-allocate bead storage for */
+	int32_t launchMode;         /* 0 = auto (one thread-block cluster when nChains <= 256, else cooperative grid); 1 = force grid */
+	int32_t reserved;
 } sarw_params;
 
 typedef struct sarw_stats {

@@ -370,6 +370,26 @@ int sarw_initiate(sarw_ctx* c, int32_t* ok)
 	return check_overflow(c);
 }
 
+// one chain per warp inside a single thread-block cluster when the chain count allows it (hardware cluster barrier)
+static int use_cluster(const sarw_ctx* c)
+{
+	if (c->p.launchMode == 1) return 0;
+	return (int64_t)c->g.nChains <= (int64_t)grow_cluster_max_chains() ? 1 : 0;
+}
+
+static cudaError_t launch_grow_auto(sarw_ctx* c, const Geom& g, uint32_t roundEnd, int blocks)
+{
+	if (use_cluster(c)) {
+		cudaError_t e = launch_grow(g, c->T, c->chains, c->resTrial, c->resPos, c->prev, c->ctl, c->roundAcc, c->roundProg, c->dirtyCount,
+			c->dirtyList, roundEnd, blocks, 1, c->stream);
+		if (e == cudaSuccess) return e;
+		cudaGetLastError();          // launch-configuration error (nothing ran): fall back to the cooperative grid for good
+		c->p.launchMode = 1;
+	}
+	return launch_grow(g, c->T, c->chains, c->resTrial, c->resPos, c->prev, c->ctl, c->roundAcc, c->roundProg, c->dirtyCount,
+		c->dirtyList, roundEnd, blocks, 0, c->stream);
+}
+
 static int grow_impl(sarw_ctx* c, int64_t target, int64_t maxRounds, sarw_stats* stats)
 {
 	if (!c->initiateCalled) return fail(c, "sarw_initiate must be called before growing");
@@ -386,8 +406,7 @@ static int grow_impl(sarw_ctx* c, int64_t target, int64_t maxRounds, sarw_stats*
 		int blocks = (int)std::min<int64_t>(c->growBlocksMax, ((int64_t)g.nChains + 7) / 8);
 		if (blocks < 1) blocks = 1;
 		CU(c, cudaEventRecord(c->ev0, c->stream));
-		CU(c, launch_grow(g, c->T, c->chains, c->resTrial, c->resPos, c->prev, c->ctl, c->roundAcc, c->roundProg, c->dirtyCount,
-			c->dirtyList, roundEnd, blocks, c->stream));
+		CU(c, launch_grow_auto(c, g, roundEnd, blocks));
 		CU(c, cudaEventRecord(c->ev1, c->stream));
 		uint32_t before = h.round;
 		if (read_control(c, &h)) return 1;
@@ -422,8 +441,7 @@ int sarw_propagate_round(sarw_ctx* c, int32_t* progressed)
 	CU(c, cudaMemcpyAsync(&c->ctl->lastProgressed, &one, sizeof one, cudaMemcpyHostToDevice, c->stream));
 	int blocks = (int)std::min<int64_t>(c->growBlocksMax, ((int64_t)g.nChains + 7) / 8);
 	CU(c, cudaEventRecord(c->ev0, c->stream));
-	CU(c, launch_grow(g, c->T, c->chains, c->resTrial, c->resPos, c->prev, c->ctl, c->roundAcc, c->roundProg, c->dirtyCount,
-		c->dirtyList, h.round + 1, blocks, c->stream));
+	CU(c, launch_grow_auto(c, g, h.round + 1, blocks));
 	CU(c, cudaEventRecord(c->ev1, c->stream));
 	if (read_control(c, &h)) return 1;
 	float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);

@@ -25,7 +25,8 @@ cudaError_t launch_seed(const Geom& g, const Tables& T, ChainState* chains, uint
 	Control* ctl, uint32_t* dirtyList, int numSMs, cudaStream_t st, int* launches);
 cudaError_t grow_max_blocks(int numSMs, int* maxBlocks);
 cudaError_t launch_grow(const Geom& g, const Tables& T, ChainState* chains, uint32_t* resTrial, double* resPos, uint32_t* prev, Control* ctl,
-	uint32_t* roundAcc, uint32_t* roundProg, uint32_t* dirtyCount, uint32_t* dirtyList, uint32_t roundEnd, int blocks, cudaStream_t st);
+	uint32_t* roundAcc, uint32_t* roundProg, uint32_t* dirtyCount, uint32_t* dirtyList, uint32_t roundEnd, int blocks, int useCluster, cudaStream_t st);
+int grow_cluster_max_chains();
 cudaError_t download_scan_bytes(uint64_t nSlots, size_t* bytes);
 cudaError_t launch_download(const Geom& g, const Tables& T, const uint32_t* prev, const ChainState* chains, uint64_t nSlots, uint32_t nSeeded,
 	int terminated, uint32_t* flags, uint32_t* scan, void* cubTemp, size_t cubBytes,

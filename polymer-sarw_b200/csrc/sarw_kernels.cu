@@ -19,8 +19,9 @@
 
 namespace sarw {
 
-constexpr int GROW_WARPS = 8;
-constexpr int GROW_THREADS = GROW_WARPS * 32;
+constexpr int GROW_WARPS = 8;            // grid mode: warps per CTA of the cooperative launch
+constexpr int CLUSTER_WARPS = 16;        // cluster mode: warps per CTA; one chain per warp, one cluster for the whole round
+constexpr int CLUSTER_MAX_CTAS = 16;     // non-portable cluster size (8 is the portable limit)
 constexpr int NBMAX = 128;          // staged neighbour beads per chain (shared memory, 16 B each)
 constexpr int NARCMAX = 128;        // blocked torsion arcs per chain (shared memory, 8 B each)
 constexpr uint32_t CHAIN_DEAD = 1u; // ChainState.flags: every torsion angle is permanently blocked
@@ -559,10 +560,26 @@ __device__ void cleanup_round(const GrowArgs& A, uint32_t round, int lane)
 	}
 }
 
-__global__ void __launch_bounds__(GROW_THREADS) grow_kernel(GrowArgs A)
+// barrier across every CTA taking part in a round: the hardware cluster barrier when the whole launch is ONE
+// thread-block cluster (small chain counts: a few hundred cycles), else the software grid barrier (cooperative launch)
+template <bool CLUSTER>
+__device__ __forceinline__ void round_barrier(Control* ctl)
 {
-	__shared__ float4 nbShared[GROW_WARPS][NBMAX];
-	__shared__ float2 arcShared[GROW_WARPS][NARCMAX];
+	if (CLUSTER) {
+		asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+		asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+	} else {
+		grid_barrier(&ctl->barCount, &ctl->barGen, gridDim.x);
+	}
+}
+
+template <int WARPS, bool CLUSTER>
+__global__ void __launch_bounds__(WARPS * 32) grow_kernel(GrowArgs A)
+{
+	constexpr int GROW_WARPS = WARPS;
+	extern __shared__ __align__(16) unsigned char growSmem[];
+	float4 (*nbShared)[NBMAX] = reinterpret_cast<float4 (*)[NBMAX]>(growSmem);
+	float2 (*arcShared)[NARCMAX] = reinterpret_cast<float2 (*)[NARCMAX]>(growSmem + sizeof(float4) * NBMAX * WARPS);
 	const Geom& g = A.g;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const uint32_t gw = blockIdx.x * GROW_WARPS + warp, nW = gridDim.x * GROW_WARPS;
@@ -649,7 +666,7 @@ __global__ void __launch_bounds__(GROW_THREADS) grow_kernel(GrowArgs A)
 			}
 		}
 		pendingValid = true;
-		grid_barrier(&A.ctl->barCount, &A.ctl->barGen, gridDim.x);
+		round_barrier<CLUSTER>(A.ctl);
 		const long long tk1 = clock64();
 
 		// ---------------- phase V: conflicts with tentative beads of lower-indexed chains of this round
@@ -686,13 +703,13 @@ __global__ void __launch_bounds__(GROW_THREADS) grow_kernel(GrowArgs A)
 				myTrials += tr;
 			}
 		}
-		grid_barrier(&A.ctl->barCount, &A.ctl->barGen, gridDim.x);
+		round_barrier<CLUSTER>(A.ctl);
 
 		const long long tk2 = clock64();
 		// ---------------- clean-up (rare): serial re-resolution in chain order
 		if (__ldcg(&A.dirtyCount[round]) != 0u) {
 			if (gw == 0) cleanup_round(A, round, lane);
-			grid_barrier(&A.ctl->barCount, &A.ctl->barGen, gridDim.x);
+			round_barrier<CLUSTER>(A.ctl);
 			cleanRounds++;
 		}
 		cycA += tk1 - tk0; cycV += tk2 - tk1; cycC += clock64() - tk2;
@@ -799,20 +816,42 @@ cudaError_t launch_seed(const Geom& g, const Tables& T, ChainState* chains, uint
 	return cudaGetLastError();
 }
 
+constexpr size_t grow_smem_bytes(int warps) { return (size_t)warps * (NBMAX * sizeof(float4) + NARCMAX * sizeof(float2)); }
+
 cudaError_t grow_max_blocks(int numSMs, int* maxBlocks)
 {
 	int perSM = 0;
-	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, grow_kernel, GROW_THREADS, 0));
+	CK(cudaFuncSetAttribute(grow_kernel<GROW_WARPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grow_smem_bytes(GROW_WARPS)));
+	CK(cudaFuncSetAttribute(grow_kernel<CLUSTER_WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grow_smem_bytes(CLUSTER_WARPS)));
+	CK(cudaFuncSetAttribute(grow_kernel<CLUSTER_WARPS, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, grow_kernel<GROW_WARPS, false>, GROW_WARPS * 32, grow_smem_bytes(GROW_WARPS)));
 	*maxBlocks = perSM * numSMs;
 	return cudaSuccess;
 }
 
+// largest chain count the single-cluster launch covers with one chain per warp
+int grow_cluster_max_chains() { return CLUSTER_WARPS * CLUSTER_MAX_CTAS; }
+
 cudaError_t launch_grow(const Geom& g, const Tables& T, ChainState* chains, uint32_t* resTrial, double* resPos, uint32_t* prev, Control* ctl,
-	uint32_t* roundAcc, uint32_t* roundProg, uint32_t* dirtyCount, uint32_t* dirtyList, uint32_t roundEnd, int blocks, cudaStream_t st)
+	uint32_t* roundAcc, uint32_t* roundProg, uint32_t* dirtyCount, uint32_t* dirtyList, uint32_t roundEnd, int blocks, int useCluster, cudaStream_t st)
 {
 	GrowArgs A{ g, T, chains, resTrial, resPos, prev, ctl, roundAcc, roundProg, dirtyCount, dirtyList, roundEnd };
+	if (useCluster) {
+		// the whole launch is one cluster: CTAs are co-scheduled by the hardware and synchronise with barrier.cluster
+		int ctas = (int)((g.nChains + CLUSTER_WARPS - 1) / CLUSTER_WARPS);
+		if (ctas < 1) ctas = 1;
+		cudaLaunchConfig_t cfg = {};
+		cfg.gridDim = dim3((unsigned)ctas); cfg.blockDim = dim3(CLUSTER_WARPS * 32);
+		cfg.dynamicSmemBytes = grow_smem_bytes(CLUSTER_WARPS); cfg.stream = st;
+		cudaLaunchAttribute attr[1];
+		attr[0].id = cudaLaunchAttributeClusterDimension;
+		attr[0].val.clusterDim.x = (unsigned)ctas; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+		cfg.attrs = attr; cfg.numAttrs = 1;
+		return cudaLaunchKernelEx(&cfg, grow_kernel<CLUSTER_WARPS, true>, A);
+	}
 	void* args[] = { &A };
-	return cudaLaunchCooperativeKernel((const void*)grow_kernel, dim3((unsigned)blocks), dim3(GROW_THREADS), args, 0, st);
+	return cudaLaunchCooperativeKernel((const void*)grow_kernel<GROW_WARPS, false>, dim3((unsigned)blocks), dim3(GROW_WARPS * 32), args,
+		grow_smem_bytes(GROW_WARPS), st);
 }
 
 cudaError_t launch_download(const Geom& g, const Tables& T, const uint32_t* prev, const ChainState* chains, uint64_t nSlots, uint32_t nSeeded,

@@ -1,0 +1,226 @@
+// sarw — drop-in for the reference CLI `sarw -i <input> [-o <log>]` (README.md:22; sarw.cpp:13-89), with the chain-growth
+// hot path running on a B200 through the C ABI of libsarw_b200.so (include/sarw_abi.h). No CPU fallback.
+//
+// Same input keys (union of what the code reads, sarw.cpp:22-38, and what README.md:26-41 documents), same log blocks
+// (INPUTS / LOG FLAGS / PROGRESS / SUMMARY, sarw.cpp:41-56,64-77,491-503), same output files in the CWD
+// (polymer.dat, polymer.xyz, polymer.xsf, chains.dat: sarw.cpp:373,383,433,506) plus the README's names
+// (polymer.data, polymer.XYZ, polymer.XSF, README.md:44-46) as symlinks. Exit 0 after export even when jammed
+// (sarw.cpp:88); exit 1 on a missing input file or required key (InputMap.cpp:30,51).
+#include "input_map.h"
+#include "polymer_io.h"
+#include "sarw_abi.h"
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <string>
+#include <unistd.h>
+#include <vector>
+
+using namespace sarwhost;
+
+static FILE* globalLog = stdout;
+static void logPrintf(const char* fmt, ...)
+{	va_list ap; va_start(ap, fmt); vfprintf(globalLog, fmt, ap); va_end(ap);
+}
+[[noreturn]] static void die(const char* fmt, ...)
+{	va_list ap; va_start(ap, fmt); vfprintf(globalLog, fmt, ap); va_end(ap);
+	if (globalLog != stdout) { va_start(ap, fmt); vfprintf(stderr, fmt, ap); va_end(ap); }
+	exit(1);
+}
+static double seconds_since(std::chrono::steady_clock::time_point t0)
+{	return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+int main(int argc, char** argv)
+{
+	std::string inputFilename, logFilename, outDir;
+	bool haveSeedOpt = false; unsigned long long seedOpt = 0; int device = -1, ioThreads = 0; bool timing = false;
+	for (int i = 1; i < argc; i++) {
+		if (!strcmp(argv[i], "-i") && i + 1 < argc) inputFilename = argv[++i];
+		else if (!strcmp(argv[i], "-o") && i + 1 < argc) logFilename = argv[++i];
+		else if (!strcmp(argv[i], "--seed") && i + 1 < argc) { seedOpt = strtoull(argv[++i], 0, 10); haveSeedOpt = true; }
+		else if (!strcmp(argv[i], "--device") && i + 1 < argc) device = atoi(argv[++i]);
+		else if (!strcmp(argv[i], "--io-threads") && i + 1 < argc) ioThreads = atoi(argv[++i]);
+		else if (!strcmp(argv[i], "--timing")) timing = true;
+		else if (!strcmp(argv[i], "-h") || !strcmp(argv[i], "--help")) {
+			printf("usage: sarw -i <input> [-o <log>] [--seed N] [--device D] [--io-threads T] [--timing]\n");
+			return 0;
+		}
+	}
+	if (!logFilename.empty()) { FILE* fp = fopen(logFilename.c_str(), "w"); if (fp) globalLog = fp; }
+	logPrintf("\n*************** sarw (B200) 0.2.alpha ***************\nSelf Avoiding Random Walk\n");
+	if (inputFilename.empty()) die("No input file given (use -i <file>).\n");
+
+	InputMap inputMap; std::string err;
+	if (!inputMap.load(inputFilename, err)) die("%s", err.c_str());
+
+	// sarw.cpp:22-38, same defaults
+	sarw_params P; memset(&P, 0, sizeof P);
+	P.nChains = (int64_t)inputMap.get("nChains", 1);
+	Vec3 boxSize = inputMap.getVector("boxSize", Vec3{ { 10, 10, 10 } });
+	for (int k = 0; k < 3; k++) P.boxSize[k] = boxSize[k];
+	P.minDist = inputMap.get("minDist", 2.0);
+	P.targetMassDensity = inputMap.get("targetMassDensity", 0.92);
+	bool haveNGraft = false;
+	P.nGraftChains = (int64_t)inputMap.get("nGraftChains", 0, &haveNGraft);
+	std::string graftLoc = inputMap.getString("graftLoc", "file");
+	std::string growthOrder = inputMap.getString("growthOrder", "roundRobin");
+	std::string boundary = inputMap.getString("boundary", "ppp");
+	P.maxTrials = (int32_t)inputMap.get("maxTrials", 100);
+	std::string polymer = inputMap.getString("polymer", "Polyethylene");
+	bool logProgress = inputMap.getString("logProgress", "yes") == "yes";
+	const bool logSteps = inputMap.getString("logSteps", "no") == "yes";
+	if (logSteps) logProgress = true;                                           // sarw.cpp:511-516
+	std::string obstacle = inputMap.getString("obstacle", "none");
+
+	// README-only keys (README.md:32-33,40): not read by the reference code. graftFraction maps onto nGraftChains only
+	// when it amounts to at least one chain and nGraftChains is absent (so test/pe.in, graftFraction 0.01 of 20 chains,
+	// behaves exactly like the reference binary); roundRobin is accepted and, like in the reference, has no effect.
+	std::vector<std::string> notes;
+	bool haveFrac = false; double graftFraction = inputMap.get("graftFraction", 0.0, &haveFrac);
+	if (haveFrac && !haveNGraft) {
+		int64_t n = (int64_t)nearbyint(graftFraction * (double)P.nChains);
+		if (n > 0) { P.nGraftChains = n; notes.push_back("graftFraction -> nGraftChains = " + std::to_string(n) + " (graftLoc " + graftLoc + ")"); }
+	}
+	bool haveBias = false; Vec3 bias = inputMap.getVector("growthBias", Vec3{ { 0, 0, 0 } }, &haveBias);
+	for (int k = 0; k < 3; k++) P.growthBias[k] = bias[k];
+	if (haveBias && (bias[0] != 0 || bias[1] != 0 || bias[2] != 0))
+		notes.push_back("growthBias: trials whose step has growthBias.step < 0 are rejected (no reference implementation exists)");
+	if (inputMap.has("roundRobin") && inputMap.getString("roundRobin", "yes") != "yes")
+		notes.push_back("roundRobin no: the reference code ignores this key and grows round-robin; so does this build");
+	bool haveSeedKey = false; double seedKey = inputMap.get("seed", 0, &haveSeedKey);
+	if (haveSeedOpt) P.seed = seedOpt;
+	else if (haveSeedKey) P.seed = (uint64_t)seedKey;
+	else P.seed = (uint64_t)time(NULL) * 2654435761ull + (uint64_t)getpid();    // sarw.cpp:16: a different walk every run
+	P.device = device;
+
+	P.graftLoc = graftLoc == "file" ? SARW_GRAFT_FILE : graftLoc == "z" ? SARW_GRAFT_Z : graftLoc == "zCenter" ? SARW_GRAFT_ZCENTER : SARW_GRAFT_OTHER;
+	P.growthOrder = growthOrder == "grafted" ? SARW_ORDER_GRAFTED : SARW_ORDER_ROUNDROBIN;
+	P.boundary = boundary == "ppf" ? SARW_BOUNDARY_PPF : boundary == "pfp" ? SARW_BOUNDARY_PFP : boundary == "fpp" ? SARW_BOUNDARY_FPP : SARW_BOUNDARY_PPP;
+
+	// sarw.cpp:41-56
+	logPrintf("\nINPUTS:\n");
+	logPrintf("nChains = %d\n", (int)P.nChains);
+	logPrintf("boxSize = (%lg x %lg x %lg)\n", P.boxSize[0], P.boxSize[1], P.boxSize[2]);
+	logPrintf("minDist = %lg\n", P.minDist);
+	logPrintf("targetMassDensity = %lg\n", P.targetMassDensity);
+	logPrintf("nGraftChains = %d\n", (int)P.nGraftChains);
+	logPrintf("graftLoc = %s\n", graftLoc.c_str());
+	logPrintf("growthOrder = %s\n", growthOrder.c_str());
+	logPrintf("boundary = %s\n", boundary.c_str());
+	logPrintf("maxTrials = %d\n", P.maxTrials);
+	logPrintf("polymer = %s\n", polymer.c_str());
+	logPrintf("obstacle = %s\n", obstacle.c_str());
+	logPrintf("\nLOG FLAGS:\n");
+	logPrintf("logProgress = %s\n", logProgress ? "yes" : "no");
+	logPrintf("logSteps = %s\n", logSteps ? "yes" : "no");
+	if (!notes.empty() || haveSeedKey || haveSeedOpt) {
+		logPrintf("\nB200 NOTES:\n");
+		if (haveSeedKey || haveSeedOpt) logPrintf("seed = %llu\n", (unsigned long long)P.seed);
+		for (const std::string& n : notes) logPrintf("%s\n", n.c_str());
+		if (boundary != "ppp" && boundary != "ppf" && boundary != "pfp" && boundary != "fpp")
+			logPrintf("boundary %s: only ppf, pfp, fpp act in the reference (sarw.cpp:201-203); treated as ppp\n", boundary.c_str());
+	}
+
+	auto tAll = std::chrono::steady_clock::now();
+	sarw_ctx* ctx = nullptr;
+	if (sarw_create(&P, &ctx) != 0) die("\nsarw_create failed: %s\n", sarw_last_error(nullptr));
+
+	// sarw.cpp:59, 102-123
+	if (P.nGraftChains > 0 && graftLoc == "file") {
+		std::vector<double> grafts;
+		if (read_xyz_records("grafts.dat", grafts)) {
+			int64_t n = (int64_t)grafts.size() / 3;
+			logPrintf("\nReading grafts.dat: %d graft seeds found\n", (int)n);
+			if (n < P.nGraftChains) die("Inadequate number of seeds! Expected %d seeds.\n", (int)P.nGraftChains);   // the reference only logs, then reads out of bounds
+			if (n > P.nGraftChains) { logPrintf("Removing extra seeds!\n"); n = P.nGraftChains; }
+			if (sarw_set_grafts(ctx, grafts.data(), n) != 0) die("%s\n", sarw_last_error(ctx));
+		} else die("\nFailed to open grafts.dat, needed for %d grafted chains.\n", (int)P.nGraftChains);
+	}
+	// sarw.cpp:62, 126-145
+	if (obstacle != "none") {
+		std::vector<double> obst;
+		if (read_xyz_records(obstacle, obst)) {
+			logPrintf("\nReading %s: %d obstacles found\n", obstacle.c_str(), (int)(obst.size() / 3));
+			if (sarw_add_obstacles(ctx, obst.data(), (int64_t)obst.size() / 3) != 0) die("%s\n", sarw_last_error(ctx));
+		} else logPrintf("\nFailed to open %s. Assuming no obstacles.\n", obstacle.c_str());
+	}
+
+	// sarw.cpp:64-80: the loop runs on the device; the PROGRESS line is reproduced from the per-round bead counts
+	if (logProgress) logPrintf("\nPROGRESS: ");
+	auto tGrow = std::chrono::steady_clock::now();
+	int32_t ok = 0;
+	sarw_stats st; memset(&st, 0, sizeof st);
+	if (sarw_initiate(ctx, &ok) != 0) die("\n%s\n", sarw_last_error(ctx));
+	if (sarw_grow(ctx, 0, -1, &st) != 0) die("\n%s\n", sarw_last_error(ctx));
+	if (sarw_terminate(ctx) != 0) die("\n%s\n", sarw_last_error(ctx));
+	const double growSeconds = seconds_since(tGrow);
+	if (logProgress) {
+		std::vector<int64_t> counts((size_t)st.rounds);
+		if (st.rounds > 0 && sarw_round_counts(ctx, counts.data(), st.rounds) != 0) die("\n%s\n", sarw_last_error(ctx));
+		int oldProgress = 0;
+		for (int64_t r = 0; r < st.rounds; r++) {
+			int currentProgress = (int)(100. * (double)counts[(size_t)r] / (double)st.target);   // sarw.cpp:70
+			if (currentProgress > oldProgress) { oldProgress = currentProgress; logPrintf("%d, ", currentProgress); }
+		}
+		logPrintf("\n");
+	}
+
+	Polymer pm;
+	pm.name = polymer; pm.nChains = P.nChains;
+	for (int k = 0; k < 3; k++) pm.box[k] = P.boxSize[k];
+	pm.xyz.resize((size_t)st.nBeads * 3); pm.chainID.resize((size_t)st.nBeads); pm.type.resize((size_t)st.nBeads);
+	pm.bonds.resize((size_t)st.nBonds * 2); pm.chainLengths.resize((size_t)P.nChains);
+	auto tDown = std::chrono::steady_clock::now();
+	if (sarw_download(ctx, pm.xyz.data(), pm.chainID.data(), pm.type.data(), pm.bonds.data()) != 0) die("\n%s\n", sarw_last_error(ctx));
+	if (sarw_chain_lengths(ctx, pm.chainLengths.data()) != 0) die("\n%s\n", sarw_last_error(ctx));
+	const double downSeconds = seconds_since(tDown);
+	sarw_get_stats(ctx, &st);
+	sarw_destroy(ctx);
+
+	// sarw.cpp:489-509
+	const long long vol = (long long)(P.boxSize[0] * P.boxSize[1] * P.boxSize[2]);
+	const double actualMassDensity = 14.0 * (double)st.nBeads / (6.022e23 * (double)vol * 1e-24);
+	logPrintf("\nSUMMARY:\n");
+	logPrintf("No. of united atoms: ");
+	logPrintf("desired = %lld, ", (long long)st.target);
+	logPrintf("actual = %lld\n", (long long)st.nBeads);
+	logPrintf("Number density: ");
+	logPrintf("desired = %.3e, ", 6.022e23 * P.targetMassDensity / 14.0);
+	logPrintf("actual = %.3e\n", 6.022e23 * actualMassDensity / 14.0);
+	logPrintf("Mass density: ");
+	logPrintf("desired = %.2f, ", P.targetMassDensity);
+	logPrintf("actual = %.2f\n", actualMassDensity);
+	logPrintf("\nExporting distribution of chain lengths: chains.dat\n");
+	if (!export_chain_lengths(pm, "chains.dat", err)) die("%s\n", err.c_str());
+
+	auto tTopo = std::chrono::steady_clock::now();
+	build_topology(pm);
+	const double topoSeconds = seconds_since(tTopo);
+	auto tExp = std::chrono::steady_clock::now();
+	logPrintf("\nExporting LAMMPS data file: polymer.dat\n");
+	if (!export_lammps(pm, "polymer.dat", ioThreads, err)) die("%s\n", err.c_str());
+	logPrintf("Exporting XYZ file: polymer.xyz\n");
+	if (!export_xyz(pm, "polymer.xyz", ioThreads, err)) die("%s\n", err.c_str());
+	logPrintf("Exporting XSF file: polymer.xsf\n");
+	if (!export_xsf(pm, "polymer.xsf", ioThreads, err)) die("%s\n", err.c_str());
+	const double expSeconds = seconds_since(tExp);
+	// README.md:44-46 names, as aliases
+	const char* alias[3][2] = { { "polymer.dat", "polymer.data" }, { "polymer.xyz", "polymer.XYZ" }, { "polymer.xsf", "polymer.XSF" } };
+	for (auto& a : alias) { unlink(a[1]); if (symlink(a[0], a[1]) != 0) { /* case-insensitive or read-only file systems: skip */ } }
+
+	if (timing) {
+		logPrintf("\nTIMING (B200):\n");
+		logPrintf("seeding + growth: %.3f ms on device (%.3f s wall incl. launches), %lld rounds, %.3e accepted beads/s\n",
+			st.seedMs + st.growMs, growSeconds, (long long)st.rounds, (double)st.nBeads / ((st.seedMs + st.growMs) * 1e-3));
+		logPrintf("trials per accepted bead (reference terms): %.2f; exact overlap queries evaluated: %llu; same-round conflicts: %llu; dead chains: %lld\n",
+			(double)st.trials / (double)(st.nBeads ? st.nBeads : 1), (unsigned long long)st.queries, (unsigned long long)st.conflicts, (long long)st.deadChains);
+		logPrintf("download %.3f s, topology %.3f s, export %.3f s, total %.3f s\n", downSeconds, topoSeconds, expSeconds, seconds_since(tAll));
+	}
+	if (globalLog != stdout) fclose(globalLog);
+	return 0;
+}

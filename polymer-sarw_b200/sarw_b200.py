@@ -36,7 +36,8 @@ class Params(C.Structure):
                 ("targetMassDensity", C.c_double), ("nGraftChains", C.c_int64), ("maxTrials", C.c_int32),
                 ("graftLoc", C.c_int32), ("growthOrder", C.c_int32), ("boundary", C.c_int32),
                 ("growthBias", C.c_double * 3), ("seed", C.c_uint64), ("device", C.c_int32),
-                ("cellCapacity", C.c_int32), ("cellEdge", C.c_double), ("reserveRounds", C.c_int64)]
+                ("cellCapacity", C.c_int32), ("cellEdge", C.c_double), ("reserveRounds", C.c_int64),
+                ("launchMode", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -101,7 +102,7 @@ class Context:
 
     def __init__(self, nChains=1, boxSize=(10, 10, 10), minDist=2.0, targetMassDensity=0.92, maxTrials=100,
                  boundary="ppp", nGraftChains=0, graftLoc="file", growthOrder="roundRobin", growthBias=(0, 0, 0),
-                 seed=1, device=-1, cellCapacity=0, cellEdge=0.0, reserveRounds=0):
+                 seed=1, device=-1, cellCapacity=0, cellEdge=0.0, reserveRounds=0, launchMode=0):
         self.lib = load_library()
         p = Params()
         p.nChains = nChains; p.boxSize = (C.c_double * 3)(*boxSize); p.minDist = minDist
@@ -109,7 +110,7 @@ class Context:
         p.graftLoc = GRAFT.get(graftLoc, 3); p.growthOrder = ORDER.get(growthOrder, 0)
         p.boundary = BOUNDARY.get(boundary, 0)   # only exact ppf/pfp/fpp act, anything else == ppp (sarw.cpp:201-203)
         p.growthBias = (C.c_double * 3)(*growthBias); p.seed = seed; p.device = device
-        p.cellCapacity = cellCapacity; p.cellEdge = cellEdge; p.reserveRounds = reserveRounds
+        p.cellCapacity = cellCapacity; p.cellEdge = cellEdge; p.reserveRounds = reserveRounds; p.launchMode = launchMode
         self.params = p
         self.nChains = nChains
         h = C.c_void_p()

@@ -6,13 +6,16 @@ import sarw_b200, cases
 
 which = sys.argv[1:] or ["PE_IN", "C2", "C3"]
 seeds = (1, 2)
+mode = 0
+if which and which[0].startswith("mode="):
+    mode = int(which[0][5:]); which = which[1:]
 if which and which[0].startswith("seeds="):
     seeds = tuple(int(x) for x in which[0][6:].split(",")); which = which[1:]
 for name in which:
     cfg = getattr(cases, name)
     for seed in seeds:
         t0 = time.time()
-        s = sarw_b200.SARW(cfg["nChains"], cfg["boxSize"], cfg["minDist"], seed=seed,
+        s = sarw_b200.SARW(cfg["nChains"], cfg["boxSize"], cfg["minDist"], seed=seed, launchMode=mode,
                            **{k: v for k, v in cfg.items() if k not in ("nChains", "boxSize", "minDist")})
         t1 = time.time()
         st = s.run()

@@ -5,7 +5,7 @@ PE_IN = dict(nChains=20, boxSize=(10.0, 10.0, 40.0), minDist=1.0, maxTrials=1000
 C2 = dict(nChains=100, boxSize=(136.2, 136.2, 136.2), minDist=1.0, maxTrials=1000)                  # BASELINE configs[1]
 C3 = dict(nChains=10000, boxSize=(632.2, 632.2, 632.2), minDist=1.0, maxTrials=1000)                # BASELINE configs[2]
 SMALL_DEFAULTS = dict(nChains=30, boxSize=(30.0, 30.0, 30.0), minDist=2.0, maxTrials=100)            # the code's default minDist/maxTrials
-DENSE_TINY = dict(nChains=40, boxSize=(12.0, 12.0, 12.0), minDist=1.0, maxTrials=200)                # many same-round conflicts
+DENSE_TINY = dict(nChains=40, boxSize=(14.0, 14.0, 14.0), minDist=1.0, maxTrials=200, targetMassDensity=4.0)   # crowded: many same-round conflicts, jams
 MID = dict(nChains=400, boxSize=(60.0, 60.0, 60.0), minDist=1.0, maxTrials=300)
 
 
