@@ -155,6 +155,23 @@ def run_reference(args, w):
 
 
 # ------------------------------------------------------------------ our arm
+def rank_seeds(rank, total_steps):
+    """Distinct Philox keys per (rank, step): ranks shard the work as independent melts."""
+    return [10_000 * (rank + 1) + s for s in range(total_steps)]
+
+
+def aggregate_ranks(dist, device, t_dev, t_e2e, beads, e2e_beads):
+    """Contract: time = MAX over ranks, work = SUM over ranks. `dist` is torch.distributed (any backend) or None."""
+    import torch
+    if dist is None:
+        return t_dev, t_e2e, float(beads), float(e2e_beads)
+    t = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device=device)
+    w = torch.tensor([float(beads), float(e2e_beads)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(w, op=dist.ReduceOp.SUM)
+    return t[0].item(), t[1].item(), w[0].item(), w[1].item()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -204,7 +221,7 @@ def main():
         return c
 
     total = args.warmup + args.steps
-    seeds = [10_000 * (rank + 1) + s for s in range(total)]
+    seeds = rank_seeds(rank, total)
     # -------- device-resident arm
     ctxs = [make_ctx(s) for s in seeds]
     for i in range(args.warmup):
@@ -247,14 +264,7 @@ def main():
 
     # -------- aggregate over ranks (max time, summed work)
     t_e2e = sum(e2e_times)
-    agg = torch.tensor([t_dev, t_e2e, float(beads), float(e2e_beads), float(queries), grow_ms, float(launches)], dtype=torch.float64, device="cuda")
-    if dist:
-        tmax = agg.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = agg.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        t_dev, t_e2e = tmax[0].item(), tmax[1].item()
-        beads_all, e2e_beads_all = tsum[2].item(), tsum[3].item()
-    else:
-        beads_all, e2e_beads_all = float(beads), float(e2e_beads)
+    t_dev, t_e2e, beads_all, e2e_beads_all = aggregate_ranks(dist, "cuda", t_dev, t_e2e, beads, e2e_beads)
 
     if rank == 0:
         value = beads_all / t_dev
