@@ -181,6 +181,22 @@ __device__ __forceinline__ bool exact_pair(const Geom& g, const double v[3], con
 	return dist <= g.thresh;
 }
 
+// same decision with the stored bead's Cartesian position already in registers
+__device__ __forceinline__ bool exact_pair_reg(const Geom& g, const double v[3], const double p[3])
+{
+	double c[3];
+#pragma unroll
+	for (int k = 0; k < 3; k++) {
+		double t = p[k] * g.Linv[k];
+		double vp = t - floor(t);
+		double dv = v[k] - vp;
+		dv = dv - floor(0.5 + dv);
+		c[k] = g.L[k] * dv;
+	}
+	double dist = sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+	return dist <= g.thresh;
+}
+
 // fixed walls (sarw.cpp:201-203), zCenter half-space rule (:206-211) and the growthBias extension
 __device__ __forceinline__ bool walls_reject(const Geom& g, const double pos[3])
 {

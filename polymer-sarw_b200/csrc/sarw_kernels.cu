@@ -16,12 +16,11 @@
 #include "sarw_device.cuh"
 #include "sarw_host.h"
 #include <cub/device/device_scan.cuh>
+#include <cooperative_groups.h>
 
 namespace sarw {
 
 constexpr int GROW_WARPS = 8;            // grid mode: warps per CTA of the cooperative launch
-constexpr int CLUSTER_WARPS = 16;        // cluster mode: warps per CTA; one chain per warp, one cluster for the whole round
-constexpr int CLUSTER_MAX_CTAS = 16;     // non-portable cluster size (8 is the portable limit)
 constexpr int NBMAX = 128;          // staged neighbour beads per chain (shared memory, 16 B each)
 constexpr int NARCMAX = 128;        // blocked torsion arcs per chain (shared memory, 8 B each)
 constexpr uint32_t CHAIN_DEAD = 1u; // ChainState.flags: every torsion angle is permanently blocked
@@ -303,7 +302,7 @@ __device__ __forceinline__ void round_range(const Geom& g, unsigned long long nB
 // stage every bead that can be within thresh of any point of the cone circle into shared memory, as positions
 // relative to the (wrapped) last bead; returns the number staged or -1 when NBMAX does not suffice
 __device__ __forceinline__ int stage_region(const Geom& g, const Tables& T, const double lw[3], const Frame& f,
-	uint32_t idLimit, uint32_t ignoreId, float4* nb, int lane, bool& regionOvf)
+	uint32_t idLimit, uint32_t ignoreId, float4* nb, int lane, bool& regionOvf, int64_t* stagedCell = nullptr, uint32_t* stagedCnt = nullptr)
 {
 	int lo[3], nn[3];
 	bool ovf = false;
@@ -329,6 +328,7 @@ __device__ __forceinline__ int stage_region(const Geom& g, const Tables& T, cons
 			s0 = __ldcg(&cell->slot[0]);
 			ovf |= (hdr.y != ID_NONE);
 			cnt = hdr.x + 1u; if (cnt > (uint32_t)g.cap) cnt = (uint32_t)g.cap;
+			if (stagedCell && cbase < 64) { stagedCell[cbase >> 5] = cell - T.cells; stagedCnt[cbase >> 5] = cnt; }
 			sh[0] = (float)((double)cx * g.a[0] - lw[0]); sh[1] = (float)((double)cy * g.a[1] - lw[1]); sh[2] = (float)((double)cz * g.a[2] - lw[2]);
 		}
 		uint32_t incl = cnt;
@@ -734,6 +734,8 @@ __global__ void __launch_bounds__(WARPS * 32) grow_kernel(GrowArgs A)
 	if (timer) { A.ctl->cycPropose += cycA; A.ctl->cycVerify += cycV; A.ctl->cycCleanup += cycC; A.ctl->cleanupRounds += cleanRounds; }
 }
 
+#include "sarw_cluster.cuh"
+
 // ------------------------------------------------------------------ K7: compaction into acceptance order
 __global__ void flag_slots_kernel(const double* __restrict__ lpos, uint32_t idAtomBase, uint64_t nSlots, uint32_t* __restrict__ flags)
 {
@@ -822,32 +824,33 @@ cudaError_t grow_max_blocks(int numSMs, int* maxBlocks)
 {
 	int perSM = 0;
 	CK(cudaFuncSetAttribute(grow_kernel<GROW_WARPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grow_smem_bytes(GROW_WARPS)));
-	CK(cudaFuncSetAttribute(grow_kernel<CLUSTER_WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grow_smem_bytes(CLUSTER_WARPS)));
-	CK(cudaFuncSetAttribute(grow_kernel<CLUSTER_WARPS, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+	CK(cudaFuncSetAttribute(grow_cluster_kernel<CL_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cluster_smem_bytes()));
+	CK(cudaFuncSetAttribute(grow_cluster_kernel<CL_WARPS>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
 	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, grow_kernel<GROW_WARPS, false>, GROW_WARPS * 32, grow_smem_bytes(GROW_WARPS)));
 	*maxBlocks = perSM * numSMs;
 	return cudaSuccess;
 }
 
-// largest chain count the single-cluster launch covers with one chain per warp
-int grow_cluster_max_chains() { return CLUSTER_WARPS * CLUSTER_MAX_CTAS; }
+// largest chain count the single-cluster kernel covers (one chain per warp)
+int grow_cluster_max_chains() { return CL_MAXCH; }
 
 cudaError_t launch_grow(const Geom& g, const Tables& T, ChainState* chains, uint32_t* resTrial, double* resPos, uint32_t* prev, Control* ctl,
 	uint32_t* roundAcc, uint32_t* roundProg, uint32_t* dirtyCount, uint32_t* dirtyList, uint32_t roundEnd, int blocks, int useCluster, cudaStream_t st)
 {
 	GrowArgs A{ g, T, chains, resTrial, resPos, prev, ctl, roundAcc, roundProg, dirtyCount, dirtyList, roundEnd };
 	if (useCluster) {
-		// the whole launch is one cluster: CTAs are co-scheduled by the hardware and synchronise with barrier.cluster
-		int ctas = (int)((g.nChains + CLUSTER_WARPS - 1) / CLUSTER_WARPS);
+		// the whole launch is one thread-block cluster: CTAs are co-scheduled by the hardware, synchronise with
+		// barrier.cluster and exchange tentative beads through distributed shared memory
+		int ctas = (int)((g.nChains + CL_WARPS - 1) / CL_WARPS);
 		if (ctas < 1) ctas = 1;
 		cudaLaunchConfig_t cfg = {};
-		cfg.gridDim = dim3((unsigned)ctas); cfg.blockDim = dim3(CLUSTER_WARPS * 32);
-		cfg.dynamicSmemBytes = grow_smem_bytes(CLUSTER_WARPS); cfg.stream = st;
+		cfg.gridDim = dim3((unsigned)ctas); cfg.blockDim = dim3(CL_WARPS * 32);
+		cfg.dynamicSmemBytes = cluster_smem_bytes(); cfg.stream = st;
 		cudaLaunchAttribute attr[1];
 		attr[0].id = cudaLaunchAttributeClusterDimension;
 		attr[0].val.clusterDim.x = (unsigned)ctas; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
 		cfg.attrs = attr; cfg.numAttrs = 1;
-		return cudaLaunchKernelEx(&cfg, grow_kernel<CLUSTER_WARPS, true>, A);
+		return cudaLaunchKernelEx(&cfg, grow_cluster_kernel<CL_WARPS>, A);
 	}
 	void* args[] = { &A };
 	return cudaLaunchCooperativeKernel((const void*)grow_kernel<GROW_WARPS, false>, dim3((unsigned)blocks), dim3(GROW_WARPS * 32), args,
