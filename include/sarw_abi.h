@@ -70,6 +70,7 @@ typedef struct sarw_stats {
 	uint64_t cycCleanup;
 	int64_t cleanupRounds;      /* rounds that needed the serial conflict clean-up */
 	int64_t deadChains;         /* chains proven permanently blocked (skipped from then on; the reference retries them) */
+	uint64_t cycSub[8];         /* finer split of cycPropose for warp 0 of block 0: frame, stage, arcs, classify, evaluate, publish, barrier, - */
 } sarw_stats;
 
 /* SARW::SARW + PeriodicLookup::PeriodicLookup (sarw.h:88-94, PeriodicLookup.h:26-34): allocates the device cell list. */

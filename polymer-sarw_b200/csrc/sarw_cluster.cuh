@@ -16,9 +16,9 @@
 // (sarw_kernels.cu includes <cooperative_groups.h> at file scope before opening namespace sarw)
 namespace cgx = ::cooperative_groups;
 
-constexpr int CL_WARPS = 16;            // warps (= chains) per CTA
 constexpr int CL_MAX_CTAS = 16;         // non-portable cluster size
-constexpr int CL_MAXCH = CL_WARPS * CL_MAX_CTAS;
+constexpr int CL_MAXCH = 16 * CL_MAX_CTAS;   // table capacity: 16 warps per CTA x 16 CTAs (the 8-warp variant uses half of it)
+constexpr int CL_REGION_CELLS = 64;     // staged region: at most 4 x 4 x 4 cells of 128 bytes
 constexpr int CL_NARC = 64;             // blocked arcs kept per chain (more: no pre-classification, still exact)
 
 // tentative bead of one chain in one round, as broadcast to every CTA
@@ -29,8 +29,9 @@ struct __align__(8) TentRec {
 };
 static_assert(sizeof(TentRec) == 40, "TentRec is 40 bytes");
 
-constexpr size_t cluster_smem_bytes()
-{	return (size_t)CL_WARPS * NBMAX * sizeof(float4) + (size_t)CL_WARPS * CL_NARC * sizeof(float4) + 2 * (size_t)CL_MAXCH * sizeof(TentRec) + 16;
+constexpr size_t cluster_smem_bytes(int warps)
+{	return (size_t)warps * CL_REGION_CELLS * sizeof(Cell) + (size_t)warps * NBMAX * sizeof(float4) + (size_t)warps * CL_NARC * sizeof(float4)
+		+ 2 * (size_t)CL_MAXCH * sizeof(TentRec) + (size_t)warps * 8 + 16;
 }
 
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
@@ -104,14 +105,128 @@ __device__ __forceinline__ bool arcs_cs_cover_circle(const float4* arcs, int nar
 	return allCovered;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// TMA staging: the region (<= 4x4x4 cells, x-rows contiguous in memory) is copied row by row into the warp's shared
+// memory with cp.async.bulk (one lane per row, completion on a per-warp mbarrier). The copies cost no registers and
+// no issue slots while in flight, so the warp prepares its exact candidates meanwhile.
+struct RegionPlan { int lo[3], nn[3], ncell; float base[3]; };
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void* mbar, unsigned count)
+{	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(mbar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(void* mbar, unsigned bytes)
+{	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(mbar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* mbar, unsigned parity)
+{
+	asm volatile(
+		"{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n"
+		:: "r"(smem_u32(mbar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dstSmem, const void* srcGlobal, unsigned bytes, void* mbar)
+{	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+		:: "r"(smem_u32(dstSmem)), "l"(srcGlobal), "r"(bytes), "r"(smem_u32(mbar)) : "memory");
+}
+
+__device__ __forceinline__ int wrap_near(int c, int S)   // c is within a few cells of [0,S): no integer division
+{	while (c < 0) c += S;
+	while (c >= S) c -= S;
+	return c;
+}
+
+// frame, wrapped tip and region of the chain's next proposal; depends only on the chain state
+__device__ __forceinline__ void prepare_chain(const Geom& g, const ChainState& cs, Frame& f, RegionPlan& rp)
+{
+	cone_frame(cs.last, cs.pen, f);
+	double vl[3];
+	to_frac(g, cs.last, vl);
+	rp.ncell = 1;
+#pragma unroll
+	for (int k = 0; k < 3; k++) {
+		const double lw = vl[k] * g.L[k];
+		// cell-space bounds of the cone circle +- reach, in fp32 with a margin that dominates the rounding (conservative)
+		const float cenc = (float)((lw + g.dCosPhi * f.Z[k]) * g.ainv[k]);
+		const float w = 1.0f - (float)f.Z[k] * (float)f.Z[k];
+		const float ec = ((float)g.dSinPhi * sqrtf(w > 0.f ? w : 0.f) + (float)g.regionReach) * (float)g.ainv[k] + 1e-3f + 4e-7f * fabsf(cenc);
+		rp.lo[k] = (int)floorf(cenc - ec);
+		rp.nn[k] = (int)floorf(cenc + ec) - rp.lo[k] + 1;
+		rp.ncell *= rp.nn[k];
+		rp.base[k] = (float)((double)rp.lo[k] * g.a[k] - lw);
+	}
+}
+
+// one lane per x-row: bulk-copy its nn0 cells (split in two when the row crosses the periodic boundary)
+__device__ __forceinline__ void region_issue_tma(const Geom& g, const Tables& T, const RegionPlan& rp, Cell* raw, void* mbar, int lane)
+{
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of `raw` are done before the async writes
+	if (lane == 0) mbar_expect_tx(mbar, (unsigned)rp.ncell * (unsigned)sizeof(Cell));
+	__syncwarp();
+	const int rows = rp.nn[1] * rp.nn[2];
+	if (lane < rows) {
+		const int iz = lane / rp.nn[1], iy = lane - iz * rp.nn[1];
+		const int wy = wrap_near(rp.lo[1] + iy, g.S[1]), wz = wrap_near(rp.lo[2] + iz, g.S[2]);
+		Cell* dst = raw + lane * rp.nn[0];
+		int ix = 0;
+		while (ix < rp.nn[0]) {   // contiguous run in x up to the periodic boundary
+			const int wx = wrap_near(rp.lo[0] + ix, g.S[0]);
+			int run = rp.nn[0] - ix; if (run > g.S[0] - wx) run = g.S[0] - wx;
+			tma_load_1d(dst + ix, T.cells + cell_index(g, wx, wy, wz), (unsigned)run * (unsigned)sizeof(Cell), mbar);
+			ix += run;
+		}
+	}
+}
+
+// compaction of the staged cells into the warp's neighbour list, positions relative to the (wrapped) last bead
+__device__ __forceinline__ int region_consume(const Geom& g, const RegionPlan& rp, const Cell* raw, uint32_t idLimit, uint32_t ignoreId,
+	float4* nb, int lane, bool& regionOvf)
+{
+	const float inv0 = 1.0f / (float)rp.nn[0], inv1 = 1.0f / (float)rp.nn[1];
+	uint32_t cnt[2] = { 0, 0 }; float sh[2][3]; bool ovf = false;
+#pragma unroll
+	for (int q = 0; q < 2; q++) {
+		const int ci = lane + 32 * q;
+		sh[q][0] = sh[q][1] = sh[q][2] = 0.f;
+		if (ci < rp.ncell) {
+			const uint2 hdr = *reinterpret_cast<const uint2*>(raw + ci);
+			cnt[q] = hdr.x + 1u; if (cnt[q] > (uint32_t)g.cap) cnt[q] = (uint32_t)g.cap;
+			ovf |= (hdr.y != ID_NONE);
+			const int rest = (int)(((float)ci + 0.5f) * inv0), ix = ci - rest * rp.nn[0];
+			const int iz = (int)(((float)rest + 0.5f) * inv1), iy = rest - iz * rp.nn[1];
+			sh[q][0] = rp.base[0] + (float)ix * (float)g.a[0]; sh[q][1] = rp.base[1] + (float)iy * (float)g.a[1]; sh[q][2] = rp.base[2] + (float)iz * (float)g.a[2];
+		}
+	}
+	const uint32_t mine = cnt[0] + cnt[1];                 // <= 14
+	const unsigned lt = (1u << lane) - 1u;
+	uint32_t excl = 0, total = 0;
+#pragma unroll
+	for (int b = 0; b < 4; b++) { const unsigned m = __ballot_sync(FULL, (mine >> b) & 1u); excl += (uint32_t)__popc(m & lt) << b; total += (uint32_t)__popc(m) << b; }
+	regionOvf = __any_sync(FULL, ovf);
+	if (total > (uint32_t)NBMAX) return -1;
+	uint32_t at = excl;
+#pragma unroll
+	for (int q = 0; q < 2; q++)
+		for (uint32_t k = 0; k < cnt[q]; ++k) {
+			const float4 b = raw[lane + 32 * q].slot[k];
+			const uint32_t id = __float_as_uint(b.w);
+			nb[at++] = (id >= idLimit || id == ignoreId) ? make_float4(1e30f, 1e30f, 1e30f, __uint_as_float(ID_NONE))
+				: make_float4(sh[q][0] + b.x, sh[q][1] + b.y, sh[q][2] + b.z, b.w);
+		}
+	__syncwarp();
+	return (int)total;
+}
+
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1) grow_cluster_kernel(GrowArgs A)
 {
-	extern __shared__ __align__(16) unsigned char clSmem[];
-	float4* nbAll = reinterpret_cast<float4*>(clSmem);
+	extern __shared__ __align__(128) unsigned char clSmem[];
+	Cell* rawAll = reinterpret_cast<Cell*>(clSmem);
+	float4* nbAll = reinterpret_cast<float4*>(rawAll + WARPS * CL_REGION_CELLS);
 	float4* arcAll = nbAll + WARPS * NBMAX;
 	TentRec* table = reinterpret_cast<TentRec*>(arcAll + WARPS * CL_NARC);
-	volatile uint32_t* dirtyWord = reinterpret_cast<volatile uint32_t*>(table + 2 * CL_MAXCH);
+	unsigned long long* mbarAll = reinterpret_cast<unsigned long long*>(table + 2 * CL_MAXCH);
+	volatile uint32_t* dirtyWord = reinterpret_cast<volatile uint32_t*>(mbarAll + WARPS);
 
 	cgx::cluster_group cluster = cgx::this_cluster();
 	const Geom& g = A.g;
@@ -119,13 +234,22 @@ __global__ void __launch_bounds__(WARPS * 32, 1) grow_cluster_kernel(GrowArgs A)
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const uint32_t i = myCta * WARPS + warp;            // the chain this warp owns for the whole launch
 	const bool owner = i < g.nChains;
+	Cell* raw = rawAll + warp * CL_REGION_CELLS;
 	float4* nb = nbAll + warp * NBMAX;
 	float4* arcs = arcAll + warp * CL_NARC;
+	void* mbar = mbarAll + warp;
 	const uint32_t T_ = (uint32_t)g.maxTrials;
 
 	if (threadIdx.x == 0) { dirtyWord[0] = 0; dirtyWord[1] = 0; }
+	if (lane == 0) mbar_init(mbar, 1);
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	ChainState cs;
 	if (owner) cs = load_chain(A.chains + i); else memset(&cs, 0, sizeof cs);
+	Frame f; RegionPlan rp;
+	memset(&f, 0, sizeof f); memset(&rp, 0, sizeof rp);
+	if (owner && cs.lastId != ID_NONE) prepare_chain(g, cs, f, rp);
+	bool hard = false;                                   // no trial among the first 32 passed last round: go straight to the arcs
+	unsigned tmaParity = 0;
 	cluster_arrive(); cluster_wait();                    // every CTA is running and its shared memory is initialised
 
 	uint32_t round = __ldcg(&A.ctl->round);
@@ -134,97 +258,181 @@ __global__ void __launch_bounds__(WARPS * 32, 1) grow_cluster_kernel(GrowArgs A)
 	unsigned long long myTrials = 0, myQueries = 0;
 	const bool timer = (myCta == 0 && threadIdx.x == 0);
 	long long cycA = 0, cycV = 0, cycC = 0; uint32_t cleanRounds = 0;
+	long long sub[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }, ts0 = 0, ts1 = 0;
+#define SUBT(k) do { ts1 = clock64(); sub[k] += ts1 - ts0; ts0 = ts1; } while (0)
 
 	while (round < A.roundEnd && (long long)nBeads < g.target && lastProg) {
 		const long long tk0 = clock64();
+		ts0 = tk0;
 		uint32_t start, end;
 		round_range(g, nBeads, start, end);
 		const uint32_t idRound = round_id_base(g, round);
 		const int par = (int)(round & 1u);
 		const bool active = owner && i >= start && i < end;
 
-		// ---------------- phase A: stage, classify, evaluate — no global writes
+		// ---------------- phase A: no global writes
 		uint32_t accepted = 0; double cand[3] = { 0, 0, 0 };
-		int64_t stagedCell[2] = { -1, -1 }; uint32_t stagedCnt[2] = { 0, 0 };   // cells this lane staged (for the slot computation)
 		TentRec rec; rec.x = rec.y = rec.z = 0; rec.trial = 0; rec.cx = rec.cy = rec.cz = 0;
+		float offs[3] = { 0, 0, 0 };                       // in-cell offset of the accepted bead (for the slot store)
+		double vAcc[3] = { 0, 0, 0 };                     // its fractional coordinates
+		uint32_t oldCount = 0xFFFFFFFFu;                   // beads its cell held at round start (from the staged copy)
 		if (active && (cs.flags & CHAIN_DEAD)) rec.trial = T_ + 1u;
 		else if (active) {
-			Frame f; cone_frame(cs.last, cs.pen, f);
-			double lw[3];
-			{ double vl[3]; to_frac(g, cs.last, vl); for (int k = 0; k < 3; k++) lw[k] = vl[k] * g.L[k]; }
-			bool regionOvf = false;
-			const int nnb = stage_region(g, A.T, lw, f, idRound, cs.lastId, nb, lane, regionOvf, stagedCell, stagedCnt);
-			const int narcs = nnb >= 0 ? build_arcs_cs(g, f, nb, nnb, arcs, lane) : -1;
+			bool regionOvf = false; int nnb = -1; int narcs = -1;
+			const bool canStage = rp.ncell <= CL_REGION_CELLS;
+			if (canStage) region_issue_tma(g, A.T, rp, raw, mbar, lane);   // bulk copies in flight ...
+			// ... while every lane prepares the exact candidate of trial lane+1 (reference arithmetic)
+			double candL[3], vL[3]; bool okL = false; float rel[3] = { 0, 0, 0 };
+			if (!hard) {
+				const uint4 w = philox4x32_10(make_uint4(i, round, (uint32_t)lane >> 2, 0u), g.key0, g.key1);
+				cone_candidate(g, f, cs.last, (double)pick(w, (uint32_t)lane & 3u) * (1.0 / 4294967296.0), candL);
+				okL = (uint32_t)lane < T_ && !growth_rules_reject(g, candL, cs.last);
+				to_frac(g, candL, vL);
+				rel[0] = (float)(candL[0] - cs.last[0]); rel[1] = (float)(candL[1] - cs.last[1]); rel[2] = (float)(candL[2] - cs.last[2]);
+			}
+			SUBT(0);
+			if (canStage) {
+				mbar_wait(mbar, tmaParity); tmaParity ^= 1u;
+				nnb = region_consume(g, rp, raw, idRound, cs.lastId, nb, lane, regionOvf);
+			} else regionOvf = true;
 			const uint32_t novf = regionOvf ? __ldcg(A.T.ovfCount) : 0u;
-			for (uint32_t base = 0; base < T_ && !accepted; base += 128) {
-				const uint32_t blk = (base >> 2) + lane;
-				const uint4 w = philox4x32_10(make_uint4(i, round, blk, 0u), g.key0, g.key1);
-				const uint32_t wj[4] = { w.x, w.y, w.z, w.w };
-				unsigned cm[4];
-#pragma unroll
-				for (int j = 0; j < 4; ++j) {
-					const uint32_t t = base + 4 * lane + j + 1;
-					bool candidate = t <= T_;
-					if (candidate && narcs > 0) {
-						const float theta = (float)wj[j] * (float)(359.0 * 3.14159265358979323846 / 180 / 4294967296.0);
-						float s, c;
-						__sincosf(theta - 3.14159265358979323846f, &s, &c);   // |arg| <= pi: fast intrinsic is accurate to ~1e-6
-						s = -s; c = -c;
-						for (int a = 0; a < narcs; ++a) {
-							const float4 arc = arcs[a];
-							if (arc.x * c + arc.y * s >= arc.z) { candidate = false; break; }
+			SUBT(1);
+			if (!hard) {
+				// fast path: lane-per-trial exact test of trials 1..32 against the staged neighbourhood
+				if (okL) {
+					if (nnb >= 0) {
+						for (int j = 0; j < nnb; ++j) {
+							const float4 b = nb[j];
+							const float dx = rel[0] - b.x, dy = rel[1] - b.y, dz = rel[2] - b.z;
+							const float d2 = dx * dx + dy * dy + dz * dz;
+							if (d2 < g.lo2) { okL = false; break; }
+							if (d2 <= g.hi2 && exact_pair(g, vL, A.T.lpos + 3 * (size_t)__float_as_uint(b.w))) { okL = false; break; }
 						}
-					}
-					cm[j] = __ballot_sync(FULL, candidate);
+						if (okL && novf) {
+							const uint32_t m = novf > A.T.ovfCap ? A.T.ovfCap : novf;
+							for (uint32_t j = 0; j < m && okL; ++j) {
+								const uint32_t id = __ldcg(A.T.ovf + j);
+								if (id < idRound && id != cs.lastId && exact_pair(g, vL, A.T.lpos + 3 * (size_t)id)) okL = false;
+							}
+						}
+					} else okL = !probe_cells<1>(g, A.T, vL, 0u, idRound, cs.lastId, 0);
 				}
-				unsigned any = cm[0] | cm[1] | cm[2] | cm[3];
-				while (any) {   // candidates in increasing trial order
-					const int l = __ffs(any) - 1;
-					int j = 0;
-#pragma unroll
-					for (int jj = 3; jj >= 0; --jj) if ((cm[jj] >> l) & 1u) j = jj;
-					const uint32_t word = __shfl_sync(FULL, wj[0], l) * (j == 0) + __shfl_sync(FULL, wj[1], l) * (j == 1)
-						+ __shfl_sync(FULL, wj[2], l) * (j == 2) + __shfl_sync(FULL, wj[3], l) * (j == 3);
-					myQueries += (lane == 0);
-					if (eval_trial_coop(g, A.T, f, cs, (double)word * (1.0 / 4294967296.0), nb, nnb, idRound, novf, lane, cand)) {
-						accepted = base + 4 * l + j + 1;
-						break;
-					}
-#pragma unroll
-					for (int jj = 0; jj < 4; ++jj) if (jj == j) cm[jj] &= ~(1u << l);
-					any = cm[0] | cm[1] | cm[2] | cm[3];
+				const unsigned m = __ballot_sync(FULL, okL);
+				myQueries += (lane == 0) ? (T_ < 32u ? T_ : 32u) : 0u;
+				if (m) {
+					const int first = __ffs(m) - 1;
+					accepted = (uint32_t)first + 1u;
+					for (int k = 0; k < 3; k++) { cand[k] = __shfl_sync(FULL, candL[k], first); vAcc[k] = __shfl_sync(FULL, vL[k], first); }
 				}
 			}
-			if (!accepted && narcs > 0 && arcs_cs_cover_circle(arcs, narcs, lane)) {
-				cs.flags |= CHAIN_DEAD;
-				if (lane == 0) { A.chains[i].flags = cs.flags; atomicAdd(&A.ctl->deadChains, 1u); }
+			SUBT(2);
+			if (!accepted && T_ > (hard ? 0u : 32u)) {
+				// hard chain: blocked-arc classification of the remaining trials, exact evaluation of the survivors
+				narcs = nnb >= 0 ? build_arcs_cs(g, f, nb, nnb, arcs, lane) : -1;
+				const uint32_t skip = hard ? 0u : 32u;          // trials <= skip were just evaluated exactly and failed
+				for (uint32_t base = 0; base < T_ && !accepted; base += 128) {
+					const uint32_t blk = (base >> 2) + lane;
+					const uint4 w = philox4x32_10(make_uint4(i, round, blk, 0u), g.key0, g.key1);
+					const uint32_t wj[4] = { w.x, w.y, w.z, w.w };
+					unsigned cm[4];
+#pragma unroll
+					for (int j = 0; j < 4; ++j) {
+						const uint32_t t = base + 4 * lane + j + 1;
+						bool candidate = t <= T_ && t > skip;
+						if (candidate && narcs > 0) {
+							const float theta = (float)wj[j] * (float)(359.0 * 3.14159265358979323846 / 180 / 4294967296.0);
+							float s, c;
+							__sincosf(theta - 3.14159265358979323846f, &s, &c);   // |arg| <= pi: fast intrinsic is accurate to ~1e-6
+							s = -s; c = -c;
+							for (int a = 0; a < narcs; ++a) {
+								const float4 arc = arcs[a];
+								if (arc.x * c + arc.y * s >= arc.z) { candidate = false; break; }
+							}
+						}
+						cm[j] = __ballot_sync(FULL, candidate);
+					}
+					unsigned any = cm[0] | cm[1] | cm[2] | cm[3];
+					while (any) {   // candidates in increasing trial order
+						const int l = __ffs(any) - 1;
+						int j = 0;
+#pragma unroll
+						for (int jj = 3; jj >= 0; --jj) if ((cm[jj] >> l) & 1u) j = jj;
+						const uint32_t word = __shfl_sync(FULL, wj[0], l) * (j == 0) + __shfl_sync(FULL, wj[1], l) * (j == 1)
+							+ __shfl_sync(FULL, wj[2], l) * (j == 2) + __shfl_sync(FULL, wj[3], l) * (j == 3);
+						myQueries += (lane == 0);
+						if (eval_trial_coop(g, A.T, f, cs, (double)word * (1.0 / 4294967296.0), nb, nnb, idRound, novf, lane, cand)) {
+							accepted = base + 4 * l + j + 1;
+							to_frac(g, cand, vAcc);
+							break;
+						}
+#pragma unroll
+						for (int jj = 0; jj < 4; ++jj) if (jj == j) cm[jj] &= ~(1u << l);
+						any = cm[0] | cm[1] | cm[2] | cm[3];
+					}
+				}
+				if (!accepted && narcs > 0 && arcs_cs_cover_circle(arcs, narcs, lane)) {
+					cs.flags |= CHAIN_DEAD;
+					if (lane == 0) { A.chains[i].flags = cs.flags; atomicAdd(&A.ctl->deadChains, 1u); }
+				}
 			}
+			hard = accepted == 0u || accepted > 32u;
 			rec.trial = accepted ? accepted : T_ + 1u;
 			if (accepted) {
-				double v[3];
-				to_frac(g, cand, v);
 				rec.x = cand[0]; rec.y = cand[1]; rec.z = cand[2];
+				int cc[3];
 #pragma unroll
 				for (int k = 0; k < 3; k++) {
-					int ci = (int)floor(v[k] * g.sOverL[k]);
+					const double s = vAcc[k] * g.sOverL[k];
+					int ci = (int)floor(s);
 					if (ci >= g.S[k]) ci = g.S[k] - 1;
 					if (ci < 0) ci = 0;
-					(k == 0 ? rec.cx : (k == 1 ? rec.cy : rec.cz)) = ci;
+					cc[k] = ci; offs[k] = (float)((s - (double)ci) * g.a[k]);
+				}
+				rec.cx = cc[0]; rec.cy = cc[1]; rec.cz = cc[2];
+				if (canStage) {   // count of the bead's cell at round start: find the cell in the staged copy (wrapped coordinates match)
+					uint32_t mine = 0xFFFFFFFFu;
+					const float inv0 = 1.0f / (float)rp.nn[0], inv1 = 1.0f / (float)rp.nn[1];
+#pragma unroll
+					for (int q = 0; q < 2; q++) {
+						const int ci = lane + 32 * q;
+						if (ci < rp.ncell) {
+							const int rest = (int)(((float)ci + 0.5f) * inv0), ix = ci - rest * rp.nn[0];
+							const int iz = (int)(((float)rest + 0.5f) * inv1), iy = rest - iz * rp.nn[1];
+							if (wrap_near(rp.lo[0] + ix, g.S[0]) == cc[0] && wrap_near(rp.lo[1] + iy, g.S[1]) == cc[1] && wrap_near(rp.lo[2] + iz, g.S[2]) == cc[2]) {
+								uint32_t c0 = raw[ci].countMinus1 + 1u; if (c0 > (uint32_t)g.cap) c0 = (uint32_t)g.cap;
+								mine = c0;
+							}
+						}
+					}
+					const unsigned bm = __ballot_sync(FULL, mine != 0xFFFFFFFFu);
+					if (bm) oldCount = __shfl_sync(FULL, mine, __ffs(bm) - 1);
 				}
 			}
+			SUBT(3);
 		}
 		// broadcast the record into every CTA's table (distributed shared memory)
 		if (owner)
 			for (unsigned c = lane; c < nCta; c += 32) *cluster.map_shared_rank(&table[par * CL_MAXCH + i], c) = rec;
-		cluster_arrive(); cluster_wait();
+		SUBT(4);
+		cluster_arrive();
+		// in the shadow of the barrier: next round's chain state, frame and region, assuming the tentative bead stands (it almost
+		// always does). The old state is recoverable: old last = new pen, old lastId = new penId; only the old pen is kept aside.
+		double oldPen[3] = { cs.pen[0], cs.pen[1], cs.pen[2] }; const uint32_t oldPenId = cs.penId;
+		const bool advanced = active && accepted;
+		if (advanced) {
+			for (int k = 0; k < 3; k++) { cs.pen[k] = cs.last[k]; cs.last[k] = cand[k]; }
+			cs.penId = cs.lastId; cs.lastId = idRound + i; cs.length += 1;
+			prepare_chain(g, cs, f, rp);
+		}
+		SUBT(5);
+		cluster_wait();
+		SUBT(6);
 		if (threadIdx.x == 0) dirtyWord[par ^ 1] = 0;    // last round's flag has been read by every warp of this CTA
 		const long long tk1 = clock64();
 
 		// ---------------- phase V from the local table: round totals, conflicts with lower chains, slot rank
 		uint32_t acc = 0, prog = 0, rank = 0, tot = 0; bool conflict = false;
 		{
-			double vi[3] = { 0, 0, 0 };
-			if (accepted) to_frac(g, cand, vi);
 			for (uint32_t jb = start; jb < end; jb += 32) {
 				const uint32_t j = jb + lane;
 				if (j >= end) continue;
@@ -236,48 +444,37 @@ __global__ void __launch_bounds__(WARPS * 32, 1) grow_cluster_kernel(GrowArgs A)
 				if (dx == 0 && dy == 0 && dz == 0) { tot++; rank += (j < i); }
 				if (j < i) {   // only beads in the same or an adjacent cell (periodic) can be within thresh
 					dx = min(dx, g.S[0] - dx); dy = min(dy, g.S[1] - dy); dz = min(dz, g.S[2] - dz);
-					if (dx <= 1 && dy <= 1 && dz <= 1) { const double pj[3] = { r.x, r.y, r.z }; conflict = conflict || exact_pair_reg(g, vi, pj); }
+					if (dx <= 1 && dy <= 1 && dz <= 1) { const double pj[3] = { r.x, r.y, r.z }; conflict = conflict || exact_pair_reg(g, vAcc, pj); }
 				}
 			}
-#pragma unroll
-			for (int d = 16; d > 0; d >>= 1) {
-				acc += __shfl_xor_sync(FULL, acc, d); prog += __shfl_xor_sync(FULL, prog, d);
-				rank += __shfl_xor_sync(FULL, rank, d); tot += __shfl_xor_sync(FULL, tot, d);
-			}
+			// one hardware warp reduction over packed counters (each <= 256 chains: 10 bits are plenty)
+			const unsigned packed = __reduce_add_sync(FULL, acc | (prog << 10) | (rank << 20));
+			acc = packed & 1023u; prog = (packed >> 10) & 1023u; rank = packed >> 20;
+			tot = __reduce_add_sync(FULL, tot);
 			conflict = __any_sync(FULL, conflict);
 		}
 		// ---------------- insert with plain stores: slot = count seen while staging + rank among this round's beads of the cell
 		if (active) {
-			if (accepted) {
+			if (accepted && lane == 0) {
 				const uint32_t id = idRound + i;
-				const int64_t cellIdx = cell_index(g, rec.cx, rec.cy, rec.cz);
-				uint32_t old = 0xFFFFFFFFu;
-				{	// the bead's cell is inside the staged region: take its count from the lane that staged it
-					const bool m0 = stagedCell[0] == cellIdx, m1 = stagedCell[1] == cellIdx;
-					const unsigned bm = __ballot_sync(FULL, m0 || m1);
-					if (bm) { const int src = __ffs(bm) - 1; const uint32_t mine = m0 ? stagedCnt[0] : stagedCnt[1]; old = __shfl_sync(FULL, mine, src); }
-				}
-				if (lane == 0) {
-					Cell* cell = A.T.cells + cellIdx;
-					if (old == 0xFFFFFFFFu) { old = __ldcg(&cell->countMinus1) + 1u; if (old > (uint32_t)g.cap) old = (uint32_t)g.cap; }
-					double* lp = A.T.lpos + 3 * (size_t)id;
-					lp[0] = cand[0]; lp[1] = cand[1]; lp[2] = cand[2];
-					const uint32_t slot = old + rank;
-					if (slot < (uint32_t)g.cap) {
-						double v[3]; float o[3];
-						to_frac(g, cand, v); bead_cell(g, v, o);
-						__stcg(&cell->slot[slot], make_float4(o[0], o[1], o[2], __uint_as_float(id)));
-						if (rank == 0) {   // one writer per cell: the new count of this round
-							uint32_t nc = old + tot + 1u; if (nc > (uint32_t)g.cap) nc = (uint32_t)g.cap;
-							cell->countMinus1 = nc - 1u;
-						}
-					} else {           // cell full: overflow list (rare); the header count is written by the rank-0 bead, if it fits
-						atomicExch(&cell->ovfFlagInv, 0u);
-						const uint32_t at = atomicAdd(A.T.ovfCount, 1u);
-						if (at < A.T.ovfCap) A.T.ovf[at] = id;
+				Cell* cell = A.T.cells + cell_index(g, rec.cx, rec.cy, rec.cz);
+				uint32_t old = oldCount;
+				if (old == 0xFFFFFFFFu) { old = __ldcg(&cell->countMinus1) + 1u; if (old > (uint32_t)g.cap) old = (uint32_t)g.cap; }
+				double* lp = A.T.lpos + 3 * (size_t)id;
+				lp[0] = cand[0]; lp[1] = cand[1]; lp[2] = cand[2];
+				const uint32_t slot = old + rank;
+				if (slot < (uint32_t)g.cap) {
+					__stcg(&cell->slot[slot], make_float4(offs[0], offs[1], offs[2], __uint_as_float(id)));
+					if (rank == 0) {   // one writer per cell: the new count of this round
+						uint32_t nc = old + tot + 1u; if (nc > (uint32_t)g.cap) nc = (uint32_t)g.cap;
+						cell->countMinus1 = nc - 1u;
 					}
-					for (int k = 0; k < 3; k++) A.resPos[3 * (size_t)i + k] = cand[k];
+				} else {           // cell full: overflow list (rare); the header count is written by the rank-0 bead, if it fits
+					atomicExch(&cell->ovfFlagInv, 0u);
+					const uint32_t at = atomicAdd(A.T.ovfCount, 1u);
+					if (at < A.T.ovfCap) A.T.ovf[at] = id;
 				}
+				for (int k = 0; k < 3; k++) A.resPos[3 * (size_t)i + k] = cand[k];
 			}
 			if (lane == 0) {
 				A.resTrial[i] = rec.trial;
@@ -293,35 +490,47 @@ __global__ void __launch_bounds__(WARPS * 32, 1) grow_cluster_kernel(GrowArgs A)
 
 		// ---------------- clean-up (rare): the shared serial path through global memory
 		if (dirtyWord[par] != 0u) {
+			// the clean-up reads chain states from global memory as of round start: they are (commits happen below)
 			if (i == 0) cleanup_round(A, round, lane);
 			cluster_arrive(); cluster_wait();
 			cleanRounds++;
 			if (active) {
 				const uint32_t t = __ldcg(&A.resTrial[i]);
-				accepted = (t >= 1u && t <= T_) ? t : 0u;
-				if (accepted) for (int k = 0; k < 3; k++) cand[k] = __ldcg(&A.resPos[3 * (size_t)i + k]);
+				const uint32_t nowAcc = (t >= 1u && t <= T_) ? t : 0u;
+				double np[3] = { 0, 0, 0 };
+				if (nowAcc) for (int k = 0; k < 3; k++) np[k] = __ldcg(&A.resPos[3 * (size_t)i + k]);
+				const bool same = (nowAcc != 0u) == advanced && (!nowAcc || (np[0] == cand[0] && np[1] == cand[1] && np[2] == cand[2]));
+				if (!same) {   // roll the speculative state back to round start, then apply what the clean-up decided
+					if (advanced) {
+						for (int k = 0; k < 3; k++) { cs.last[k] = cs.pen[k]; cs.pen[k] = oldPen[k]; }
+						cs.lastId = cs.penId; cs.penId = oldPenId; cs.length -= 1;
+					}
+					if (nowAcc) {
+						for (int k = 0; k < 3; k++) { cs.pen[k] = cs.last[k]; cs.last[k] = np[k]; }
+						cs.penId = cs.lastId; cs.lastId = idRound + i; cs.length += 1;
+					}
+					prepare_chain(g, cs, f, rp);
+				}
+				accepted = nowAcc;
+				hard = hard || accepted == 0u;
 			}
 			acc = __ldcg(&A.roundAcc[round]); prog = __ldcg(&A.roundProg[round]);
 		}
-		// ---------------- commit into the register-resident chain state (sarw.cpp:270-273)
-		if (active) {
-			if (accepted) {
-				const uint32_t id = idRound + i;
-				if (lane == 0) A.prev[id - g.idAtomBase] = cs.lastId;
-				for (int k = 0; k < 3; k++) { cs.pen[k] = cs.last[k]; cs.last[k] = cand[k]; }
-				cs.penId = cs.lastId; cs.lastId = id; cs.length += 1;
-				if (lane == 0) A.chains[i] = cs;
-			}
-			if (lane == 0) A.resTrial[i] = 0;
+		// ---------------- publish the committed chain state (sarw.cpp:270-273)
+		if (active && lane == 0) {
+			if (accepted) { A.prev[idRound + i - g.idAtomBase] = cs.penId; A.chains[i] = cs; }
+			A.resTrial[i] = 0;
 		}
 		nBeads += acc; lastProg = prog != 0u; round++;
 		cycA += tk1 - tk0; cycV += tk2 - tk1; cycC += clock64() - tk2;
 	}
+#undef SUBT
 	if (lane == 0) {
 		if (myTrials) atomicAdd(&A.ctl->trials, myTrials);
 		if (myQueries) atomicAdd(&A.ctl->queries, myQueries);
 	}
 	if (i == 0 && lane == 0) { A.ctl->round = round; A.ctl->nBeads = nBeads; A.ctl->lastProgressed = lastProg ? 1u : 0u; }
+	if (timer) for (int k = 0; k < 8; k++) A.ctl->cycSub[k] += sub[k];
 	if (timer) { A.ctl->cycPropose += cycA; A.ctl->cycVerify += cycV; A.ctl->cycCleanup += cycC; A.ctl->cleanupRounds += cleanRounds; }
 	cluster_arrive(); cluster_wait();                    // no CTA may exit while others can still write into its shared memory
 }

@@ -824,8 +824,10 @@ cudaError_t grow_max_blocks(int numSMs, int* maxBlocks)
 {
 	int perSM = 0;
 	CK(cudaFuncSetAttribute(grow_kernel<GROW_WARPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grow_smem_bytes(GROW_WARPS)));
-	CK(cudaFuncSetAttribute(grow_cluster_kernel<CL_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cluster_smem_bytes()));
-	CK(cudaFuncSetAttribute(grow_cluster_kernel<CL_WARPS>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+	CK(cudaFuncSetAttribute(grow_cluster_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cluster_smem_bytes(8)));
+	CK(cudaFuncSetAttribute(grow_cluster_kernel<8>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+	CK(cudaFuncSetAttribute(grow_cluster_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cluster_smem_bytes(16)));
+	CK(cudaFuncSetAttribute(grow_cluster_kernel<16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
 	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, grow_kernel<GROW_WARPS, false>, GROW_WARPS * 32, grow_smem_bytes(GROW_WARPS)));
 	*maxBlocks = perSM * numSMs;
 	return cudaSuccess;
@@ -834,23 +836,30 @@ cudaError_t grow_max_blocks(int numSMs, int* maxBlocks)
 // largest chain count the single-cluster kernel covers (one chain per warp)
 int grow_cluster_max_chains() { return CL_MAXCH; }
 
+template <int WARPS>
+static cudaError_t launch_cluster(const GrowArgs& A, cudaStream_t st)
+{
+	int ctas = (int)((A.g.nChains + WARPS - 1) / WARPS);
+	if (ctas < 1) ctas = 1;
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3((unsigned)ctas); cfg.blockDim = dim3(WARPS * 32);
+	cfg.dynamicSmemBytes = cluster_smem_bytes(WARPS); cfg.stream = st;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeClusterDimension;
+	attr[0].val.clusterDim.x = (unsigned)ctas; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+	cfg.attrs = attr; cfg.numAttrs = 1;
+	return cudaLaunchKernelEx(&cfg, grow_cluster_kernel<WARPS>, A);
+}
+
 cudaError_t launch_grow(const Geom& g, const Tables& T, ChainState* chains, uint32_t* resTrial, double* resPos, uint32_t* prev, Control* ctl,
 	uint32_t* roundAcc, uint32_t* roundProg, uint32_t* dirtyCount, uint32_t* dirtyList, uint32_t roundEnd, int blocks, int useCluster, cudaStream_t st)
 {
 	GrowArgs A{ g, T, chains, resTrial, resPos, prev, ctl, roundAcc, roundProg, dirtyCount, dirtyList, roundEnd };
 	if (useCluster) {
 		// the whole launch is one thread-block cluster: CTAs are co-scheduled by the hardware, synchronise with
-		// barrier.cluster and exchange tentative beads through distributed shared memory
-		int ctas = (int)((g.nChains + CL_WARPS - 1) / CL_WARPS);
-		if (ctas < 1) ctas = 1;
-		cudaLaunchConfig_t cfg = {};
-		cfg.gridDim = dim3((unsigned)ctas); cfg.blockDim = dim3(CL_WARPS * 32);
-		cfg.dynamicSmemBytes = cluster_smem_bytes(); cfg.stream = st;
-		cudaLaunchAttribute attr[1];
-		attr[0].id = cudaLaunchAttributeClusterDimension;
-		attr[0].val.clusterDim.x = (unsigned)ctas; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-		cfg.attrs = attr; cfg.numAttrs = 1;
-		return cudaLaunchKernelEx(&cfg, grow_cluster_kernel<CL_WARPS>, A);
+		// barrier.cluster and exchange tentative beads through distributed shared memory. 8 warps per CTA (255
+		// registers per thread) up to 128 chains, 16 warps per CTA beyond.
+		return g.nChains <= 8u * CL_MAX_CTAS ? launch_cluster<8>(A, st) : launch_cluster<16>(A, st);
 	}
 	void* args[] = { &A };
 	return cudaLaunchCooperativeKernel((const void*)grow_kernel<GROW_WARPS, false>, dim3((unsigned)blocks), dim3(GROW_WARPS * 32), args,
