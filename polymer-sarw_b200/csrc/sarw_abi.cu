@@ -141,6 +141,15 @@ void fill_stats(sarw_ctx* c, const Control& h, sarw_stats* s)
 
 extern "C" {
 
+// diagnostics (not part of the public header): per-warp busy cycles of the cluster kernel
+int sarw_debug_busy(sarw_ctx* c, unsigned long long* out, int n)
+{
+	if (!c || !out) return 1;
+	Control h; if (read_control(c, &h)) return 1;
+	for (int k = 0; k < n && k < 256; k++) out[k] = h.busy[k];
+	return 0;
+}
+
 int64_t sarw_target_count(const double boxSize[3], double targetMassDensity)
 {
 	// sarw.h:103-104: int vol() truncates; kept, but in 64 bits

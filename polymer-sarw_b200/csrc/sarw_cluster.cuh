@@ -160,12 +160,13 @@ __device__ __forceinline__ void prepare_chain(const Geom& g, const ChainState& c
 // one lane per x-row: bulk-copy its nn0 cells (split in two when the row crosses the periodic boundary)
 __device__ __forceinline__ void region_issue_tma(const Geom& g, const Tables& T, const RegionPlan& rp, Cell* raw, void* mbar, int lane)
 {
-	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of `raw` are done before the async writes
+	// (the generic-proxy reads of `raw` from the previous round completed long ago: their results were consumed and two
+	// cluster barriers lie in between, so the async-proxy writes issued here cannot overtake them)
 	if (lane == 0) mbar_expect_tx(mbar, (unsigned)rp.ncell * (unsigned)sizeof(Cell));
 	__syncwarp();
 	const int rows = rp.nn[1] * rp.nn[2];
 	if (lane < rows) {
-		const int iz = lane / rp.nn[1], iy = lane - iz * rp.nn[1];
+		const int iz = (int)(((float)lane + 0.5f) / (float)rp.nn[1]), iy = lane - iz * rp.nn[1];
 		const int wy = wrap_near(rp.lo[1] + iy, g.S[1]), wz = wrap_near(rp.lo[2] + iz, g.S[2]);
 		Cell* dst = raw + lane * rp.nn[0];
 		int ix = 0;
@@ -176,6 +177,32 @@ __device__ __forceinline__ void region_issue_tma(const Geom& g, const Tables& T,
 			ix += run;
 		}
 	}
+}
+
+// Alternative staging with per-lane 16-byte cp.async (LDGSTS): lane handles cells lane, lane+32 (8 chunks of 16 B each).
+// Kept because the issue cost of bulk copies matters here: 16 row copies issued by 16 lanes measured ~1.7k cycles
+// of issue time per round, against ~0.3k for 16 LDGSTS per lane (profiles/).
+__device__ __forceinline__ void region_issue_ldgsts(const Geom& g, const Tables& T, const RegionPlan& rp, Cell* raw, int lane)
+{
+	const float inv0 = 1.0f / (float)rp.nn[0], inv1 = 1.0f / (float)rp.nn[1];
+#pragma unroll
+	for (int q = 0; q < 2; q++) {
+		const int ci = lane + 32 * q;
+		if (ci < rp.ncell) {
+			const int rest = (int)(((float)ci + 0.5f) * inv0), ix = ci - rest * rp.nn[0];
+			const int iz = (int)(((float)rest + 0.5f) * inv1), iy = rest - iz * rp.nn[1];
+			const Cell* src = T.cells + cell_index(g, wrap_near(rp.lo[0] + ix, g.S[0]), wrap_near(rp.lo[1] + iy, g.S[1]), wrap_near(rp.lo[2] + iz, g.S[2]));
+			const uint32_t dst = smem_u32(raw + ci);
+#pragma unroll
+			for (int k = 0; k < 8; k++)
+				asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + 16u * k), "l"(reinterpret_cast<const char*>(src) + 16 * k) : "memory");
+		}
+	}
+	asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void region_wait_ldgsts()
+{	asm volatile("cp.async.wait_group 0;" ::: "memory");
+	__syncwarp();
 }
 
 // compaction of the staged cells into the warp's neighbour list, positions relative to the (wrapped) last bead
@@ -217,6 +244,134 @@ __device__ __forceinline__ int region_consume(const Geom& g, const RegionPlan& r
 	return (int)total;
 }
 
+// One chain, one round, one warp: returns the accepted trial (1-based) or 0, with the bead in cand / vAcc (fractional).
+// No global writes except marking a chain dead. Fast path: the exact candidates of trials 1..32 are prepared lane-parallel
+// while the region is being staged, then tested lane-per-trial; chains that found nothing there (`hard`) go through the
+// blocked-arc classification of all remaining trials.
+__device__ __forceinline__ uint32_t propose_chain(const Geom& g, const Tables& T, Control* ctl, ChainState* chains, uint32_t i, uint32_t round,
+	uint32_t idRound, ChainState& cs, const Frame& f, const RegionPlan& rp, bool hard, Cell* raw, float4* nb, float4* arcs, void* mbar,
+	unsigned& tmaParity, int lane, double cand[3], double vAcc[3], unsigned long long& queries)
+{
+	const uint32_t T_ = (uint32_t)g.maxTrials;
+	uint32_t accepted = 0;
+	bool regionOvf = false; int nnb = -1; int narcs = -1;
+	const bool canStage = rp.ncell <= CL_REGION_CELLS;
+#ifndef SARW_STAGE_LDGSTS
+	if (canStage) region_issue_tma(g, T, rp, raw, mbar, lane);   // bulk copies in flight ...
+#else
+	if (canStage) region_issue_ldgsts(g, T, rp, raw, lane);      // async copies in flight ...
+#endif
+	// ... while every lane prepares the exact candidate of trial lane+1 (reference arithmetic)
+	double candL[3], vL[3]; bool okL = false; float rel[3] = { 0, 0, 0 };
+	if (!hard) {
+		const uint4 w = philox4x32_10(make_uint4(i, round, (uint32_t)lane >> 2, 0u), g.key0, g.key1);
+		cone_candidate(g, f, cs.last, (double)pick(w, (uint32_t)lane & 3u) * (1.0 / 4294967296.0), candL);
+		okL = (uint32_t)lane < T_ && !growth_rules_reject(g, candL, cs.last);
+		to_frac(g, candL, vL);
+		rel[0] = (float)(candL[0] - cs.last[0]); rel[1] = (float)(candL[1] - cs.last[1]); rel[2] = (float)(candL[2] - cs.last[2]);
+	}
+	if (canStage) {
+#ifndef SARW_STAGE_LDGSTS
+		mbar_wait(mbar, tmaParity); tmaParity ^= 1u;
+#else
+		region_wait_ldgsts();
+#endif
+		nnb = region_consume(g, rp, raw, idRound, cs.lastId, nb, lane, regionOvf);
+	} else regionOvf = true;
+	const uint32_t novf = regionOvf ? __ldcg(T.ovfCount) : 0u;
+	if (!hard) {
+		// fast path: lane-per-trial exact test of trials 1..32 against the staged neighbourhood
+		if (okL) {
+			if (nnb >= 0) {
+				// branch-free pass over the staged beads: smallest squared distance and the bead that attains it
+				float dmin = 3.0e38f; int jmin = -1; int inBand = 0;
+#pragma unroll 4
+				for (int j = 0; j < nnb; ++j) {
+					const float4 b = nb[j];
+					const float dx = rel[0] - b.x, dy = rel[1] - b.y, dz = rel[2] - b.z;
+					const float d2 = dx * dx + dy * dy + dz * dz;
+					inBand += (d2 <= g.hi2);
+					if (d2 < dmin) { dmin = d2; jmin = j; }
+				}
+				if (dmin < g.lo2) okL = false;
+				else if (inBand) {   // some bead within the undecided band (rare): exact reference arithmetic on those
+					for (int j = 0; j < nnb && okL; ++j) {
+						const float4 b = nb[j];
+						const float dx = rel[0] - b.x, dy = rel[1] - b.y, dz = rel[2] - b.z;
+						const float d2 = dx * dx + dy * dy + dz * dz;
+						if (d2 <= g.hi2 && exact_pair(g, vL, T.lpos + 3 * (size_t)__float_as_uint(b.w))) okL = false;
+					}
+				}
+				(void)jmin;
+				if (okL && novf) {
+					const uint32_t m = novf > T.ovfCap ? T.ovfCap : novf;
+					for (uint32_t j = 0; j < m && okL; ++j) {
+						const uint32_t id = __ldcg(T.ovf + j);
+						if (id < idRound && id != cs.lastId && exact_pair(g, vL, T.lpos + 3 * (size_t)id)) okL = false;
+					}
+				}
+			} else okL = !probe_cells<1>(g, T, vL, 0u, idRound, cs.lastId, 0);
+		}
+		const unsigned m = __ballot_sync(FULL, okL);
+		queries += (lane == 0) ? (T_ < 32u ? T_ : 32u) : 0u;
+		if (m) {
+			const int first = __ffs(m) - 1;
+			accepted = (uint32_t)first + 1u;
+			for (int k = 0; k < 3; k++) { cand[k] = __shfl_sync(FULL, candL[k], first); vAcc[k] = __shfl_sync(FULL, vL[k], first); }
+		}
+	}
+	if (!accepted && T_ > (hard ? 0u : 32u)) {
+		// hard chain: blocked-arc classification of the remaining trials, exact evaluation of the survivors
+		narcs = nnb >= 0 ? build_arcs_cs(g, f, nb, nnb, arcs, lane) : -1;
+		const uint32_t skip = hard ? 0u : 32u;          // trials <= skip were just evaluated exactly and failed
+		for (uint32_t base = 0; base < T_ && !accepted; base += 128) {
+			const uint32_t blk = (base >> 2) + lane;
+			const uint4 w = philox4x32_10(make_uint4(i, round, blk, 0u), g.key0, g.key1);
+			const uint32_t wj[4] = { w.x, w.y, w.z, w.w };
+			unsigned cm[4];
+#pragma unroll
+			for (int j = 0; j < 4; ++j) {
+				const uint32_t t = base + 4 * lane + j + 1;
+				bool candidate = t <= T_ && t > skip;
+				if (candidate && narcs > 0) {
+					const float theta = (float)wj[j] * (float)(359.0 * 3.14159265358979323846 / 180 / 4294967296.0);
+					float s, c;
+					__sincosf(theta - 3.14159265358979323846f, &s, &c);   // |arg| <= pi: fast intrinsic is accurate to ~1e-6
+					s = -s; c = -c;
+					for (int a = 0; a < narcs; ++a) {
+						const float4 arc = arcs[a];
+						if (arc.x * c + arc.y * s >= arc.z) { candidate = false; break; }
+					}
+				}
+				cm[j] = __ballot_sync(FULL, candidate);
+			}
+			unsigned any = cm[0] | cm[1] | cm[2] | cm[3];
+			while (any) {   // candidates in increasing trial order
+				const int l = __ffs(any) - 1;
+				int j = 0;
+#pragma unroll
+				for (int jj = 3; jj >= 0; --jj) if ((cm[jj] >> l) & 1u) j = jj;
+				const uint32_t word = __shfl_sync(FULL, wj[0], l) * (j == 0) + __shfl_sync(FULL, wj[1], l) * (j == 1)
+					+ __shfl_sync(FULL, wj[2], l) * (j == 2) + __shfl_sync(FULL, wj[3], l) * (j == 3);
+				queries += (lane == 0);
+				if (eval_trial_coop(g, T, f, cs, (double)word * (1.0 / 4294967296.0), nb, nnb, idRound, novf, lane, cand)) {
+					accepted = base + 4 * l + j + 1;
+					to_frac(g, cand, vAcc);
+					break;
+				}
+#pragma unroll
+				for (int jj = 0; jj < 4; ++jj) if (jj == j) cm[jj] &= ~(1u << l);
+				any = cm[0] | cm[1] | cm[2] | cm[3];
+			}
+		}
+		if (!accepted && narcs > 0 && arcs_cs_cover_circle(arcs, narcs, lane)) {
+			cs.flags |= CHAIN_DEAD;
+			if (lane == 0) { chains[i].flags = cs.flags; atomicAdd(&ctl->deadChains, 1u); }
+		}
+	}
+	return accepted;
+}
+
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1) grow_cluster_kernel(GrowArgs A)
 {
@@ -255,7 +410,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) grow_cluster_kernel(GrowArgs A)
 	uint32_t round = __ldcg(&A.ctl->round);
 	unsigned long long nBeads = __ldcg(&A.ctl->nBeads);
 	uint32_t lastProg = __ldcg(&A.ctl->lastProgressed);
-	unsigned long long myTrials = 0, myQueries = 0;
+	unsigned long long myTrials = 0, myQueries = 0; long long myBusy = 0;
 	const bool timer = (myCta == 0 && threadIdx.x == 0);
 	long long cycA = 0, cycV = 0, cycC = 0; uint32_t cleanRounds = 0;
 	long long sub[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }, ts0 = 0, ts1 = 0;
@@ -278,103 +433,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) grow_cluster_kernel(GrowArgs A)
 		uint32_t oldCount = 0xFFFFFFFFu;                   // beads its cell held at round start (from the staged copy)
 		if (active && (cs.flags & CHAIN_DEAD)) rec.trial = T_ + 1u;
 		else if (active) {
-			bool regionOvf = false; int nnb = -1; int narcs = -1;
-			const bool canStage = rp.ncell <= CL_REGION_CELLS;
-			if (canStage) region_issue_tma(g, A.T, rp, raw, mbar, lane);   // bulk copies in flight ...
-			// ... while every lane prepares the exact candidate of trial lane+1 (reference arithmetic)
-			double candL[3], vL[3]; bool okL = false; float rel[3] = { 0, 0, 0 };
-			if (!hard) {
-				const uint4 w = philox4x32_10(make_uint4(i, round, (uint32_t)lane >> 2, 0u), g.key0, g.key1);
-				cone_candidate(g, f, cs.last, (double)pick(w, (uint32_t)lane & 3u) * (1.0 / 4294967296.0), candL);
-				okL = (uint32_t)lane < T_ && !growth_rules_reject(g, candL, cs.last);
-				to_frac(g, candL, vL);
-				rel[0] = (float)(candL[0] - cs.last[0]); rel[1] = (float)(candL[1] - cs.last[1]); rel[2] = (float)(candL[2] - cs.last[2]);
-			}
-			SUBT(0);
-			if (canStage) {
-				mbar_wait(mbar, tmaParity); tmaParity ^= 1u;
-				nnb = region_consume(g, rp, raw, idRound, cs.lastId, nb, lane, regionOvf);
-			} else regionOvf = true;
-			const uint32_t novf = regionOvf ? __ldcg(A.T.ovfCount) : 0u;
-			SUBT(1);
-			if (!hard) {
-				// fast path: lane-per-trial exact test of trials 1..32 against the staged neighbourhood
-				if (okL) {
-					if (nnb >= 0) {
-						for (int j = 0; j < nnb; ++j) {
-							const float4 b = nb[j];
-							const float dx = rel[0] - b.x, dy = rel[1] - b.y, dz = rel[2] - b.z;
-							const float d2 = dx * dx + dy * dy + dz * dz;
-							if (d2 < g.lo2) { okL = false; break; }
-							if (d2 <= g.hi2 && exact_pair(g, vL, A.T.lpos + 3 * (size_t)__float_as_uint(b.w))) { okL = false; break; }
-						}
-						if (okL && novf) {
-							const uint32_t m = novf > A.T.ovfCap ? A.T.ovfCap : novf;
-							for (uint32_t j = 0; j < m && okL; ++j) {
-								const uint32_t id = __ldcg(A.T.ovf + j);
-								if (id < idRound && id != cs.lastId && exact_pair(g, vL, A.T.lpos + 3 * (size_t)id)) okL = false;
-							}
-						}
-					} else okL = !probe_cells<1>(g, A.T, vL, 0u, idRound, cs.lastId, 0);
-				}
-				const unsigned m = __ballot_sync(FULL, okL);
-				myQueries += (lane == 0) ? (T_ < 32u ? T_ : 32u) : 0u;
-				if (m) {
-					const int first = __ffs(m) - 1;
-					accepted = (uint32_t)first + 1u;
-					for (int k = 0; k < 3; k++) { cand[k] = __shfl_sync(FULL, candL[k], first); vAcc[k] = __shfl_sync(FULL, vL[k], first); }
-				}
-			}
-			SUBT(2);
-			if (!accepted && T_ > (hard ? 0u : 32u)) {
-				// hard chain: blocked-arc classification of the remaining trials, exact evaluation of the survivors
-				narcs = nnb >= 0 ? build_arcs_cs(g, f, nb, nnb, arcs, lane) : -1;
-				const uint32_t skip = hard ? 0u : 32u;          // trials <= skip were just evaluated exactly and failed
-				for (uint32_t base = 0; base < T_ && !accepted; base += 128) {
-					const uint32_t blk = (base >> 2) + lane;
-					const uint4 w = philox4x32_10(make_uint4(i, round, blk, 0u), g.key0, g.key1);
-					const uint32_t wj[4] = { w.x, w.y, w.z, w.w };
-					unsigned cm[4];
-#pragma unroll
-					for (int j = 0; j < 4; ++j) {
-						const uint32_t t = base + 4 * lane + j + 1;
-						bool candidate = t <= T_ && t > skip;
-						if (candidate && narcs > 0) {
-							const float theta = (float)wj[j] * (float)(359.0 * 3.14159265358979323846 / 180 / 4294967296.0);
-							float s, c;
-							__sincosf(theta - 3.14159265358979323846f, &s, &c);   // |arg| <= pi: fast intrinsic is accurate to ~1e-6
-							s = -s; c = -c;
-							for (int a = 0; a < narcs; ++a) {
-								const float4 arc = arcs[a];
-								if (arc.x * c + arc.y * s >= arc.z) { candidate = false; break; }
-							}
-						}
-						cm[j] = __ballot_sync(FULL, candidate);
-					}
-					unsigned any = cm[0] | cm[1] | cm[2] | cm[3];
-					while (any) {   // candidates in increasing trial order
-						const int l = __ffs(any) - 1;
-						int j = 0;
-#pragma unroll
-						for (int jj = 3; jj >= 0; --jj) if ((cm[jj] >> l) & 1u) j = jj;
-						const uint32_t word = __shfl_sync(FULL, wj[0], l) * (j == 0) + __shfl_sync(FULL, wj[1], l) * (j == 1)
-							+ __shfl_sync(FULL, wj[2], l) * (j == 2) + __shfl_sync(FULL, wj[3], l) * (j == 3);
-						myQueries += (lane == 0);
-						if (eval_trial_coop(g, A.T, f, cs, (double)word * (1.0 / 4294967296.0), nb, nnb, idRound, novf, lane, cand)) {
-							accepted = base + 4 * l + j + 1;
-							to_frac(g, cand, vAcc);
-							break;
-						}
-#pragma unroll
-						for (int jj = 0; jj < 4; ++jj) if (jj == j) cm[jj] &= ~(1u << l);
-						any = cm[0] | cm[1] | cm[2] | cm[3];
-					}
-				}
-				if (!accepted && narcs > 0 && arcs_cs_cover_circle(arcs, narcs, lane)) {
-					cs.flags |= CHAIN_DEAD;
-					if (lane == 0) { A.chains[i].flags = cs.flags; atomicAdd(&A.ctl->deadChains, 1u); }
-				}
-			}
+			accepted = propose_chain(g, A.T, A.ctl, A.chains, i, round, idRound, cs, f, rp, hard, raw, nb, arcs, mbar, tmaParity, lane, cand, vAcc, myQueries);
 			hard = accepted == 0u || accepted > 32u;
 			rec.trial = accepted ? accepted : T_ + 1u;
 			if (accepted) {
@@ -389,23 +448,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) grow_cluster_kernel(GrowArgs A)
 					cc[k] = ci; offs[k] = (float)((s - (double)ci) * g.a[k]);
 				}
 				rec.cx = cc[0]; rec.cy = cc[1]; rec.cz = cc[2];
-				if (canStage) {   // count of the bead's cell at round start: find the cell in the staged copy (wrapped coordinates match)
-					uint32_t mine = 0xFFFFFFFFu;
-					const float inv0 = 1.0f / (float)rp.nn[0], inv1 = 1.0f / (float)rp.nn[1];
-#pragma unroll
-					for (int q = 0; q < 2; q++) {
-						const int ci = lane + 32 * q;
-						if (ci < rp.ncell) {
-							const int rest = (int)(((float)ci + 0.5f) * inv0), ix = ci - rest * rp.nn[0];
-							const int iz = (int)(((float)rest + 0.5f) * inv1), iy = rest - iz * rp.nn[1];
-							if (wrap_near(rp.lo[0] + ix, g.S[0]) == cc[0] && wrap_near(rp.lo[1] + iy, g.S[1]) == cc[1] && wrap_near(rp.lo[2] + iz, g.S[2]) == cc[2]) {
-								uint32_t c0 = raw[ci].countMinus1 + 1u; if (c0 > (uint32_t)g.cap) c0 = (uint32_t)g.cap;
-								mine = c0;
-							}
-						}
+				if (rp.ncell <= CL_REGION_CELLS) {   // count of the bead's cell at round start, from the staged copy (the cell lies inside the region)
+					const int ix = wrap_near(cc[0] - rp.lo[0], g.S[0]), iy = wrap_near(cc[1] - rp.lo[1], g.S[1]), iz = wrap_near(cc[2] - rp.lo[2], g.S[2]);
+					if (ix < rp.nn[0] && iy < rp.nn[1] && iz < rp.nn[2]) {
+						uint32_t c0 = raw[(iz * rp.nn[1] + iy) * rp.nn[0] + ix].countMinus1 + 1u;
+						oldCount = c0 > (uint32_t)g.cap ? (uint32_t)g.cap : c0;
 					}
-					const unsigned bm = __ballot_sync(FULL, mine != 0xFFFFFFFFu);
-					if (bm) oldCount = __shfl_sync(FULL, mine, __ffs(bm) - 1);
 				}
 			}
 			SUBT(3);
@@ -414,6 +462,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) grow_cluster_kernel(GrowArgs A)
 		if (owner)
 			for (unsigned c = lane; c < nCta; c += 32) *cluster.map_shared_rank(&table[par * CL_MAXCH + i], c) = rec;
 		SUBT(4);
+		myBusy += clock64() - tk0;
 		cluster_arrive();
 		// in the shadow of the barrier: next round's chain state, frame and region, assuming the tentative bead stands (it almost
 		// always does). The old state is recoverable: old last = new pen, old lastId = new penId; only the old pen is kept aside.
@@ -531,6 +580,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) grow_cluster_kernel(GrowArgs A)
 	}
 	if (i == 0 && lane == 0) { A.ctl->round = round; A.ctl->nBeads = nBeads; A.ctl->lastProgressed = lastProg ? 1u : 0u; }
 	if (timer) for (int k = 0; k < 8; k++) A.ctl->cycSub[k] += sub[k];
+	if (lane == 0 && i < 256) A.ctl->busy[i] += (unsigned long long)myBusy;
 	if (timer) { A.ctl->cycPropose += cycA; A.ctl->cycVerify += cycV; A.ctl->cycCleanup += cycC; A.ctl->cleanupRounds += cleanRounds; }
 	cluster_arrive(); cluster_wait();                    // no CTA may exit while others can still write into its shared memory
 }

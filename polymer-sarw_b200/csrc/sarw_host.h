@@ -18,6 +18,7 @@ struct Control {
 	unsigned long long cycPropose, cycVerify, cycCleanup;   // SM cycles of block 0 per phase (incl. the closing barrier)
 	unsigned cleanupRounds, deadChains;
 	unsigned long long cycSub[8];       // finer split of the propose phase of block 0 / warp 0 (diagnostics)
+	unsigned long long busy[256];       // cluster kernel: per-warp cycles from round start to the first barrier arrive, summed (diagnostics)
 };
 
 cudaError_t launch_find_batch(const Geom& g, const Tables& T, const double* xyz, const int64_t* ignore, int64_t n, uint8_t* hit, int numSMs, cudaStream_t st);

@@ -24,6 +24,7 @@ constexpr int GROW_WARPS = 8;            // grid mode: warps per CTA of the coop
 constexpr int NBMAX = 128;          // staged neighbour beads per chain (shared memory, 16 B each)
 constexpr int NARCMAX = 128;        // blocked torsion arcs per chain (shared memory, 8 B each)
 constexpr uint32_t CHAIN_DEAD = 1u; // ChainState.flags: every torsion angle is permanently blocked
+constexpr uint32_t CHAIN_HARD = 2u; // ChainState.flags: none of the first 32 trials passed last round (skip the fast path)
 constexpr unsigned FULL = 0xFFFFFFFFu;
 constexpr uint32_t DONE_BIT = 0x80000000u;
 
@@ -560,6 +561,8 @@ __device__ void cleanup_round(const GrowArgs& A, uint32_t round, int lane)
 	}
 }
 
+#include "sarw_cluster.cuh"
+
 // barrier across every CTA taking part in a round: the hardware cluster barrier when the whole launch is ONE
 // thread-block cluster (small chain counts: a few hundred cycles), else the software grid barrier (cooperative launch)
 template <bool CLUSTER>
@@ -577,14 +580,22 @@ template <int WARPS, bool CLUSTER>
 __global__ void __launch_bounds__(WARPS * 32) grow_kernel(GrowArgs A)
 {
 	constexpr int GROW_WARPS = WARPS;
-	extern __shared__ __align__(16) unsigned char growSmem[];
-	float4 (*nbShared)[NBMAX] = reinterpret_cast<float4 (*)[NBMAX]>(growSmem);
-	float2 (*arcShared)[NARCMAX] = reinterpret_cast<float2 (*)[NARCMAX]>(growSmem + sizeof(float4) * NBMAX * WARPS);
+	extern __shared__ __align__(128) unsigned char growSmem[];
+	Cell* rawAll = reinterpret_cast<Cell*>(growSmem);
+	float4* nbAll = reinterpret_cast<float4*>(rawAll + WARPS * CL_REGION_CELLS);
+	float4* arcAll = nbAll + WARPS * NBMAX;
+	unsigned long long* mbarAll = reinterpret_cast<unsigned long long*>(arcAll + WARPS * CL_NARC);
 	const Geom& g = A.g;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const uint32_t gw = blockIdx.x * GROW_WARPS + warp, nW = gridDim.x * GROW_WARPS;
-	float4* nb = nbShared[warp];
-	float2* arcs = arcShared[warp];
+	Cell* raw = rawAll + warp * CL_REGION_CELLS;
+	float4* nb = nbAll + warp * NBMAX;
+	float4* arcs = arcAll + warp * CL_NARC;
+	void* mbar = mbarAll + warp;
+	unsigned tmaParity = 0;
+	if (lane == 0) mbar_init(mbar, 1);
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	__syncwarp();
 	const uint32_t T_ = (uint32_t)g.maxTrials;
 
 	uint32_t round = __ldcg(&A.ctl->round);
@@ -610,57 +621,20 @@ __global__ void __launch_bounds__(WARPS * 32) grow_kernel(GrowArgs A)
 				if (lane == 0) A.resTrial[i] = T_ + 1u;
 				continue;
 			}
-			Frame f; cone_frame(cs.last, cs.pen, f);
-			double lw[3];
-			{ double vl[3]; to_frac(g, cs.last, vl); for (int k = 0; k < 3; k++) lw[k] = vl[k] * g.L[k]; }
-			bool regionOvf = false;
-			const int nnb = stage_region(g, A.T, lw, f, idRound, cs.lastId, nb, lane, regionOvf);
-			const int narcs = nnb >= 0 ? build_arcs(g, f, nb, nnb, arcs, lane) : -1;
-			const uint32_t novf = regionOvf ? __ldcg(A.T.ovfCount) : 0u;   // overflowed beads near this chain? (rare)
-
-			// 128 trials per pass: lane l owns trials base+4l+1 .. base+4l+4 (one Philox block)
-			uint32_t accepted = 0; double cand[3] = { 0, 0, 0 };
-			for (uint32_t base = 0; base < T_ && !accepted; base += 128) {
-				const uint32_t blk = (base >> 2) + lane;
-				const uint4 w = philox4x32_10(make_uint4(i, round, blk, 0u), g.key0, g.key1);
-				const uint32_t wj[4] = { w.x, w.y, w.z, w.w };
-				unsigned cm[4];
-#pragma unroll
-				for (int j = 0; j < 4; ++j) {
-					const uint32_t t = base + 4 * lane + j + 1;
-					bool candidate = t <= T_;
-					if (candidate && narcs > 0) {
-						const float theta = (float)wj[j] * (float)(359.0 * 3.14159265358979323846 / 180 / 4294967296.0);
-						candidate = !theta_blocked(theta, arcs, narcs);
-					}
-					cm[j] = __ballot_sync(FULL, candidate);
-				}
-				unsigned any = cm[0] | cm[1] | cm[2] | cm[3];
-				while (any) {   // candidates in increasing trial order
-					const int l = __ffs(any) - 1;
-					int j = 0;
-#pragma unroll
-					for (int jj = 3; jj >= 0; --jj) if ((cm[jj] >> l) & 1u) j = jj;
-					const uint32_t word = __shfl_sync(FULL, wj[0], l) * (j == 0) + __shfl_sync(FULL, wj[1], l) * (j == 1)
-						+ __shfl_sync(FULL, wj[2], l) * (j == 2) + __shfl_sync(FULL, wj[3], l) * (j == 3);
-					myQueries += (lane == 0);
-					if (eval_trial_coop(g, A.T, f, cs, (double)word * (1.0 / 4294967296.0), nb, nnb, idRound, novf, lane, cand)) {
-						accepted = base + 4 * l + j + 1;
-						break;
-					}
-#pragma unroll
-					for (int jj = 0; jj < 4; ++jj) if (jj == j) cm[jj] &= ~(1u << l);
-					any = cm[0] | cm[1] | cm[2] | cm[3];
-				}
-			}
-			if (!accepted && narcs > 0 && arcs_cover_circle(arcs, narcs, lane)) {
-				cs.flags |= CHAIN_DEAD;
-				if (lane == 0) { A.chains[i].flags = cs.flags; atomicAdd(&A.ctl->deadChains, 1u); }
-			}
+			Frame f; RegionPlan rp;
+			prepare_chain(g, cs, f, rp);
+			const bool hard = (cs.flags & CHAIN_HARD) != 0u;
+			double cand[3] = { 0, 0, 0 }, vAcc[3] = { 0, 0, 0 };
+			const uint32_t flagsBefore = cs.flags;
+			const uint32_t accepted = propose_chain(g, A.T, A.ctl, A.chains, i, round, idRound, cs, f, rp, hard, raw, nb, arcs, mbar, tmaParity, lane,
+				cand, vAcc, myQueries);
+			const bool hardNow = accepted == 0u || accepted > 32u;
+			cs.flags = (cs.flags & ~CHAIN_HARD) | (hardNow ? CHAIN_HARD : 0u);
 			if (lane == 0) {
+				if (cs.flags != flagsBefore) A.chains[i].flags = cs.flags;
 				if (accepted) {
 					insert_bead(g, A.T, cand, idRound + i);
-					for (int k = 0; k < 3; k++) A.resPos[3 * (size_t)i + k] = cand[k];
+					for (int k2 = 0; k2 < 3; k2++) A.resPos[3 * (size_t)i + k2] = cand[k2];
 				}
 				A.resTrial[i] = accepted ? accepted : T_ + 1u;
 			}
@@ -733,8 +707,6 @@ __global__ void __launch_bounds__(WARPS * 32) grow_kernel(GrowArgs A)
 	}
 	if (timer) { A.ctl->cycPropose += cycA; A.ctl->cycVerify += cycV; A.ctl->cycCleanup += cycC; A.ctl->cleanupRounds += cleanRounds; }
 }
-
-#include "sarw_cluster.cuh"
 
 // ------------------------------------------------------------------ K7: compaction into acceptance order
 __global__ void flag_slots_kernel(const double* __restrict__ lpos, uint32_t idAtomBase, uint64_t nSlots, uint32_t* __restrict__ flags)
@@ -818,7 +790,9 @@ cudaError_t launch_seed(const Geom& g, const Tables& T, ChainState* chains, uint
 	return cudaGetLastError();
 }
 
-constexpr size_t grow_smem_bytes(int warps) { return (size_t)warps * (NBMAX * sizeof(float4) + NARCMAX * sizeof(float2)); }
+constexpr size_t grow_smem_bytes(int warps)
+{	return (size_t)warps * (CL_REGION_CELLS * sizeof(Cell) + NBMAX * sizeof(float4) + CL_NARC * sizeof(float4) + 8);
+}
 
 cudaError_t grow_max_blocks(int numSMs, int* maxBlocks)
 {
