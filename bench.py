@@ -269,8 +269,9 @@ def main():
     if rank == 0:
         value = beads_all / t_dev
         # roofline of the dominant kernel (grow_kernel: ~all of the step): algorithmic bytes / its CUDA-event duration
-        alg_bytes = queries * B_QUERY + beads * B_BEAD
-        n_launch = max(1, sum(1 for _ in range(args.steps)))   # one growth launch per step unless storage had to grow
+        # bytes per bead = T*B_q + B_a with T = trials per accepted bead in the reference's terms (what the serial
+        # loop of sarw.cpp:259 evaluates; trials of provably dead chains are decided without memory traffic here)
+        alg_bytes = trials * B_QUERY + beads * B_BEAD
         achieved = alg_bytes / (grow_ms / 1e3) / 1e9
         line = {
             "metric": "accepted beads/sec", "value": value, "unit": "beads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -286,7 +287,8 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
                          "kernel": "sarw::grow_kernel (persistent, one launch per step)", "peak_source": peak_src,
-                         "algorithmic_bytes": f"queries*{B_QUERY:.0f} + beads*{B_BEAD:.0f} (SURVEY §8d)", "queries_per_launch": queries / args.steps,
+                         "algorithmic_bytes": f"trials*{B_QUERY:.0f} + beads*{B_BEAD:.0f} (SURVEY §8d, trials in reference terms)",
+                         "trials_per_launch": trials / args.steps, "candidates_evaluated_per_launch": queries / args.steps,
                          "avg_launch_ms": grow_ms / args.steps, "note": "latency-bound: ~1e2 chains per round, ~1e3 dependent rounds"},
         }
         if not args.no_extra:

@@ -57,6 +57,11 @@ int fail(sarw_ctx* c, const char* fmt, ...)
 }
 #define CU(c, x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(c, "%s: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
 
+// stream-ordered allocations from the device's default memory pool (blocks are reused across contexts: no cudaMalloc /
+// cudaFree round trips to the driver once the pool is warm)
+template <typename T> cudaError_t dev_alloc(sarw_ctx* c, T** p, size_t bytes) { return cudaMallocAsync((void**)p, bytes ? bytes : 16, c->stream); }
+template <typename T> void dev_free(sarw_ctx* c, T* p) { if (p) cudaFreeAsync((void*)p, c->stream); }
+
 uint64_t slots_for_rounds(const sarw_ctx* c, uint64_t rounds) { return 2ull * c->g.nChains + rounds * c->g.nChains; }
 
 // grow (or create) lpos to hold `cap` lookup indices; new entries get the all-ones "never accepted" pattern
@@ -67,11 +72,10 @@ int ensure_ids(sarw_ctx* c, uint64_t cap)
 	uint64_t newCap = std::max<uint64_t>(cap, c->idCapacity + c->idCapacity / 2);
 	if (newCap >= 0xFFFFFFF0ull) newCap = 0xFFFFFFEFull;
 	double* np = nullptr;
-	CU(c, cudaMalloc(&np, newCap * 3 * sizeof(double)));
+	CU(c, dev_alloc(c, &np, newCap * 3 * sizeof(double)));
 	if (c->idCapacity) CU(c, cudaMemcpyAsync(np, c->T.lpos, c->idCapacity * 3 * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
 	CU(c, cudaMemsetAsync(np + 3 * c->idCapacity, 0xFF, (newCap - c->idCapacity) * 3 * sizeof(double), c->stream));
-	CU(c, cudaStreamSynchronize(c->stream));
-	if (c->T.lpos) cudaFree(c->T.lpos);
+	dev_free(c, c->T.lpos);
 	c->T.lpos = np; c->idCapacity = newCap;
 	return 0;
 }
@@ -88,18 +92,17 @@ int ensure_rounds(sarw_ctx* c, uint32_t rounds)
 	if (ensure_ids(c, c->g.idAtomBase + slots)) return 1;
 	// prev[] per slot
 	uint32_t* np = nullptr;
-	CU(c, cudaMalloc(&np, slots * sizeof(uint32_t)));
+	CU(c, dev_alloc(c, &np, slots * sizeof(uint32_t)));
 	if (c->prevCap) CU(c, cudaMemcpyAsync(np, c->prev, c->prevCap * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
 	// per-round counters
 	uint32_t* arrs[3]; uint32_t** olds[3] = { &c->roundAcc, &c->roundProg, &c->dirtyCount };
 	for (int k = 0; k < 3; k++) {
-		CU(c, cudaMalloc(&arrs[k], (size_t)newCap * sizeof(uint32_t)));
+		CU(c, dev_alloc(c, &arrs[k], (size_t)newCap * sizeof(uint32_t)));
 		CU(c, cudaMemsetAsync(arrs[k], 0, (size_t)newCap * sizeof(uint32_t), c->stream));
 		if (c->roundCap) CU(c, cudaMemcpyAsync(arrs[k], *olds[k], (size_t)c->roundCap * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
 	}
-	CU(c, cudaStreamSynchronize(c->stream));
-	if (c->prev) cudaFree(c->prev);
-	for (int k = 0; k < 3; k++) { if (*olds[k]) cudaFree(*olds[k]); *olds[k] = arrs[k]; }
+	dev_free(c, c->prev);
+	for (int k = 0; k < 3; k++) { dev_free(c, *olds[k]); *olds[k] = arrs[k]; }
 	c->prev = np; c->prevCap = slots; c->roundCap = newCap;
 	return 0;
 }
@@ -220,28 +223,39 @@ int sarw_create(const sarw_params* p, sarw_ctx** out)
 
 	if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { fail(c, "cudaStreamCreate failed"); return bail(1); }
 	c->ownStream = true;
+	{	// keep freed blocks in the pool instead of returning them to the driver
+		cudaMemPool_t pool; unsigned long long keep = ~0ull;
+		if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+	}
 	cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
 
 	const size_t nCells = (size_t)g.S[0] * g.S[1] * g.S[2];
 #define CUB_(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fail(c, "%s: %s", #x, cudaGetErrorString(e_)); return bail(1); } } while (0)
-	CUB_(cudaMalloc(&c->T.cells, nCells * sizeof(Cell)));
+	CUB_(dev_alloc(c, &c->T.cells, nCells * sizeof(Cell)));
 	CUB_(cudaMemsetAsync(c->T.cells, 0xFF, nCells * sizeof(Cell), c->stream));
 	c->T.ovfCap = 1u << 16;
-	CUB_(cudaMalloc(&c->T.ovf, c->T.ovfCap * sizeof(uint32_t)));
-	CUB_(cudaMalloc(&c->T.ovfCount, sizeof(uint32_t)));
+	CUB_(dev_alloc(c, &c->T.ovf, c->T.ovfCap * sizeof(uint32_t)));
+	CUB_(dev_alloc(c, &c->T.ovfCount, sizeof(uint32_t)));
 	CUB_(cudaMemsetAsync(c->T.ovfCount, 0, sizeof(uint32_t), c->stream));
-	CUB_(cudaMalloc(&c->ctl, sizeof(Control)));
+	CUB_(dev_alloc(c, &c->ctl, sizeof(Control)));
 	CUB_(cudaMemsetAsync(c->ctl, 0, sizeof(Control), c->stream));
-	CUB_(cudaMalloc(&c->chains, (size_t)g.nChains * sizeof(ChainState)));
+	CUB_(dev_alloc(c, &c->chains, (size_t)g.nChains * sizeof(ChainState)));
 	CUB_(cudaMemsetAsync(c->chains, 0, (size_t)g.nChains * sizeof(ChainState), c->stream));
-	CUB_(cudaMalloc(&c->resTrial, (size_t)g.nChains * sizeof(uint32_t)));
+	CUB_(dev_alloc(c, &c->resTrial, (size_t)g.nChains * sizeof(uint32_t)));
 	CUB_(cudaMemsetAsync(c->resTrial, 0, (size_t)g.nChains * sizeof(uint32_t), c->stream));
-	CUB_(cudaMalloc(&c->resPos, (size_t)g.nChains * 3 * sizeof(double)));
-	CUB_(cudaMalloc(&c->dirtyList, (size_t)g.nChains * sizeof(uint32_t)));
+	CUB_(dev_alloc(c, &c->resPos, (size_t)g.nChains * 3 * sizeof(double)));
+	CUB_(dev_alloc(c, &c->dirtyList, (size_t)g.nChains * sizeof(uint32_t)));
 	CUB_(grow_max_blocks(c->numSMs, &c->growBlocksMax));
 	CUB_(cudaStreamSynchronize(c->stream));
 #undef CUB_
 	if (c->growBlocksMax < 1) { fail(c, "growth kernel does not fit on the device"); return bail(1); }
+	{	// bead storage for the expected number of rounds (grown later if the walk needs more, or if obstacles shift the index space)
+		uint64_t wantRounds = p->reserveRounds > 0 ? (uint64_t)p->reserveRounds
+			: (uint64_t)std::max<int64_t>(0, (g.target - 2 * (int64_t)g.nChains) / (int64_t)g.nChains) * 9 / 8 + 32;
+		if (wantRounds > 0xFFFFFFFFull) wantRounds = 0xFFFFFFFFull;
+		if (slots_for_rounds(c, wantRounds) < 0xFFFFFFF0ull && ensure_rounds(c, (uint32_t)std::max<uint64_t>(wantRounds, 1))) return bail(1);
+		cudaStreamSynchronize(c->stream);
+	}
 	*out = c;
 	return 0;
 }
@@ -251,9 +265,12 @@ void sarw_destroy(sarw_ctx* c)
 	if (!c) return;
 	cudaSetDevice(c->device);
 	if (c->stream) cudaStreamSynchronize(c->stream);
-	cudaFree(c->T.cells); cudaFree(c->T.lpos); cudaFree(c->T.ovf); cudaFree(c->T.ovfCount);
-	cudaFree(c->ctl); cudaFree(c->chains); cudaFree(c->resTrial); cudaFree(c->resPos); cudaFree(c->prev);
-	cudaFree(c->roundAcc); cudaFree(c->roundProg); cudaFree(c->dirtyCount); cudaFree(c->dirtyList); cudaFree(c->grafts);
+	if (c->stream) {
+		dev_free(c, c->T.cells); dev_free(c, c->T.lpos); dev_free(c, c->T.ovf); dev_free(c, c->T.ovfCount);
+		dev_free(c, c->ctl); dev_free(c, c->chains); dev_free(c, c->resTrial); dev_free(c, c->resPos); dev_free(c, c->prev);
+		dev_free(c, c->roundAcc); dev_free(c, c->roundProg); dev_free(c, c->dirtyCount); dev_free(c, c->dirtyList); dev_free(c, c->grafts);
+		cudaStreamSynchronize(c->stream);
+	}
 	if (c->ev0) cudaEventDestroy(c->ev0);
 	if (c->ev1) cudaEventDestroy(c->ev1);
 	if (c->ownStream && c->stream) cudaStreamDestroy(c->stream);
@@ -278,11 +295,11 @@ int sarw_lookup_add_points(sarw_ctx* c, const double* xyz, int64_t n)
 	cudaSetDevice(c->device);
 	if (ensure_ids(c, (uint64_t)c->nextId + (uint64_t)n)) return 1;
 	double* d = nullptr;
-	CU(c, cudaMalloc(&d, (size_t)n * 3 * sizeof(double)));
+	CU(c, dev_alloc(c, &d, (size_t)n * 3 * sizeof(double)));
 	CU(c, cudaMemcpyAsync(d, xyz, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
 	cudaError_t e = launch_add_points(c->g, c->T, d, n, c->nextId, c->stream);
+	dev_free(c, d);
 	cudaError_t e2 = cudaStreamSynchronize(c->stream);
-	cudaFree(d);
 	if (e != cudaSuccess || e2 != cudaSuccess) return fail(c, "add_points failed: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
 	c->nextId += (uint32_t)n;
 	return check_overflow(c);
@@ -303,10 +320,10 @@ int sarw_set_grafts(sarw_ctx* c, const double* xyz, int64_t n)
 	if (!c) return 1;
 	if (n < 0 || (n > 0 && !xyz)) return fail(c, "sarw_set_grafts: bad arguments");
 	cudaSetDevice(c->device);
-	if (c->grafts) { cudaFree(c->grafts); c->grafts = nullptr; }
+	if (c->grafts) { dev_free(c, c->grafts); c->grafts = nullptr; }
 	c->nGrafts = n;
 	if (n == 0) return 0;
-	CU(c, cudaMalloc(&c->grafts, (size_t)n * 3 * sizeof(double)));
+	CU(c, dev_alloc(c, &c->grafts, (size_t)n * 3 * sizeof(double)));
 	CU(c, cudaMemcpyAsync(c->grafts, xyz, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
 	CU(c, cudaStreamSynchronize(c->stream));
 	return 0;
@@ -329,13 +346,13 @@ int sarw_lookup_find_batch(sarw_ctx* c, const double* xyz, const int64_t* ignore
 	cudaSetDevice(c->device);
 	double* dx = nullptr; int64_t* di = nullptr; uint8_t* dh = nullptr;
 	int rc = 0;
-	auto cleanup = [&]() { cudaFree(dx); cudaFree(di); cudaFree(dh); };
+	auto cleanup = [&]() { dev_free(c, dx); dev_free(c, di); dev_free(c, dh); };
 #define CUF(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { rc = fail(c, "%s: %s", #x, cudaGetErrorString(e_)); cleanup(); return rc; } } while (0)
-	CUF(cudaMalloc(&dx, (size_t)n * 3 * sizeof(double)));
-	CUF(cudaMalloc(&dh, (size_t)n));
+	CUF(dev_alloc(c, &dx, (size_t)n * 3 * sizeof(double)));
+	CUF(dev_alloc(c, &dh, (size_t)n));
 	CUF(cudaMemcpyAsync(dx, xyz, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
 	if (ignore) {
-		CUF(cudaMalloc(&di, (size_t)n * sizeof(int64_t)));
+		CUF(dev_alloc(c, &di, (size_t)n * sizeof(int64_t)));
 		CUF(cudaMemcpyAsync(di, ignore, (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
 	}
 	CUF(launch_find_batch(c->g, c->T, dx, di, n, dh, c->numSMs, c->stream));
@@ -357,11 +374,8 @@ int sarw_initiate(sarw_ctx* c, int32_t* ok)
 		return fail(c, "Inadequate number of graft seeds: %lld given, %u grafted chains", (long long)c->nGrafts, g.nGraft);
 	g.idAtomBase = c->nextId;                                  // = nObstacles
 	g.seedIgnoreId = c->nextId > 0 ? c->nextId - 1 : ID_NONE;  // sarw.cpp:198,353: find(pos, -1 + nObstacles)
-	uint64_t wantRounds = c->p.reserveRounds > 0 ? (uint64_t)c->p.reserveRounds
-		: (uint64_t)std::max<int64_t>(0, (g.target - 2 * (int64_t)g.nChains) / (int64_t)g.nChains) * 9 / 8 + 32;
-	if (wantRounds > 0xFFFFFFFFull) wantRounds = 0xFFFFFFFFull;
-	if ((uint64_t)g.idAtomBase + slots_for_rounds(c, wantRounds) >= 0xFFFFFFF0ull) wantRounds = 0;
-	if (ensure_rounds(c, (uint32_t)std::max<uint64_t>(wantRounds, 1))) return 1;
+	if (ensure_rounds(c, std::max<uint32_t>(c->roundCap, 1))) return 1;
+	if (ensure_ids(c, (uint64_t)g.idAtomBase + slots_for_rounds(c, c->roundCap))) return 1;   // obstacles shift the atom index space
 
 	Control h0; memset(&h0, 0, sizeof h0);
 	h0.seedFailChain = ID_NONE; h0.lastProgressed = 1;
@@ -492,16 +506,16 @@ int sarw_download(sarw_ctx* c, double* xyz, int32_t* chainID, int32_t* type, int
 	uint32_t *flags = nullptr, *scan = nullptr; void* tmp = nullptr; size_t tmpBytes = 0;
 	double* dx = nullptr; int32_t *dc = nullptr, *dt = nullptr; int64_t* db = nullptr;
 	int rc = 0;
-	auto cleanup = [&]() { cudaFree(flags); cudaFree(scan); cudaFree(tmp); cudaFree(dx); cudaFree(dc); cudaFree(dt); cudaFree(db); };
+	auto cleanup = [&]() { dev_free(c, flags); dev_free(c, scan); dev_free(c, (char*)tmp); dev_free(c, dx); dev_free(c, dc); dev_free(c, dt); dev_free(c, db); };
 #define CUF(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { rc = fail(c, "%s: %s", #x, cudaGetErrorString(e_)); cleanup(); return rc; } } while (0)
-	CUF(cudaMalloc(&flags, nSlots * sizeof(uint32_t)));
-	CUF(cudaMalloc(&scan, nSlots * sizeof(uint32_t)));
+	CUF(dev_alloc(c, &flags, nSlots * sizeof(uint32_t)));
+	CUF(dev_alloc(c, &scan, nSlots * sizeof(uint32_t)));
 	CUF(download_scan_bytes(nSlots, &tmpBytes));
-	CUF(cudaMalloc(&tmp, tmpBytes ? tmpBytes : 16));
-	if (xyz) CUF(cudaMalloc(&dx, N * 3 * sizeof(double)));
-	if (chainID) CUF(cudaMalloc(&dc, N * sizeof(int32_t)));
-	if (type) CUF(cudaMalloc(&dt, N * sizeof(int32_t)));
-	if (bonds && nBonds) CUF(cudaMalloc(&db, nBonds * 2 * sizeof(int64_t)));
+	CUF(dev_alloc(c, (char**)&tmp, tmpBytes ? tmpBytes : 16));
+	if (xyz) CUF(dev_alloc(c, &dx, N * 3 * sizeof(double)));
+	if (chainID) CUF(dev_alloc(c, &dc, N * sizeof(int32_t)));
+	if (type) CUF(dev_alloc(c, &dt, N * sizeof(int32_t)));
+	if (bonds && nBonds) CUF(dev_alloc(c, &db, nBonds * 2 * sizeof(int64_t)));
 	CUF(launch_download(c->g, c->T, c->prev, c->chains, nSlots, c->nSeeded, c->terminated ? 1 : 0, flags, scan, tmp, tmpBytes, dx, dc, dt, db, c->stream));
 	if (dx) CUF(cudaMemcpyAsync(xyz, dx, N * 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
 	if (dc) CUF(cudaMemcpyAsync(chainID, dc, N * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
@@ -518,11 +532,11 @@ int sarw_chain_lengths(sarw_ctx* c, int32_t* lengths)
 	if (!c || !lengths) return 1;
 	cudaSetDevice(c->device);
 	int32_t* d = nullptr;
-	CU(c, cudaMalloc(&d, (size_t)c->g.nChains * sizeof(int32_t)));
+	CU(c, dev_alloc(c, &d, (size_t)c->g.nChains * sizeof(int32_t)));
 	cudaError_t e = launch_chain_lengths(c->chains, c->g.nChains, d, c->stream);
 	if (e == cudaSuccess) e = cudaMemcpyAsync(lengths, d, (size_t)c->g.nChains * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream);
+	dev_free(c, d);
 	if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-	cudaFree(d);
 	if (e != cudaSuccess) return fail(c, "sarw_chain_lengths: %s", cudaGetErrorString(e));
 	return 0;
 }
