@@ -3,6 +3,7 @@ where /root/reference does not exist. Run from the repo root:  python tests/gold
 
   walk_<name>_seed<k>.npz   full walks of the reference SARW class driven by the keyed Philox stand-in RNG
   find_truth.npz            PeriodicLookup::find truth tables on random + adversarial candidates
+  stats_c2_reference_mt.npz RDF (intra/inter), <Ree^2>, <Rg^2>, chain-length moments of 12 reference melts (native mt RNG)
   pe_seed1/                 the four output files + summary log the reference's own exporters write for pe.in
 """
 import os
@@ -77,6 +78,14 @@ def main():
         tables[f"box{ti}"] = np.array(box); tables[f"thresh{ti}"] = np.array(thresh); tables[f"pts{ti}"] = pts
         tables[f"q{ti}"] = q; tables[f"ig{ti}"] = ig; tables[f"hit{ti}"] = hit
     np.savez_compressed(os.path.join(HERE, "find_truth.npz"), n=np.array(5), **tables)
+    # ---- structure statistics of the reference with its NATIVE random numbers (mt19937_64 re-seeded per trial), 12 seeds of C2
+    import stats
+    walks = []
+    for seed in range(101, 113):
+        r = R.walk(seed=seed, rng="mt", **cases.oracle_kwargs(cases.C2))
+        walks.append((r.xyz, r.chainID))
+    st = stats.summarize(walks, cases.C2["boxSize"], cases.C2["nChains"])
+    np.savez_compressed(os.path.join(HERE, "stats_c2_reference_mt.npz"), **st)
     # ---- the reference's own exporters on pe.in (seed 1)
     out = os.path.join(HERE, "pe_seed1")
     os.makedirs(out, exist_ok=True)
