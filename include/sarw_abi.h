@@ -93,6 +93,20 @@ int sarw_propagate_round(sarw_ctx* ctx, int32_t* progressed);
 /* main()'s loop (sarw.cpp:67-78) on the device: rounds until actualCount >= target, a round makes no progress, or
  * maxRounds more rounds were run (maxRounds < 0: unbounded). target <= 0 means SARW::targetCount(). */
 int sarw_grow(sarw_ctx* ctx, int64_t target, int64_t maxRounds, sarw_stats* stats);
+/* ---- multi-rank: ONE melt over several GPUs, one context per GPU (rank), every context created with identical
+ * parameters, obstacles and grafts. State is replicated; only the proposals of a round are partitioned (chain i is
+ * proposed by rank i % nranks). Per round: sarw_mr_propose on every rank writes `recordsPerRank` 32-byte records into a
+ * caller-owned DEVICE buffer; the caller all-gathers the buffers of all ranks, in rank order, into one device buffer
+ * (NCCL over NVLink: torch.distributed.all_gather_into_tensor, ncclAllGather, ...); sarw_mr_finish on every rank applies
+ * the other ranks' tentative beads, then verifies, resolves same-round conflicts in chain order and finishes the round
+ * exactly like the single-GPU path. Results are identical to sarw_grow for any nranks. After the last round call
+ * sarw_mr_commit. The loop is:  while (more) { propose; all-gather; finish(&more); }  commit;                        */
+int sarw_mr_setup(sarw_ctx* ctx, int32_t rank, int32_t nranks, int64_t* recordsPerRank, int64_t* recordBytes);
+int sarw_mr_more(sarw_ctx* ctx, int32_t* more);       /* same predicate as main()'s loop, sarw.cpp:67-69 */
+int sarw_mr_propose(sarw_ctx* ctx, void* d_localRecords);
+int sarw_mr_finish(sarw_ctx* ctx, const void* d_allRecords, int32_t* more);
+int sarw_mr_commit(sarw_ctx* ctx);
+
 /* SARW::terminateChain (sarw.cpp:359-368) */
 int sarw_terminate(sarw_ctx* ctx);
 

@@ -44,6 +44,7 @@ struct sarw_ctx {
 	double* grafts = nullptr; int64_t nGrafts = 0;
 
 	double seedMs = 0, growMs = 0; int64_t growLaunches = 0, seedLaunches = 0;
+	uint32_t mrRank = 0, mrRanks = 1; bool mrPending = false;   // multi-rank mode (sarw_mr_*)
 };
 
 namespace {
@@ -472,6 +473,73 @@ int sarw_propagate_round(sarw_ctx* c, int32_t* progressed)
 	c->growMs += ms; c->growLaunches += 1;
 	if (progressed) *progressed = (int32_t)h.lastProgressed;
 	return check_overflow(c);
+}
+
+// ------------------------------------------------------------------ one melt over several GPUs (include/sarw_abi.h, "multi-rank")
+int sarw_mr_setup(sarw_ctx* c, int32_t rank, int32_t nranks, int64_t* recordsPerRank, int64_t* recordBytes)
+{
+	if (!c) return 1;
+	if (nranks < 1 || rank < 0 || rank >= nranks) return fail(c, "sarw_mr_setup: rank %d of %d", rank, nranks);
+	c->mrRank = (uint32_t)rank; c->mrRanks = (uint32_t)nranks;
+	if (recordsPerRank) *recordsPerRank = ((int64_t)c->g.nChains + nranks - 1) / nranks;
+	if (recordBytes) *recordBytes = 32;
+	return 0;
+}
+
+static int mr_launch(sarw_ctx* c, uint32_t phase, void* localRec, const void* allRec, Control* hOut)
+{
+	if (!c->initiateCalled) return fail(c, "sarw_initiate must be called before the multi-rank rounds");
+	cudaSetDevice(c->device);
+	Control h; if (read_control(c, &h)) return 1;
+	if (h.round >= c->roundCap && ensure_rounds(c, h.round + 1)) return 1;
+	int blocks = (int)std::min<int64_t>(c->growBlocksMax, ((int64_t)c->g.nChains + 7) / 8);
+	if (blocks < 1) blocks = 1;
+	CU(c, cudaEventRecord(c->ev0, c->stream));
+	CU(c, launch_grow_mr(c->g, c->T, c->chains, c->resTrial, c->resPos, c->prev, c->ctl, c->roundAcc, c->roundProg, c->dirtyCount, c->dirtyList,
+		h.round + 1, blocks, c->mrRank, c->mrRanks, phase, localRec, allRec, c->stream));
+	CU(c, cudaEventRecord(c->ev1, c->stream));
+	c->growLaunches += 1;
+	if (hOut) {
+		if (read_control(c, hOut)) return 1;
+		float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); c->growMs += ms;
+		return check_overflow(c);
+	}
+	return 0;
+}
+
+int sarw_mr_more(sarw_ctx* c, int32_t* more)
+{
+	if (!c || !more) return 1;
+	Control h; if (read_control(c, &h)) return 1;
+	*more = (c->initiated && (int64_t)h.nBeads < c->g.target && h.lastProgressed) ? 1 : 0;
+	return 0;
+}
+
+int sarw_mr_propose(sarw_ctx* c, void* d_localRecords)
+{
+	if (!c || !d_localRecords) return 1;
+	if (mr_launch(c, 1u, d_localRecords, nullptr, nullptr)) return 1;
+	c->mrPending = true;
+	return 0;
+}
+
+int sarw_mr_finish(sarw_ctx* c, const void* d_allRecords, int32_t* more)
+{
+	if (!c || !d_allRecords) return 1;
+	Control h;
+	if (mr_launch(c, 2u, nullptr, d_allRecords, &h)) return 1;
+	if (more) *more = (c->initiated && (int64_t)h.nBeads < c->g.target && h.lastProgressed) ? 1 : 0;
+	return 0;
+}
+
+int sarw_mr_commit(sarw_ctx* c)
+{
+	if (!c) return 1;
+	if (!c->mrPending) return 0;
+	Control h;
+	if (mr_launch(c, 3u, nullptr, nullptr, &h)) return 1;
+	c->mrPending = false;
+	return 0;
 }
 
 int sarw_terminate(sarw_ctx* c)

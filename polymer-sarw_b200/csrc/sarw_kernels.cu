@@ -273,6 +273,10 @@ __global__ void seed_commit_kernel(SeedArgs A)
 }
 
 // ------------------------------------------------------------------ K2-K4: persistent growth kernel
+// tentative bead of one chain as exchanged between ranks (all-gather once per round)
+struct __align__(8) MrRecord { double x, y, z; uint32_t trial; uint32_t pad; };
+static_assert(sizeof(MrRecord) == 32, "MrRecord is 32 bytes");
+
 struct GrowArgs {
 	Geom g; Tables T;
 	ChainState* chains;
@@ -285,6 +289,12 @@ struct GrowArgs {
 	uint32_t* dirtyCount;   // per round
 	uint32_t* dirtyList;
 	uint32_t roundEnd;      // run rounds [ctl->round, roundEnd)
+	// multi-rank mode (one melt over several GPUs, replicated state, partitioned proposals)
+	uint32_t mrRank, mrRanks;     // chain i is proposed by rank i % mrRanks
+	uint32_t mrPhase;             // 0 whole rounds (single GPU); 1 commit + propose one round; 2 apply remote + verify + clean-up; 3 commit only
+	uint32_t mrK;                 // records per rank = ceil(nChains / mrRanks)
+	MrRecord* mrLocal;            // phase 1 output: this rank's records, chain i at [i / mrRanks]
+	const MrRecord* mrAll;        // phase 2 input: all ranks' records, chain i at [(i % mrRanks) * mrK + i / mrRanks]
 };
 
 __device__ __forceinline__ uint32_t round_id_base(const Geom& g, uint32_t round)
@@ -602,7 +612,12 @@ __global__ void __launch_bounds__(WARPS * 32) grow_kernel(GrowArgs A)
 	unsigned long long nBeads = __ldcg(&A.ctl->nBeads);
 	uint32_t lastProg = __ldcg(&A.ctl->lastProgressed);
 	unsigned long long myTrials = 0, myQueries = 0;
-	bool pendingValid = false;   // is there a round of this launch whose results are not yet committed?
+	bool pendingValid = (A.mrPhase == 1u);   // is there a round whose results are not yet committed? (always possible between multi-rank launches)
+	const bool mr = A.mrPhase != 0u;
+	if (A.mrPhase == 3u) {       // multi-rank: commit the last round, nothing else
+		for (uint32_t i = gw; i < g.nChains; i += nW) { ChainState cs = load_chain(A.chains + i); commit_pending(A, i, round - 1, cs, lane); }
+		return;
+	}
 
 	const bool timer = (blockIdx.x == 0 && threadIdx.x == 0);
 	long long cycA = 0, cycV = 0, cycC = 0; uint32_t cleanRounds = 0;
@@ -613,12 +628,17 @@ __global__ void __launch_bounds__(WARPS * 32) grow_kernel(GrowArgs A)
 		const uint32_t idRound = round_id_base(g, round);
 
 		// ---------------- phase A: commit last round, then propose + tentatively insert
+		if (A.mrPhase != 2u)
 		for (uint32_t i = gw; i < g.nChains; i += nW) {
 			ChainState cs = load_chain(A.chains + i);
 			if (pendingValid) commit_pending(A, i, round - 1, cs, lane);
 			if (i < start || i >= end) continue;
+			if (mr && (i % A.mrRanks) != A.mrRank) continue;          // another rank proposes for this chain
 			if (cs.flags & CHAIN_DEAD) {   // permanently blocked: the reference burns maxTrials here every round
-				if (lane == 0) A.resTrial[i] = T_ + 1u;
+				if (lane == 0) {
+					A.resTrial[i] = T_ + 1u;
+					if (mr) { MrRecord r; r.x = r.y = r.z = 0; r.trial = T_ + 1u; r.pad = 0; A.mrLocal[i / A.mrRanks] = r; }
+				}
 				continue;
 			}
 			Frame f; RegionPlan rp;
@@ -637,8 +657,21 @@ __global__ void __launch_bounds__(WARPS * 32) grow_kernel(GrowArgs A)
 					for (int k2 = 0; k2 < 3; k2++) A.resPos[3 * (size_t)i + k2] = cand[k2];
 				}
 				A.resTrial[i] = accepted ? accepted : T_ + 1u;
+				if (mr) { MrRecord r; r.x = cand[0]; r.y = cand[1]; r.z = cand[2]; r.trial = accepted ? accepted : T_ + 1u; r.pad = 0; A.mrLocal[i / A.mrRanks] = r; }
 			}
 		}
+		if (A.mrPhase == 1u) break;                                  // the host all-gathers the records, then launches phase 2
+		if (A.mrPhase == 2u)                                         // tentative beads proposed by the other ranks
+			for (uint32_t i = start + gw * 32 + lane; i < end; i += nW * 32) {
+				if ((i % A.mrRanks) == A.mrRank) continue;
+				const MrRecord r = A.mrAll[(size_t)(i % A.mrRanks) * A.mrK + i / A.mrRanks];
+				A.resTrial[i] = r.trial;
+				if (r.trial >= 1u && r.trial <= T_) {
+					const double p[3] = { r.x, r.y, r.z };
+					insert_bead(g, A.T, p, idRound + i);
+					for (int k2 = 0; k2 < 3; k2++) A.resPos[3 * (size_t)i + k2] = p[k2];
+				}
+			}
 		pendingValid = true;
 		round_barrier<CLUSTER>(A.ctl);
 		const long long tk1 = clock64();
@@ -692,8 +725,8 @@ __global__ void __launch_bounds__(WARPS * 32) grow_kernel(GrowArgs A)
 		round++;
 	}
 
-	// commit the last round of this launch
-	if (pendingValid)
+	// commit the last round of this launch (multi-rank: the next phase-1 launch, or phase 3, commits)
+	if (pendingValid && !mr)
 		for (uint32_t i = gw; i < g.nChains; i += nW) {
 			ChainState cs = load_chain(A.chains + i);
 			commit_pending(A, i, round - 1, cs, lane);
@@ -828,13 +861,26 @@ static cudaError_t launch_cluster(const GrowArgs& A, cudaStream_t st)
 cudaError_t launch_grow(const Geom& g, const Tables& T, ChainState* chains, uint32_t* resTrial, double* resPos, uint32_t* prev, Control* ctl,
 	uint32_t* roundAcc, uint32_t* roundProg, uint32_t* dirtyCount, uint32_t* dirtyList, uint32_t roundEnd, int blocks, int useCluster, cudaStream_t st)
 {
-	GrowArgs A{ g, T, chains, resTrial, resPos, prev, ctl, roundAcc, roundProg, dirtyCount, dirtyList, roundEnd };
+	GrowArgs A{ g, T, chains, resTrial, resPos, prev, ctl, roundAcc, roundProg, dirtyCount, dirtyList, roundEnd, 0u, 1u, 0u, 0u, nullptr, nullptr };
 	if (useCluster) {
 		// the whole launch is one thread-block cluster: CTAs are co-scheduled by the hardware, synchronise with
 		// barrier.cluster and exchange tentative beads through distributed shared memory. 8 warps per CTA (255
 		// registers per thread) up to 128 chains, 16 warps per CTA beyond.
 		return g.nChains <= 8u * CL_MAX_CTAS ? launch_cluster<8>(A, st) : launch_cluster<16>(A, st);
 	}
+	void* args[] = { &A };
+	return cudaLaunchCooperativeKernel((const void*)grow_kernel<GROW_WARPS, false>, dim3((unsigned)blocks), dim3(GROW_WARPS * 32), args,
+		grow_smem_bytes(GROW_WARPS), st);
+}
+
+// one phase of a multi-rank round (grow_kernel with mrPhase != 0); always the cooperative grid kernel
+cudaError_t launch_grow_mr(const Geom& g, const Tables& T, ChainState* chains, uint32_t* resTrial, double* resPos, uint32_t* prev, Control* ctl,
+	uint32_t* roundAcc, uint32_t* roundProg, uint32_t* dirtyCount, uint32_t* dirtyList, uint32_t roundEnd, int blocks,
+	uint32_t rank, uint32_t ranks, uint32_t phase, void* localRec, const void* allRec, cudaStream_t st)
+{
+	const uint32_t K = (g.nChains + ranks - 1) / ranks;
+	GrowArgs A{ g, T, chains, resTrial, resPos, prev, ctl, roundAcc, roundProg, dirtyCount, dirtyList, roundEnd, rank, ranks, phase, K,
+		(MrRecord*)localRec, (const MrRecord*)allRec };
 	void* args[] = { &A };
 	return cudaLaunchCooperativeKernel((const void*)grow_kernel<GROW_WARPS, false>, dim3((unsigned)blocks), dim3(GROW_WARPS * 32), args,
 		grow_smem_bytes(GROW_WARPS), st);

@@ -24,6 +24,7 @@ ABI_SYMBOLS = [
     "sarw_initiate", "sarw_propagate_round", "sarw_grow", "sarw_terminate", "sarw_get_stats", "sarw_target_count",
     "sarw_download", "sarw_chain_lengths", "sarw_round_counts", "sarw_lookup_add_points", "sarw_lookup_find_batch",
     "sarw_lookup_find_batch_device", "sarw_lookup_size",
+    "sarw_mr_setup", "sarw_mr_more", "sarw_mr_propose", "sarw_mr_finish", "sarw_mr_commit",
 ]
 
 
@@ -84,6 +85,11 @@ def load_library(path=LIB_PATH):
     lib.sarw_lookup_find_batch.argtypes = [vp, vp, vp, C.c_int64, vp]
     lib.sarw_lookup_find_batch_device.argtypes = [vp, vp, vp, C.c_int64, vp]
     lib.sarw_lookup_size.argtypes = [vp]; lib.sarw_lookup_size.restype = C.c_int64
+    lib.sarw_mr_setup.argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.sarw_mr_more.argtypes = [vp, C.POINTER(C.c_int32)]
+    lib.sarw_mr_propose.argtypes = [vp, vp]
+    lib.sarw_mr_finish.argtypes = [vp, vp, C.POINTER(C.c_int32)]
+    lib.sarw_mr_commit.argtypes = [vp]
     _lib = lib
     return lib
 
@@ -182,6 +188,28 @@ class Context:
         self._ck(self.lib.sarw_grow(self.h, target, maxRounds, C.byref(s)))
         return s
 
+    # ---- one melt over several GPUs (replicated state, partitioned proposals; include/sarw_abi.h "multi-rank")
+    def mr_setup(self, rank, nranks):
+        k, b = C.c_int64(), C.c_int64()
+        self._ck(self.lib.sarw_mr_setup(self.h, rank, nranks, C.byref(k), C.byref(b)))
+        return k.value, b.value
+
+    def mr_more(self):
+        m = C.c_int32()
+        self._ck(self.lib.sarw_mr_more(self.h, C.byref(m)))
+        return bool(m.value)
+
+    def mr_propose(self, d_local_ptr):
+        self._ck(self.lib.sarw_mr_propose(self.h, d_local_ptr))
+
+    def mr_finish(self, d_all_ptr):
+        m = C.c_int32()
+        self._ck(self.lib.sarw_mr_finish(self.h, d_all_ptr, C.byref(m)))
+        return bool(m.value)
+
+    def mr_commit(self):
+        self._ck(self.lib.sarw_mr_commit(self.h))
+
     def terminate(self):
         self._ck(self.lib.sarw_terminate(self.h))
 
@@ -265,3 +293,27 @@ class SARW:
 
     def close(self):
         self.ctx.close()
+
+
+def grow_multirank(ctx, dist, rank, nranks, device="cuda"):
+    """main()'s growth loop (sarw.cpp:67-78) for ONE melt over `nranks` GPUs: every rank holds a context created with the same
+    parameters; proposals are partitioned, one all-gather of 32-byte records per round (torch.distributed, NCCL on GPUs).
+    `dist` is torch.distributed (initialised) or an object with all_gather_into_tensor(out, inp). Returns rounds run."""
+    import torch
+    K, B = ctx.mr_setup(rank, nranks)
+    local = torch.zeros(K * B, dtype=torch.uint8, device=device)
+    allrec = torch.zeros(nranks * K * B, dtype=torch.uint8, device=device)
+    rounds = 0
+    more = ctx.mr_more()
+    while more:
+        ctx.mr_propose(local.data_ptr())
+        dist.all_gather_into_tensor(allrec, local)
+        more = ctx.mr_finish(allrec.data_ptr())
+        rounds += 1
+    ctx.mr_commit()
+    return rounds
+
+
+def mr_chain_slot(i, nranks, K):
+    """Where chain i's record sits after the all-gather (rank-major): (i % nranks) * K + i // nranks."""
+    return (i % nranks) * K + i // nranks

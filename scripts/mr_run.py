@@ -1,0 +1,40 @@
+"""One melt over N GPUs under torchrun (NCCL all-gather per round): checks bit-identity with the single-GPU walk and times it.
+   torchrun --nproc-per-node N scripts/mr_run.py [nChains] [beadsPerChain]"""
+import os, sys, time, json
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "polymer-sarw_b200"))
+import numpy as np, torch, torch.distributed as dist
+import sarw_b200
+
+rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
+per = int(sys.argv[2]) if len(sys.argv) > 2 else 100
+L = (n * per / 0.03957) ** (1.0 / 3.0)
+cfg = dict(nChains=n, boxSize=(L, L, L), minDist=1.0, maxTrials=1000, seed=7, device=local)
+stream = torch.cuda.current_stream()
+
+def run(multi):
+    c = sarw_b200.Context(launchMode=1, **cfg); c.set_stream(stream.cuda_stream)
+    c.initiate()
+    torch.cuda.synchronize(); dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    if multi: rounds = sarw_b200.grow_multirank(c, dist, rank, world)
+    else: rounds = c.grow(0, -1).rounds
+    e1.record(stream); e1.synchronize()
+    c.terminate()
+    out = c.download(); st = c.stats().as_dict(); c.close()
+    return out, st, e0.elapsed_time(e1), rounds
+
+single, st1, ms1, r1 = run(False)
+multi, stN, msN, rN = run(True)
+same = all(np.array_equal(a, b) for a, b in zip(single, multi)) and r1 == rN
+t = torch.tensor([msN, ms1], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+ok = torch.tensor([1.0 if same else 0.0], device="cuda"); dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print(json.dumps(dict(n_gpus=world, nChains=n, beads=st1["nBeads"], rounds=r1, identical_on_all_ranks=bool(ok.item() == 1.0),
+                          single_gpu_ms=t[1].item(), multi_gpu_ms=t[0].item(), single_beads_per_s=st1["nBeads"] / t[1].item() * 1e3,
+                          multi_beads_per_s=st1["nBeads"] / t[0].item() * 1e3, us_per_round_multi=t[0].item() * 1e3 / max(1, rN))))
+dist.barrier(); dist.destroy_process_group()

@@ -1,0 +1,91 @@
+"""One melt over several ranks (replicated state, partitioned proposals, one all-gather per round).
+
+The protocol and kernels are exercised on ONE GPU by running R contexts ("ranks") side by side in one process and doing the
+all-gather with a device concatenation; the result must be bit-identical to the single-context walk for every R. The NCCL
+plumbing itself (torch.distributed over NVLink) is exercised by scripts/mr_run.py under torchrun on >= 2 GPUs."""
+import numpy as np
+import pytest
+
+import cases
+
+pytestmark = pytest.mark.gpu
+
+
+class CatGather:
+    """stands in for torch.distributed when all ranks live in one process: ranks deposit their buffer, the last one concatenates"""
+    def __init__(self, n):
+        self.n, self.parts = n, {}
+
+
+def run_ranks(sarw, cfg, seed, R, grafts=None, obstacles=None):
+    import torch
+    stream = torch.cuda.current_stream()
+    ctxs = []
+    for r in range(R):
+        c = sarw.Context(seed=seed, launchMode=1, **cfg)
+        c.set_stream(stream.cuda_stream)
+        if obstacles is not None: c.add_obstacles(obstacles)
+        if grafts is not None: c.set_grafts(grafts)
+        c.initiate()
+        ctxs.append(c)
+    KB = [c.mr_setup(r, R) for r, c in enumerate(ctxs)]
+    K, B = KB[0]
+    local = [torch.zeros(K * B, dtype=torch.uint8, device="cuda") for _ in range(R)]
+    more = [c.mr_more() for c in ctxs]
+    rounds = 0
+    while more[0]:
+        assert all(m == more[0] for m in more)
+        for c, l in zip(ctxs, local):
+            c.mr_propose(l.data_ptr())
+        allrec = torch.cat(local)                      # what the NCCL all-gather delivers, in rank order
+        more = [c.mr_finish(allrec.data_ptr()) for c in ctxs]
+        rounds += 1
+    outs = []
+    for c in ctxs:
+        c.mr_commit(); c.terminate()
+        xyz, chainID, typ, bonds = c.download()
+        outs.append((xyz, chainID, typ, bonds, c.chain_lengths(), c.stats().as_dict()))
+        c.close()
+    return outs, rounds
+
+
+def run_single(sarw, cfg, seed, grafts=None, obstacles=None):
+    c = sarw.Context(seed=seed, **cfg)
+    if obstacles is not None: c.add_obstacles(obstacles)
+    if grafts is not None: c.set_grafts(grafts)
+    c.initiate(); st = c.grow(0, -1); c.terminate()
+    out = c.download() + (c.chain_lengths(), c.stats().as_dict())
+    c.close()
+    return out
+
+
+@pytest.mark.parametrize("R", [2, 3])
+@pytest.mark.parametrize("name,cfg", [("mid", cases.MID), ("dense", cases.DENSE_TINY), ("pe_in", cases.PE_IN)])
+def test_ranks_give_the_single_gpu_walk_bit_for_bit(sarw, name, cfg, R):
+    ref = run_single(sarw, cfg, 13)
+    outs, rounds = run_ranks(sarw, cfg, 13, R)
+    assert rounds == ref[5]["rounds"]
+    for o in outs:                                      # every rank holds the complete, identical result
+        for a, b in zip(o[:5], ref[:5]):
+            assert np.array_equal(a, b)
+        assert (o[5]["nBeads"], o[5]["trials"], o[5]["conflicts"]) == (ref[5]["nBeads"], ref[5]["trials"], ref[5]["conflicts"])
+
+
+def test_ranks_with_grafts_and_growth_order(sarw):
+    cfg = dict(nChains=24, boxSize=(24.0, 24.0, 30.0), minDist=1.0, maxTrials=200, boundary="ppf", nGraftChains=12, graftLoc="file", growthOrder="grafted")
+    grafts = cases.make_grafts(12, cfg["boxSize"], seed=5)
+    obst = cases.make_obstacles(30, cfg["boxSize"], seed=2)
+    ref = run_single(sarw, cfg, 4, grafts=grafts, obstacles=obst)
+    outs, _ = run_ranks(sarw, cfg, 4, 2, grafts=grafts, obstacles=obst)
+    for o in outs:
+        for a, b in zip(o[:5], ref[:5]):
+            assert np.array_equal(a, b)
+
+
+def test_ranks_c2_full_size_matches_oracle(sarw, oracle):
+    outs, rounds = run_ranks(sarw, cases.C2, 3, 4)
+    o = oracle.walk(seed=3, trig="portable", **cases.oracle_kwargs(cases.C2))
+    assert rounds == o.rounds
+    xyz, chainID, typ, bonds, lengths, st = outs[2]
+    assert np.array_equal(xyz, o.xyz) and np.array_equal(bonds, o.bonds) and np.array_equal(typ, o.type)
+    assert st["trials"] == o.trials

@@ -46,3 +46,39 @@ def test_reference_arm_prints_only_on_rank0(tmp_path):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
                        capture_output=True, text=True, env=env, timeout=120)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+WORKER2 = textwrap.dedent("""
+    import os, sys, json
+    sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "polymer-sarw_b200"))
+    import torch, torch.distributed as dist
+    import sarw_b200
+    dist.init_process_group("gloo")
+    r, R = dist.get_rank(), dist.get_world_size()
+    n = 11                                   # chains; not a multiple of the rank count
+    K = (n + R - 1) // R
+    # each rank writes the chain index into the 32-byte records of the chains it proposes for (chain i -> rank i %% R, slot i // R)
+    local = torch.full((K, 4), -1.0, dtype=torch.float64)
+    for i in range(n):
+        if i %% R == r:
+            local[i // R, 0] = float(i)
+    allrec = torch.empty((R * K, 4), dtype=torch.float64)
+    dist.all_gather_into_tensor(allrec, local)
+    got = [int(allrec[sarw_b200.mr_chain_slot(i, R, K), 0].item()) for i in range(n)]
+    if r == 0:
+        print(json.dumps(got))
+    dist.barrier(); dist.destroy_process_group()
+""") % (ROOT, ROOT)
+
+
+def test_record_layout_after_all_gather_with_gloo(tmp_path):
+    """The layout contract of include/sarw_abi.h "multi-rank": after a rank-ordered all-gather chain i's record sits at
+    (i % nranks) * K + i // nranks — checked with a real 2-process gloo all_gather_into_tensor."""
+    w = tmp_path / "worker2.py"
+    w.write_text(WORKER2)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29618", str(w)], capture_output=True, text=True, env=env, timeout=240)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = json.loads([l for l in r.stdout.splitlines() if l.startswith("[")][-1])
+    assert got == list(range(11))
