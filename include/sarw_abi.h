@@ -106,6 +106,14 @@ int sarw_mr_more(sarw_ctx* ctx, int32_t* more);       /* same predicate as main(
 int sarw_mr_propose(sarw_ctx* ctx, void* d_localRecords);
 int sarw_mr_finish(sarw_ctx* ctx, const void* d_allRecords, int32_t* more);
 int sarw_mr_commit(sarw_ctx* ctx);
+/* Peer-memory variant (one process per GPU on one NVLink/NVSwitch node): the whole loop runs in ONE persistent launch per GPU;
+ * each rank stores its records straight into every peer's buffer and the ranks meet on flags in peer memory, so there is no
+ * host round trip and no NCCL call per round. After sarw_mr_setup: sarw_mr_peer_export fills a 64-byte CUDA IPC handle; the
+ * caller exchanges the handles of all ranks (rank order, 64 bytes each); sarw_mr_peer_connect opens them; then
+ * sarw_mr_grow_peer replaces the propose/all-gather/finish loop (call it on every rank at the same time). */
+int sarw_mr_peer_export(sarw_ctx* ctx, void* handle64);
+int sarw_mr_peer_connect(sarw_ctx* ctx, const void* allHandles);
+int sarw_mr_grow_peer(sarw_ctx* ctx, int64_t maxRounds, sarw_stats* stats);
 
 /* SARW::terminateChain (sarw.cpp:359-368) */
 int sarw_terminate(sarw_ctx* ctx);

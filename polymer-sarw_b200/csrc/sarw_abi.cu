@@ -45,6 +45,8 @@ struct sarw_ctx {
 
 	double seedMs = 0, growMs = 0; int64_t growLaunches = 0, seedLaunches = 0;
 	uint32_t mrRank = 0, mrRanks = 1; bool mrPending = false;   // multi-rank mode (sarw_mr_*)
+	void* xbuf = nullptr; size_t xbufRecBytes = 0;               // peer-memory exchange buffer (plain cudaMalloc: IPC-exportable)
+	void* peerRec[8] = {}; void* peerFlags[8] = {}; bool peersOpen = false;
 };
 
 namespace {
@@ -272,6 +274,8 @@ void sarw_destroy(sarw_ctx* c)
 		dev_free(c, c->roundAcc); dev_free(c, c->roundProg); dev_free(c, c->dirtyCount); dev_free(c, c->dirtyList); dev_free(c, c->grafts);
 		cudaStreamSynchronize(c->stream);
 	}
+	if (c->peersOpen) for (uint32_t p = 0; p < c->mrRanks; ++p) if (p != c->mrRank && c->peerRec[p]) cudaIpcCloseMemHandle(c->peerRec[p]);
+	if (c->xbuf) cudaFree(c->xbuf);
 	if (c->ev0) cudaEventDestroy(c->ev0);
 	if (c->ev1) cudaEventDestroy(c->ev1);
 	if (c->ownStream && c->stream) cudaStreamDestroy(c->stream);
@@ -496,7 +500,7 @@ static int mr_launch(sarw_ctx* c, uint32_t phase, void* localRec, const void* al
 	if (blocks < 1) blocks = 1;
 	CU(c, cudaEventRecord(c->ev0, c->stream));
 	CU(c, launch_grow_mr(c->g, c->T, c->chains, c->resTrial, c->resPos, c->prev, c->ctl, c->roundAcc, c->roundProg, c->dirtyCount, c->dirtyList,
-		h.round + 1, blocks, c->mrRank, c->mrRanks, phase, localRec, allRec, c->stream));
+		h.round + 1, blocks, c->mrRank, c->mrRanks, phase, localRec, allRec, nullptr, nullptr, c->stream));
 	CU(c, cudaEventRecord(c->ev1, c->stream));
 	c->growLaunches += 1;
 	if (hOut) {
@@ -539,6 +543,71 @@ int sarw_mr_commit(sarw_ctx* c)
 	Control h;
 	if (mr_launch(c, 3u, nullptr, nullptr, &h)) return 1;
 	c->mrPending = false;
+	return 0;
+}
+
+// ---- peer-memory variant: the whole loop in one persistent launch per GPU, exchange over NVLink inside the kernel
+int sarw_mr_peer_export(sarw_ctx* c, void* handle64)
+{
+	if (!c || !handle64) return 1;
+	if (c->mrRanks < 2 || c->mrRanks > 8) return fail(c, "sarw_mr_peer_export: call sarw_mr_setup with 2..8 ranks first");
+	cudaSetDevice(c->device);
+	const size_t K = ((size_t)c->g.nChains + c->mrRanks - 1) / c->mrRanks;
+	c->xbufRecBytes = 2 * (size_t)c->mrRanks * K * 32;
+	if (!c->xbuf) {
+		CU(c, cudaMalloc(&c->xbuf, c->xbufRecBytes + 256));
+		CU(c, cudaMemset(c->xbuf, 0, c->xbufRecBytes + 256));
+	}
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+	CU(c, cudaIpcGetMemHandle((cudaIpcMemHandle_t*)handle64, c->xbuf));
+	return 0;
+}
+
+int sarw_mr_peer_connect(sarw_ctx* c, const void* allHandles)
+{
+	if (!c || !allHandles) return 1;
+	if (!c->xbuf) return fail(c, "sarw_mr_peer_connect: call sarw_mr_peer_export first");
+	cudaSetDevice(c->device);
+	for (uint32_t p = 0; p < c->mrRanks; ++p) {
+		void* base = c->xbuf;
+		if (p != c->mrRank) {
+			cudaIpcMemHandle_t h; memcpy(&h, (const char*)allHandles + 64 * p, 64);
+			CU(c, cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+		}
+		c->peerRec[p] = base; c->peerFlags[p] = (char*)base + c->xbufRecBytes;
+	}
+	c->peersOpen = true;
+	return 0;
+}
+
+int sarw_mr_grow_peer(sarw_ctx* c, int64_t maxRounds, sarw_stats* stats)
+{
+	if (!c) return 1;
+	if (!c->peersOpen) return fail(c, "sarw_mr_grow_peer: peers are not connected");
+	if (!c->initiateCalled) return fail(c, "sarw_initiate must be called before growing");
+	cudaSetDevice(c->device);
+	Control h; if (read_control(c, &h)) return 1;
+	int64_t roundsLeft = maxRounds < 0 ? INT64_MAX : maxRounds;
+	while (c->initiated && roundsLeft > 0 && (int64_t)h.nBeads < c->g.target && h.lastProgressed) {
+		if (h.round >= c->roundCap && ensure_rounds(c, h.round + 1)) return 1;
+		uint32_t roundEnd = c->roundCap;
+		if ((int64_t)(roundEnd - h.round) > roundsLeft) roundEnd = h.round + (uint32_t)roundsLeft;
+		int blocks = (int)std::min<int64_t>(c->growBlocksMax, ((int64_t)c->g.nChains / c->mrRanks + 7) / 8);
+		if (blocks < 1) blocks = 1;
+		CU(c, cudaEventRecord(c->ev0, c->stream));
+		CU(c, launch_grow_mr(c->g, c->T, c->chains, c->resTrial, c->resPos, c->prev, c->ctl, c->roundAcc, c->roundProg, c->dirtyCount, c->dirtyList,
+			roundEnd, blocks, c->mrRank, c->mrRanks, 4u, nullptr, nullptr, c->peerRec, c->peerFlags, c->stream));
+		CU(c, cudaEventRecord(c->ev1, c->stream));
+		uint32_t before = h.round;
+		if (read_control(c, &h)) return 1;
+		float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+		c->growMs += ms; c->growLaunches += 1;
+		roundsLeft -= (int64_t)(h.round - before);
+		if (h.abort) return fail(c, "multi-rank growth aborted: a peer stopped answering (round %u)", h.round);
+		if (check_overflow(c)) return 1;
+		if (h.round == before) break;
+	}
+	if (stats) fill_stats(c, h, stats);
 	return 0;
 }
 

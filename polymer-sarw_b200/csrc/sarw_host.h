@@ -12,7 +12,7 @@ struct Control {
 	unsigned initiated;               // return value of initiateChain(), sarw.cpp:290
 	unsigned seedFailChain;           // first chain whose seeding failed, ID_NONE if none
 	unsigned seedDirtyCount;
-	unsigned pad0;
+	unsigned abort;                   // set when a peer stopped answering in the peer-memory multi-rank loop
 	unsigned long long nBeads;        // SARW::actualCount()
 	unsigned long long trials, queries, conflicts, seedTrials;
 	unsigned long long cycPropose, cycVerify, cycCleanup;   // SM cycles of block 0 per phase (incl. the closing barrier)
@@ -31,7 +31,7 @@ cudaError_t launch_grow(const Geom& g, const Tables& T, ChainState* chains, uint
 int grow_cluster_max_chains();
 cudaError_t launch_grow_mr(const Geom& g, const Tables& T, ChainState* chains, uint32_t* resTrial, double* resPos, uint32_t* prev, Control* ctl,
 	uint32_t* roundAcc, uint32_t* roundProg, uint32_t* dirtyCount, uint32_t* dirtyList, uint32_t roundEnd, int blocks,
-	uint32_t rank, uint32_t ranks, uint32_t phase, void* localRec, const void* allRec, cudaStream_t st);
+	uint32_t rank, uint32_t ranks, uint32_t phase, void* localRec, const void* allRec, void* const* peerRec, void* const* peerFlags, cudaStream_t st);
 cudaError_t download_scan_bytes(uint64_t nSlots, size_t* bytes);
 cudaError_t launch_download(const Geom& g, const Tables& T, const uint32_t* prev, const ChainState* chains, uint64_t nSlots, uint32_t nSeeded,
 	int terminated, uint32_t* flags, uint32_t* scan, void* cubTemp, size_t cubBytes,

@@ -295,6 +295,10 @@ struct GrowArgs {
 	uint32_t mrK;                 // records per rank = ceil(nChains / mrRanks)
 	MrRecord* mrLocal;            // phase 1 output: this rank's records, chain i at [i / mrRanks]
 	const MrRecord* mrAll;        // phase 2 input: all ranks' records, chain i at [(i % mrRanks) * mrK + i / mrRanks]
+	// phase 4: whole loop in one launch per GPU; records are stored straight into every peer's buffer over NVLink and the
+	// ranks meet on flags in peer memory (no host, no NCCL in the loop)
+	MrRecord* peerRec[8];         // [r]: rank r's record buffer, 2 parities x mrRanks x mrK records (own buffer at [mrRank])
+	uint32_t* peerFlags[8];       // [r]: rank r's arrival flags, 2 parities x 8 words
 };
 
 __device__ __forceinline__ uint32_t round_id_base(const Geom& g, uint32_t round)
@@ -471,6 +475,36 @@ __device__ __forceinline__ bool eval_trial_coop(const Geom& g, const Tables& T, 
 	return !__any_sync(FULL, hit);
 }
 
+// publish one chain's record: phases 1/2 into the local staging buffer, phase 4 into every rank's buffer (peer stores)
+__device__ __forceinline__ void mr_publish(const GrowArgs& A, uint32_t i, uint32_t round, const MrRecord& r)
+{
+	if (A.mrPhase == 4u) {
+		const size_t at = (size_t)(round & 1u) * A.mrRanks * A.mrK + (size_t)A.mrRank * A.mrK + i / A.mrRanks;
+		for (uint32_t p = 0; p < A.mrRanks; ++p) A.peerRec[p][at] = r;
+	} else A.mrLocal[i / A.mrRanks] = r;
+}
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
+{	uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+
+// one thread per GPU: tell every peer that this rank's records of `round` are complete, wait until all peers said so.
+// Returns false after ~3 s without progress (a peer died): the caller aborts the launch instead of hanging the GPU.
+__device__ bool mr_peer_meet(const GrowArgs& A, uint32_t round)
+{
+	const uint32_t par = round & 1u, tag = round + 1u;
+	__threadfence_system();
+	for (uint32_t p = 0; p < A.mrRanks; ++p) if (p != A.mrRank) st_release_sys(A.peerFlags[p] + par * 8u + A.mrRank, tag);
+	const long long t0 = clock64();
+	for (uint32_t p = 0; p < A.mrRanks; ++p) {
+		if (p == A.mrRank) continue;
+		while (ld_acquire_sys(A.peerFlags[A.mrRank] + par * 8u + p) != tag)
+			if (clock64() - t0 > 6000000000ll) return false;
+	}
+	return true;
+}
+
 // apply the result of the previous round to the chain state (sarw.cpp:270-273); all lanes compute, lane 0 stores
 __device__ __forceinline__ void commit_pending(const GrowArgs& A, uint32_t i, uint32_t pendingRound, ChainState& cs, int lane)
 {
@@ -612,7 +646,7 @@ __global__ void __launch_bounds__(WARPS * 32) grow_kernel(GrowArgs A)
 	unsigned long long nBeads = __ldcg(&A.ctl->nBeads);
 	uint32_t lastProg = __ldcg(&A.ctl->lastProgressed);
 	unsigned long long myTrials = 0, myQueries = 0;
-	bool pendingValid = (A.mrPhase == 1u);   // is there a round whose results are not yet committed? (always possible between multi-rank launches)
+	bool pendingValid = (A.mrPhase == 1u);   // is there a round whose results are not yet committed? (always possible between phase-1/2 launches)
 	const bool mr = A.mrPhase != 0u;
 	if (A.mrPhase == 3u) {       // multi-rank: commit the last round, nothing else
 		for (uint32_t i = gw; i < g.nChains; i += nW) { ChainState cs = load_chain(A.chains + i); commit_pending(A, i, round - 1, cs, lane); }
@@ -637,7 +671,7 @@ __global__ void __launch_bounds__(WARPS * 32) grow_kernel(GrowArgs A)
 			if (cs.flags & CHAIN_DEAD) {   // permanently blocked: the reference burns maxTrials here every round
 				if (lane == 0) {
 					A.resTrial[i] = T_ + 1u;
-					if (mr) { MrRecord r; r.x = r.y = r.z = 0; r.trial = T_ + 1u; r.pad = 0; A.mrLocal[i / A.mrRanks] = r; }
+					if (mr) { MrRecord r; r.x = r.y = r.z = 0; r.trial = T_ + 1u; r.pad = 0; mr_publish(A, i, round, r); }
 				}
 				continue;
 			}
@@ -657,14 +691,24 @@ __global__ void __launch_bounds__(WARPS * 32) grow_kernel(GrowArgs A)
 					for (int k2 = 0; k2 < 3; k2++) A.resPos[3 * (size_t)i + k2] = cand[k2];
 				}
 				A.resTrial[i] = accepted ? accepted : T_ + 1u;
-				if (mr) { MrRecord r; r.x = cand[0]; r.y = cand[1]; r.z = cand[2]; r.trial = accepted ? accepted : T_ + 1u; r.pad = 0; A.mrLocal[i / A.mrRanks] = r; }
+				if (mr) { MrRecord r; r.x = cand[0]; r.y = cand[1]; r.z = cand[2]; r.trial = accepted ? accepted : T_ + 1u; r.pad = 0; mr_publish(A, i, round, r); }
 			}
 		}
 		if (A.mrPhase == 1u) break;                                  // the host all-gathers the records, then launches phase 2
-		if (A.mrPhase == 2u)                                         // tentative beads proposed by the other ranks
+		const MrRecord* allRec = A.mrAll;
+		if (A.mrPhase == 4u) {                                       // exchange inside the kernel: peer stores + flag handshake
+			round_barrier<CLUSTER>(A.ctl);                            // every record store of this GPU has been issued
+			if (gw == 0 && lane == 0 && !mr_peer_meet(A, round)) atomicExch(&A.ctl->abort, 1u);
+			round_barrier<CLUSTER>(A.ctl);
+			if (__ldcg(&A.ctl->abort)) break;
+			allRec = A.peerRec[A.mrRank] + (size_t)(round & 1u) * A.mrRanks * A.mrK;
+		}
+		if (A.mrPhase == 2u || A.mrPhase == 4u)                     // tentative beads proposed by the other ranks
 			for (uint32_t i = start + gw * 32 + lane; i < end; i += nW * 32) {
 				if ((i % A.mrRanks) == A.mrRank) continue;
-				const MrRecord r = A.mrAll[(size_t)(i % A.mrRanks) * A.mrK + i / A.mrRanks];
+				const MrRecord* rp_ = allRec + (size_t)(i % A.mrRanks) * A.mrK + i / A.mrRanks;
+				MrRecord r;
+				r.x = __ldcg(&rp_->x); r.y = __ldcg(&rp_->y); r.z = __ldcg(&rp_->z); r.trial = __ldcg(&rp_->trial); r.pad = 0;
 				A.resTrial[i] = r.trial;
 				if (r.trial >= 1u && r.trial <= T_) {
 					const double p[3] = { r.x, r.y, r.z };
@@ -726,7 +770,7 @@ __global__ void __launch_bounds__(WARPS * 32) grow_kernel(GrowArgs A)
 	}
 
 	// commit the last round of this launch (multi-rank: the next phase-1 launch, or phase 3, commits)
-	if (pendingValid && !mr)
+	if (pendingValid && (A.mrPhase == 0u || A.mrPhase == 4u))
 		for (uint32_t i = gw; i < g.nChains; i += nW) {
 			ChainState cs = load_chain(A.chains + i);
 			commit_pending(A, i, round - 1, cs, lane);
@@ -861,7 +905,7 @@ static cudaError_t launch_cluster(const GrowArgs& A, cudaStream_t st)
 cudaError_t launch_grow(const Geom& g, const Tables& T, ChainState* chains, uint32_t* resTrial, double* resPos, uint32_t* prev, Control* ctl,
 	uint32_t* roundAcc, uint32_t* roundProg, uint32_t* dirtyCount, uint32_t* dirtyList, uint32_t roundEnd, int blocks, int useCluster, cudaStream_t st)
 {
-	GrowArgs A{ g, T, chains, resTrial, resPos, prev, ctl, roundAcc, roundProg, dirtyCount, dirtyList, roundEnd, 0u, 1u, 0u, 0u, nullptr, nullptr };
+	GrowArgs A{ g, T, chains, resTrial, resPos, prev, ctl, roundAcc, roundProg, dirtyCount, dirtyList, roundEnd, 0u, 1u, 0u, 0u, nullptr, nullptr, {}, {} };
 	if (useCluster) {
 		// the whole launch is one thread-block cluster: CTAs are co-scheduled by the hardware, synchronise with
 		// barrier.cluster and exchange tentative beads through distributed shared memory. 8 warps per CTA (255
@@ -876,11 +920,12 @@ cudaError_t launch_grow(const Geom& g, const Tables& T, ChainState* chains, uint
 // one phase of a multi-rank round (grow_kernel with mrPhase != 0); always the cooperative grid kernel
 cudaError_t launch_grow_mr(const Geom& g, const Tables& T, ChainState* chains, uint32_t* resTrial, double* resPos, uint32_t* prev, Control* ctl,
 	uint32_t* roundAcc, uint32_t* roundProg, uint32_t* dirtyCount, uint32_t* dirtyList, uint32_t roundEnd, int blocks,
-	uint32_t rank, uint32_t ranks, uint32_t phase, void* localRec, const void* allRec, cudaStream_t st)
+	uint32_t rank, uint32_t ranks, uint32_t phase, void* localRec, const void* allRec, void* const* peerRec, void* const* peerFlags, cudaStream_t st)
 {
 	const uint32_t K = (g.nChains + ranks - 1) / ranks;
 	GrowArgs A{ g, T, chains, resTrial, resPos, prev, ctl, roundAcc, roundProg, dirtyCount, dirtyList, roundEnd, rank, ranks, phase, K,
-		(MrRecord*)localRec, (const MrRecord*)allRec };
+		(MrRecord*)localRec, (const MrRecord*)allRec, {}, {} };
+	for (uint32_t p = 0; p < 8; ++p) { A.peerRec[p] = peerRec && p < ranks ? (MrRecord*)peerRec[p] : nullptr; A.peerFlags[p] = peerFlags && p < ranks ? (uint32_t*)peerFlags[p] : nullptr; }
 	void* args[] = { &A };
 	return cudaLaunchCooperativeKernel((const void*)grow_kernel<GROW_WARPS, false>, dim3((unsigned)blocks), dim3(GROW_WARPS * 32), args,
 		grow_smem_bytes(GROW_WARPS), st);

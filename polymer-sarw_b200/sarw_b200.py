@@ -25,6 +25,7 @@ ABI_SYMBOLS = [
     "sarw_download", "sarw_chain_lengths", "sarw_round_counts", "sarw_lookup_add_points", "sarw_lookup_find_batch",
     "sarw_lookup_find_batch_device", "sarw_lookup_size",
     "sarw_mr_setup", "sarw_mr_more", "sarw_mr_propose", "sarw_mr_finish", "sarw_mr_commit",
+    "sarw_mr_peer_export", "sarw_mr_peer_connect", "sarw_mr_grow_peer",
 ]
 
 
@@ -90,6 +91,9 @@ def load_library(path=LIB_PATH):
     lib.sarw_mr_propose.argtypes = [vp, vp]
     lib.sarw_mr_finish.argtypes = [vp, vp, C.POINTER(C.c_int32)]
     lib.sarw_mr_commit.argtypes = [vp]
+    lib.sarw_mr_peer_export.argtypes = [vp, vp]
+    lib.sarw_mr_peer_connect.argtypes = [vp, vp]
+    lib.sarw_mr_grow_peer.argtypes = [vp, C.c_int64, C.POINTER(Stats)]
     _lib = lib
     return lib
 
@@ -210,6 +214,21 @@ class Context:
     def mr_commit(self):
         self._ck(self.lib.sarw_mr_commit(self.h))
 
+    def mr_peer_export(self):
+        buf = (C.c_ubyte * 64)()
+        self._ck(self.lib.sarw_mr_peer_export(self.h, buf))
+        return bytes(buf)
+
+    def mr_peer_connect(self, all_handles):
+        raw = b"".join(all_handles)
+        buf = (C.c_ubyte * len(raw)).from_buffer_copy(raw)
+        self._ck(self.lib.sarw_mr_peer_connect(self.h, buf))
+
+    def mr_grow_peer(self, maxRounds=-1):
+        s = Stats()
+        self._ck(self.lib.sarw_mr_grow_peer(self.h, maxRounds, C.byref(s)))
+        return s
+
     def terminate(self):
         self._ck(self.lib.sarw_terminate(self.h))
 
@@ -317,3 +336,14 @@ def grow_multirank(ctx, dist, rank, nranks, device="cuda"):
 def mr_chain_slot(i, nranks, K):
     """Where chain i's record sits after the all-gather (rank-major): (i % nranks) * K + i // nranks."""
     return (i % nranks) * K + i // nranks
+
+
+def grow_multirank_peer(ctx, dist, rank, nranks):
+    """Same walk, exchange inside the kernel over NVLink peer memory: torch.distributed is used once, to swap the IPC handles."""
+    ctx.mr_setup(rank, nranks)
+    mine = ctx.mr_peer_export()
+    handles = [None] * nranks
+    dist.all_gather_object(handles, mine)
+    ctx.mr_peer_connect(handles)
+    dist.barrier()
+    return ctx.mr_grow_peer(-1).rounds

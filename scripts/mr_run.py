@@ -11,8 +11,9 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
 per = int(sys.argv[2]) if len(sys.argv) > 2 else 100
-L = (n * per / 0.03957) ** (1.0 / 3.0)
-cfg = dict(nChains=n, boxSize=(L, L, L), minDist=1.0, maxTrials=1000, seed=7, device=local)
+dens = float(sys.argv[3]) if len(sys.argv) > 3 else 0.92      # g/cc; lower = same tip density as a longer-chain melt early in its growth
+L = (n * per / (0.03957 * dens / 0.92)) ** (1.0 / 3.0)
+cfg = dict(nChains=n, boxSize=(L, L, L), minDist=1.0, maxTrials=1000, seed=7, device=local, targetMassDensity=dens)
 stream = torch.cuda.current_stream()
 
 def run(multi):
@@ -21,20 +22,27 @@ def run(multi):
     torch.cuda.synchronize(); dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    if multi: rounds = sarw_b200.grow_multirank(c, dist, rank, world)
+    if multi == 2: rounds = sarw_b200.grow_multirank_peer(c, dist, rank, world)
+    elif multi: rounds = sarw_b200.grow_multirank(c, dist, rank, world)
     else: rounds = c.grow(0, -1).rounds
     e1.record(stream); e1.synchronize()
     c.terminate()
     out = c.download(); st = c.stats().as_dict(); c.close()
     return out, st, e0.elapsed_time(e1), rounds
 
-single, st1, ms1, r1 = run(False)
-multi, stN, msN, rN = run(True)
+single, st1, ms1, r1 = run(0)
+multi, stN, msN, rN = run(1)
+peer, stP, msP, rP = run(2)
 same = all(np.array_equal(a, b) for a, b in zip(single, multi)) and r1 == rN
-t = torch.tensor([msN, ms1], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
-ok = torch.tensor([1.0 if same else 0.0], device="cuda"); dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+sameP = all(np.array_equal(a, b) for a, b in zip(single, peer)) and r1 == rP
+t = torch.tensor([msN, ms1, msP], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+ok = torch.tensor([1.0 if same else 0.0, 1.0 if sameP else 0.0], device="cuda"); dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+def cyc(st, r):
+    return [round(st[k] / max(1, r)) for k in ("cycPropose", "cycVerify", "cycCleanup")]
 if rank == 0:
-    print(json.dumps(dict(n_gpus=world, nChains=n, beads=st1["nBeads"], rounds=r1, identical_on_all_ranks=bool(ok.item() == 1.0),
+    print("cycles/round [A, V, C]  single", cyc(st1, r1), " nccl", cyc(stN, rN), " peer", cyc(stP, rP))
+    print(json.dumps(dict(n_gpus=world, nChains=n, box=L, density=dens, conflicts=st1["conflicts"], beads=st1["nBeads"], rounds=r1, nccl_identical_on_all_ranks=bool(ok[0].item() == 1.0), peer_identical_on_all_ranks=bool(ok[1].item() == 1.0),
+                          peer_gpu_ms=t[2].item(), peer_beads_per_s=st1["nBeads"] / t[2].item() * 1e3, us_per_round_peer=t[2].item() * 1e3 / max(1, rP),
                           single_gpu_ms=t[1].item(), multi_gpu_ms=t[0].item(), single_beads_per_s=st1["nBeads"] / t[1].item() * 1e3,
                           multi_beads_per_s=st1["nBeads"] / t[0].item() * 1e3, us_per_round_multi=t[0].item() * 1e3 / max(1, rN))))
 dist.barrier(); dist.destroy_process_group()
