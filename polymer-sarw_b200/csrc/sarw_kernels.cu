@@ -520,6 +520,23 @@ __device__ __forceinline__ void commit_pending(const GrowArgs& A, uint32_t i, ui
 	if (t != 0 && lane == 0) A.resTrial[i] = 0;
 }
 
+// the same commit by ONE thread (multi-rank: chains proposed by other ranks are committed thread-per-chain, fully parallel)
+__device__ __forceinline__ void commit_pending_thread(const GrowArgs& A, uint32_t i, uint32_t pendingRound)
+{
+	const Geom& g = A.g;
+	const uint32_t t = __ldcg(&A.resTrial[i]);
+	if (t >= 1u && t <= (uint32_t)g.maxTrials) {
+		const uint32_t id = round_id_base(g, pendingRound) + i;
+		ChainState* p = A.chains + i;
+		const uint32_t oldLast = __ldcg(&p->lastId);
+		for (int k = 0; k < 3; k++) { p->pen[k] = __ldcg(&p->last[k]); }
+		for (int k = 0; k < 3; k++) { p->last[k] = __ldcg(&A.resPos[3 * (size_t)i + k]); }
+		A.prev[id - g.idAtomBase] = oldLast;
+		p->penId = oldLast; p->lastId = id; p->length = __ldcg(&p->length) + 1u;
+	}
+	if (t != 0u) A.resTrial[i] = 0;
+}
+
 __device__ __forceinline__ ChainState load_chain(const ChainState* p)
 {
 	ChainState cs;
@@ -655,19 +672,24 @@ __global__ void __launch_bounds__(WARPS * 32) grow_kernel(GrowArgs A)
 
 	const bool timer = (blockIdx.x == 0 && threadIdx.x == 0);
 	long long cycA = 0, cycV = 0, cycC = 0; uint32_t cleanRounds = 0;
+	long long sub[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }, ts0 = 0, ts1 = 0;
+#define SUBT(k) do { ts1 = clock64(); sub[k] += ts1 - ts0; ts0 = ts1; } while (0)
 	while (round < A.roundEnd && (long long)nBeads < g.target && lastProg) {
 		const long long tk0 = clock64();
+		ts0 = tk0;
 		uint32_t start, end;
 		round_range(g, nBeads, start, end);
 		const uint32_t idRound = round_id_base(g, round);
 
 		// ---------------- phase A: commit last round, then propose + tentatively insert
+		if (mr && A.mrPhase != 2u && pendingValid)                   // chains proposed by other ranks: commit only, one thread each
+			for (uint32_t i = (gw * 32 + lane); i < g.nChains; i += nW * 32)
+				if ((i % A.mrRanks) != A.mrRank) commit_pending_thread(A, i, round - 1);
 		if (A.mrPhase != 2u)
-		for (uint32_t i = gw; i < g.nChains; i += nW) {
+		for (uint32_t i = mr ? A.mrRank + gw * A.mrRanks : gw; i < g.nChains; i += mr ? nW * A.mrRanks : nW) {
 			ChainState cs = load_chain(A.chains + i);
 			if (pendingValid) commit_pending(A, i, round - 1, cs, lane);
 			if (i < start || i >= end) continue;
-			if (mr && (i % A.mrRanks) != A.mrRank) continue;          // another rank proposes for this chain
 			if (cs.flags & CHAIN_DEAD) {   // permanently blocked: the reference burns maxTrials here every round
 				if (lane == 0) {
 					A.resTrial[i] = T_ + 1u;
@@ -694,12 +716,16 @@ __global__ void __launch_bounds__(WARPS * 32) grow_kernel(GrowArgs A)
 				if (mr) { MrRecord r; r.x = cand[0]; r.y = cand[1]; r.z = cand[2]; r.trial = accepted ? accepted : T_ + 1u; r.pad = 0; mr_publish(A, i, round, r); }
 			}
 		}
+		SUBT(0);
 		if (A.mrPhase == 1u) break;                                  // the host all-gathers the records, then launches phase 2
 		const MrRecord* allRec = A.mrAll;
 		if (A.mrPhase == 4u) {                                       // exchange inside the kernel: peer stores + flag handshake
 			round_barrier<CLUSTER>(A.ctl);                            // every record store of this GPU has been issued
+			SUBT(1);
 			if (gw == 0 && lane == 0 && !mr_peer_meet(A, round)) atomicExch(&A.ctl->abort, 1u);
+			SUBT(2);
 			round_barrier<CLUSTER>(A.ctl);
+			SUBT(3);
 			if (__ldcg(&A.ctl->abort)) break;
 			allRec = A.peerRec[A.mrRank] + (size_t)(round & 1u) * A.mrRanks * A.mrK;
 		}
@@ -716,8 +742,10 @@ __global__ void __launch_bounds__(WARPS * 32) grow_kernel(GrowArgs A)
 					for (int k2 = 0; k2 < 3; k2++) A.resPos[3 * (size_t)i + k2] = p[k2];
 				}
 			}
+		SUBT(4);
 		pendingValid = true;
 		round_barrier<CLUSTER>(A.ctl);
+		SUBT(5);
 		const long long tk1 = clock64();
 
 		// ---------------- phase V: conflicts with tentative beads of lower-indexed chains of this round
@@ -783,6 +811,8 @@ __global__ void __launch_bounds__(WARPS * 32) grow_kernel(GrowArgs A)
 		A.ctl->round = round; A.ctl->nBeads = nBeads; A.ctl->lastProgressed = lastProg ? 1u : 0u;
 	}
 	if (timer) { A.ctl->cycPropose += cycA; A.ctl->cycVerify += cycV; A.ctl->cycCleanup += cycC; A.ctl->cleanupRounds += cleanRounds; }
+	if (timer) for (int k2 = 0; k2 < 8; k2++) A.ctl->cycSub[k2] += sub[k2];
+#undef SUBT
 }
 
 // ------------------------------------------------------------------ K7: compaction into acceptance order

@@ -338,12 +338,18 @@ def mr_chain_slot(i, nranks, K):
     return (i % nranks) * K + i // nranks
 
 
-def grow_multirank_peer(ctx, dist, rank, nranks):
-    """Same walk, exchange inside the kernel over NVLink peer memory: torch.distributed is used once, to swap the IPC handles."""
+def connect_peers(ctx, dist, rank, nranks):
+    """One-time set-up of the peer-memory exchange: torch.distributed is used once, to swap the 64-byte CUDA IPC handles."""
     ctx.mr_setup(rank, nranks)
     mine = ctx.mr_peer_export()
     handles = [None] * nranks
     dist.all_gather_object(handles, mine)
     ctx.mr_peer_connect(handles)
     dist.barrier()
+
+
+def grow_multirank_peer(ctx, dist, rank, nranks, connected=False):
+    """Same walk, exchange inside the kernel over NVLink peer memory (no host round trip, no NCCL call per round)."""
+    if not connected:
+        connect_peers(ctx, dist, rank, nranks)
     return ctx.mr_grow_peer(-1).rounds

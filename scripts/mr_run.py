@@ -19,10 +19,11 @@ stream = torch.cuda.current_stream()
 def run(multi):
     c = sarw_b200.Context(launchMode=1, **cfg); c.set_stream(stream.cuda_stream)
     c.initiate()
+    if multi == 2: sarw_b200.connect_peers(c, dist, rank, world)
     torch.cuda.synchronize(); dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    if multi == 2: rounds = sarw_b200.grow_multirank_peer(c, dist, rank, world)
+    if multi == 2: rounds = sarw_b200.grow_multirank_peer(c, dist, rank, world, connected=True)
     elif multi: rounds = sarw_b200.grow_multirank(c, dist, rank, world)
     else: rounds = c.grow(0, -1).rounds
     e1.record(stream); e1.synchronize()
@@ -41,6 +42,7 @@ def cyc(st, r):
     return [round(st[k] / max(1, r)) for k in ("cycPropose", "cycVerify", "cycCleanup")]
 if rank == 0:
     print("cycles/round [A, V, C]  single", cyc(st1, r1), " nccl", cyc(stN, rN), " peer", cyc(stP, rP))
+    print("sub-phases/round single", [round(x / max(1, r1)) for x in st1["cycSub"]], " peer", [round(x / max(1, rP)) for x in stP["cycSub"]])
     print(json.dumps(dict(n_gpus=world, nChains=n, box=L, density=dens, conflicts=st1["conflicts"], beads=st1["nBeads"], rounds=r1, nccl_identical_on_all_ranks=bool(ok[0].item() == 1.0), peer_identical_on_all_ranks=bool(ok[1].item() == 1.0),
                           peer_gpu_ms=t[2].item(), peer_beads_per_s=st1["nBeads"] / t[2].item() * 1e3, us_per_round_peer=t[2].item() * 1e3 / max(1, rP),
                           single_gpu_ms=t[1].item(), multi_gpu_ms=t[0].item(), single_beads_per_s=st1["nBeads"] / t[1].item() * 1e3,
