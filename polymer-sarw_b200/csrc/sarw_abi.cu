@@ -38,7 +38,7 @@ struct sarw_ctx {
 
 	Control* ctl = nullptr;
 	ChainState* chains = nullptr;
-	uint32_t* resTrial = nullptr; double* resPos = nullptr;
+	uint32_t* resTrial = nullptr; uint32_t* origTrial = nullptr; double* resPos = nullptr;
 	uint32_t* prev = nullptr; uint64_t prevCap = 0;
 	uint32_t *roundAcc = nullptr, *roundProg = nullptr, *dirtyCount = nullptr, *dirtyList = nullptr;
 	double* grafts = nullptr; int64_t nGrafts = 0;
@@ -246,8 +246,10 @@ int sarw_create(const sarw_params* p, sarw_ctx** out)
 	CUB_(cudaMemsetAsync(c->chains, 0, (size_t)g.nChains * sizeof(ChainState), c->stream));
 	CUB_(dev_alloc(c, &c->resTrial, (size_t)g.nChains * sizeof(uint32_t)));
 	CUB_(cudaMemsetAsync(c->resTrial, 0, (size_t)g.nChains * sizeof(uint32_t), c->stream));
+	CUB_(dev_alloc(c, &c->origTrial, (size_t)g.nChains * sizeof(uint32_t)));
+	CUB_(cudaMemsetAsync(c->origTrial, 0, (size_t)g.nChains * sizeof(uint32_t), c->stream));
 	CUB_(dev_alloc(c, &c->resPos, (size_t)g.nChains * 3 * sizeof(double)));
-	CUB_(dev_alloc(c, &c->dirtyList, (size_t)g.nChains * sizeof(uint32_t)));
+	CUB_(dev_alloc(c, &c->dirtyList, 3 * (size_t)g.nChains * sizeof(uint32_t)));   // conflict list (n) + second list of the parallel clean-up (<= 2n: independent chains are far apart)
 	CUB_(grow_max_blocks(c->numSMs, &c->growBlocksMax));
 	CUB_(cudaStreamSynchronize(c->stream));
 #undef CUB_
@@ -270,7 +272,7 @@ void sarw_destroy(sarw_ctx* c)
 	if (c->stream) cudaStreamSynchronize(c->stream);
 	if (c->stream) {
 		dev_free(c, c->T.cells); dev_free(c, c->T.lpos); dev_free(c, c->T.ovf); dev_free(c, c->T.ovfCount);
-		dev_free(c, c->ctl); dev_free(c, c->chains); dev_free(c, c->resTrial); dev_free(c, c->resPos); dev_free(c, c->prev);
+		dev_free(c, c->ctl); dev_free(c, c->chains); dev_free(c, c->resTrial); dev_free(c, c->origTrial); dev_free(c, c->resPos); dev_free(c, c->prev);
 		dev_free(c, c->roundAcc); dev_free(c, c->roundProg); dev_free(c, c->dirtyCount); dev_free(c, c->dirtyList); dev_free(c, c->grafts);
 		cudaStreamSynchronize(c->stream);
 	}
@@ -409,13 +411,13 @@ static int use_cluster(const sarw_ctx* c)
 static cudaError_t launch_grow_auto(sarw_ctx* c, const Geom& g, uint32_t roundEnd, int blocks)
 {
 	if (use_cluster(c)) {
-		cudaError_t e = launch_grow(g, c->T, c->chains, c->resTrial, c->resPos, c->prev, c->ctl, c->roundAcc, c->roundProg, c->dirtyCount,
+		cudaError_t e = launch_grow(g, c->T, c->chains, c->resTrial, c->origTrial, c->resPos, c->prev, c->ctl, c->roundAcc, c->roundProg, c->dirtyCount,
 			c->dirtyList, roundEnd, blocks, 1, c->stream);
 		if (e == cudaSuccess) return e;
 		cudaGetLastError();          // launch-configuration error (nothing ran): fall back to the cooperative grid for good
 		c->p.launchMode = 1;
 	}
-	return launch_grow(g, c->T, c->chains, c->resTrial, c->resPos, c->prev, c->ctl, c->roundAcc, c->roundProg, c->dirtyCount,
+	return launch_grow(g, c->T, c->chains, c->resTrial, c->origTrial, c->resPos, c->prev, c->ctl, c->roundAcc, c->roundProg, c->dirtyCount,
 		c->dirtyList, roundEnd, blocks, 0, c->stream);
 }
 
@@ -499,7 +501,7 @@ static int mr_launch(sarw_ctx* c, uint32_t phase, void* localRec, const void* al
 	int blocks = (int)std::min<int64_t>(c->growBlocksMax, ((int64_t)c->g.nChains + 7) / 8);
 	if (blocks < 1) blocks = 1;
 	CU(c, cudaEventRecord(c->ev0, c->stream));
-	CU(c, launch_grow_mr(c->g, c->T, c->chains, c->resTrial, c->resPos, c->prev, c->ctl, c->roundAcc, c->roundProg, c->dirtyCount, c->dirtyList,
+	CU(c, launch_grow_mr(c->g, c->T, c->chains, c->resTrial, c->origTrial, c->resPos, c->prev, c->ctl, c->roundAcc, c->roundProg, c->dirtyCount, c->dirtyList,
 		h.round + 1, blocks, c->mrRank, c->mrRanks, phase, localRec, allRec, nullptr, nullptr, c->stream));
 	CU(c, cudaEventRecord(c->ev1, c->stream));
 	c->growLaunches += 1;
@@ -595,7 +597,7 @@ int sarw_mr_grow_peer(sarw_ctx* c, int64_t maxRounds, sarw_stats* stats)
 		int blocks = (int)std::min<int64_t>(c->growBlocksMax, ((int64_t)c->g.nChains / c->mrRanks + 7) / 8);
 		if (blocks < 1) blocks = 1;
 		CU(c, cudaEventRecord(c->ev0, c->stream));
-		CU(c, launch_grow_mr(c->g, c->T, c->chains, c->resTrial, c->resPos, c->prev, c->ctl, c->roundAcc, c->roundProg, c->dirtyCount, c->dirtyList,
+		CU(c, launch_grow_mr(c->g, c->T, c->chains, c->resTrial, c->origTrial, c->resPos, c->prev, c->ctl, c->roundAcc, c->roundProg, c->dirtyCount, c->dirtyList,
 			roundEnd, blocks, c->mrRank, c->mrRanks, 4u, nullptr, nullptr, c->peerRec, c->peerFlags, c->stream));
 		CU(c, cudaEventRecord(c->ev1, c->stream));
 		uint32_t before = h.round;

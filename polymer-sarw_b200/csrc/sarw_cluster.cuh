@@ -526,7 +526,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) grow_cluster_kernel(GrowArgs A)
 				for (int k = 0; k < 3; k++) A.resPos[3 * (size_t)i + k] = cand[k];
 			}
 			if (lane == 0) {
-				A.resTrial[i] = rec.trial;
+				A.resTrial[i] = rec.trial; A.origTrial[i] = rec.trial;
 				myTrials += rec.trial <= T_ ? rec.trial : T_;
 				if (conflict) { const uint32_t at = atomicAdd(&A.dirtyCount[round], 1u); A.dirtyList[at] = i; }
 			}

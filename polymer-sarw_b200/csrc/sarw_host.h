@@ -13,6 +13,7 @@ struct Control {
 	unsigned seedFailChain;           // first chain whose seeding failed, ID_NONE if none
 	unsigned seedDirtyCount;
 	unsigned abort;                   // set when a peer stopped answering in the peer-memory multi-rank loop
+	unsigned dirty2Count, padA;       // chains put in conflict by the parallel clean-up (second list)
 	unsigned long long nBeads;        // SARW::actualCount()
 	unsigned long long trials, queries, conflicts, seedTrials;
 	unsigned long long cycPropose, cycVerify, cycCleanup;   // SM cycles of block 0 per phase (incl. the closing barrier)
@@ -26,10 +27,10 @@ cudaError_t launch_add_points(const Geom& g, const Tables& T, const double* xyz,
 cudaError_t launch_seed(const Geom& g, const Tables& T, ChainState* chains, uint32_t* resTrial, uint32_t* prev, const double* grafts,
 	Control* ctl, uint32_t* dirtyList, int numSMs, cudaStream_t st, int* launches);
 cudaError_t grow_max_blocks(int numSMs, int* maxBlocks);
-cudaError_t launch_grow(const Geom& g, const Tables& T, ChainState* chains, uint32_t* resTrial, double* resPos, uint32_t* prev, Control* ctl,
+cudaError_t launch_grow(const Geom& g, const Tables& T, ChainState* chains, uint32_t* resTrial, uint32_t* origTrial, double* resPos, uint32_t* prev, Control* ctl,
 	uint32_t* roundAcc, uint32_t* roundProg, uint32_t* dirtyCount, uint32_t* dirtyList, uint32_t roundEnd, int blocks, int useCluster, cudaStream_t st);
 int grow_cluster_max_chains();
-cudaError_t launch_grow_mr(const Geom& g, const Tables& T, ChainState* chains, uint32_t* resTrial, double* resPos, uint32_t* prev, Control* ctl,
+cudaError_t launch_grow_mr(const Geom& g, const Tables& T, ChainState* chains, uint32_t* resTrial, uint32_t* origTrial, double* resPos, uint32_t* prev, Control* ctl,
 	uint32_t* roundAcc, uint32_t* roundProg, uint32_t* dirtyCount, uint32_t* dirtyList, uint32_t roundEnd, int blocks,
 	uint32_t rank, uint32_t ranks, uint32_t phase, void* localRec, const void* allRec, void* const* peerRec, void* const* peerFlags, cudaStream_t st);
 cudaError_t download_scan_bytes(uint64_t nSlots, size_t* bytes);

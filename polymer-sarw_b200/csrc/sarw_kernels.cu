@@ -107,7 +107,7 @@ __device__ void enumerate_hits(const Geom& g, const Tables& T, const double v[3]
 __device__ void dirty_push_unique(volatile uint32_t* list, volatile uint32_t* count, uint32_t chain)
 {
 	uint32_t n = *count;
-	for (uint32_t j = 0; j < n; ++j) if ((list[j] & ~DONE_BIT) == chain) return;
+	for (uint32_t j = 0; j < n; ++j) if ((list[j] & ~DONE_BIT) == chain) { list[j] = chain; return; }   // already listed: (re-)open it
 	list[n] = chain; *count = n + 1;
 }
 __device__ int dirty_pop_min(volatile uint32_t* list, volatile const uint32_t* count, uint32_t& chain)
@@ -281,6 +281,7 @@ struct GrowArgs {
 	Geom g; Tables T;
 	ChainState* chains;
 	uint32_t* resTrial;     // per chain: 0 nothing pending, 1..T accepted trial of the running round, T+1 failed
+	uint32_t* origTrial;    // per chain: the trial phase A stopped at this round (conflict resolution restarts there)
 	double* resPos;         // per chain: tentative / accepted bead of the running round
 	uint32_t* prev;         // per atom slot: lookup index of the previous bead of its chain (bond partner, sarw.cpp:272)
 	Control* ctl;
@@ -548,77 +549,142 @@ __device__ __forceinline__ ChainState load_chain(const ChainState* p)
 	return cs;
 }
 
-// one warp: re-resolve the conflicting chains of a round in chain order (what sarw.cpp:251-281 does serially).
-// Lanes 8g..8g+7 evaluate trial t0+g (one cell each), so four trials are in flight per pass.
-__device__ void cleanup_round(const GrowArgs& A, uint32_t round, int lane)
+// ------------------------------------------------------------------ same-round conflict resolution
+// re-resolve ONE conflicting chain with the whole warp: drop its current bead, search from the trial phase A stopped at
+// against the beads of the previous rounds plus this round's beads of LOWER chains, insert the new bead, report the
+// higher chains of this round that now collide with it. Lanes 8g..8g+7 evaluate trial t0+g (one cell each).
+template <typename Push>
+__device__ void resolve_dirty_chain(const GrowArgs& A, uint32_t round, uint32_t chain, int lane, Push&& push)
 {
 	const Geom& g = A.g;
 	const uint32_t T_ = (uint32_t)g.maxTrials;
 	const uint32_t idRound = round_id_base(g, round), idEnd = idRound + g.nChains;
 	const int sub = lane & 7, grp = lane >> 3;
+	const uint32_t myId = idRound + chain;
+	const ChainState cs = load_chain(A.chains + chain);
+	Frame f; cone_frame(cs.last, cs.pen, f);
+	const uint32_t t0 = __ldcg(&A.origTrial[chain]);       // where phase A stopped: trials before it fail against old beads alone
+	const uint32_t cur = __ldcg(&A.resTrial[chain]);        // what is booked (and inserted) right now
+	if (lane == 0 && cur <= T_) remove_bead(g, A.T, myId);
+	__syncwarp();
+	uint32_t found = 0; double cand[3] = { 0, 0, 0 }, v[3] = { 0, 0, 0 };
+	for (uint32_t tb = t0; tb <= T_ && !found; tb += 4) {
+		const uint32_t t = tb + grp;
+		bool rejected = t > T_, hit = false;
+		if (!rejected) {
+			cone_candidate(g, f, cs.last, u_grow(g, chain, round, t), cand);
+			rejected = growth_rules_reject(g, cand, cs.last);
+			if (!rejected) { to_frac(g, cand, v); hit = probe_cells<8>(g, A.T, v, 0u, myId, cs.lastId, sub); }
+		}
+		const unsigned hm = __ballot_sync(FULL, hit || rejected);
+		for (int q = 0; q < 4 && !found; ++q)
+			if (((hm >> (8 * q)) & 0xFFu) == 0u) {   // first group (lowest trial) whose 8 lanes all report "free"
+				found = tb + q;
+				for (int k2 = 0; k2 < 3; k2++) { cand[k2] = __shfl_sync(FULL, cand[k2], 8 * q); v[k2] = __shfl_sync(FULL, v[k2], 8 * q); }
+			}
+	}
+	if (lane == 0) {
+		atomicAdd(&A.ctl->conflicts, 1ull);
+		const long long before = cur <= T_ ? cur : T_, after = found ? found : T_;
+		atomicAdd(&A.ctl->trials, (unsigned long long)(after - before));
+		atomicAdd(&A.ctl->queries, (unsigned long long)(after - (long long)t0 + 1));
+		const int hadBead = cur <= T_, hasBead = found != 0u, hadProg = cur < T_, hasProg = found != 0u && found < T_;
+		if (hadBead != hasBead) atomicAdd(&A.roundAcc[round], (uint32_t)(hasBead - hadBead));
+		if (hadProg != hasProg) atomicAdd(&A.roundProg[round], (uint32_t)(hasProg - hadProg));
+		A.resTrial[chain] = found ? found : T_ + 1u;
+		if (found) {
+			for (int k2 = 0; k2 < 3; k2++) A.resPos[3 * (size_t)chain + k2] = cand[k2];
+			insert_bead(g, A.T, cand, myId);
+			__threadfence();
+		}
+	}
+	__syncwarp();
+	if (found) {   // higher-indexed chains of this round whose tentative bead now collides with the new position
+		uint32_t hits[8]; int nh = 0;
+		if (lane < 8) enumerate_hits<8>(g, A.T, v, myId, idEnd, lane, [&](uint32_t id) { if (nh < 8) hits[nh++] = id; });
+		unsigned pending = __ballot_sync(FULL, nh > 0);
+		while (pending) {
+			const int src = __ffs(pending) - 1;
+			const int cnt = __shfl_sync(FULL, nh, src);
+			for (int q = 0; q < cnt; ++q) {
+				uint32_t id = 0;
+#pragma unroll
+				for (int z = 0; z < 8; ++z) if (z == q) id = hits[z];
+				id = __shfl_sync(FULL, id, src);
+				if (lane == 0) push(id - idRound);
+			}
+			pending &= pending - 1;
+		}
+		__syncwarp();
+	}
+}
+
+// squared minimum-image distance between the (round-start) tips of two chains
+__device__ __forceinline__ double tip_dist2(const GrowArgs& A, uint32_t a, uint32_t b)
+{
+	double d2 = 0;
+	for (int k = 0; k < 3; k++) {
+		double d = __ldcg(&A.chains[a].last[k]) - __ldcg(&A.chains[b].last[k]);
+		d -= A.g.L[k] * rint(d * A.g.Linv[k]);
+		d2 += d * d;
+	}
+	return d2;
+}
+
+// radius beyond which two conflicting chains cannot influence each other's re-resolution nor touch the same cells:
+// two bonds + minDist for the geometry, four cell edges so that their beads and the cells they probe never overlap
+__device__ __forceinline__ double independence_radius(const Geom& g)
+{	const double amax = fmax(g.a[0], fmax(g.a[1], g.a[2]));
+	return 2 * 1.54 + g.thresh + 4 * amax;
+}
+
+// PARALLEL part (every warp of the grid): a conflicting chain with no LOWER conflicting chain within the independence
+// radius depends only on final beads, so all such chains are re-resolved at once, one per warp. Chains they newly put in
+// conflict go to the second list and are handled, with the dependent ones, by the ordered pass below.
+__device__ void cleanup_parallel(const GrowArgs& A, uint32_t round, uint32_t gw, uint32_t nW, int lane)
+{
+	const uint32_t nd = __ldcg(&A.dirtyCount[round]);
+	const double R2 = independence_radius(A.g) * independence_radius(A.g);
+	for (uint32_t e = gw; e < nd; e += nW) {
+		const uint32_t chain = __ldcg(&A.dirtyList[e]);
+		bool dep = false;
+		for (uint32_t j = lane; j < nd && !dep; j += 32) {
+			const uint32_t other = __ldcg(&A.dirtyList[j]) & ~DONE_BIT;
+			if (other < chain && tip_dist2(A, chain, other) <= R2) dep = true;
+		}
+		if (__any_sync(FULL, dep)) continue;
+		resolve_dirty_chain(A, round, chain, lane, [&](uint32_t c) { const uint32_t at = atomicAdd(&A.ctl->dirty2Count, 1u); A.dirtyList[A.g.nChains + at] = c; });
+		if (lane == 0) A.dirtyList[e] = chain | DONE_BIT;
+		__syncwarp();
+	}
+}
+
+// ORDERED part (one warp): what sarw.cpp:251-281 does serially. Chains are taken in increasing index; after a chain has
+// been re-resolved, every already-resolved HIGHER chain near it is re-opened (its result assumed the old bead).
+__device__ void cleanup_round(const GrowArgs& A, uint32_t round, int lane)
+{
+	volatile uint32_t* list = A.dirtyList;
+	volatile uint32_t* count = &A.dirtyCount[round];
+	const double R2 = independence_radius(A.g) * independence_radius(A.g);
+	if (lane == 0) {   // chains put in conflict by the parallel part
+		const uint32_t n2 = A.ctl->dirty2Count;
+		for (uint32_t j = 0; j < n2; ++j) dirty_push_unique(list, count, list[A.g.nChains + j]);
+		A.ctl->dirty2Count = 0;
+	}
+	__syncwarp();
 	for (;;) {
 		uint32_t chain = 0; int have = 0;
-		if (lane == 0) have = dirty_pop_min(A.dirtyList, &A.dirtyCount[round], chain);
+		if (lane == 0) have = dirty_pop_min(list, count, chain);
 		have = __shfl_sync(FULL, have, 0); chain = __shfl_sync(FULL, chain, 0);
 		if (!have) break;
-		const uint32_t myId = idRound + chain;
-		const ChainState cs = load_chain(A.chains + chain);
-		Frame f; cone_frame(cs.last, cs.pen, f);
-		const uint32_t t0 = __ldcg(&A.resTrial[chain]);
-		if (lane == 0) remove_bead(g, A.T, myId);
-		__syncwarp();
-		uint32_t found = 0; double cand[3] = { 0, 0, 0 }, v[3] = { 0, 0, 0 };
-		for (uint32_t tb = t0; tb <= T_ && !found; tb += 4) {
-			const uint32_t t = tb + grp;
-			bool rejected = t > T_, hit = false;
-			if (!rejected) {
-				cone_candidate(g, f, cs.last, u_grow(g, chain, round, t), cand);
-				rejected = growth_rules_reject(g, cand, cs.last);
-				if (!rejected) { to_frac(g, cand, v); hit = probe_cells<8>(g, A.T, v, 0u, myId, cs.lastId, sub); }
-			}
-			const unsigned hm = __ballot_sync(FULL, hit || rejected);
-			for (int q = 0; q < 4 && !found; ++q)
-				if (((hm >> (8 * q)) & 0xFFu) == 0u) {   // first group (lowest trial) whose 8 lanes all report "free"
-					found = tb + q;
-					for (int k2 = 0; k2 < 3; k2++) { cand[k2] = __shfl_sync(FULL, cand[k2], 8 * q); v[k2] = __shfl_sync(FULL, v[k2], 8 * q); }
-				}
-		}
-		if (lane == 0) {
-			atomicAdd(&A.ctl->conflicts, 1ull);
-			const unsigned long long before = t0, after = found ? found : T_;
-			atomicAdd(&A.ctl->trials, after - before);
-			atomicAdd(&A.ctl->queries, after - before + 1ull);
-			if (!found) {
-				A.resTrial[chain] = T_ + 1u;
-				atomicSub(&A.roundAcc[round], 1u);
-				if (t0 < T_) atomicSub(&A.roundProg[round], 1u);
-			} else {
-				if (t0 < T_ && !(found < T_)) atomicSub(&A.roundProg[round], 1u);
-				A.resTrial[chain] = found;
-				for (int k2 = 0; k2 < 3; k2++) A.resPos[3 * (size_t)chain + k2] = cand[k2];
-				insert_bead(g, A.T, cand, myId);
-				__threadfence();
-			}
+		resolve_dirty_chain(A, round, chain, lane, [&](uint32_t c) { dirty_push_unique(list, count, c); });
+		// re-open resolved higher chains whose neighbourhood just changed
+		const uint32_t nd = *count;
+		for (uint32_t j = lane; j < nd; j += 32) {
+			const uint32_t e = list[j];
+			if ((e & DONE_BIT) && (e & ~DONE_BIT) > chain && tip_dist2(A, e & ~DONE_BIT, chain) <= R2) list[j] = e & ~DONE_BIT;
 		}
 		__syncwarp();
-		if (found) {   // higher-indexed chains of this round whose tentative bead now collides with the new position
-			uint32_t hits[8]; int nh = 0;
-			if (lane < 8) enumerate_hits<8>(g, A.T, v, myId, idEnd, lane, [&](uint32_t id) { if (nh < 8) hits[nh++] = id; });
-			unsigned pending = __ballot_sync(FULL, nh > 0);
-			while (pending) {
-				const int src = __ffs(pending) - 1;
-				const int cnt = __shfl_sync(FULL, nh, src);
-				for (int q = 0; q < cnt; ++q) {
-					uint32_t id = 0;
-#pragma unroll
-					for (int z = 0; z < 8; ++z) if (z == q) id = hits[z];
-					id = __shfl_sync(FULL, id, src);
-					if (lane == 0) dirty_push_unique(A.dirtyList, &A.dirtyCount[round], id - idRound);
-				}
-				pending &= pending - 1;
-			}
-			__syncwarp();
-		}
 	}
 }
 
@@ -692,7 +758,7 @@ __global__ void __launch_bounds__(WARPS * 32) grow_kernel(GrowArgs A)
 			if (i < start || i >= end) continue;
 			if (cs.flags & CHAIN_DEAD) {   // permanently blocked: the reference burns maxTrials here every round
 				if (lane == 0) {
-					A.resTrial[i] = T_ + 1u;
+					A.resTrial[i] = T_ + 1u; A.origTrial[i] = T_ + 1u;
 					if (mr) { MrRecord r; r.x = r.y = r.z = 0; r.trial = T_ + 1u; r.pad = 0; mr_publish(A, i, round, r); }
 				}
 				continue;
@@ -713,6 +779,7 @@ __global__ void __launch_bounds__(WARPS * 32) grow_kernel(GrowArgs A)
 					for (int k2 = 0; k2 < 3; k2++) A.resPos[3 * (size_t)i + k2] = cand[k2];
 				}
 				A.resTrial[i] = accepted ? accepted : T_ + 1u;
+				A.origTrial[i] = accepted ? accepted : T_ + 1u;
 				if (mr) { MrRecord r; r.x = cand[0]; r.y = cand[1]; r.z = cand[2]; r.trial = accepted ? accepted : T_ + 1u; r.pad = 0; mr_publish(A, i, round, r); }
 			}
 		}
@@ -735,7 +802,7 @@ __global__ void __launch_bounds__(WARPS * 32) grow_kernel(GrowArgs A)
 				const MrRecord* rp_ = allRec + (size_t)(i % A.mrRanks) * A.mrK + i / A.mrRanks;
 				MrRecord r;
 				r.x = __ldcg(&rp_->x); r.y = __ldcg(&rp_->y); r.z = __ldcg(&rp_->z); r.trial = __ldcg(&rp_->trial); r.pad = 0;
-				A.resTrial[i] = r.trial;
+				A.resTrial[i] = r.trial; A.origTrial[i] = r.trial;
 				if (r.trial >= 1u && r.trial <= T_) {
 					const double p[3] = { r.x, r.y, r.z };
 					insert_bead(g, A.T, p, idRound + i);
@@ -787,7 +854,9 @@ __global__ void __launch_bounds__(WARPS * 32) grow_kernel(GrowArgs A)
 		const long long tk2 = clock64();
 		// ---------------- clean-up (rare): serial re-resolution in chain order
 		if (__ldcg(&A.dirtyCount[round]) != 0u) {
-			if (gw == 0) cleanup_round(A, round, lane);
+			cleanup_parallel(A, round, gw, nW, lane);          // independent conflicts, one warp each
+			round_barrier<CLUSTER>(A.ctl);
+			if (gw == 0) cleanup_round(A, round, lane);          // the rest, in chain order
 			round_barrier<CLUSTER>(A.ctl);
 			cleanRounds++;
 		}
@@ -932,10 +1001,10 @@ static cudaError_t launch_cluster(const GrowArgs& A, cudaStream_t st)
 	return cudaLaunchKernelEx(&cfg, grow_cluster_kernel<WARPS>, A);
 }
 
-cudaError_t launch_grow(const Geom& g, const Tables& T, ChainState* chains, uint32_t* resTrial, double* resPos, uint32_t* prev, Control* ctl,
+cudaError_t launch_grow(const Geom& g, const Tables& T, ChainState* chains, uint32_t* resTrial, uint32_t* origTrial, double* resPos, uint32_t* prev, Control* ctl,
 	uint32_t* roundAcc, uint32_t* roundProg, uint32_t* dirtyCount, uint32_t* dirtyList, uint32_t roundEnd, int blocks, int useCluster, cudaStream_t st)
 {
-	GrowArgs A{ g, T, chains, resTrial, resPos, prev, ctl, roundAcc, roundProg, dirtyCount, dirtyList, roundEnd, 0u, 1u, 0u, 0u, nullptr, nullptr, {}, {} };
+	GrowArgs A{ g, T, chains, resTrial, origTrial, resPos, prev, ctl, roundAcc, roundProg, dirtyCount, dirtyList, roundEnd, 0u, 1u, 0u, 0u, nullptr, nullptr, {}, {} };
 	if (useCluster) {
 		// the whole launch is one thread-block cluster: CTAs are co-scheduled by the hardware, synchronise with
 		// barrier.cluster and exchange tentative beads through distributed shared memory. 8 warps per CTA (255
@@ -948,12 +1017,12 @@ cudaError_t launch_grow(const Geom& g, const Tables& T, ChainState* chains, uint
 }
 
 // one phase of a multi-rank round (grow_kernel with mrPhase != 0); always the cooperative grid kernel
-cudaError_t launch_grow_mr(const Geom& g, const Tables& T, ChainState* chains, uint32_t* resTrial, double* resPos, uint32_t* prev, Control* ctl,
+cudaError_t launch_grow_mr(const Geom& g, const Tables& T, ChainState* chains, uint32_t* resTrial, uint32_t* origTrial, double* resPos, uint32_t* prev, Control* ctl,
 	uint32_t* roundAcc, uint32_t* roundProg, uint32_t* dirtyCount, uint32_t* dirtyList, uint32_t roundEnd, int blocks,
 	uint32_t rank, uint32_t ranks, uint32_t phase, void* localRec, const void* allRec, void* const* peerRec, void* const* peerFlags, cudaStream_t st)
 {
 	const uint32_t K = (g.nChains + ranks - 1) / ranks;
-	GrowArgs A{ g, T, chains, resTrial, resPos, prev, ctl, roundAcc, roundProg, dirtyCount, dirtyList, roundEnd, rank, ranks, phase, K,
+	GrowArgs A{ g, T, chains, resTrial, origTrial, resPos, prev, ctl, roundAcc, roundProg, dirtyCount, dirtyList, roundEnd, rank, ranks, phase, K,
 		(MrRecord*)localRec, (const MrRecord*)allRec, {}, {} };
 	for (uint32_t p = 0; p < 8; ++p) { A.peerRec[p] = peerRec && p < ranks ? (MrRecord*)peerRec[p] : nullptr; A.peerFlags[p] = peerFlags && p < ranks ? (uint32_t*)peerFlags[p] : nullptr; }
 	void* args[] = { &A };

@@ -73,3 +73,6 @@ def verify_structure(xyz, chainID, typ, bonds, box, minDist, nChains, check_pair
             out["closest_nonbonded"] = np.inf
             out["violations"] = 0
     return out
+# 1e5 chains, ~100 beads each, in the box of a 1000-bead melt (same chain-tip density as BASELINE configs[2..4]): the size at
+# which several same-round conflicts happen every round (scripts/mr_run.py, profiles/r1_multigpu_scaling.md)
+BIG = dict(nChains=100000, boxSize=(1362.107287789021,) * 3, minDist=1.0, maxTrials=1000, targetMassDensity=0.092)

@@ -187,3 +187,13 @@ def test_c3_full_size_invariants(sarw):
     assert abs(v["d13_min"] - 2.515256) < 1e-5 and abs(v["d13_max"] - 2.515256) < 1e-5
     assert v["violations"] == 0
     assert np.sum(g["type"] == 1) == 2 * 10000
+
+
+def test_many_conflicts_large_box_bit_exact(sarw, oracle):
+    """4000 short chains at full density in a 100 A box: ~10 same-round conflicts per round, most of them far apart, so the
+    parallel conflict clean-up (independent chains resolved at once) and the ordered pass both run; result == oracle."""
+    cfg = dict(nChains=4000, boxSize=(100.0, 100.0, 100.0), minDist=1.0, maxTrials=300, targetMassDensity=0.92)
+    g = run_gpu(sarw, cfg, 17)
+    o = oracle.walk(seed=17, trig="portable", **cases.oracle_kwargs(cfg))
+    assert_same_walk(g, o, exact=True)
+    assert g["stats"]["conflicts"] > 20
