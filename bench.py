@@ -35,6 +35,8 @@ WORKLOADS = {
     "C3": dict(name="PE melt 1e4 chains x 1000 beads, 0.92 g/cc, ppp, minDist 1.0, maxTrials 1000 (BASELINE configs[2])",
                nChains=10000, boxSize=(632.2, 632.2, 632.2), minDist=1.0, maxTrials=1000, boundary="ppp", targetMassDensity=0.92),
 }
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full capture
+NCU_TRAFFIC = {"C2": (33.86e6, "profiles/r1_grow_cluster_kernel_C2_raw.csv")}
 # algorithmic bytes per overlap query and per accepted bead
 B_QUERY = 121.0
 B_BEAD = 108.0
@@ -285,8 +287,8 @@ def main():
                     "includes": "sarw_create (alloc + cell-table init), seeding, growth, terminate, sarw_download to host"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
-                         "kernel": "sarw::grow_kernel (persistent, one launch per step)", "peak_source": peak_src,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": NCU_TRAFFIC.get(args.workload, (None, None))[0], "traffic_source": NCU_TRAFFIC.get(args.workload, (None, None))[1],
+                         "kernel": "sarw::grow_cluster_kernel<8> (one thread-block cluster, persistent, one launch per step)" if w["nChains"] <= 128 else "sarw::grow_kernel (persistent cooperative launch)", "peak_source": peak_src,
                          "algorithmic_bytes": f"trials*{B_QUERY:.0f} + beads*{B_BEAD:.0f} (SURVEY §8d, trials in reference terms)",
                          "trials_per_launch": trials / args.steps, "candidates_evaluated_per_launch": queries / args.steps,
                          "avg_launch_ms": grow_ms / args.steps, "note": "latency-bound: ~1e2 chains per round, ~1e3 dependent rounds"},
