@@ -130,9 +130,10 @@ __device__ __forceinline__ void tma_load_1d(void* dstSmem, const void* srcGlobal
 		:: "r"(smem_u32(dstSmem)), "l"(srcGlobal), "r"(bytes), "r"(smem_u32(mbar)) : "memory");
 }
 
-__device__ __forceinline__ int wrap_near(int c, int S)   // c is within a few cells of [0,S): no integer division
-{	while (c < 0) c += S;
-	while (c >= S) c -= S;
+__device__ __forceinline__ int wrap_near(int c, int S)   // c is normally within one period of [0,S): no integer division
+{	c += (c < 0) ? S : 0;
+	c -= (c >= S) ? S : 0;
+	if ((unsigned)c >= (unsigned)S) { c %= S; c += (c < 0) ? S : 0; }   // tiny boxes: several periods away
 	return c;
 }
 
