@@ -70,6 +70,8 @@ typedef struct sarw_stats {
 	uint64_t cycCleanup;
 	int64_t cleanupRounds;      /* rounds that needed the serial conflict clean-up */
 	int64_t deadChains;         /* chains proven permanently blocked (skipped from then on; the reference retries them) */
+	uint64_t stageFallbacks;    /* hard chain-rounds whose neighbourhood did not fit the shared-memory staging buffer */
+	uint64_t arcFallbacks;      /* hard chain-rounds with more blocked arcs than the arc buffer holds (no pre-classification) */
 	uint64_t cycSub[8];         /* finer split of cycPropose for warp 0 of block 0: frame, stage, arcs, classify, evaluate, publish, barrier, - */
 } sarw_stats;
 

@@ -140,6 +140,7 @@ void fill_stats(sarw_ctx* c, const Control& h, sarw_stats* s)
 	s->seedMs = c->seedMs; s->growMs = c->growMs; s->growLaunches = c->growLaunches; s->seedLaunches = c->seedLaunches;
 	s->cycPropose = h.cycPropose; s->cycVerify = h.cycVerify; s->cycCleanup = h.cycCleanup;
 	s->cleanupRounds = h.cleanupRounds; s->deadChains = h.deadChains;
+	s->stageFallbacks = h.stageFallbacks; s->arcFallbacks = h.arcFallbacks;
 	for (int k = 0; k < 8; k++) s->cycSub[k] = h.cycSub[k];
 }
 

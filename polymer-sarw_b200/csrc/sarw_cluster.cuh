@@ -29,8 +29,11 @@ struct __align__(8) TentRec {
 };
 static_assert(sizeof(TentRec) == 40, "TentRec is 40 bytes");
 
+// staged beads / blocked arcs kept per chain: the 8-warp variant has shared memory to spare
+__host__ __device__ constexpr int cl_nb_cap(int warps) { return warps <= 8 ? 256 : 128; }
+__host__ __device__ constexpr int cl_arc_cap(int warps) { return warps <= 8 ? 128 : 64; }
 constexpr size_t cluster_smem_bytes(int warps)
-{	return (size_t)warps * CL_REGION_CELLS * sizeof(Cell) + (size_t)warps * NBMAX * sizeof(float4) + (size_t)warps * CL_NARC * sizeof(float4)
+{	return (size_t)warps * CL_REGION_CELLS * sizeof(Cell) + (size_t)warps * cl_nb_cap(warps) * sizeof(float4) + (size_t)warps * cl_arc_cap(warps) * sizeof(float4)
 		+ 2 * (size_t)CL_MAXCH * sizeof(TentRec) + (size_t)warps * 8 + 16;
 }
 
@@ -40,7 +43,7 @@ __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.w
 // Blocked arcs as (cos alpha, sin alpha, kappa): a trial angle theta is CERTAINLY rejected by the bead iff
 // cos(alpha) cos(theta) + sin(alpha) sin(theta) >= kappa. kappa carries margins (1e-5 A in distance, 3e-5 in cos) that
 // dominate the fp32 evaluation error of both sides; arcs only ever skip trials, the exact test decides everything else.
-__device__ __forceinline__ int build_arcs_cs(const Geom& g, const Frame& f, const float4* nb, int nnb, float4* arcs, int lane)
+__device__ __forceinline__ int build_arcs_cs(const Geom& g, const Frame& f, const double last[3], const float4* nb, int nnb, float4* arcs, int arcCap, int lane)
 {
 	const double rho = g.dSinPhi, h = g.dCosPhi;
 	const double ts = g.thresh - 1e-5;
@@ -65,7 +68,41 @@ __device__ __forceinline__ int build_arcs_cs(const Geom& g, const Frame& f, cons
 			}
 		}
 		const unsigned m = __ballot_sync(FULL, have);
-		if (narcs + __popc(m) > CL_NARC) return -1;
+		if (narcs + __popc(m) > arcCap) return -1;
+		if (have) arcs[narcs + __popc(m & ((1u << lane) - 1u))] = arc;
+		narcs += __popc(m);
+	}
+	{	// the rules of sarw.cpp:201-211 and the growthBias extension have the same form: a coordinate (or bias.step) of the
+		// candidate is base + rho*R*cos(theta - beta), so each rule certainly rejects an arc of theta. Lanes 0..3: lower wall,
+		// upper wall, growthBias, zCenter half-space.
+		bool have = false; float4 arc = make_float4(0.f, 0.f, 2.f, 0.f);
+		const int wk = g.boundary == 1 ? 2 : (g.boundary == 2 ? 1 : (g.boundary == 3 ? 0 : -1));
+		double cx = 0, cy = 0, base = 0, limit = 0; int kind = 0;   // kind 1: reject below `limit`, 2: reject above `limit`
+		if (lane < 2 && wk >= 0) { cx = f.X[wk]; cy = f.Y[wk]; base = last[wk] + h * f.Z[wk]; limit = lane == 0 ? 0.0 : g.L[wk]; kind = lane == 0 ? 1 : 2; }
+		else if (lane == 2 && g.biased) {
+			cx = g.bias[0] * f.X[0] + g.bias[1] * f.X[1] + g.bias[2] * f.X[2]; cy = g.bias[0] * f.Y[0] + g.bias[1] * f.Y[1] + g.bias[2] * f.Y[2];
+			base = h * (g.bias[0] * f.Z[0] + g.bias[1] * f.Z[1] + g.bias[2] * f.Z[2]); limit = 0.0; kind = 1;
+		} else if (lane == 3 && g.graftLoc == 2) {
+			const double lastPos = last[2] - 0.5 * g.L[2];
+			cx = f.X[2]; cy = f.Y[2]; base = last[2] + h * f.Z[2]; limit = 0.5 * g.L[2];
+			kind = lastPos > 0 ? 1 : (lastPos < 0 ? 2 : 0);
+		}
+		if (kind) {
+			const double scale = (lane == 2) ? fabs(g.bias[0]) + fabs(g.bias[1]) + fabs(g.bias[2]) : 1.0;
+			const double delta = 1e-5 * (scale > 1.0 ? scale : 1.0);
+			const double R2 = cx * cx + cy * cy;
+			// certainly rejected iff value < limit - delta (kind 1) or value > limit + delta (kind 2), value = base + rho*(cx cos + cy sin)
+			if (R2 > 1e-16) {
+				const double R = sqrt(R2), sgn = kind == 1 ? -1.0 : 1.0;
+				// kind 1: cos(theta-beta) < (limit-delta-base)/(rho R)  <=>  cos(theta-(beta+pi)) > (base+delta-limit)/(rho R)
+				const double kappa = (kind == 1 ? (base + delta - limit) : (limit + delta - base)) / (rho * R);
+				if (kappa < 1.0) { have = true; arc = make_float4((float)(sgn * cx / R), (float)(sgn * cy / R), (float)kappa + 3e-5f * (1.0f + fabsf((float)kappa)), 0.f); }
+			} else if ((kind == 1 && base < limit - delta) || (kind == 2 && base > limit + delta)) {
+				have = true; arc = make_float4(1.f, 0.f, -2.f, 0.f);   // the coordinate does not depend on theta and violates: everything is rejected
+			}
+		}
+		const unsigned m = __ballot_sync(FULL, have);
+		if (narcs + __popc(m) > arcCap) return -1;
 		if (have) arcs[narcs + __popc(m & ((1u << lane) - 1u))] = arc;
 		narcs += __popc(m);
 	}
@@ -73,38 +110,46 @@ __device__ __forceinline__ int build_arcs_cs(const Geom& g, const Frame& f, cons
 	return narcs;
 }
 
-// Same coverage criterion as arcs_cover_circle, evaluated in double from the (cos, sin, kappa) form (rare path).
-__device__ __forceinline__ bool arcs_cs_cover_circle(const float4* arcs, int narcs, int lane)
+// Do the (shrunk) arcs, together with the never-sampled gap [359 deg, 360 deg) of sarw.cpp:177, cover the whole circle?
+// Closed arcs cover the circle iff every arc's upper end lies strictly inside another arc. Centre and half-width of every
+// arc are computed once (acos / atan2 in double, one arc per lane) into `scratch`, then compared pairwise. Rare path.
+__device__ __forceinline__ bool arcs_cs_cover_circle(const float4* arcs, int narcs, double2* scratch, int lane)
 {
 	if (narcs <= 0) return false;
 	const double PI = 3.14159265358979323846;
 	const double gapLo = 359.0 * PI / 180 - 1e-9, gapHi = 2 * PI;
-	auto centre = [&](int i) { return i < narcs ? atan2((double)arcs[i].y, (double)arcs[i].x) : 0.5 * (gapLo + gapHi); };
-	auto width = [&](int i) {
-		if (i >= narcs) return 0.5 * (gapHi - gapLo) - 1e-7;
-		const double k = (double)arcs[i].z;
-		return k <= -1.0 ? PI : (k >= 1.0 ? 0.0 : acos(k) - 1e-6);
-	};
+	bool full = false;
+	for (int i = lane; i <= narcs; i += 32) {
+		double c, w;
+		if (i < narcs) {
+			const double k = (double)arcs[i].z;
+			c = atan2((double)arcs[i].y, (double)arcs[i].x);
+			w = k <= -1.0 ? PI : (k >= 1.0 ? 0.0 : acos(k) - 1e-6);
+		} else { c = 0.5 * (gapLo + gapHi); w = 0.5 * (gapHi - gapLo) - 1e-7; }
+		scratch[i] = make_double2(c, w);
+		full = full || w >= PI;
+	}
+	__syncwarp();
+	if (__any_sync(FULL, full)) return true;
 	bool allCovered = true;
 	for (int ib = 0; ib <= narcs; ib += 32) {
 		const int i = ib + lane;
 		bool covered = true;
 		if (i <= narcs) {
-			const double e = centre(i) + width(i);
+			const double2 me = scratch[i];
+			const double e = me.x + me.y;
 			covered = false;
 			for (int j = 0; j <= narcs && !covered; ++j) {
-				const double wj = width(j);
-				if (wj >= PI) { covered = true; break; }
-				double d = e - centre(j);
-				d -= 2 * PI * rint(d / (2 * PI));
-				covered = fabs(d) < wj - 1e-6;
+				const double2 o = scratch[j];
+				double d = e - o.x;
+				d -= 2 * PI * rint(d * (0.5 / PI));
+				covered = fabs(d) < o.y - 1e-6;
 			}
 		}
 		allCovered = allCovered && __all_sync(FULL, covered);
 	}
 	return allCovered;
 }
-
 
 // ---------------------------------------------------------------------------------------------------------------
 // TMA staging: the region (<= 4x4x4 cells, x-rows contiguous in memory) is copied row by row into the warp's shared
@@ -208,7 +253,7 @@ __device__ __forceinline__ void region_wait_ldgsts()
 
 // compaction of the staged cells into the warp's neighbour list, positions relative to the (wrapped) last bead
 __device__ __forceinline__ int region_consume(const Geom& g, const RegionPlan& rp, const Cell* raw, uint32_t idLimit, uint32_t ignoreId,
-	float4* nb, int lane, bool& regionOvf)
+	float4* nb, int nbCap, int lane, bool& regionOvf)
 {
 	const float inv0 = 1.0f / (float)rp.nn[0], inv1 = 1.0f / (float)rp.nn[1];
 	uint32_t cnt[2] = { 0, 0 }; float sh[2][3]; bool ovf = false;
@@ -231,7 +276,7 @@ __device__ __forceinline__ int region_consume(const Geom& g, const RegionPlan& r
 #pragma unroll
 	for (int b = 0; b < 4; b++) { const unsigned m = __ballot_sync(FULL, (mine >> b) & 1u); excl += (uint32_t)__popc(m & lt) << b; total += (uint32_t)__popc(m) << b; }
 	regionOvf = __any_sync(FULL, ovf);
-	if (total > (uint32_t)NBMAX) return -1;
+	if (total > (uint32_t)nbCap) return -1;
 	uint32_t at = excl;
 #pragma unroll
 	for (int q = 0; q < 2; q++)
@@ -250,7 +295,7 @@ __device__ __forceinline__ int region_consume(const Geom& g, const RegionPlan& r
 // while the region is being staged, then tested lane-per-trial; chains that found nothing there (`hard`) go through the
 // blocked-arc classification of all remaining trials.
 __device__ __forceinline__ uint32_t propose_chain(const Geom& g, const Tables& T, Control* ctl, ChainState* chains, uint32_t i, uint32_t round,
-	uint32_t idRound, ChainState& cs, const Frame& f, const RegionPlan& rp, bool hard, Cell* raw, float4* nb, float4* arcs, void* mbar,
+	uint32_t idRound, ChainState& cs, const Frame& f, const RegionPlan& rp, bool hard, Cell* raw, float4* nb, int nbCap, float4* arcs, int arcCap, void* mbar,
 	unsigned& tmaParity, int lane, double cand[3], double vAcc[3], unsigned long long& queries)
 {
 	const uint32_t T_ = (uint32_t)g.maxTrials;
@@ -277,7 +322,7 @@ __device__ __forceinline__ uint32_t propose_chain(const Geom& g, const Tables& T
 #else
 		region_wait_ldgsts();
 #endif
-		nnb = region_consume(g, rp, raw, idRound, cs.lastId, nb, lane, regionOvf);
+		nnb = region_consume(g, rp, raw, idRound, cs.lastId, nb, nbCap, lane, regionOvf);
 	} else regionOvf = true;
 	const uint32_t novf = regionOvf ? __ldcg(T.ovfCount) : 0u;
 	if (!hard) {
@@ -323,7 +368,9 @@ __device__ __forceinline__ uint32_t propose_chain(const Geom& g, const Tables& T
 	}
 	if (!accepted && T_ > (hard ? 0u : 32u)) {
 		// hard chain: blocked-arc classification of the remaining trials, exact evaluation of the survivors
-		narcs = nnb >= 0 ? build_arcs_cs(g, f, nb, nnb, arcs, lane) : -1;
+		narcs = nnb >= 0 ? build_arcs_cs(g, f, cs.last, nb, nnb, arcs, arcCap, lane) : -1;
+		if (lane == 0 && nnb < 0) atomicAdd(&ctl->stageFallbacks, 1ull);
+		if (lane == 0 && nnb >= 0 && narcs < 0) atomicAdd(&ctl->arcFallbacks, 1ull);
 		const uint32_t skip = hard ? 0u : 32u;          // trials <= skip were just evaluated exactly and failed
 		for (uint32_t base = 0; base < T_ && !accepted; base += 128) {
 			const uint32_t blk = (base >> 2) + lane;
@@ -365,7 +412,7 @@ __device__ __forceinline__ uint32_t propose_chain(const Geom& g, const Tables& T
 				any = cm[0] | cm[1] | cm[2] | cm[3];
 			}
 		}
-		if (!accepted && narcs > 0 && arcs_cs_cover_circle(arcs, narcs, lane)) {
+		if (!accepted && narcs > 0 && arcs_cs_cover_circle(arcs, narcs, reinterpret_cast<double2*>(nb), lane)) {   // nb is no longer needed
 			cs.flags |= CHAIN_DEAD;
 			if (lane == 0) { chains[i].flags = cs.flags; atomicAdd(&ctl->deadChains, 1u); }
 		}
@@ -378,9 +425,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) grow_cluster_kernel(GrowArgs A)
 {
 	extern __shared__ __align__(128) unsigned char clSmem[];
 	Cell* rawAll = reinterpret_cast<Cell*>(clSmem);
+	constexpr int NBCAP = cl_nb_cap(WARPS), ARCCAP = cl_arc_cap(WARPS);
 	float4* nbAll = reinterpret_cast<float4*>(rawAll + WARPS * CL_REGION_CELLS);
-	float4* arcAll = nbAll + WARPS * NBMAX;
-	TentRec* table = reinterpret_cast<TentRec*>(arcAll + WARPS * CL_NARC);
+	float4* arcAll = nbAll + WARPS * NBCAP;
+	TentRec* table = reinterpret_cast<TentRec*>(arcAll + WARPS * ARCCAP);
 	unsigned long long* mbarAll = reinterpret_cast<unsigned long long*>(table + 2 * CL_MAXCH);
 	volatile uint32_t* dirtyWord = reinterpret_cast<volatile uint32_t*>(mbarAll + WARPS);
 
@@ -391,8 +439,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) grow_cluster_kernel(GrowArgs A)
 	const uint32_t i = myCta * WARPS + warp;            // the chain this warp owns for the whole launch
 	const bool owner = i < g.nChains;
 	Cell* raw = rawAll + warp * CL_REGION_CELLS;
-	float4* nb = nbAll + warp * NBMAX;
-	float4* arcs = arcAll + warp * CL_NARC;
+	float4* nb = nbAll + warp * NBCAP;
+	float4* arcs = arcAll + warp * ARCCAP;
 	void* mbar = mbarAll + warp;
 	const uint32_t T_ = (uint32_t)g.maxTrials;
 
@@ -434,7 +482,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) grow_cluster_kernel(GrowArgs A)
 		uint32_t oldCount = 0xFFFFFFFFu;                   // beads its cell held at round start (from the staged copy)
 		if (active && (cs.flags & CHAIN_DEAD)) rec.trial = T_ + 1u;
 		else if (active) {
-			accepted = propose_chain(g, A.T, A.ctl, A.chains, i, round, idRound, cs, f, rp, hard, raw, nb, arcs, mbar, tmaParity, lane, cand, vAcc, myQueries);
+			accepted = propose_chain(g, A.T, A.ctl, A.chains, i, round, idRound, cs, f, rp, hard, raw, nb, NBCAP, arcs, ARCCAP, mbar, tmaParity, lane, cand, vAcc, myQueries);
 			hard = accepted == 0u || accepted > 32u;
 			rec.trial = accepted ? accepted : T_ + 1u;
 			if (accepted) {

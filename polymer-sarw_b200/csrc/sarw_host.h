@@ -14,6 +14,7 @@ struct Control {
 	unsigned seedDirtyCount;
 	unsigned abort;                   // set when a peer stopped answering in the peer-memory multi-rank loop
 	unsigned dirty2Count, padA;       // chains put in conflict by the parallel clean-up (second list)
+	unsigned long long stageFallbacks, arcFallbacks;   // chain-rounds whose neighbourhood / arcs did not fit the shared-memory buffers
 	unsigned long long nBeads;        // SARW::actualCount()
 	unsigned long long trials, queries, conflicts, seedTrials;
 	unsigned long long cycPropose, cycVerify, cycCleanup;   // SM cycles of block 0 per phase (incl. the closing barrier)

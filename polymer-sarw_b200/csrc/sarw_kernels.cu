@@ -21,7 +21,9 @@
 namespace sarw {
 
 constexpr int GROW_WARPS = 8;            // grid mode: warps per CTA of the cooperative launch
-constexpr int NBMAX = 128;          // staged neighbour beads per chain (shared memory, 16 B each)
+constexpr int NBMAX = 128;          // staged neighbour beads per chain in the legacy staging helper
+constexpr int GROW_NB_CAP = 256;    // grid kernel: staged beads per chain (shared memory, 16 B each)
+constexpr int GROW_ARC_CAP = 128;   // grid kernel: blocked arcs per chain
 constexpr int NARCMAX = 128;        // blocked torsion arcs per chain (shared memory, 8 B each)
 constexpr uint32_t CHAIN_DEAD = 1u; // ChainState.flags: every torsion angle is permanently blocked
 constexpr uint32_t CHAIN_HARD = 2u; // ChainState.flags: none of the first 32 trials passed last round (skip the fast path)
@@ -710,14 +712,14 @@ __global__ void __launch_bounds__(WARPS * 32) grow_kernel(GrowArgs A)
 	extern __shared__ __align__(128) unsigned char growSmem[];
 	Cell* rawAll = reinterpret_cast<Cell*>(growSmem);
 	float4* nbAll = reinterpret_cast<float4*>(rawAll + WARPS * CL_REGION_CELLS);
-	float4* arcAll = nbAll + WARPS * NBMAX;
-	unsigned long long* mbarAll = reinterpret_cast<unsigned long long*>(arcAll + WARPS * CL_NARC);
+	float4* arcAll = nbAll + WARPS * GROW_NB_CAP;
+	unsigned long long* mbarAll = reinterpret_cast<unsigned long long*>(arcAll + WARPS * GROW_ARC_CAP);
 	const Geom& g = A.g;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const uint32_t gw = blockIdx.x * GROW_WARPS + warp, nW = gridDim.x * GROW_WARPS;
 	Cell* raw = rawAll + warp * CL_REGION_CELLS;
-	float4* nb = nbAll + warp * NBMAX;
-	float4* arcs = arcAll + warp * CL_NARC;
+	float4* nb = nbAll + warp * GROW_NB_CAP;
+	float4* arcs = arcAll + warp * GROW_ARC_CAP;
 	void* mbar = mbarAll + warp;
 	unsigned tmaParity = 0;
 	if (lane == 0) mbar_init(mbar, 1);
@@ -768,7 +770,7 @@ __global__ void __launch_bounds__(WARPS * 32) grow_kernel(GrowArgs A)
 			const bool hard = (cs.flags & CHAIN_HARD) != 0u;
 			double cand[3] = { 0, 0, 0 }, vAcc[3] = { 0, 0, 0 };
 			const uint32_t flagsBefore = cs.flags;
-			const uint32_t accepted = propose_chain(g, A.T, A.ctl, A.chains, i, round, idRound, cs, f, rp, hard, raw, nb, arcs, mbar, tmaParity, lane,
+			const uint32_t accepted = propose_chain(g, A.T, A.ctl, A.chains, i, round, idRound, cs, f, rp, hard, raw, nb, GROW_NB_CAP, arcs, GROW_ARC_CAP, mbar, tmaParity, lane,
 				cand, vAcc, myQueries);
 			const bool hardNow = accepted == 0u || accepted > 32u;
 			cs.flags = (cs.flags & ~CHAIN_HARD) | (hardNow ? CHAIN_HARD : 0u);
@@ -967,7 +969,7 @@ cudaError_t launch_seed(const Geom& g, const Tables& T, ChainState* chains, uint
 }
 
 constexpr size_t grow_smem_bytes(int warps)
-{	return (size_t)warps * (CL_REGION_CELLS * sizeof(Cell) + NBMAX * sizeof(float4) + CL_NARC * sizeof(float4) + 8);
+{	return (size_t)warps * (CL_REGION_CELLS * sizeof(Cell) + GROW_NB_CAP * sizeof(float4) + GROW_ARC_CAP * sizeof(float4) + 8);
 }
 
 cudaError_t grow_max_blocks(int numSMs, int* maxBlocks)

@@ -49,7 +49,8 @@ class Stats(C.Structure):
                 ("overflowBeads", C.c_uint64), ("seedMs", C.c_double), ("growMs", C.c_double),
                 ("growLaunches", C.c_int64), ("seedLaunches", C.c_int64), ("cycPropose", C.c_uint64),
                 ("cycVerify", C.c_uint64), ("cycCleanup", C.c_uint64), ("cleanupRounds", C.c_int64),
-                ("deadChains", C.c_int64), ("cycSub", C.c_uint64 * 8)]
+                ("deadChains", C.c_int64), ("stageFallbacks", C.c_uint64), ("arcFallbacks", C.c_uint64),
+                ("cycSub", C.c_uint64 * 8)]
 
     def as_dict(self):
         return {n: (list(getattr(self, n)) if n == "cycSub" else getattr(self, n)) for n, _ in self._fields_}

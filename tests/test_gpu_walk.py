@@ -197,3 +197,23 @@ def test_many_conflicts_large_box_bit_exact(sarw, oracle):
     o = oracle.walk(seed=17, trig="portable", **cases.oracle_kwargs(cfg))
     assert_same_walk(g, o, exact=True)
     assert g["stats"]["conflicts"] > 20
+
+
+@pytest.mark.parametrize("bias", [(0.0, 0.0, 0.0), (0.0, 0.0, 1.0)])
+def test_brush_mid_size_walls_and_bias_bit_exact(sarw, oracle, bias):
+    """BASELINE configs[3] in small: half of 400 chains grafted on z = 0, boundary ppf, with and without growthBias. Chains pile
+    up at the walls, so the wall / bias arcs, dead-chain detection and crowded neighbourhoods are all exercised; == oracle."""
+    cfg = dict(nChains=400, boxSize=(60.0, 60.0, 60.0), minDist=1.0, maxTrials=300, boundary="ppf", nGraftChains=200, graftLoc="file",
+               growthBias=bias)
+    rng = np.random.default_rng(11)
+    pts = []
+    while len(pts) < 200:      # graft points farther apart than bond + minDist, so no graft can be blocked by an earlier chain's second bead
+        p = np.array([rng.uniform(0, 60), rng.uniform(0, 60), 0.0])
+        if all(np.hypot(*(((p - q)[:2] + 30) % 60 - 30)) > 2.6 for q in pts):
+            pts.append(p)
+    grafts = np.array(pts)
+    g = run_gpu(sarw, cfg, 23, grafts=grafts)
+    o = oracle.walk(seed=23, trig="portable", grafts=grafts, **cases.oracle_kwargs(cfg))
+    assert_same_walk(g, o, exact=True)
+    assert g["stats"]["deadChains"] > 0
+    assert g["xyz"][:, 2].min() >= 0.0 and g["xyz"][:, 2].max() <= 60.0
