@@ -246,7 +246,10 @@ def main():
         c.close()
     t_dev = sum(step_ms) / 1e3
 
-    # -------- end-to-end arm through the C ABI with host buffers
+    # -------- end-to-end arm through the C ABI with host buffers (results land in pinned host memory)
+    cap = int(sarw_b200.target_count(w["boxSize"], w["targetMassDensity"]) + w["nChains"] + 16)
+    pinned = {"xyz": torch.empty((cap, 3), dtype=torch.float64, pin_memory=True).numpy(), "chainID": torch.empty(cap, dtype=torch.int32, pin_memory=True).numpy(),
+              "type": torch.empty(cap, dtype=torch.int32, pin_memory=True).numpy(), "bonds": torch.empty((cap, 2), dtype=torch.int64, pin_memory=True).numpy()}
     e2e_times, e2e_beads, h2d, d2h, e2e_launch = [], 0, 0, 0, 0
     for i in range(total):
         flush.fill_(float(i)); torch.cuda.synchronize()
@@ -254,7 +257,7 @@ def main():
         c = sarw_b200.Context(device=local, **ctx_kwargs(w, seeds[i] + 5_000))
         c.set_stream(stream.cuda_stream)
         c.initiate(); st = c.grow(0, -1); c.terminate()
-        xyz, cid, typ, bonds = c.download()
+        xyz, cid, typ, bonds = c.download(pinned)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         c.close()

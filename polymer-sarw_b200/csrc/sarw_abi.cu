@@ -186,11 +186,23 @@ int sarw_create(const sarw_params* p, sarw_ctx** out)
 	auto bail = [&](int rc) { g_createError = c->err; sarw_destroy(c); return rc; };
 	if (p->device >= 0) { if (cudaSetDevice(p->device) != cudaSuccess) { fail(c, "cudaSetDevice(%d) failed", p->device); return bail(1); } }
 	cudaGetDevice(&c->device);
-	cudaDeviceProp prop;
-	if (cudaGetDeviceProperties(&prop, c->device) != cudaSuccess) { fail(c, "cudaGetDeviceProperties failed"); return bail(1); }
-	if (prop.major < 10) { fail(c, "device %d is sm_%d%d; libsarw_b200 is built for sm_100a only", c->device, prop.major, prop.minor); return bail(1); }
-	c->numSMs = prop.multiProcessorCount;
-	if (!prop.cooperativeLaunch) { fail(c, "device lacks cooperative launch"); return bail(1); }
+	// device facts are queried once per device and process (cudaGetDeviceProperties alone costs milliseconds)
+	struct DevInfo { bool valid; int major, minor, numSMs, coop, growBlocksMax; };
+	static DevInfo devInfo[64] = {};
+	DevInfo& di = devInfo[c->device & 63];
+	if (!di.valid) {
+		if (cudaDeviceGetAttribute(&di.major, cudaDevAttrComputeCapabilityMajor, c->device) != cudaSuccess
+			|| cudaDeviceGetAttribute(&di.minor, cudaDevAttrComputeCapabilityMinor, c->device) != cudaSuccess
+			|| cudaDeviceGetAttribute(&di.numSMs, cudaDevAttrMultiProcessorCount, c->device) != cudaSuccess
+			|| cudaDeviceGetAttribute(&di.coop, cudaDevAttrCooperativeLaunch, c->device) != cudaSuccess) { fail(c, "cudaDeviceGetAttribute failed"); return bail(1); }
+		di.growBlocksMax = 0;
+		if (di.major >= 10 && grow_max_blocks(di.numSMs, &di.growBlocksMax) != cudaSuccess) { fail(c, "growth kernels cannot be configured: %s", cudaGetErrorString(cudaGetLastError())); return bail(1); }
+		di.valid = true;
+	}
+	if (di.major < 10) { fail(c, "device %d is sm_%d%d; libsarw_b200 is built for sm_100a only", c->device, di.major, di.minor); return bail(1); }
+	c->numSMs = di.numSMs;
+	if (!di.coop) { fail(c, "device lacks cooperative launch"); return bail(1); }
+	c->growBlocksMax = di.growBlocksMax;
 
 	Geom& g = c->g;
 	g.thresh = p->minDist;
@@ -225,8 +237,15 @@ int sarw_create(const sarw_params* p, sarw_ctx** out)
 	g.target = sarw_target_count(p->boxSize, p->targetMassDensity);
 	g.nGraftAtoms = (p->nGraftChains * g.target / p->nChains) + (p->nChains - p->nGraftChains) * 2;   // sarw.cpp:232
 
-	if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { fail(c, "cudaStreamCreate failed"); return bail(1); }
-	c->ownStream = true;
+	{	// one long-lived stream per device, shared by the contexts that do not bring their own (sarw_set_stream): stream-ordered
+		// pool allocations are only reused cheaply by the stream that freed them, so per-context streams would pay the
+		// driver for fresh memory on every sarw_create
+		static cudaStream_t homeStream[64] = {};
+		const int d = c->device & 63;
+		if (!homeStream[d] && cudaStreamCreateWithFlags(&homeStream[d], cudaStreamNonBlocking) != cudaSuccess) { fail(c, "cudaStreamCreate failed"); return bail(1); }
+		c->stream = homeStream[d];
+		c->ownStream = false;
+	}
 	{	// keep freed blocks in the pool instead of returning them to the driver
 		cudaMemPool_t pool; unsigned long long keep = ~0ull;
 		if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
@@ -251,7 +270,6 @@ int sarw_create(const sarw_params* p, sarw_ctx** out)
 	CUB_(cudaMemsetAsync(c->origTrial, 0, (size_t)g.nChains * sizeof(uint32_t), c->stream));
 	CUB_(dev_alloc(c, &c->resPos, (size_t)g.nChains * 3 * sizeof(double)));
 	CUB_(dev_alloc(c, &c->dirtyList, 3 * (size_t)g.nChains * sizeof(uint32_t)));   // conflict list (n) + second list of the parallel clean-up (<= 2n: independent chains are far apart)
-	CUB_(grow_max_blocks(c->numSMs, &c->growBlocksMax));
 	CUB_(cudaStreamSynchronize(c->stream));
 #undef CUB_
 	if (c->growBlocksMax < 1) { fail(c, "growth kernel does not fit on the device"); return bail(1); }

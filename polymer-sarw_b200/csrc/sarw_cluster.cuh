@@ -19,7 +19,7 @@ namespace cgx = ::cooperative_groups;
 constexpr int CL_MAX_CTAS = 16;         // non-portable cluster size
 constexpr int CL_MAXCH = 16 * CL_MAX_CTAS;   // table capacity: 16 warps per CTA x 16 CTAs (the 8-warp variant uses half of it)
 constexpr int CL_REGION_CELLS = 64;     // staged region: at most 4 x 4 x 4 cells of 128 bytes
-constexpr int CL_NARC = 64;             // blocked arcs kept per chain (more: no pre-classification, still exact)
+
 
 // tentative bead of one chain in one round, as broadcast to every CTA
 struct __align__(8) TentRec {

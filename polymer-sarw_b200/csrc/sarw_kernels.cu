@@ -21,10 +21,8 @@
 namespace sarw {
 
 constexpr int GROW_WARPS = 8;            // grid mode: warps per CTA of the cooperative launch
-constexpr int NBMAX = 128;          // staged neighbour beads per chain in the legacy staging helper
 constexpr int GROW_NB_CAP = 256;    // grid kernel: staged beads per chain (shared memory, 16 B each)
 constexpr int GROW_ARC_CAP = 128;   // grid kernel: blocked arcs per chain
-constexpr int NARCMAX = 128;        // blocked torsion arcs per chain (shared memory, 8 B each)
 constexpr uint32_t CHAIN_DEAD = 1u; // ChainState.flags: every torsion angle is permanently blocked
 constexpr uint32_t CHAIN_HARD = 2u; // ChainState.flags: none of the first 32 trials passed last round (skip the fast path)
 constexpr unsigned FULL = 0xFFFFFFFFu;
@@ -315,136 +313,6 @@ __device__ __forceinline__ void round_range(const Geom& g, unsigned long long nB
 	if (g.growthOrder == 1 && g.nGraft > 0) {
 		if ((long long)nBeads < g.nGraftAtoms) end = g.nGraft; else start = g.nGraft;
 	}
-}
-
-// stage every bead that can be within thresh of any point of the cone circle into shared memory, as positions
-// relative to the (wrapped) last bead; returns the number staged or -1 when NBMAX does not suffice
-__device__ __forceinline__ int stage_region(const Geom& g, const Tables& T, const double lw[3], const Frame& f,
-	uint32_t idLimit, uint32_t ignoreId, float4* nb, int lane, bool& regionOvf, int64_t* stagedCell = nullptr, uint32_t* stagedCnt = nullptr)
-{
-	int lo[3], nn[3];
-	bool ovf = false;
-#pragma unroll
-	for (int k = 0; k < 3; k++) {
-		double cen = lw[k] + g.dCosPhi * f.Z[k];
-		double w = 1.0 - f.Z[k] * f.Z[k];
-		double e = g.dSinPhi * sqrt(w > 0 ? w : 0.0) + g.regionReach;
-		lo[k] = (int)floor((cen - e) * g.ainv[k]);
-		nn[k] = (int)floor((cen + e) * g.ainv[k]) - lo[k] + 1;
-	}
-	const int ncell = nn[0] * nn[1] * nn[2];
-	int total = 0;
-	for (int cbase = 0; cbase < ncell; cbase += 32) {
-		const int ci = cbase + lane;
-		uint32_t cnt = 0; float4 s0 = make_float4(0, 0, 0, 0); const Cell* cell = nullptr; float sh[3] = { 0, 0, 0 };
-		if (ci < ncell) {
-			int ix = ci % nn[0], rest = ci / nn[0];
-			int iy = rest % nn[1], iz = rest / nn[1];
-			int cx = lo[0] + ix, cy = lo[1] + iy, cz = lo[2] + iz;
-			cell = T.cells + cell_index(g, wrap_cell(cx, g.S[0]), wrap_cell(cy, g.S[1]), wrap_cell(cz, g.S[2]));
-			const uint2 hdr = __ldcg(reinterpret_cast<const uint2*>(cell));
-			s0 = __ldcg(&cell->slot[0]);
-			ovf |= (hdr.y != ID_NONE);
-			cnt = hdr.x + 1u; if (cnt > (uint32_t)g.cap) cnt = (uint32_t)g.cap;
-			if (stagedCell && cbase < 64) { stagedCell[cbase >> 5] = cell - T.cells; stagedCnt[cbase >> 5] = cnt; }
-			sh[0] = (float)((double)cx * g.a[0] - lw[0]); sh[1] = (float)((double)cy * g.a[1] - lw[1]); sh[2] = (float)((double)cz * g.a[2] - lw[2]);
-		}
-		uint32_t incl = cnt;
-#pragma unroll
-		for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += y; }
-		const int sum = (int)__shfl_sync(FULL, incl, 31);
-		if (total + sum > NBMAX) { regionOvf = true; return -1; }
-		int at = total + (int)(incl - cnt);
-		for (uint32_t s = 0; s < cnt; ++s) {
-			float4 b = s == 0 ? s0 : __ldcg(&cell->slot[s]);
-			uint32_t id = __float_as_uint(b.w);
-			if (id >= idLimit || id == ignoreId) nb[at + s] = make_float4(1e30f, 1e30f, 1e30f, __uint_as_float(ID_NONE));
-			else nb[at + s] = make_float4(sh[0] + b.x, sh[1] + b.y, sh[2] + b.z, b.w);
-		}
-		total += sum;
-	}
-	regionOvf = __any_sync(FULL, ovf);
-	__syncwarp();
-	return total;
-}
-
-
-// ------------------------------------------------------------------ blocked torsion arcs
-// A candidate is last + rho*(cos(theta) X + sin(theta) Y) + h Z (sarw.cpp:178-184). For a staged bead at w (relative to
-// the circle centre) its distance satisfies d^2 = |w|^2 + rho^2 - 2 rho R cos(theta - alpha), so the bead blocks the arc
-// |theta - alpha| <= omega. Arcs are used ONLY to skip trials that are CERTAINLY rejected: they are shrunk by margins
-// that dominate every rounding error (1e-5 A in distance, 1e-9 in cos, 2e-5 rad in angle), and every trial that is not
-// certainly blocked still goes through the exact reference arithmetic. Decisions are therefore unchanged.
-__device__ __forceinline__ int build_arcs(const Geom& g, const Frame& f, const float4* nb, int nnb, float2* arcs, int lane)
-{
-	const double rho = g.dSinPhi, h = g.dCosPhi;
-	const double ts = g.thresh - 1e-5;
-	int narcs = 0;
-	for (int jb = 0; jb < nnb; jb += 32) {
-		const int j = jb + lane;
-		bool have = false; float2 arc = make_float2(0.f, 0.f);
-		if (j < nnb && ts > 0) {
-			const float4 b = nb[j];
-			if (b.x < 1e29f) {
-				const double wx = (double)b.x - h * f.Z[0], wy = (double)b.y - h * f.Z[1], wz = (double)b.z - h * f.Z[2];
-				const double px = wx * f.X[0] + wy * f.X[1] + wz * f.X[2];
-				const double py = wx * f.Y[0] + wy * f.Y[1] + wz * f.Y[2];
-				const double pz = wx * f.Z[0] + wy * f.Z[1] + wz * f.Z[2];
-				const double R2 = px * px + py * py, R = sqrt(R2);
-				if (R > 1e-6) {
-					const double kappa = (R2 + pz * pz + rho * rho - ts * ts) / (2.0 * rho * R) + 1e-9;
-					if (kappa < 1.0) {
-						const double omega = (kappa <= -1.0 ? 3.14159265358979323846 : acos(kappa)) - 2e-5;
-						if (omega > 0) { have = true; arc = make_float2((float)atan2(py, px), (float)omega); }
-					}
-				}
-			}
-		}
-		const unsigned m = __ballot_sync(FULL, have);
-		if (narcs + __popc(m) > NARCMAX) return -1;
-		if (have) arcs[narcs + __popc(m & ((1u << lane) - 1u))] = arc;
-		narcs += __popc(m);
-	}
-	__syncwarp();
-	return narcs;
-}
-
-__device__ __forceinline__ float wrap_pi(float d)
-{	return d - 6.28318530717958647692f * rintf(d * 0.15915494309189533577f);
-}
-__device__ __forceinline__ bool theta_blocked(float theta, const float2* arcs, int narcs)
-{
-	for (int a = 0; a < narcs; ++a) {
-		const float2 arc = arcs[a];
-		if (fabsf(wrap_pi(theta - arc.x)) <= arc.y) return true;
-	}
-	return false;
-}
-
-// do the (shrunk) arcs, together with the never-sampled gap [359 deg, 360 deg) of sarw.cpp:177, cover the whole circle?
-// Closed arcs cover the circle iff every arc's upper end lies strictly inside another arc.
-__device__ __forceinline__ bool arcs_cover_circle(const float2* arcs, int narcs, int lane)
-{
-	if (narcs <= 0) return false;
-	const float gapLo = (float)(359.0 * 3.14159265358979323846 / 180 - 1e-9), gapHi = 6.28318530717958647692f;
-	const float gapC = 0.5f * (gapLo + gapHi), gapW = 0.5f * (gapHi - gapLo) - 1e-6f;   // virtual arc, index narcs
-	bool allCovered = true;
-	for (int ib = 0; ib <= narcs; ib += 32) {
-		const int i = ib + lane;
-		bool covered = true;
-		if (i <= narcs) {
-			const float c = i < narcs ? arcs[i].x : gapC, w = i < narcs ? arcs[i].y : gapW;
-			const float e = c + w;
-			covered = false;
-			for (int j = 0; j <= narcs && !covered; ++j) {
-				const float cj = j < narcs ? arcs[j].x : gapC, wj = j < narcs ? arcs[j].y : gapW;
-				if (wj >= 3.1415f) covered = true;
-				else covered = fabsf(wrap_pi(e - cj)) < wj - 2e-6f;
-			}
-		}
-		allCovered = allCovered && __all_sync(FULL, covered);
-	}
-	return allCovered;
 }
 
 // exact evaluation of one trial by the whole warp (reference arithmetic; neighbours split across lanes)

@@ -238,12 +238,15 @@ class Context:
         self._ck(self.lib.sarw_get_stats(self.h, C.byref(s)))
         return s
 
-    def download(self):
+    def download(self, out=None):
+        """The public state vectors (sarw.h:77-83). `out` may hold preallocated host buffers (e.g. views of pinned torch tensors)
+        xyz (>= N x 3 f64), chainID, type (>= N i32), bonds (>= N x 2 i64); views of the right length are returned."""
         s = self.stats()
-        xyz = np.zeros((s.nBeads, 3), np.float64)
-        chainID = np.zeros(s.nBeads, np.int32)
-        typ = np.zeros(s.nBeads, np.int32)
-        bonds = np.zeros((s.nBonds, 2), np.int64)
+        if out is None:
+            xyz = np.empty((s.nBeads, 3), np.float64); chainID = np.empty(s.nBeads, np.int32)
+            typ = np.empty(s.nBeads, np.int32); bonds = np.empty((s.nBonds, 2), np.int64)
+        else:
+            xyz, chainID, typ, bonds = out["xyz"][:s.nBeads], out["chainID"][:s.nBeads], out["type"][:s.nBeads], out["bonds"][:s.nBonds]
         self._ck(self.lib.sarw_download(self.h, xyz.ctypes.data, chainID.ctypes.data, typ.ctypes.data, bonds.ctypes.data))
         return xyz, chainID, typ, bonds
 
