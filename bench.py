@@ -251,16 +251,24 @@ def main():
     pinned = {"xyz": torch.empty((cap, 3), dtype=torch.float64, pin_memory=True).numpy(), "chainID": torch.empty(cap, dtype=torch.int32, pin_memory=True).numpy(),
               "type": torch.empty(cap, dtype=torch.int32, pin_memory=True).numpy(), "bonds": torch.empty((cap, 2), dtype=torch.int64, pin_memory=True).numpy()}
     e2e_times, e2e_beads, h2d, d2h, e2e_launch = [], 0, 0, 0, 0
+    import gc
     for i in range(total):
+        gc.collect(); gc.disable()                 # no collector pauses inside the timed call sequence
         flush.fill_(float(i)); torch.cuda.synchronize()
         t0 = time.perf_counter()
         c = sarw_b200.Context(device=local, **ctx_kwargs(w, seeds[i] + 5_000))
         c.set_stream(stream.cuda_stream)
+        ta = time.perf_counter()
         c.initiate(); st = c.grow(0, -1); c.terminate()
+        tb = time.perf_counter()
         xyz, cid, typ, bonds = c.download(pinned)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        tc = time.perf_counter()
         c.close()
+        gc.enable()
+        if os.environ.get("SARW_BENCH_DEBUG"): print(f"   create {1e3*(ta-t0):.2f} run {1e3*(tb-ta):.2f} download {1e3*(tc-tb):.2f} close {1e3*(time.perf_counter()-tc):.2f}", file=sys.stderr)
+        if os.environ.get("SARW_BENCH_DEBUG"): print(f"e2e step {i}: {dt*1e3:.3f} ms", file=sys.stderr)
         if i >= args.warmup:
             e2e_times.append(dt); e2e_beads += st.nBeads
             h2d += sarw_b200.C.sizeof(sarw_b200.Params) + 64                      # parameters + control block

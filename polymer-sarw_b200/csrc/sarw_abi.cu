@@ -26,6 +26,7 @@ struct sarw_ctx {
 	Tables T{};
 	int device = 0, numSMs = 0, growBlocksMax = 0;
 	cudaStream_t stream = nullptr; bool ownStream = false;
+	cudaStream_t allocStream = nullptr;   // all pool allocations / frees go through the device's home stream (cheap reuse)
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	std::string err;
 
@@ -62,8 +63,18 @@ int fail(sarw_ctx* c, const char* fmt, ...)
 
 // stream-ordered allocations from the device's default memory pool (blocks are reused across contexts: no cudaMalloc /
 // cudaFree round trips to the driver once the pool is warm)
-template <typename T> cudaError_t dev_alloc(sarw_ctx* c, T** p, size_t bytes) { return cudaMallocAsync((void**)p, bytes ? bytes : 16, c->stream); }
-template <typename T> void dev_free(sarw_ctx* c, T* p) { if (p) cudaFreeAsync((void*)p, c->stream); }
+template <typename T> cudaError_t dev_alloc(sarw_ctx* c, T** p, size_t bytes)
+{
+	cudaError_t e = cudaMallocAsync((void**)p, bytes ? bytes : 16, c->allocStream);
+	if (e == cudaSuccess && c->allocStream != c->stream) e = cudaStreamSynchronize(c->allocStream);   // work runs on a caller's stream
+	return e;
+}
+template <typename T> void dev_free(sarw_ctx* c, T* p)
+{
+	if (!p) return;
+	if (c->allocStream != c->stream && c->stream) cudaStreamSynchronize(c->stream);   // nothing on the work stream may still use it
+	cudaFreeAsync((void*)p, c->allocStream);
+}
 
 uint64_t slots_for_rounds(const sarw_ctx* c, uint64_t rounds) { return 2ull * c->g.nChains + rounds * c->g.nChains; }
 
@@ -244,6 +255,7 @@ int sarw_create(const sarw_params* p, sarw_ctx** out)
 		const int d = c->device & 63;
 		if (!homeStream[d] && cudaStreamCreateWithFlags(&homeStream[d], cudaStreamNonBlocking) != cudaSuccess) { fail(c, "cudaStreamCreate failed"); return bail(1); }
 		c->stream = homeStream[d];
+		c->allocStream = homeStream[d];
 		c->ownStream = false;
 	}
 	{	// keep freed blocks in the pool instead of returning them to the driver
@@ -293,7 +305,6 @@ void sarw_destroy(sarw_ctx* c)
 		dev_free(c, c->T.cells); dev_free(c, c->T.lpos); dev_free(c, c->T.ovf); dev_free(c, c->T.ovfCount);
 		dev_free(c, c->ctl); dev_free(c, c->chains); dev_free(c, c->resTrial); dev_free(c, c->origTrial); dev_free(c, c->resPos); dev_free(c, c->prev);
 		dev_free(c, c->roundAcc); dev_free(c, c->roundProg); dev_free(c, c->dirtyCount); dev_free(c, c->dirtyList); dev_free(c, c->grafts);
-		cudaStreamSynchronize(c->stream);
 	}
 	if (c->peersOpen) for (uint32_t p = 0; p < c->mrRanks; ++p) if (p != c->mrRank && c->peerRec[p]) cudaIpcCloseMemHandle(c->peerRec[p]);
 	if (c->xbuf) cudaFree(c->xbuf);
