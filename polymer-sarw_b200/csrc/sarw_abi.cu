@@ -268,8 +268,8 @@ int sarw_create(const sarw_params* p, sarw_ctx** out)
 #define CUB_(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fail(c, "%s: %s", #x, cudaGetErrorString(e_)); return bail(1); } } while (0)
 	CUB_(dev_alloc(c, &c->T.cells, nCells * sizeof(Cell)));
 	CUB_(cudaMemsetAsync(c->T.cells, 0xFF, nCells * sizeof(Cell), c->stream));
-	c->T.ovfCap = 1u << 16;
-	CUB_(dev_alloc(c, &c->T.ovf, c->T.ovfCap * sizeof(uint32_t)));
+	c->T.ovfCap = 1u << 20;
+	CUB_(dev_alloc(c, &c->T.ovf, (size_t)c->T.ovfCap * sizeof(uint4)));
 	CUB_(dev_alloc(c, &c->T.ovfCount, sizeof(uint32_t)));
 	CUB_(cudaMemsetAsync(c->T.ovfCount, 0, sizeof(uint32_t), c->stream));
 	CUB_(dev_alloc(c, &c->ctl, sizeof(Control)));

@@ -351,9 +351,10 @@ __device__ __forceinline__ uint32_t propose_chain(const Geom& g, const Tables& T
 				(void)jmin;
 				if (okL && novf) {
 					const uint32_t m = novf > T.ovfCap ? T.ovfCap : novf;
+					int cq[3]; cell_of_frac(g, vL, cq);
 					for (uint32_t j = 0; j < m && okL; ++j) {
-						const uint32_t id = __ldcg(T.ovf + j);
-						if (id < idRound && id != cs.lastId && exact_pair(g, vL, T.lpos + 3 * (size_t)id)) okL = false;
+						const uint4 e = __ldcg(T.ovf + j);
+						if (e.w < idRound && e.w != cs.lastId && ovf_entry_near(g, e, cq) && exact_pair(g, vL, T.lpos + 3 * (size_t)e.w)) okL = false;
 					}
 				}
 			} else okL = !probe_cells<1>(g, T, vL, 0u, idRound, cs.lastId, 0);
@@ -570,7 +571,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) grow_cluster_kernel(GrowArgs A)
 				} else {           // cell full: overflow list (rare); the header count is written by the rank-0 bead, if it fits
 					atomicExch(&cell->ovfFlagInv, 0u);
 					const uint32_t at = atomicAdd(A.T.ovfCount, 1u);
-					if (at < A.T.ovfCap) A.T.ovf[at] = id;
+					if (at < A.T.ovfCap) A.T.ovf[at] = make_uint4((uint32_t)rec.cx, (uint32_t)rec.cy, (uint32_t)rec.cz, id);
 				}
 				for (int k = 0; k < 3; k++) A.resPos[3 * (size_t)i + k] = cand[k];
 			}

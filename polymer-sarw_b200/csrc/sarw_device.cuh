@@ -66,7 +66,7 @@ struct Geom {
 struct Tables {
 	Cell* cells;
 	double* lpos;             // Cartesian position by lookup index, 3 doubles each; all-ones bit pattern = never accepted
-	uint32_t* ovf;            // overflow list: lookup indices of beads whose cell was full
+	uint4* ovf;               // overflow list: {cell x, cell y, cell z, lookup index} of beads whose cell was full
 	uint32_t* ovfCount;
 	uint32_t ovfCap;
 };
@@ -229,9 +229,8 @@ __device__ __forceinline__ int64_t cell_index(const Geom& g, int wx, int wy, int
 }
 
 // cell + in-cell offset of a bead from its fractional coordinates
-__device__ __forceinline__ int64_t bead_cell(const Geom& g, const double v[3], float o[3])
+__device__ __forceinline__ int64_t bead_cell(const Geom& g, const double v[3], float o[3], int c[3])
 {
-	int c[3];
 #pragma unroll
 	for (int k = 0; k < 3; k++) {
 		double s = v[k] * g.sOverL[k];
@@ -242,6 +241,27 @@ __device__ __forceinline__ int64_t bead_cell(const Geom& g, const double v[3], f
 		o[k] = (float)((s - (double)ci) * g.a[k]);
 	}
 	return cell_index(g, c[0], c[1], c[2]);
+}
+__device__ __forceinline__ int64_t bead_cell(const Geom& g, const double v[3], float o[3])
+{	int c[3];
+	return bead_cell(g, v, o, c);
+}
+
+// wrapped cell coordinates of a point given by its fractional coordinates
+__device__ __forceinline__ void cell_of_frac(const Geom& g, const double v[3], int c[3])
+{
+#pragma unroll
+	for (int k = 0; k < 3; k++) {
+		int ci = (int)floor(v[k] * g.sOverL[k]);
+		c[k] = ci >= g.S[k] ? g.S[k] - 1 : (ci < 0 ? 0 : ci);
+	}
+}
+// can an overflow-list entry be within thresh of a point in cell c? (cells are wider than 2*thresh: same or adjacent cell, periodic)
+__device__ __forceinline__ bool ovf_entry_near(const Geom& g, const uint4& e, const int c[3])
+{
+	int dx = abs((int)e.x - c[0]), dy = abs((int)e.y - c[1]), dz = abs((int)e.z - c[2]);
+	dx = min(dx, g.S[0] - dx); dy = min(dy, g.S[1] - dy); dz = min(dz, g.S[2] - dz);
+	return dx <= 1 && dy <= 1 && dz <= 1;
 }
 
 // ------------------------------------------------------------------ overlap query against the cell list
@@ -286,9 +306,11 @@ __device__ __forceinline__ bool probe_cells(const Geom& g, const Tables& T, cons
 	if (!hit && anyOvf) {   // only lanes whose own cells overflowed scan the list: the overflowed beads of a cell are in range of it
 		uint32_t novf = __ldcg(T.ovfCount);
 		if (novf > T.ovfCap) novf = T.ovfCap;
+		int cq[3]; cell_of_frac(g, v, cq);
 		for (uint32_t j = 0; j < novf && !hit; ++j) {
-			uint32_t id = __ldcg(T.ovf + j);
-			if (id < idLo || id >= idHi || id == ignoreId) continue;
+			const uint4 e = __ldcg(T.ovf + j);
+			const uint32_t id = e.w;
+			if (id < idLo || id >= idHi || id == ignoreId || !ovf_entry_near(g, e, cq)) continue;
 			hit = exact_pair(g, v, T.lpos + 3 * (size_t)id);
 		}
 	}
@@ -298,9 +320,9 @@ __device__ __forceinline__ bool probe_cells(const Geom& g, const Tables& T, cons
 // insert a bead (PeriodicLookup.h:37-47 + the atom store of sarw.h:123-126); any number of threads may insert concurrently
 __device__ __forceinline__ void insert_bead(const Geom& g, const Tables& T, const double pos[3], uint32_t id)
 {
-	double v[3]; float o[3];
+	double v[3]; float o[3]; int cc[3];
 	to_frac(g, pos, v);
-	int64_t ci = bead_cell(g, v, o);
+	int64_t ci = bead_cell(g, v, o, cc);
 	double* lp = T.lpos + 3 * (size_t)id;
 	lp[0] = pos[0]; lp[1] = pos[1]; lp[2] = pos[2];
 	Cell* cell = T.cells + ci;
@@ -311,7 +333,7 @@ __device__ __forceinline__ void insert_bead(const Geom& g, const Tables& T, cons
 		atomicSub(&cell->countMinus1, 1u);
 		atomicExch(&cell->ovfFlagInv, 0u);
 		uint32_t j = atomicAdd(T.ovfCount, 1u);
-		if (j < T.ovfCap) T.ovf[j] = id;   // beyond ovfCap the host sees ovfCount > ovfCap and fails the call
+		if (j < T.ovfCap) T.ovf[j] = make_uint4((uint32_t)cc[0], (uint32_t)cc[1], (uint32_t)cc[2], id);   // beyond ovfCap the host sees ovfCount > ovfCap and fails the call
 	}
 }
 
@@ -341,7 +363,7 @@ __device__ inline void remove_bead(const Geom& g, const Tables& T, uint32_t id)
 		uint32_t novf = __ldcg(T.ovfCount);
 		if (novf > T.ovfCap) novf = T.ovfCap;
 		for (uint32_t j = 0; j < novf; ++j)
-			if (__ldcg(T.ovf + j) == id) { T.ovf[j] = __ldcg(T.ovf + novf - 1); *T.ovfCount = novf - 1; break; }
+			if (__ldcg(T.ovf + j).w == id) { T.ovf[j] = __ldcg(T.ovf + novf - 1); *T.ovfCount = novf - 1; break; }
 	}
 	unsigned long long ones = ~0ull;
 	lp[0] = __longlong_as_double((long long)ones); lp[1] = lp[0]; lp[2] = lp[0];

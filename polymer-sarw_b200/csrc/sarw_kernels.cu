@@ -96,9 +96,11 @@ __device__ void enumerate_hits(const Geom& g, const Tables& T, const double v[3]
 	if (!anyOvf) return;
 	uint32_t novf = __ldcg(T.ovfCount);
 	if (novf > T.ovfCap) novf = T.ovfCap;
+	int cq[3]; cell_of_frac(g, v, cq);
 	for (uint32_t j = 0; j < novf; ++j) {
-		uint32_t id = __ldcg(T.ovf + j);
-		if (id <= idLoExcl || id >= idHi) continue;
+		const uint4 e = __ldcg(T.ovf + j);
+		const uint32_t id = e.w;
+		if (id <= idLoExcl || id >= idHi || !ovf_entry_near(g, e, cq)) continue;
 		if (exact_pair(g, v, T.lpos + 3 * (size_t)id)) fn(id);
 	}
 }
@@ -335,9 +337,10 @@ __device__ __forceinline__ bool eval_trial_coop(const Geom& g, const Tables& T, 
 		}
 		if (novf) {   // beads that did not fit their cell live in the overflow list
 			const uint32_t m = novf > T.ovfCap ? T.ovfCap : novf;
+			int cq[3]; cell_of_frac(g, v, cq);
 			for (uint32_t j = lane; j < m && !hit; j += 32) {
-				const uint32_t id = __ldcg(T.ovf + j);
-				if (id < idRound && id != cs.lastId) hit = exact_pair(g, v, T.lpos + 3 * (size_t)id);
+				const uint4 e = __ldcg(T.ovf + j);
+				if (e.w < idRound && e.w != cs.lastId && ovf_entry_near(g, e, cq)) hit = exact_pair(g, v, T.lpos + 3 * (size_t)e.w);
 			}
 		}
 	} else {   // region too crowded for the staging buffer: query the cell list directly (8 cells over 8 lanes)

@@ -15,7 +15,7 @@ for name in which:
     cfg = getattr(cases, name)
     for seed in seeds:
         t0 = time.time()
-        s = sarw_b200.SARW(cfg["nChains"], cfg["boxSize"], cfg["minDist"], seed=seed, launchMode=mode,
+        s = sarw_b200.SARW(cfg["nChains"], cfg["boxSize"], cfg["minDist"], seed=seed, launchMode=mode, cellEdge=float(os.environ.get("SARW_CELL_EDGE", "0")),
                            **{k: v for k, v in cfg.items() if k not in ("nChains", "boxSize", "minDist")})
         t1 = time.time()
         st = s.run()
