@@ -47,7 +47,7 @@ struct sarw_ctx {
 	double seedMs = 0, growMs = 0; int64_t growLaunches = 0, seedLaunches = 0;
 	uint32_t mrRank = 0, mrRanks = 1; bool mrPending = false;   // multi-rank mode (sarw_mr_*)
 	void* xbuf = nullptr; size_t xbufRecBytes = 0;               // peer-memory exchange buffer (plain cudaMalloc: IPC-exportable)
-	void* peerRec[8] = {}; void* peerFlags[8] = {}; bool peersOpen = false;
+	void* peerRec[8] = {}; void* peerFlags[8] = {}; void* peerDirty[8] = {}; bool peersOpen = false;
 };
 
 namespace {
@@ -532,7 +532,7 @@ static int mr_launch(sarw_ctx* c, uint32_t phase, void* localRec, const void* al
 	if (blocks < 1) blocks = 1;
 	CU(c, cudaEventRecord(c->ev0, c->stream));
 	CU(c, launch_grow_mr(c->g, c->T, c->chains, c->resTrial, c->origTrial, c->resPos, c->prev, c->ctl, c->roundAcc, c->roundProg, c->dirtyCount, c->dirtyList,
-		h.round + 1, blocks, c->mrRank, c->mrRanks, phase, localRec, allRec, nullptr, nullptr, c->stream));
+		h.round + 1, blocks, c->mrRank, c->mrRanks, phase, localRec, allRec, nullptr, nullptr, nullptr, 0u, c->stream));
 	CU(c, cudaEventRecord(c->ev1, c->stream));
 	c->growLaunches += 1;
 	if (hOut) {
@@ -586,9 +586,10 @@ int sarw_mr_peer_export(sarw_ctx* c, void* handle64)
 	cudaSetDevice(c->device);
 	const size_t K = ((size_t)c->g.nChains + c->mrRanks - 1) / c->mrRanks;
 	c->xbufRecBytes = 2 * (size_t)c->mrRanks * K * 32;
+	const size_t dirtyBytes = 2 * (size_t)c->mrRanks * (1 + K) * sizeof(uint32_t);   // conflict-list inboxes
 	if (!c->xbuf) {
-		CU(c, cudaMalloc(&c->xbuf, c->xbufRecBytes + 256));
-		CU(c, cudaMemset(c->xbuf, 0, c->xbufRecBytes + 256));
+		CU(c, cudaMalloc(&c->xbuf, c->xbufRecBytes + 256 + dirtyBytes));
+		CU(c, cudaMemset(c->xbuf, 0, c->xbufRecBytes + 256 + dirtyBytes));
 	}
 	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
 	CU(c, cudaIpcGetMemHandle((cudaIpcMemHandle_t*)handle64, c->xbuf));
@@ -606,7 +607,7 @@ int sarw_mr_peer_connect(sarw_ctx* c, const void* allHandles)
 			cudaIpcMemHandle_t h; memcpy(&h, (const char*)allHandles + 64 * p, 64);
 			CU(c, cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
 		}
-		c->peerRec[p] = base; c->peerFlags[p] = (char*)base + c->xbufRecBytes;
+		c->peerRec[p] = base; c->peerFlags[p] = (char*)base + c->xbufRecBytes; c->peerDirty[p] = (char*)base + c->xbufRecBytes + 256;
 	}
 	c->peersOpen = true;
 	return 0;
@@ -628,7 +629,8 @@ int sarw_mr_grow_peer(sarw_ctx* c, int64_t maxRounds, sarw_stats* stats)
 		if (blocks < 1) blocks = 1;
 		CU(c, cudaEventRecord(c->ev0, c->stream));
 		CU(c, launch_grow_mr(c->g, c->T, c->chains, c->resTrial, c->origTrial, c->resPos, c->prev, c->ctl, c->roundAcc, c->roundProg, c->dirtyCount, c->dirtyList,
-			roundEnd, blocks, c->mrRank, c->mrRanks, 4u, nullptr, nullptr, c->peerRec, c->peerFlags, c->stream));
+			roundEnd, blocks, c->mrRank, c->mrRanks, 4u, nullptr, nullptr, c->peerRec, c->peerFlags, c->peerDirty,
+			(c->p.launchMode & 2) ? 0u : 1u, c->stream));   // launchMode bit 1: keep the verification replicated (diagnostics)
 		CU(c, cudaEventRecord(c->ev1, c->stream));
 		uint32_t before = h.round;
 		if (read_control(c, &h)) return 1;

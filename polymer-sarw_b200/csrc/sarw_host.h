@@ -33,7 +33,8 @@ cudaError_t launch_grow(const Geom& g, const Tables& T, ChainState* chains, uint
 int grow_cluster_max_chains();
 cudaError_t launch_grow_mr(const Geom& g, const Tables& T, ChainState* chains, uint32_t* resTrial, uint32_t* origTrial, double* resPos, uint32_t* prev, Control* ctl,
 	uint32_t* roundAcc, uint32_t* roundProg, uint32_t* dirtyCount, uint32_t* dirtyList, uint32_t roundEnd, int blocks,
-	uint32_t rank, uint32_t ranks, uint32_t phase, void* localRec, const void* allRec, void* const* peerRec, void* const* peerFlags, cudaStream_t st);
+	uint32_t rank, uint32_t ranks, uint32_t phase, void* localRec, const void* allRec, void* const* peerRec, void* const* peerFlags,
+	void* const* peerDirty, uint32_t splitVerify, cudaStream_t st);
 cudaError_t download_scan_bytes(uint64_t nSlots, size_t* bytes);
 cudaError_t launch_download(const Geom& g, const Tables& T, const uint32_t* prev, const ChainState* chains, uint64_t nSlots, uint32_t nSeeded,
 	int terminated, uint32_t* flags, uint32_t* scan, void* cubTemp, size_t cubBytes,

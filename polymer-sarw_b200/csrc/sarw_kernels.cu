@@ -301,7 +301,9 @@ struct GrowArgs {
 	// phase 4: whole loop in one launch per GPU; records are stored straight into every peer's buffer over NVLink and the
 	// ranks meet on flags in peer memory (no host, no NCCL in the loop)
 	MrRecord* peerRec[8];         // [r]: rank r's record buffer, 2 parities x mrRanks x mrK records (own buffer at [mrRank])
-	uint32_t* peerFlags[8];       // [r]: rank r's arrival flags, 2 parities x 8 words
+	uint32_t* peerFlags[8];       // [r]: rank r's arrival flags: 2 parities x 8 words for the records, then 2 x 8 for the conflict lists
+	uint32_t* peerDirty[8];       // [r]: rank r's conflict-list inbox, 2 parities x mrRanks x (1 + mrK) words (count, chains...)
+	uint32_t mrSplitVerify;       // phase 4: each rank verifies only the chains it proposed and the conflict lists are exchanged
 };
 
 __device__ __forceinline__ uint32_t round_id_base(const Geom& g, uint32_t round)
@@ -365,15 +367,15 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
 
 // one thread per GPU: tell every peer that this rank's records of `round` are complete, wait until all peers said so.
 // Returns false after ~3 s without progress (a peer died): the caller aborts the launch instead of hanging the GPU.
-__device__ bool mr_peer_meet(const GrowArgs& A, uint32_t round)
+__device__ bool mr_peer_meet(const GrowArgs& A, uint32_t round, uint32_t which = 0u)
 {
-	const uint32_t par = round & 1u, tag = round + 1u;
+	const uint32_t par = round & 1u, tag = round + 1u, off = which * 16u + par * 8u;
 	__threadfence_system();
-	for (uint32_t p = 0; p < A.mrRanks; ++p) if (p != A.mrRank) st_release_sys(A.peerFlags[p] + par * 8u + A.mrRank, tag);
+	for (uint32_t p = 0; p < A.mrRanks; ++p) if (p != A.mrRank) st_release_sys(A.peerFlags[p] + off + A.mrRank, tag);
 	const long long t0 = clock64();
 	for (uint32_t p = 0; p < A.mrRanks; ++p) {
 		if (p == A.mrRank) continue;
-		while (ld_acquire_sys(A.peerFlags[A.mrRank] + par * 8u + p) != tag)
+		while (ld_acquire_sys(A.peerFlags[A.mrRank] + off + p) != tag)
 			if (clock64() - t0 > 6000000000ll) return false;
 	}
 	return true;
@@ -689,11 +691,19 @@ __global__ void __launch_bounds__(WARPS * 32) grow_kernel(GrowArgs A)
 		const long long tk1 = clock64();
 
 		// ---------------- phase V: conflicts with tentative beads of lower-indexed chains of this round
+		const bool splitV = A.mrPhase == 4u && A.mrSplitVerify != 0u;
 		{
 			const int sub = lane & 7, grp = lane >> 3;
 			uint32_t acc = 0, prog = 0; unsigned long long tr = 0;
-			for (uint32_t base = start + gw * 4; base < end; base += nW * 4) {
-				const uint32_t i = base + grp;
+			if (splitV)   // round totals from the trial numbers every rank knows; the probing below covers this rank's chains only
+				for (uint32_t i = start + gw * 32 + lane; i < end; i += nW * 32) {
+					const uint32_t t = __ldcg(&A.resTrial[i]);
+					if (t <= T_) { acc++; tr += t; if (t < T_) prog++; } else tr += T_;
+				}
+			const uint32_t stride = splitV ? A.mrRanks : 1u;
+			const uint32_t first = splitV ? A.mrRank + ((start > A.mrRank ? start - A.mrRank + stride - 1u : 0u) / stride) * stride : start;   // first chain >= start of this rank
+			for (uint32_t base = first + gw * 4 * stride; base < end; base += nW * 4 * stride) {
+				const uint32_t i = base + grp * stride;
 				bool h = false; uint32_t t = 0;
 				if (i < end) {
 					t = __ldcg(&A.resTrial[i]);
@@ -705,7 +715,7 @@ __global__ void __launch_bounds__(WARPS * 32) grow_kernel(GrowArgs A)
 				}
 				const unsigned bal = __ballot_sync(FULL, h);
 				if (sub == 0 && i < end) {
-					if (t <= T_) { acc++; tr += t; if (t < T_) prog++; } else tr += T_;
+					if (!splitV) { if (t <= T_) { acc++; tr += t; if (t < T_) prog++; } else tr += T_; }
 					if ((bal >> (grp * 8)) & 0xFFu) {
 						uint32_t at = atomicAdd(&A.dirtyCount[round], 1u);
 						A.dirtyList[at] = i;
@@ -722,7 +732,33 @@ __global__ void __launch_bounds__(WARPS * 32) grow_kernel(GrowArgs A)
 				myTrials += tr;
 			}
 		}
+		if (splitV) {   // exchange the conflict lists: block 0 stores this rank's list into every rank's inbox, ranks meet, lists are merged
+			round_barrier<CLUSTER>(A.ctl);
+			if (blockIdx.x == 0) {
+				const uint32_t par = round & 1u, mine = __ldcg(&A.dirtyCount[round]);
+				const size_t slot = ((size_t)par * A.mrRanks + A.mrRank) * (1u + A.mrK);
+				for (uint32_t p = 0; p < A.mrRanks; ++p) {
+					for (uint32_t j = threadIdx.x; j < mine; j += blockDim.x) A.peerDirty[p][slot + 1u + j] = __ldcg(&A.dirtyList[j]);
+					if (threadIdx.x == 0) A.peerDirty[p][slot] = mine;
+				}
+				__threadfence_system();
+				__syncthreads();
+				if (threadIdx.x == 0 && !mr_peer_meet(A, round, 1u)) atomicExch(&A.ctl->abort, 1u);
+				__syncthreads();
+				// merge (rank order; the clean-up does not depend on the order of the list)
+				uint32_t total = 0;
+				for (uint32_t p = 0; p < A.mrRanks; ++p) {
+					const uint32_t* in = A.peerDirty[A.mrRank] + ((size_t)par * A.mrRanks + p) * (1u + A.mrK);
+					const uint32_t cnt = __ldcg(in);
+					for (uint32_t j = threadIdx.x; j < cnt; j += blockDim.x) A.dirtyList[total + j] = __ldcg(in + 1u + j);
+					total += cnt;
+				}
+				__syncthreads();
+				if (threadIdx.x == 0) A.dirtyCount[round] = total;
+			}
+		}
 		round_barrier<CLUSTER>(A.ctl);
+		if (splitV && __ldcg(&A.ctl->abort)) break;
 
 		const long long tk2 = clock64();
 		// ---------------- clean-up (rare): serial re-resolution in chain order
@@ -877,7 +913,7 @@ static cudaError_t launch_cluster(const GrowArgs& A, cudaStream_t st)
 cudaError_t launch_grow(const Geom& g, const Tables& T, ChainState* chains, uint32_t* resTrial, uint32_t* origTrial, double* resPos, uint32_t* prev, Control* ctl,
 	uint32_t* roundAcc, uint32_t* roundProg, uint32_t* dirtyCount, uint32_t* dirtyList, uint32_t roundEnd, int blocks, int useCluster, cudaStream_t st)
 {
-	GrowArgs A{ g, T, chains, resTrial, origTrial, resPos, prev, ctl, roundAcc, roundProg, dirtyCount, dirtyList, roundEnd, 0u, 1u, 0u, 0u, nullptr, nullptr, {}, {} };
+	GrowArgs A{ g, T, chains, resTrial, origTrial, resPos, prev, ctl, roundAcc, roundProg, dirtyCount, dirtyList, roundEnd, 0u, 1u, 0u, 0u, nullptr, nullptr, {}, {}, {}, 0u };
 	if (useCluster) {
 		// the whole launch is one thread-block cluster: CTAs are co-scheduled by the hardware, synchronise with
 		// barrier.cluster and exchange tentative beads through distributed shared memory. 8 warps per CTA (255
@@ -892,12 +928,16 @@ cudaError_t launch_grow(const Geom& g, const Tables& T, ChainState* chains, uint
 // one phase of a multi-rank round (grow_kernel with mrPhase != 0); always the cooperative grid kernel
 cudaError_t launch_grow_mr(const Geom& g, const Tables& T, ChainState* chains, uint32_t* resTrial, uint32_t* origTrial, double* resPos, uint32_t* prev, Control* ctl,
 	uint32_t* roundAcc, uint32_t* roundProg, uint32_t* dirtyCount, uint32_t* dirtyList, uint32_t roundEnd, int blocks,
-	uint32_t rank, uint32_t ranks, uint32_t phase, void* localRec, const void* allRec, void* const* peerRec, void* const* peerFlags, cudaStream_t st)
+	uint32_t rank, uint32_t ranks, uint32_t phase, void* localRec, const void* allRec, void* const* peerRec, void* const* peerFlags,
+	void* const* peerDirty, uint32_t splitVerify, cudaStream_t st)
 {
 	const uint32_t K = (g.nChains + ranks - 1) / ranks;
 	GrowArgs A{ g, T, chains, resTrial, origTrial, resPos, prev, ctl, roundAcc, roundProg, dirtyCount, dirtyList, roundEnd, rank, ranks, phase, K,
-		(MrRecord*)localRec, (const MrRecord*)allRec, {}, {} };
-	for (uint32_t p = 0; p < 8; ++p) { A.peerRec[p] = peerRec && p < ranks ? (MrRecord*)peerRec[p] : nullptr; A.peerFlags[p] = peerFlags && p < ranks ? (uint32_t*)peerFlags[p] : nullptr; }
+		(MrRecord*)localRec, (const MrRecord*)allRec, {}, {}, {}, splitVerify };
+	for (uint32_t p = 0; p < 8; ++p) {
+		A.peerRec[p] = peerRec && p < ranks ? (MrRecord*)peerRec[p] : nullptr; A.peerFlags[p] = peerFlags && p < ranks ? (uint32_t*)peerFlags[p] : nullptr;
+		A.peerDirty[p] = peerDirty && p < ranks ? (uint32_t*)peerDirty[p] : nullptr;
+	}
 	void* args[] = { &A };
 	return cudaLaunchCooperativeKernel((const void*)grow_kernel<GROW_WARPS, false>, dim3((unsigned)blocks), dim3(GROW_WARPS * 32), args,
 		grow_smem_bytes(GROW_WARPS), st);
