@@ -217,3 +217,41 @@ def test_brush_mid_size_walls_and_bias_bit_exact(sarw, oracle, bias):
     assert_same_walk(g, o, exact=True)
     assert g["stats"]["deadChains"] > 0
     assert g["xyz"][:, 2].min() >= 0.0 and g["xyz"][:, 2].max() <= 60.0
+
+
+EDGE_CASES = {
+    "one_chain": dict(nChains=1, boxSize=(20.0, 20.0, 20.0), minDist=1.0, maxTrials=100),
+    "max_trials_1": dict(nChains=30, boxSize=(20.0, 20.0, 20.0), minDist=1.0, maxTrials=1),            # seeding can never succeed (sarw.cpp:355)
+    "max_trials_2": dict(nChains=30, boxSize=(20.0, 20.0, 20.0), minDist=1.0, maxTrials=2),
+    "max_trials_31": dict(nChains=60, boxSize=(18.0, 18.0, 18.0), minDist=1.0, maxTrials=31, targetMassDensity=2.0),
+    "max_trials_33": dict(nChains=60, boxSize=(18.0, 18.0, 18.0), minDist=1.0, maxTrials=33, targetMassDensity=2.0),
+    "max_trials_129": dict(nChains=60, boxSize=(18.0, 18.0, 18.0), minDist=1.0, maxTrials=129, targetMassDensity=2.5),
+    "tiny_box_one_cell": dict(nChains=2, boxSize=(4.1, 4.1, 4.1), minDist=2.0, maxTrials=50, targetMassDensity=3.0),   # S = 1 per dimension here, 2 in the reference
+    "flat_box": dict(nChains=12, boxSize=(40.0, 30.0, 4.2), minDist=2.0, maxTrials=100, targetMassDensity=1.5),
+    "anisotropic": dict(nChains=50, boxSize=(17.3, 41.9, 9.7), minDist=1.3, maxTrials=150, targetMassDensity=1.2),
+    "mindist_above_bond": dict(nChains=20, boxSize=(30.0, 30.0, 30.0), minDist=1.6, maxTrials=200, targetMassDensity=0.5),  # the bonded neighbour is inside minDist: ignoreIndex matters
+    "mindist_2_4": dict(nChains=20, boxSize=(40.0, 40.0, 40.0), minDist=2.4, maxTrials=200, targetMassDensity=0.3),
+    "small_mindist": dict(nChains=40, boxSize=(16.0, 16.0, 16.0), minDist=0.35, maxTrials=60, targetMassDensity=3.0),
+    "nothing_to_grow": dict(nChains=50, boxSize=(12.0, 12.0, 12.0), minDist=1.0, maxTrials=100, targetMassDensity=0.05),     # seeds already exceed the target
+    "fractional_box": dict(nChains=25, boxSize=(23.7, 19.2, 31.4), minDist=1.0, maxTrials=120),
+    "ppf_zcenter_wall": dict(nChains=30, boxSize=(20.0, 20.0, 24.0), minDist=1.0, maxTrials=150, boundary="ppf", nGraftChains=30, graftLoc="zCenter", targetMassDensity=1.4),
+    "grafted_order_z": dict(nChains=30, boxSize=(20.0, 20.0, 30.0), minDist=1.0, maxTrials=150, boundary="ppf", nGraftChains=10, graftLoc="z", growthOrder="grafted"),
+}
+
+
+@pytest.mark.parametrize("name", sorted(EDGE_CASES))
+def test_edge_cases_bit_exact(sarw, oracle, name):
+    cfg = EDGE_CASES[name]
+    for seed in (1, 2):
+        g = run_gpu(sarw, cfg, seed)
+        o = oracle.walk(seed=seed, trig="portable", **cases.oracle_kwargs(cfg))
+        assert_same_walk(g, o, exact=True)
+
+
+def test_obstacle_ignore_quirk_bit_exact(sarw, oracle):
+    """sarw.cpp:198,353: seeding ignores the LAST obstacle (ignoreIndex -1 + nObstacles); growth offsets ignoreIndex by nObstacles."""
+    cfg = dict(nChains=16, boxSize=(14.0, 14.0, 14.0), minDist=1.0, maxTrials=100, targetMassDensity=1.5)
+    obst = cases.make_obstacles(300, cfg["boxSize"], seed=4)
+    g = run_gpu(sarw, cfg, 9, obstacles=obst)
+    o = oracle.walk(seed=9, trig="portable", obstacles=obst, **cases.oracle_kwargs(cfg))
+    assert_same_walk(g, o, exact=True)
