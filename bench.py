@@ -60,6 +60,8 @@ class ClockSampler:
         self.gpu = gpu_index
 
     def start(self):
+        if os.environ.get("SARW_BENCH_NOSAMPLER"):
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -294,7 +296,7 @@ def main():
                        "multi_gpu": "independent melts per rank, no data-path collective" if world > 1 else "single GPU",
                        "rounds_per_step": rounds / args.steps, "trials_per_bead": trials / max(1, beads), "conflicts_per_step": conflicts / args.steps},
             "e2e": {"value": e2e_beads_all / t_e2e, "unit": "beads/s", "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps,
-                    "ms_per_step": 1e3 * t_e2e / args.steps,
+                    "ms_per_step": 1e3 * t_e2e / args.steps, "ms_per_step_median": 1e3 * statistics.median(e2e_times), "ms_per_step_max": 1e3 * max(e2e_times),
                     "includes": "sarw_create (alloc + cell-table init), seeding, growth, terminate, sarw_download to host"},
             "gpu_launches": int(launches),
             "clocks": clocks,

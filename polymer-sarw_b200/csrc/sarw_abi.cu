@@ -9,6 +9,10 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <chrono>
+#include <map>
+#include <mutex>
+#include <unordered_map>
 
 using namespace sarw;
 
@@ -61,19 +65,76 @@ int fail(sarw_ctx* c, const char* fmt, ...)
 }
 #define CU(c, x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(c, "%s: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
 
-// stream-ordered allocations from the device's default memory pool (blocks are reused across contexts: no cudaMalloc /
-// cudaFree round trips to the driver once the pool is warm)
+// Device memory. Transient buffers are stream-ordered allocations from the device's default pool. The large long-lived tables
+// (cell table, bead storage) of a destroyed context are parked in a per-device cache and handed to the next context that asks for
+// the same size: the pool alone made sarw_create erratic (0.4 - 37 ms for the 40 MB cell table of BASELINE configs[1], measured),
+// because a warm but fragmented pool remaps physical memory inside cudaMallocAsync.
+struct BlockCache {
+	std::mutex m;
+	std::multimap<size_t, void*> parked;       // size -> block, idle and safe to reuse on any stream
+	std::unordered_map<void*, size_t> sizeOf;  // every live large block handed out by dev_alloc
+	size_t parkedBytes = 0;
+};
+static BlockCache g_blocks[64];
+constexpr size_t CACHE_MIN_BYTES = (size_t)1 << 20;
+constexpr size_t CACHE_MAX_BYTES = (size_t)24 << 30;
+
+static void cache_flush(sarw_ctx* c)
+{
+	BlockCache& bc = g_blocks[c->device & 63];
+	std::lock_guard<std::mutex> lk(bc.m);
+	for (auto& kv : bc.parked) cudaFreeAsync(kv.second, c->allocStream);
+	bc.parked.clear(); bc.parkedBytes = 0;
+	cudaStreamSynchronize(c->allocStream);
+}
 template <typename T> cudaError_t dev_alloc(sarw_ctx* c, T** p, size_t bytes)
 {
+	if (bytes >= CACHE_MIN_BYTES) {
+		BlockCache& bc = g_blocks[c->device & 63];
+		std::lock_guard<std::mutex> lk(bc.m);
+		auto it = bc.parked.lower_bound(bytes);
+		if (it != bc.parked.end() && it->first <= bytes + bytes / 8) {
+			*p = (T*)it->second; bc.sizeOf[it->second] = it->first; bc.parkedBytes -= it->first; bc.parked.erase(it);
+			return cudaSuccess;
+		}
+	}
 	cudaError_t e = cudaMallocAsync((void**)p, bytes ? bytes : 16, c->allocStream);
+	if (e == cudaErrorMemoryAllocation) {   // give the parked blocks back and try once more
+		cudaGetLastError(); cache_flush(c);
+		e = cudaMallocAsync((void**)p, bytes ? bytes : 16, c->allocStream);
+	}
 	if (e == cudaSuccess && c->allocStream != c->stream) e = cudaStreamSynchronize(c->allocStream);   // work runs on a caller's stream
+	if (e == cudaSuccess && bytes >= CACHE_MIN_BYTES) {
+		BlockCache& bc = g_blocks[c->device & 63];
+		std::lock_guard<std::mutex> lk(bc.m);
+		bc.sizeOf[(void*)*p] = bytes;
+	}
 	return e;
 }
+// stream-ordered free (the caller may still have work queued that uses the block on the context's own home stream)
 template <typename T> void dev_free(sarw_ctx* c, T* p)
 {
 	if (!p) return;
+	{	BlockCache& bc = g_blocks[c->device & 63];
+		std::lock_guard<std::mutex> lk(bc.m);
+		bc.sizeOf.erase((void*)p);
+	}
 	if (c->allocStream != c->stream && c->stream) cudaStreamSynchronize(c->stream);   // nothing on the work stream may still use it
 	cudaFreeAsync((void*)p, c->allocStream);
+}
+// free of a long-lived table once the context's stream is idle (the caller synchronised it): park it for the next context
+template <typename T> void dev_park(sarw_ctx* c, T* p)
+{
+	if (!p) return;
+	{	BlockCache& bc = g_blocks[c->device & 63];
+		std::lock_guard<std::mutex> lk(bc.m);
+		auto it = bc.sizeOf.find((void*)p);
+		if (it != bc.sizeOf.end() && bc.parkedBytes + it->second <= CACHE_MAX_BYTES) {
+			bc.parked.emplace(it->second, (void*)p); bc.parkedBytes += it->second; bc.sizeOf.erase(it);
+			return;
+		}
+	}
+	dev_free(c, p);
 }
 
 uint64_t slots_for_rounds(const sarw_ctx* c, uint64_t rounds) { return 2ull * c->g.nChains + rounds * c->g.nChains; }
@@ -194,6 +255,10 @@ int sarw_create(const sarw_params* p, sarw_ctx** out)
 	if (e != cudaSuccess || nDev == 0) return fail(nullptr, "no CUDA device available (%s); libsarw_b200 has no CPU fallback", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
 	sarw_ctx* c = new sarw_ctx();
 	c->p = *p;
+	// SARW_TRACE=1: host-side timestamps of the phases of sarw_create on stderr (diagnostics)
+	static const bool trace = getenv("SARW_TRACE") && atoi(getenv("SARW_TRACE")) != 0;
+	const auto tr0 = std::chrono::steady_clock::now();
+	auto mark = [&](const char* what) { if (trace) fprintf(stderr, "[sarw_create] %-14s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tr0).count()); };
 	auto bail = [&](int rc) { g_createError = c->err; sarw_destroy(c); return rc; };
 	if (p->device >= 0) { if (cudaSetDevice(p->device) != cudaSuccess) { fail(c, "cudaSetDevice(%d) failed", p->device); return bail(1); } }
 	cudaGetDevice(&c->device);
@@ -262,11 +327,14 @@ int sarw_create(const sarw_params* p, sarw_ctx** out)
 		cudaMemPool_t pool; unsigned long long keep = ~0ull;
 		if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
 	}
+	mark("device+stream");
 	cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
+	mark("events");
 
 	const size_t nCells = (size_t)g.S[0] * g.S[1] * g.S[2];
 #define CUB_(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fail(c, "%s: %s", #x, cudaGetErrorString(e_)); return bail(1); } } while (0)
 	CUB_(dev_alloc(c, &c->T.cells, nCells * sizeof(Cell)));
+	mark("cells alloc");
 	CUB_(cudaMemsetAsync(c->T.cells, 0xFF, nCells * sizeof(Cell), c->stream));
 	c->T.ovfCap = 1u << 20;
 	CUB_(dev_alloc(c, &c->T.ovf, (size_t)c->T.ovfCap * sizeof(uint4)));
@@ -282,7 +350,9 @@ int sarw_create(const sarw_params* p, sarw_ctx** out)
 	CUB_(cudaMemsetAsync(c->origTrial, 0, (size_t)g.nChains * sizeof(uint32_t), c->stream));
 	CUB_(dev_alloc(c, &c->resPos, (size_t)g.nChains * 3 * sizeof(double)));
 	CUB_(dev_alloc(c, &c->dirtyList, 3 * (size_t)g.nChains * sizeof(uint32_t)));   // conflict list (n) + second list of the parallel clean-up (<= 2n: independent chains are far apart)
+	mark("small allocs");
 	CUB_(cudaStreamSynchronize(c->stream));
+	mark("sync");
 #undef CUB_
 	if (c->growBlocksMax < 1) { fail(c, "growth kernel does not fit on the device"); return bail(1); }
 	{	// bead storage for the expected number of rounds (grown later if the walk needs more, or if obstacles shift the index space)
@@ -292,6 +362,7 @@ int sarw_create(const sarw_params* p, sarw_ctx** out)
 		if (slots_for_rounds(c, wantRounds) < 0xFFFFFFF0ull && ensure_rounds(c, (uint32_t)std::max<uint64_t>(wantRounds, 1))) return bail(1);
 		cudaStreamSynchronize(c->stream);
 	}
+	mark("bead storage");
 	*out = c;
 	return 0;
 }
@@ -302,9 +373,10 @@ void sarw_destroy(sarw_ctx* c)
 	cudaSetDevice(c->device);
 	if (c->stream) cudaStreamSynchronize(c->stream);
 	if (c->stream) {
-		dev_free(c, c->T.cells); dev_free(c, c->T.lpos); dev_free(c, c->T.ovf); dev_free(c, c->T.ovfCount);
-		dev_free(c, c->ctl); dev_free(c, c->chains); dev_free(c, c->resTrial); dev_free(c, c->origTrial); dev_free(c, c->resPos); dev_free(c, c->prev);
-		dev_free(c, c->roundAcc); dev_free(c, c->roundProg); dev_free(c, c->dirtyCount); dev_free(c, c->dirtyList); dev_free(c, c->grafts);
+		if (c->allocStream != c->stream) cudaStreamSynchronize(c->allocStream);   // both streams idle: the blocks may be parked
+		dev_park(c, c->T.cells); dev_park(c, c->T.lpos); dev_park(c, c->T.ovf); dev_free(c, c->T.ovfCount);
+		dev_free(c, c->ctl); dev_park(c, c->chains); dev_park(c, c->resTrial); dev_park(c, c->origTrial); dev_park(c, c->resPos); dev_park(c, c->prev);
+		dev_park(c, c->roundAcc); dev_park(c, c->roundProg); dev_park(c, c->dirtyCount); dev_park(c, c->dirtyList); dev_park(c, c->grafts);
 	}
 	if (c->peersOpen) for (uint32_t p = 0; p < c->mrRanks; ++p) if (p != c->mrRank && c->peerRec[p]) cudaIpcCloseMemHandle(c->peerRec[p]);
 	if (c->xbuf) cudaFree(c->xbuf);
@@ -366,12 +438,27 @@ int sarw_set_grafts(sarw_ctx* c, const double* xyz, int64_t n)
 	return 0;
 }
 
+// Batches that revisit cell lines (several candidates per cell line, table larger than L2) are processed in cell-layer order so
+// that a line is fetched from HBM once per batch: scratch for the counting sort, or nullptr when ordering would not pay.
+static cudaError_t find_batch_ordered(sarw_ctx* c, const double* d_xyz, const int64_t* d_ignore, int64_t n, uint8_t* d_hit)
+{
+	uint8_t* scratch = nullptr;
+	static const bool orderOff = getenv("SARW_FIND_ORDER") && atoi(getenv("SARW_FIND_ORDER")) == 0;   // diagnostics
+	const size_t tableBytes = (size_t)c->g.S[0] * c->g.S[1] * c->g.S[2] * sizeof(Cell);
+	if (!orderOff && n >= (1 << 18) && c->g.S[2] >= 8 && c->g.S[2] <= 8192 && n < 0xFFFFFFF0ll && tableBytes > ((size_t)96 << 20) && (size_t)n * 8 * sizeof(Cell) > tableBytes) {
+		if (dev_alloc(c, &scratch, find_scratch_bytes(c->g, n)) != cudaSuccess) { scratch = nullptr; cudaGetLastError(); }   // no room: unordered
+	}
+	cudaError_t e = launch_find_batch(c->g, c->T, d_xyz, d_ignore, n, d_hit, c->numSMs, scratch, c->stream);
+	if (scratch) dev_free(c, scratch);
+	return e;
+}
+
 int sarw_lookup_find_batch_device(sarw_ctx* c, const double* d_xyz, const int64_t* d_ignore, int64_t n, uint8_t* d_hit)
 {
 	if (!c) return 1;
 	if (n < 0 || (n > 0 && (!d_xyz || !d_hit))) return fail(c, "sarw_lookup_find_batch_device: bad arguments");
 	cudaSetDevice(c->device);
-	CU(c, launch_find_batch(c->g, c->T, d_xyz, d_ignore, n, d_hit, c->numSMs, c->stream));
+	CU(c, find_batch_ordered(c, d_xyz, d_ignore, n, d_hit));
 	return 0;
 }
 
@@ -392,7 +479,7 @@ int sarw_lookup_find_batch(sarw_ctx* c, const double* xyz, const int64_t* ignore
 		CUF(dev_alloc(c, &di, (size_t)n * sizeof(int64_t)));
 		CUF(cudaMemcpyAsync(di, ignore, (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
 	}
-	CUF(launch_find_batch(c->g, c->T, dx, di, n, dh, c->numSMs, c->stream));
+	CUF(find_batch_ordered(c, dx, di, n, dh));
 	CUF(cudaMemcpyAsync(hit, dh, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
 	CUF(cudaStreamSynchronize(c->stream));
 #undef CUF

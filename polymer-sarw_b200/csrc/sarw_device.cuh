@@ -165,6 +165,32 @@ __device__ __forceinline__ void to_frac(const Geom& g, const double pos[3], doub
 	for (int k = 0; k < 3; k++) { double t = pos[k] * g.Linv[k]; v[k] = t - floor(t); }
 }
 
+// floor() without the conversion unit. On B200 FRND/F2I/I2F/F2F on doubles issue on the XU pipe (16 lanes/clk/SM); the overlap-query
+// kernel was bound by it (ncu: xu 92 %). Adding and subtracting 1.5*2^52 rounds to the nearest integer with two DADDs (exact, |t| < 2^51),
+// one compare turns that into floor; the integer itself is the low word of the biased sum. Same values as floor(), bit for bit.
+constexpr double FLOOR_MAGIC = 6755399441055744.0;
+__device__ __forceinline__ double floor_noxu(double t)
+{
+	if (!(fabs(t) < 2251799813685248.0)) return floor(t);   // out of range of the trick (or NaN): the plain instruction
+	const double r = (t + FLOOR_MAGIC) - FLOOR_MAGIC;
+	return r > t ? r - 1.0 : r;
+}
+// floor(t) as int and as double, for |t| < 2^31
+__device__ __forceinline__ int floor_int_noxu(double t, double& fl)
+{
+	const double tm = t + FLOOR_MAGIC;
+	const double r = tm - FLOOR_MAGIC;
+	const int i = __double2loint(tm);
+	const bool down = r > t;
+	fl = down ? r - 1.0 : r;
+	return down ? i - 1 : i;
+}
+__device__ __forceinline__ void to_frac_noxu(const Geom& g, const double pos[3], double v[3])
+{
+#pragma unroll
+	for (int k = 0; k < 3; k++) { double t = pos[k] * g.Linv[k]; v[k] = t - floor_noxu(t); }
+}
+
 // the per-pair decision of PeriodicLookup.h:67-71 between candidate (fractional v) and stored bead (Cartesian p)
 __device__ __forceinline__ bool exact_pair(const Geom& g, const double v[3], const double* __restrict__ p)
 {
@@ -222,7 +248,10 @@ __device__ __forceinline__ bool growth_rules_reject(const Geom& g, const double 
 
 // ------------------------------------------------------------------ cell addressing
 __device__ __forceinline__ int wrap_cell(int c, int S)
-{	c %= S; return c < 0 ? c + S : c;
+{	// callers are at most one period off: the integer division (I2F + MUFU.RCP + F2I on the XU pipe, ~70 cycles) is the rare path
+	if (c < 0) c += S; else if (c >= S) c -= S;
+	if ((unsigned)c >= (unsigned)S) { c %= S; if (c < 0) c += S; }
+	return c;
 }
 __device__ __forceinline__ int64_t cell_index(const Geom& g, int wx, int wy, int wz)
 {	return wx + (int64_t)g.S[0] * (wy + (int64_t)g.S[1] * wz);

@@ -23,7 +23,9 @@ struct Control {
 	unsigned long long busy[256];       // cluster kernel: per-warp cycles from round start to the first barrier arrive, summed (diagnostics)
 };
 
-cudaError_t launch_find_batch(const Geom& g, const Tables& T, const double* xyz, const int64_t* ignore, int64_t n, uint8_t* hit, int numSMs, cudaStream_t st);
+cudaError_t launch_find_batch(const Geom& g, const Tables& T, const double* xyz, const int64_t* ignore, int64_t n, uint8_t* hit, int numSMs,
+	void* scratch, cudaStream_t st);
+size_t find_scratch_bytes(const Geom& g, int64_t n);
 cudaError_t launch_add_points(const Geom& g, const Tables& T, const double* xyz, int64_t n, uint32_t baseId, cudaStream_t st);
 cudaError_t launch_seed(const Geom& g, const Tables& T, ChainState* chains, uint32_t* resTrial, uint32_t* prev, const double* grafts,
 	Control* ctl, uint32_t* dirtyList, int numSMs, cudaStream_t st, int* launches);

@@ -29,26 +29,179 @@ constexpr unsigned FULL = 0xFFFFFFFFu;
 constexpr uint32_t DONE_BIT = 0x80000000u;
 
 // ------------------------------------------------------------------ K5: overlap query on caller-supplied candidates
-__global__ void __launch_bounds__(256) find_batch_kernel(Geom g, Tables T, const double* __restrict__ xyz,
-	const int64_t* __restrict__ ignore, int64_t n, uint8_t* __restrict__ hit)
+// Large batches are processed in order of the candidates' z cell layer (counting sort by layer: zbin_* kernels below), so that
+// candidates running at the same time touch the same two or three layers of the cell table and those lines are served by
+// the 126 MB L2 instead of HBM: a 128-byte cell line is then fetched once per batch rather than once per candidate near it.
+constexpr int ZBIN_MAX = 8192;                    // layers the shared-memory histogram holds
+__device__ __forceinline__ int zbin_of(const Geom& g, const double* __restrict__ xyz, int64_t q)
 {
-	const int sub = threadIdx.x & 7;
-	const int grp = (threadIdx.x & 31) >> 3;
-	int64_t q0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-	const int64_t stride = ((int64_t)gridDim.x * blockDim.x) >> 3;
-	// all 32 lanes of a warp iterate together (q0 - grp is warp-uniform)
-	for (int64_t qb = q0 - grp; qb < n; qb += stride) {
-		int64_t q = qb + grp;
-		bool h = false;
-		if (q < n) {
-			double pos[3] = { xyz[3 * q], xyz[3 * q + 1], xyz[3 * q + 2] }, v[3];
-			to_frac(g, pos, v);
-			int64_t ig = ignore ? ignore[q] : -1;
-			// PeriodicLookup.h:65: ignoreIndex<0 || int(index)!=ignoreIndex
-			h = probe_cells<8>(g, T, v, 0u, ID_NONE, ig < 0 ? ID_NONE : (uint32_t)ig, sub);
+	const double t = xyz[3 * q + 2] * g.Linv[2];
+	const int cz = (int)floor((t - floor(t)) * g.sOverL[2]);
+	return cz >= g.S[2] ? g.S[2] - 1 : (cz < 0 ? 0 : cz);
+}
+// block b owns the candidates [b*chunk, (b+1)*chunk) in both passes: per-block histogram in shared memory, one global atomic per
+// (block, non-empty layer)
+__global__ void __launch_bounds__(512) zbin_count_kernel(Geom g, const double* __restrict__ xyz, int64_t n, int64_t chunk, uint32_t* __restrict__ counts)
+{
+	extern __shared__ uint32_t hist[];
+	for (int i = threadIdx.x; i < g.S[2]; i += blockDim.x) hist[i] = 0;
+	__syncthreads();
+	const int64_t lo = (int64_t)blockIdx.x * chunk, hi = lo + chunk < n ? lo + chunk : n;
+	for (int64_t q = lo + threadIdx.x; q < hi; q += blockDim.x) atomicAdd(&hist[zbin_of(g, xyz, q)], 1u);
+	__syncthreads();
+	for (int i = threadIdx.x; i < g.S[2]; i += blockDim.x) if (hist[i]) atomicAdd(&counts[i], hist[i]);
+}
+__global__ void zbin_scan_kernel(uint32_t* __restrict__ counts, int nb)   // one block: exclusive scan in place (counts -> cursors)
+{
+	__shared__ uint32_t carry;
+	if (threadIdx.x == 0) carry = 0;
+	__syncthreads();
+	for (int base = 0; base < nb; base += blockDim.x) {
+		const int i = base + threadIdx.x;
+		uint32_t v = i < nb ? counts[i] : 0u, incl = v;
+		const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+		__shared__ uint32_t wsum[32];
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += y; }
+		if (lane == 31) wsum[warp] = incl;
+		__syncthreads();
+		if (warp == 0) {
+			uint32_t w = lane < (int)(blockDim.x >> 5) ? wsum[lane] : 0u, wi = w;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(FULL, wi, d); if (lane >= d) wi += y; }
+			wsum[lane] = wi - w;
 		}
-		unsigned b = __ballot_sync(FULL, h);
-		if (sub == 0 && q < n) hit[q] = ((b >> (grp * 8)) & 0xFFu) ? 1 : 0;
+		__syncthreads();
+		const uint32_t excl = carry + wsum[warp] + incl - v;
+		if (i < nb) counts[i] = excl;
+		__syncthreads();
+		if (threadIdx.x == blockDim.x - 1) carry = excl + v;
+		__syncthreads();
+	}
+}
+// candidate in processing order: position, ignore index, original index
+struct __align__(32) SortedCand { double x, y, z; int64_t ignore; };
+__global__ void __launch_bounds__(512) zbin_scatter_kernel(Geom g, const double* __restrict__ xyz, const int64_t* __restrict__ ignore, int64_t n, int64_t chunk,
+	uint32_t* __restrict__ cursors, SortedCand* __restrict__ rec, uint32_t* __restrict__ perm)
+{
+	extern __shared__ uint32_t hist[];
+	for (int i = threadIdx.x; i < g.S[2]; i += blockDim.x) hist[i] = 0;
+	__syncthreads();
+	const int64_t lo = (int64_t)blockIdx.x * chunk, hi = lo + chunk < n ? lo + chunk : n;
+	for (int64_t q = lo + threadIdx.x; q < hi; q += blockDim.x) atomicAdd(&hist[zbin_of(g, xyz, q)], 1u);
+	__syncthreads();
+	for (int i = threadIdx.x; i < g.S[2]; i += blockDim.x) { const uint32_t h = hist[i]; hist[i] = h ? atomicAdd(&cursors[i], h) : 0u; }
+	__syncthreads();
+	for (int64_t q = lo + threadIdx.x; q < hi; q += blockDim.x) {
+		const double x = xyz[3 * q], y = xyz[3 * q + 1], z = xyz[3 * q + 2];
+		const double t = z * g.Linv[2];
+		int cz = (int)floor((t - floor(t)) * g.sOverL[2]);
+		cz = cz >= g.S[2] ? g.S[2] - 1 : (cz < 0 ? 0 : cz);
+		const uint32_t p = atomicAdd(&hist[cz], 1u);
+		SortedCand r; r.x = x; r.y = y; r.z = z; r.ignore = ignore ? ignore[q] : -1;
+		rec[p] = r;
+		perm[p] = (uint32_t)q;
+	}
+}
+
+// One lane per candidate. The (up to) 8 cells a candidate's sphere touches are fetched with eight independent 256-bit loads
+// (header + first slot = the first 32-byte sector of the cell's line) issued back to back, so a warp keeps 256 sectors in flight:
+// the kernel is bound by HBM/L2 bandwidth, not by the latency of a chain of dependent loads. Cells holding more than one bead
+// (a few per cent at melt density) are finished in a second, rarely taken loop.
+__device__ __forceinline__ void ld_cell_head(const Cell* cell, uint32_t (&w)[8])
+{
+	asm volatile("ld.global.cg.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+		: "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(cell));
+}
+__global__ void __launch_bounds__(256, 3) find_batch_kernel(Geom g, Tables T, const double* __restrict__ xyz,
+	const int64_t* __restrict__ ignore, int64_t n, uint8_t* __restrict__ hit, const SortedCand* __restrict__ rec, const uint32_t* __restrict__ perm)
+{
+	// one block per 256 consecutive candidates, no grid-stride loop: blocks are dispatched in order, so the candidates in flight at
+	// any time are a narrow window of the processing order (measured: a persistent grid-stride sweep drifts apart and loses the L2 reuse)
+	const int64_t qs = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (qs < n) {
+		int64_t q = qs, ig;
+		double pos[3];
+		if (rec) {
+			const SortedCand r = rec[qs];
+			pos[0] = r.x; pos[1] = r.y; pos[2] = r.z; ig = r.ignore; q = (int64_t)perm[qs];
+		} else {
+			pos[0] = xyz[3 * q]; pos[1] = xyz[3 * q + 1]; pos[2] = xyz[3 * q + 2]; ig = ignore ? ignore[q] : -1;
+		}
+		double v[3];
+		to_frac_noxu(g, pos, v);
+		// PeriodicLookup.h:65: ignoreIndex<0 || int(index)!=ignoreIndex
+		const uint32_t ignoreId = ig < 0 ? ID_NONE : (uint32_t)ig;
+		int c[3][2];
+		bool two[3];
+		float qo[3][2];
+#pragma unroll
+		for (int k = 0; k < 3; k++) {
+			const double s = v[k] * g.sOverL[k];
+			double lod;
+			const int lo = floor_int_noxu(s - g.reachCells[k], lod);
+			two[k] = (s + g.reachCells[k]) >= lod + 1.0;               // reach < 0.5 cell: the sphere touches 1 or 2 cells per dimension
+			c[k][0] = wrap_cell(lo, g.S[k]); c[k][1] = wrap_cell(lo + 1, g.S[k]);
+			const float d = (float)(lod - s), af = (float)g.a[k];      // one double->float conversion per dimension; errors are inside the band
+			qo[k][0] = d * af;
+			qo[k][1] = (d + 1.0f) * af;
+		}
+		uint32_t w[8][8];
+#pragma unroll
+		for (int ci = 0; ci < 8; ci++) {
+			const int ix = ci & 1, iy = (ci >> 1) & 1, iz = ci >> 2;
+			const bool valid = (ix == 0 || two[0]) && (iy == 0 || two[1]) && (iz == 0 || two[2]);
+			if (valid) ld_cell_head(T.cells + cell_index(g, c[0][ix], c[1][iy], c[2][iz]), w[ci]);
+			else { w[ci][0] = ID_NONE; w[ci][1] = ID_NONE; }   // count-1 = all ones: empty, not overflowed
+		}
+		bool h = false, anyOvf = false;
+		uint32_t cntPack = 0;   // 4 bits per cell: beads beyond the first
+#pragma unroll
+		for (int ci = 0; ci < 8; ci++) {
+			const int ix = ci & 1, iy = (ci >> 1) & 1, iz = ci >> 2;
+			const uint32_t cnt = w[ci][0] + 1u;
+			anyOvf |= (w[ci][1] != ID_NONE);
+			if (cnt > 1u) cntPack |= ((cnt > (uint32_t)g.cap ? (uint32_t)g.cap : cnt) - 1u) << (4 * ci);
+			if (cnt >= 1u && !h) {
+				const uint32_t id = w[ci][7];
+				if (id != ignoreId) {
+					const float dx = qo[0][ix] + __uint_as_float(w[ci][4]), dy = qo[1][iy] + __uint_as_float(w[ci][5]), dz = qo[2][iz] + __uint_as_float(w[ci][6]);
+					const float d2 = dx * dx + dy * dy + dz * dz;
+					if (d2 < g.lo2) h = true;
+					else if (d2 <= g.hi2 && exact_pair(g, v, T.lpos + 3 * (size_t)id)) h = true;
+				}
+			}
+		}
+		if (!h && cntPack) {
+#pragma unroll 1
+			for (int ci = 0; ci < 8 && !h; ci++) {
+				const uint32_t extra = (cntPack >> (4 * ci)) & 15u;
+				if (!extra) continue;
+				const bool ix = ci & 1, iy = (ci >> 1) & 1, iz = ci >> 2;
+				const Cell* cell = T.cells + cell_index(g, ix ? c[0][1] : c[0][0], iy ? c[1][1] : c[1][0], iz ? c[2][1] : c[2][0]);
+				const float ox = ix ? qo[0][1] : qo[0][0], oy = iy ? qo[1][1] : qo[1][0], oz = iz ? qo[2][1] : qo[2][0];
+				for (uint32_t s = 1; s <= extra; ++s) {
+					const float4 b = __ldcg(&cell->slot[s]);
+					const uint32_t id = __float_as_uint(b.w);
+					if (id == ignoreId) continue;
+					const float dx = ox + b.x, dy = oy + b.y, dz = oz + b.z;
+					const float d2 = dx * dx + dy * dy + dz * dz;
+					if (d2 < g.lo2) { h = true; break; }
+					if (d2 <= g.hi2 && exact_pair(g, v, T.lpos + 3 * (size_t)id)) { h = true; break; }
+				}
+			}
+		}
+		if (!h && anyOvf) {   // a visited cell overflowed: its extra beads are in the overflow list
+			uint32_t novf = __ldcg(T.ovfCount);
+			if (novf > T.ovfCap) novf = T.ovfCap;
+			int cq[3]; cell_of_frac(g, v, cq);
+			for (uint32_t j = 0; j < novf && !h; ++j) {
+				const uint4 e = __ldcg(T.ovf + j);
+				if (e.w == ignoreId || !ovf_entry_near(g, e, cq)) continue;
+				h = exact_pair(g, v, T.lpos + 3 * (size_t)e.w);
+			}
+		}
+		hit[q] = h ? 1 : 0;
 	}
 }
 
@@ -836,13 +989,31 @@ __global__ void fill_u32_kernel(uint32_t* p, uint64_t n, uint32_t v)
 // ------------------------------------------------------------------ launch wrappers (called from sarw_abi.cpp)
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
 
-cudaError_t launch_find_batch(const Geom& g, const Tables& T, const double* xyz, const int64_t* ignore, int64_t n, uint8_t* hit, int numSMs, cudaStream_t st)
+// `scratch`: find_scratch_bytes(g, n) bytes of device scratch for the layer-ordered processing of large batches, or nullptr
+size_t find_scratch_bytes(const Geom& g, int64_t n)
+{	return ((size_t)n * sizeof(SortedCand)) + (((size_t)n + (size_t)g.S[2]) * sizeof(uint32_t));
+}
+cudaError_t launch_find_batch(const Geom& g, const Tables& T, const double* xyz, const int64_t* ignore, int64_t n, uint8_t* hit, int numSMs,
+	void* scratch, cudaStream_t st)
 {
 	if (n <= 0) return cudaSuccess;
-	int64_t blocks = (n * 8 + 255) / 256;
-	int64_t maxBlocks = (int64_t)numSMs * 8 * 4;
-	if (blocks > maxBlocks) blocks = maxBlocks;
-	find_batch_kernel<<<(unsigned)blocks, 256, 0, st>>>(g, T, xyz, ignore, n, hit);
+	const int64_t blocks = (n + 255) / 256;
+	if (blocks > 0x7FFFFFFFll) return cudaErrorInvalidValue;
+	const SortedCand* rec = nullptr; const uint32_t* perm = nullptr;
+	if (scratch) {
+		SortedCand* r = static_cast<SortedCand*>(scratch);
+		uint32_t* p = reinterpret_cast<uint32_t*>(r + n);
+		uint32_t* cursors = p + n;
+		CK(cudaMemsetAsync(cursors, 0, (size_t)g.S[2] * sizeof(uint32_t), st));
+		const unsigned cb = (unsigned)numSMs * 4;
+		const int64_t chunk = (n + cb - 1) / cb;
+		const size_t sm = (size_t)g.S[2] * sizeof(uint32_t);
+		zbin_count_kernel<<<cb, 512, sm, st>>>(g, xyz, n, chunk, cursors);
+		zbin_scan_kernel<<<1, 1024, 0, st>>>(cursors, g.S[2]);
+		zbin_scatter_kernel<<<cb, 512, sm, st>>>(g, xyz, ignore, n, chunk, cursors, r, p);
+		rec = r; perm = p;
+	}
+	find_batch_kernel<<<(unsigned)blocks, 256, 0, st>>>(g, T, xyz, ignore, n, hit, rec, perm);
 	return cudaGetLastError();
 }
 

@@ -22,6 +22,20 @@ pts = rng.random((npts, 3)) * L
 ctx.add_points(pts)
 g = torch.Generator(device="cuda"); g.manual_seed(5)
 q = torch.rand((nq, 3), dtype=torch.float64, device="cuda", generator=g) * L
+if os.environ.get("PRESORT") == "z":
+    q = q[torch.argsort(q[:, 2])].contiguous()
+elif os.environ.get("PRESORT") == "zy":
+    a = 632.2 / 316
+    key = torch.floor(q[:, 2] / a) * 1000 + torch.floor(q[:, 1] / (8 * a))
+    q = q[torch.argsort(key)].contiguous()
+if os.environ.get("PRESORT") == "cell":
+    a = L / int(L / 2.002)
+    c = torch.floor(q / a).to(torch.int64)
+    q = q[torch.argsort((c[:, 2] * 1000 + c[:, 1]) * 1000 + c[:, 0])].contiguous()
+if os.environ.get("PRESORT") == "tile":     # 4x4x4-cell tiles, tiles in x-fastest order
+    a = L / int(L / 2.002)
+    c = torch.floor(q / (4 * a)).to(torch.int64)
+    q = q[torch.argsort((c[:, 2] * 1000 + c[:, 1]) * 1000 + c[:, 0])].contiguous()
 hit = torch.empty(nq, dtype=torch.uint8, device="cuda")
 flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device="cuda")
 ms = []

@@ -57,6 +57,27 @@ def test_find_large_melt_like_density(sarw, oracle):
     assert np.array_equal(got, want)
 
 
+def test_find_layer_ordered_large_batch(sarw, oracle):
+    """Batches of >= 2^18 candidates on a table larger than L2 are processed in cell-layer order (counting sort on the device);
+    results must not depend on that: 4e5 candidates incl. unwrapped images and ignore indices, against the oracle."""
+    rng = np.random.default_rng(11)
+    box, thresh = (190.0, 186.0, 200.0), 1.0
+    pts = rng.random((270000, 3)) * np.array(box)
+    n = 400000
+    q = np.concatenate([rng.random((n // 2, 3)) * np.array(box) * 3 - np.array(box),
+                        pts[rng.integers(0, len(pts), n // 2)] + rng.normal(size=(n // 2, 3)) * 0.6])
+    ig = np.where(rng.random(n) < 0.3, rng.integers(0, len(pts), n), -1).astype(np.int64)
+    olk = oracle.lookup(box, thresh); olk.add(pts)
+    want = olk.find(q, ig); olk.close()
+    lk = sarw.PeriodicLookup(box, thresh); lk.addPoint(pts)
+    got = lk.find(q, ig)
+    got_small = np.concatenate([lk.find(q[k:k + 100000], ig[k:k + 100000]) for k in range(0, n, 100000)])   # unordered path
+    lk.close()
+    assert np.array_equal(got, want), int(np.sum(got != want))
+    assert np.array_equal(got_small, want)
+    assert 0.05 < want.mean() < 0.95
+
+
 def test_find_empty_and_edge_inputs(sarw):
     lk = sarw.PeriodicLookup((10.0, 10.0, 10.0), 1.0)
     assert lk.find(np.zeros((0, 3))).shape == (0,)
