@@ -11,9 +11,9 @@ CLI := $(PKG)/bin/sarw
 all: lib cli oracle
 
 lib: $(LIB)
-$(LIB): $(PKG)/csrc/sarw_kernels.cu $(PKG)/csrc/sarw_abi.cu $(PKG)/csrc/sarw_device.cuh $(PKG)/csrc/sarw_cluster.cuh $(PKG)/csrc/sarw_host.h include/sarw_abi.h
+$(LIB): $(PKG)/csrc/sarw_kernels.cu $(PKG)/csrc/sarw_abi.cu $(PKG)/csrc/sarw_analysis.cu $(PKG)/csrc/sarw_device.cuh $(PKG)/csrc/sarw_cluster.cuh $(PKG)/csrc/sarw_host.h include/sarw_abi.h
 	mkdir -p $(PKG)/lib
-	$(NVCC) $(NVFLAGS) -Xptxas -v -shared -o $@ $(PKG)/csrc/sarw_kernels.cu $(PKG)/csrc/sarw_abi.cu 2> $(PKG)/lib/ptxas.log || (cat $(PKG)/lib/ptxas.log; exit 1)
+	$(NVCC) $(NVFLAGS) -Xptxas -v -shared -o $@ $(PKG)/csrc/sarw_kernels.cu $(PKG)/csrc/sarw_abi.cu $(PKG)/csrc/sarw_analysis.cu 2> $(PKG)/lib/ptxas.log || (cat $(PKG)/lib/ptxas.log; exit 1)
 
 HOSTSRC := $(PKG)/host/input_map.cpp $(PKG)/host/polymer_io.cpp
 cli: $(CLI) $(PKG)/bin/sarw_hosttest

@@ -133,6 +133,17 @@ int sarw_chain_lengths(sarw_ctx* ctx, int32_t* lengths);
 /* actualCount() after each completed round, for the PROGRESS log of sarw.cpp:70-76: counts[min(n, rounds)] */
 int sarw_round_counts(sarw_ctx* ctx, int64_t* counts, int64_t n);
 
+/* ---- analysis of the walk on the device (the reference does this off line with scripts/rdf.py) ----
+ * scripts/rdf.py:13-20 (rdfPair) + 39-57 (rdfChains), as the integer pair counts they accumulate before normalisation: histograms
+ * of the minimum-image distance of all ordered bead pairs, bin k = [rMin + k*dr, rMin + (k+1)*dr) with the last bin closed
+ * (numpy.histogram over numpy.arange edges); intra[nBins] = pairs within a chain (both orders and self pairs, rdf.py:49-50),
+ * inter[nBins] = pairs of different chains, counted as rdf.py:51-52 does (twice the pairs taken from the higher chain id).
+ * Distances beyond the last edge are skipped with a spatial sort + tile bounding boxes, so a cut-off RDF of 1e7 beads is cheap. */
+int sarw_rdf(sarw_ctx* ctx, double rMin, double dr, int32_t nBins, uint64_t* intra, uint64_t* inter);
+/* end-to-end distance^2 and radius of gyration^2 of every chain from the unwrapped coordinates (sarw.cpp:184 never wraps):
+ * ree2[nChains], rg2[nChains]; chains without beads give 0 */
+int sarw_chain_shapes(sarw_ctx* ctx, double* ree2, double* rg2);
+
 /* PeriodicLookup::addPoint (PeriodicLookup.h:37-47) for n points; they take the next n lookup indices. */
 int sarw_lookup_add_points(sarw_ctx* ctx, const double* xyz, int64_t n);
 /* PeriodicLookup::find (PeriodicLookup.h:51-75) for n candidates: hit[i] = any stored point other than ignore[i]

@@ -402,3 +402,76 @@ void oracle_walk_free(oracle_walk* w)
 	free(w->lastIdx); free(w->penIdx); free(w->chainLen); free(w->countAfterRound);
 	free(w);
 }
+
+/* ------------------------------------------------------------------ analysis: scripts/rdf.py:13-20, 39-57 */
+void oracle_rdf_edges(double rMin, double dr, int32_t nBins, double* edges)
+{
+	/* numpy.arange for doubles: the first two values are computed, the rest filled as start + k*delta with
+	 * delta = second - first (rdf.py:19) */
+	volatile double second = rMin + dr;
+	double delta = second - rMin;
+	for (int32_t k = 0; k <= nBins; k++) edges[k] = rMin + (double)k * delta;
+}
+
+void oracle_rdf(const double box[3], const double* xyz, const int32_t* chain, int64_t n, double rMin, double dr, int32_t nBins,
+	uint64_t* intra, uint64_t* inter)
+{
+	double* edges = (double*)malloc(((size_t)nBins + 1) * sizeof(double));
+	double Linv[3] = { 1. / box[0], 1. / box[1], 1. / box[2] };          /* rdf.py:14 (1./L) */
+	oracle_rdf_edges(rMin, dr, nBins, edges);
+	for (int32_t k = 0; k < nBins; k++) { intra[k] = 0; inter[k] = 0; }
+	for (int64_t i = 0; i < n; i++) {
+		for (int64_t j = 0; j < n; j++) {
+			/* rdf.py:49-52: same chain -> rdfPair(chain, chain) (every ordered pair, i == j too); different chains -> only
+			 * iChain1 > iChain2 is evaluated and counted twice: every ordered pair contributes one count of (higher - lower) */
+			int same = chain[i] == chain[j];
+			const double* a1 = (same || chain[i] > chain[j]) ? xyz + 3 * i : xyz + 3 * j;
+			const double* a2 = (same || chain[i] > chain[j]) ? xyz + 3 * j : xyz + 3 * i;
+			double sum = 0;
+			for (int k = 0; k < 3; k++) {
+				double d = (a1[k] - a2[k]) * Linv[k];                    /* rdf.py:14 */
+				d -= floor(0.5 + d);                                     /* rdf.py:15 */
+				d *= box[k];                                             /* rdf.py:16 */
+				sum += d * d;                                            /* rdf.py:17 */
+			}
+			double r = sqrt(sum);
+			/* numpy.histogram with explicit edges: edges[k] <= r < edges[k+1], last bin closed on the right */
+			if (!(r >= edges[0]) || r > edges[nBins]) continue;
+			int32_t lo = 0, hi = nBins;                                  /* largest k with edges[k] <= r */
+			while (hi - lo > 1) { int32_t mid = (lo + hi) / 2; if (edges[mid] <= r) lo = mid; else hi = mid; }
+			if (r == edges[nBins]) lo = nBins - 1;
+			if (same) intra[lo]++; else inter[lo]++;
+		}
+	}
+	free(edges);
+}
+
+void oracle_chain_shapes(const double* xyz, const int32_t* chain, int64_t n, int32_t nChains, double* ree2, double* rg2)
+{
+	double* sum = (double*)calloc((size_t)nChains * 3, sizeof(double));
+	int64_t* cnt = (int64_t*)calloc((size_t)nChains, sizeof(int64_t));
+	int64_t* first = (int64_t*)malloc((size_t)nChains * sizeof(int64_t));
+	int64_t* last = (int64_t*)malloc((size_t)nChains * sizeof(int64_t));
+	for (int64_t i = 0; i < n; i++) {
+		int32_t c = chain[i] - 1;
+		if (!cnt[c]) first[c] = i;
+		last[c] = i; cnt[c]++;
+		for (int k = 0; k < 3; k++) sum[3 * c + k] += xyz[3 * i + k];
+	}
+	for (int32_t c = 0; c < nChains; c++) {
+		rg2[c] = 0; ree2[c] = 0;
+		if (!cnt[c]) continue;
+		for (int k = 0; k < 3; k++) sum[3 * c + k] = sum[3 * c + k] / (double)cnt[c];
+		double d[3];
+		for (int k = 0; k < 3; k++) d[k] = xyz[3 * last[c] + k] - xyz[3 * first[c] + k];
+		ree2[c] = (d[0] * d[0] + d[1] * d[1]) + d[2] * d[2];
+	}
+	for (int64_t i = 0; i < n; i++) {
+		int32_t c = chain[i] - 1;
+		double d[3];
+		for (int k = 0; k < 3; k++) d[k] = xyz[3 * i + k] - sum[3 * c + k];
+		rg2[c] += (d[0] * d[0] + d[1] * d[1]) + d[2] * d[2];
+	}
+	for (int32_t c = 0; c < nChains; c++) if (cnt[c]) rg2[c] = rg2[c] / (double)cnt[c];
+	free(sum); free(cnt); free(first); free(last);
+}

@@ -62,6 +62,18 @@ void oracle_walk_get(const oracle_walk* w, double* xyz, int32_t* chainID, int32_
 	int64_t* countAfterRound, int32_t* acceptedTrial);
 void oracle_walk_free(oracle_walk* w);
 
+/* ---- analysis: scripts/rdf.py restated for the counts it accumulates ----
+ * rdf.py:13-20 rdfPair: dist = (a1 - a2)*(1/L); dist -= floor(0.5 + dist); dist *= L; r = sqrt(sum(dist^2)); numpy.histogram
+ * over edges arange(rMin, ., dr) (bins half open, the last one closed). rdf.py:39-57 rdfChains: intra = all ordered pairs of a
+ * chain with itself (self pairs included); inter = 2 x pairs with the first atom taken from the chain with the HIGHER id.
+ * edges[nBins+1] as numpy.arange fills them: start + k*((start+dr)-start). chain ids as in polymer.dat (any integers). */
+void oracle_rdf_edges(double rMin, double dr, int32_t nBins, double* edges);
+void oracle_rdf(const double box[3], const double* xyz, const int32_t* chain, int64_t n, double rMin, double dr, int32_t nBins,
+	uint64_t* intra, uint64_t* inter);
+/* per-chain end-to-end distance^2 and radius of gyration^2 from unwrapped coordinates in acceptance order (chain ids 1..nChains);
+ * sums run over the beads of a chain in chain order, (x+y)+z per bead */
+void oracle_chain_shapes(const double* xyz, const int32_t* chain, int64_t n, int32_t nChains, double* ree2, double* rg2);
+
 /* building blocks exposed for unit tests */
 void oracle_sincos_portable(double x, double* s, double* c);
 void oracle_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);

@@ -785,6 +785,80 @@ int sarw_download(sarw_ctx* c, double* xyz, int32_t* chainID, int32_t* type, int
 	return 0;
 }
 
+// ---- analysis of the finished walk (scripts/rdf.py)
+// smallest double x >= 0 whose correctly rounded square root is >= e (strict: > e): pairs are binned on squared distances
+static double sqrt_threshold(double e, bool strict)
+{
+	if (e < 0 || (!strict && e == 0)) return 0;
+	auto reaches = [&](double x) { const double r = sqrt(x); return strict ? r > e : r >= e; };
+	double x = e * e;
+	while (x > 0 && reaches(nextafter(x, 0.0))) x = nextafter(x, 0.0);
+	while (!reaches(x)) x = nextafter(x, INFINITY);
+	return x;
+}
+
+int sarw_rdf(sarw_ctx* c, double rMin, double dr, int32_t nBins, uint64_t* intra, uint64_t* inter)
+{
+	if (!c) return 1;
+	if (!intra || !inter || nBins < 1 || nBins > 4096 || !(dr > 0) || !std::isfinite(rMin)) return fail(c, "sarw_rdf: bad arguments (1 <= nBins <= 4096, dr > 0)");
+	if (!c->initiateCalled) return fail(c, "nothing to analyse before sarw_initiate");
+	cudaSetDevice(c->device);
+	Control h; if (read_control(c, &h)) return 1;
+	const uint64_t N = h.nBeads;
+	for (int32_t k = 0; k < nBins; k++) { intra[k] = 0; inter[k] = 0; }
+	if (N == 0) return 0;
+	// bin edges as numpy.arange fills them (rdf.py:19): start + k*((start + dr) - start)
+	std::vector<double> t2((size_t)nBins + 1);
+	volatile double second = rMin + dr;
+	const double delta = second - rMin;
+	double lastEdge = 0;
+	for (int32_t k = 0; k <= nBins; k++) { const double e = rMin + (double)k * delta; t2[(size_t)k] = sqrt_threshold(e, k == nBins); lastEdge = e; }
+	if (lastEdge < 0) return 0;
+	const uint64_t nSlots = slots_for_rounds(c, h.round);
+	uint32_t *flags = nullptr, *scan = nullptr; char *tmp = nullptr, *scratch = nullptr; size_t tmpBytes = 0;
+	double *dx = nullptr, *dT = nullptr; int32_t* dc = nullptr; unsigned long long* dh = nullptr;
+	int rc = 0;
+	auto cleanup = [&]() { dev_free(c, flags); dev_free(c, scan); dev_free(c, tmp); dev_free(c, scratch); dev_free(c, dx); dev_free(c, dT); dev_free(c, dc); dev_free(c, dh); };
+#define CUF(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { rc = fail(c, "%s: %s", #x, cudaGetErrorString(e_)); cleanup(); return rc; } } while (0)
+	CUF(dev_alloc(c, &flags, nSlots * sizeof(uint32_t)));
+	CUF(dev_alloc(c, &scan, nSlots * sizeof(uint32_t)));
+	CUF(download_scan_bytes(nSlots, &tmpBytes));
+	CUF(dev_alloc(c, &tmp, tmpBytes ? tmpBytes : 16));
+	CUF(dev_alloc(c, &dx, N * 3 * sizeof(double)));
+	CUF(dev_alloc(c, &dc, N * sizeof(int32_t)));
+	CUF(dev_alloc(c, &dT, t2.size() * sizeof(double)));
+	CUF(dev_alloc(c, &dh, 2 * (size_t)nBins * sizeof(unsigned long long)));
+	CUF(dev_alloc(c, &scratch, rdf_scratch_bytes((int64_t)N, nullptr)));
+	CUF(launch_download(c->g, c->T, c->prev, c->chains, nSlots, c->nSeeded, 0, flags, scan, tmp, tmpBytes, dx, dc, nullptr, nullptr, c->stream));
+	CUF(cudaMemcpyAsync(dT, t2.data(), t2.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	CUF(cudaMemsetAsync(dh, 0, 2 * (size_t)nBins * sizeof(unsigned long long), c->stream));
+	CUF(launch_rdf(c->g.L, dx, dc, (int64_t)N, dT, nBins, rMin, delta, lastEdge, scratch, dh, dh + nBins, c->stream));
+	CUF(cudaMemcpyAsync(intra, dh, (size_t)nBins * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+	CUF(cudaMemcpyAsync(inter, dh + nBins, (size_t)nBins * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+	CUF(cudaStreamSynchronize(c->stream));
+#undef CUF
+	cleanup();
+	return 0;
+}
+
+int sarw_chain_shapes(sarw_ctx* c, double* ree2, double* rg2)
+{
+	if (!c || !ree2 || !rg2) return 1;
+	if (!c->initiateCalled) return fail(c, "nothing to analyse before sarw_initiate");
+	cudaSetDevice(c->device);
+	Control h; if (read_control(c, &h)) return 1;
+	double* d = nullptr;
+	const size_t n = c->g.nChains;
+	CU(c, dev_alloc(c, &d, 2 * n * sizeof(double)));
+	cudaError_t e = launch_chain_shapes(c->T, c->g.idAtomBase, c->g.nChains, (uint32_t)h.round, d, d + n, c->stream);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(ree2, d, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(rg2, d + n, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+	dev_free(c, d);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+	if (e != cudaSuccess) return fail(c, "sarw_chain_shapes: %s", cudaGetErrorString(e));
+	return 0;
+}
+
 int sarw_chain_lengths(sarw_ctx* c, int32_t* lengths)
 {
 	if (!c || !lengths) return 1;

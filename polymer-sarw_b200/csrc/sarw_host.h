@@ -26,6 +26,11 @@ struct Control {
 cudaError_t launch_find_batch(const Geom& g, const Tables& T, const double* xyz, const int64_t* ignore, int64_t n, uint8_t* hit, int numSMs,
 	void* scratch, cudaStream_t st);
 size_t find_scratch_bytes(const Geom& g, int64_t n);
+// analysis (sarw_analysis.cu)
+size_t rdf_scratch_bytes(int64_t n, size_t* cubBytes);
+cudaError_t launch_rdf(const double box[3], const double* d_xyz, const int32_t* d_chain, int64_t n, const double* d_thresh2, int nBins,
+	double rMin, double dr, double lastEdge, void* scratch, unsigned long long* d_intra, unsigned long long* d_inter, cudaStream_t st);
+cudaError_t launch_chain_shapes(const Tables& T, uint32_t idAtomBase, uint32_t nChains, uint32_t rounds, double* d_ree2, double* d_rg2, cudaStream_t st);
 cudaError_t launch_add_points(const Geom& g, const Tables& T, const double* xyz, int64_t n, uint32_t baseId, cudaStream_t st);
 cudaError_t launch_seed(const Geom& g, const Tables& T, ChainState* chains, uint32_t* resTrial, uint32_t* prev, const double* grafts,
 	Control* ctl, uint32_t* dirtyList, int numSMs, cudaStream_t st, int* launches);

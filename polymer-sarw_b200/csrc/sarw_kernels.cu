@@ -32,7 +32,7 @@ constexpr uint32_t DONE_BIT = 0x80000000u;
 // Large batches are processed in order of the candidates' z cell layer (counting sort by layer: zbin_* kernels below), so that
 // candidates running at the same time touch the same two or three layers of the cell table and those lines are served by
 // the 126 MB L2 instead of HBM: a 128-byte cell line is then fetched once per batch rather than once per candidate near it.
-constexpr int ZBIN_MAX = 8192;                    // layers the shared-memory histogram holds
+
 __device__ __forceinline__ int zbin_of(const Geom& g, const double* __restrict__ xyz, int64_t q)
 {
 	const double t = xyz[3 * q + 2] * g.Linv[2];

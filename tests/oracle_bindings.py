@@ -109,6 +109,29 @@ class OracleLib:
         lib.oracle_sincos_portable.argtypes = [C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         lib.oracle_philox.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         lib.oracle_cone_pos.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double, C.c_int, C.POINTER(C.c_double)]
+        lib.oracle_rdf_edges.argtypes = [C.c_double, C.c_double, C.c_int32, C.c_void_p]
+        lib.oracle_rdf.argtypes = [C.POINTER(C.c_double), C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_int32, C.c_void_p, C.c_void_p]
+        lib.oracle_chain_shapes.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
+
+    def rdf_edges(self, rMin, dr, nBins):
+        e = np.zeros(nBins + 1)
+        self.lib.oracle_rdf_edges(rMin, dr, nBins, e.ctypes.data_as(C.c_void_p))
+        return e
+
+    def rdf(self, box, xyz, chain, rMin, dr, nBins):
+        """scripts/rdf.py:13-20,39-57 as integer pair counts: (intra, inter)"""
+        xyz, _ = _xyz(xyz); chain = np.ascontiguousarray(chain, np.int32)
+        intra = np.zeros(nBins, np.uint64); inter = np.zeros(nBins, np.uint64)
+        self.lib.oracle_rdf((C.c_double * 3)(*box), xyz.ctypes.data_as(C.c_void_p), chain.ctypes.data_as(C.c_void_p), len(xyz), rMin, dr, nBins,
+                            intra.ctypes.data_as(C.c_void_p), inter.ctypes.data_as(C.c_void_p))
+        return intra, inter
+
+    def chain_shapes(self, xyz, chain, nChains):
+        xyz, _ = _xyz(xyz); chain = np.ascontiguousarray(chain, np.int32)
+        ree2 = np.zeros(nChains); rg2 = np.zeros(nChains)
+        self.lib.oracle_chain_shapes(xyz.ctypes.data_as(C.c_void_p), chain.ctypes.data_as(C.c_void_p), len(xyz), nChains,
+                                     ree2.ctypes.data_as(C.c_void_p), rg2.ctypes.data_as(C.c_void_p))
+        return ree2, rg2
 
     def target_count(self, box, density):
         b = (C.c_double * 3)(*box)

@@ -110,3 +110,27 @@ def test_golden_structure_is_valid():
     # sarw.cpp:351-352,365: CH3 ends
     assert g["type"][0] == 1 and g["type"][1] == 2
     assert len(g["angles"]) == len(g["xyz"]) - 2 * 20 and len(g["dihedrals"]) == len(g["xyz"]) - 3 * 20
+
+
+# ------------------------------------------------------------------ analysis row: scripts/rdf.py
+def test_rdf_oracle_matches_reference_rdf_py_counts(oracle):
+    """tests/golden/rdf_reference.npz was written by the reference's own scripts/rdf.py (rdfPair / rdfChains, imported) on walks of
+    the unmodified reference: the oracle's integer pair counts and bin edges must be identical."""
+    gold = np.load(os.path.join(GOLDEN, "rdf_reference.npz"))
+    for k in range(int(gold["n"])):
+        w = np.load(os.path.join(GOLDEN, str(gold[f"file{k}"])))
+        edges = gold[f"edges{k}"]; nBins = len(edges) - 1
+        rMin, dr = float(gold[f"rMin{k}"]), float(gold[f"dr{k}"])
+        assert np.array_equal(oracle.rdf_edges(rMin, dr, nBins), edges)
+        intra, inter = oracle.rdf(tuple(gold[f"box{k}"]), w["xyz"], w["chainID"], rMin, dr, nBins)
+        assert np.array_equal(intra.astype(np.int64), gold[f"intra{k}"]), k
+        assert np.array_equal(inter.astype(np.int64), gold[f"inter{k}"]), k
+
+
+def test_chain_shapes_oracle_matches_numpy(oracle):
+    import stats
+    w = np.load(os.path.join(GOLDEN, "walk_small_defaults_seed1.npz"))
+    nChains = int(w["chainID"].max())
+    ree2, rg2 = oracle.chain_shapes(w["xyz"], w["chainID"], nChains)
+    ree2n, rg2n, _ = stats.chain_shapes(w["xyz"], w["chainID"], nChains)
+    assert np.allclose(ree2, ree2n, rtol=1e-12, atol=0) and np.allclose(rg2, rg2n, rtol=1e-10, atol=0)
