@@ -39,6 +39,7 @@ int main(int argc, char** argv)
 {
 	std::string inputFilename, logFilename, outDir;
 	bool haveSeedOpt = false; unsigned long long seedOpt = 0; int device = -1, ioThreads = 0; bool timing = false;
+	bool wantRdf = false; double rdfMin = 2.0, rdfDr = 0.5; int rdfBins = 20;   // scripts/rdf.py:84-85 defaults, 12 A range
 	for (int i = 1; i < argc; i++) {
 		if (!strcmp(argv[i], "-i") && i + 1 < argc) inputFilename = argv[++i];
 		else if (!strcmp(argv[i], "-o") && i + 1 < argc) logFilename = argv[++i];
@@ -46,8 +47,12 @@ int main(int argc, char** argv)
 		else if (!strcmp(argv[i], "--device") && i + 1 < argc) device = atoi(argv[++i]);
 		else if (!strcmp(argv[i], "--io-threads") && i + 1 < argc) ioThreads = atoi(argv[++i]);
 		else if (!strcmp(argv[i], "--timing")) timing = true;
+		else if (!strcmp(argv[i], "--rdf")) {   // optional "rMin,dr,nBins"
+			wantRdf = true;
+			if (i + 1 < argc && argv[i + 1][0] != '-') { if (sscanf(argv[++i], "%lf,%lf,%d", &rdfMin, &rdfDr, &rdfBins) != 3) { fprintf(stderr, "--rdf expects rMin,dr,nBins\n"); return 1; } }
+		}
 		else if (!strcmp(argv[i], "-h") || !strcmp(argv[i], "--help")) {
-			printf("usage: sarw -i <input> [-o <log>] [--seed N] [--device D] [--io-threads T] [--timing]\n");
+			printf("usage: sarw -i <input> [-o <log>] [--seed N] [--device D] [--io-threads T] [--timing] [--rdf [rMin,dr,nBins]]\n");
 			return 0;
 		}
 	}
@@ -180,6 +185,33 @@ int main(int argc, char** argv)
 	if (sarw_chain_lengths(ctx, pm.chainLengths.data()) != 0) die("\n%s\n", sarw_last_error(ctx));
 	const double downSeconds = seconds_since(tDown);
 	sarw_get_stats(ctx, &st);
+	double rdfSeconds = 0;
+	if (wantRdf) {
+		// what scripts/rdf.py computes off line, on the device: pair histograms (rdf.py:13-20,39-57) + chain shapes
+		auto tRdf = std::chrono::steady_clock::now();
+		std::vector<uint64_t> intra((size_t)rdfBins), inter((size_t)rdfBins);
+		std::vector<double> ree2((size_t)P.nChains), rg2((size_t)P.nChains);
+		if (sarw_rdf(ctx, rdfMin, rdfDr, rdfBins, intra.data(), inter.data()) != 0) die("\n%s\n", sarw_last_error(ctx));
+		if (sarw_chain_shapes(ctx, ree2.data(), rg2.data()) != 0) die("\n%s\n", sarw_last_error(ctx));
+		rdfSeconds = seconds_since(tRdf);
+		FILE* fp = fopen("rdf.dat", "w");
+		if (!fp) die("Failed to open rdf.dat for writing\n");
+		const double N = (double)st.nBeads, V = P.boxSize[0] * P.boxSize[1] * P.boxSize[2];
+		fprintf(fp, "# r_lo r_hi intra_pairs inter_pairs g_intra g_inter   (ordered pairs as scripts/rdf.py counts them; g = pairs / (N(N-1)/V * shell volume))\n");
+		for (int k = 0; k < rdfBins; k++) {
+			const double lo = rdfMin + k * rdfDr, hi = rdfMin + (k + 1) * rdfDr;
+			const double ideal = N * (N - 1) / V * 4.0 / 3.0 * M_PI * (hi * hi * hi - lo * lo * lo);
+			fprintf(fp, "%.6f %.6f %llu %llu %.6e %.6e\n", lo, hi, (unsigned long long)intra[(size_t)k], (unsigned long long)inter[(size_t)k],
+				ideal > 0 ? (double)intra[(size_t)k] / ideal : 0.0, ideal > 0 ? (double)inter[(size_t)k] / ideal : 0.0);
+		}
+		fclose(fp);
+		fp = fopen("shapes.dat", "w");
+		if (!fp) die("Failed to open shapes.dat for writing\n");
+		fprintf(fp, "# chain length Ree^2 Rg^2\n");
+		for (int64_t c = 0; c < P.nChains; c++) fprintf(fp, "%lld %d %.10e %.10e\n", (long long)c + 1, pm.chainLengths[(size_t)c], ree2[(size_t)c], rg2[(size_t)c]);
+		fclose(fp);
+		logPrintf("\nExporting pair distribution and chain shapes: rdf.dat, shapes.dat\n");
+	}
 	sarw_destroy(ctx);
 
 	// sarw.cpp:489-509
@@ -220,6 +252,7 @@ int main(int argc, char** argv)
 		logPrintf("trials per accepted bead (reference terms): %.2f; exact overlap queries evaluated: %llu; same-round conflicts: %llu; dead chains: %lld\n",
 			(double)st.trials / (double)(st.nBeads ? st.nBeads : 1), (unsigned long long)st.queries, (unsigned long long)st.conflicts, (long long)st.deadChains);
 		logPrintf("download %.3f s, topology %.3f s, export %.3f s, total %.3f s\n", downSeconds, topoSeconds, expSeconds, seconds_since(tAll));
+		if (wantRdf) logPrintf("analysis (rdf + chain shapes) %.3f s\n", rdfSeconds);
 	}
 	if (globalLog != stdout) fclose(globalLog);
 	return 0;

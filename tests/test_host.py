@@ -137,3 +137,22 @@ def test_cli_grafted_brush_with_files(tmp_path):
     got = np.array([[float(x) for x in l.split()[1:]] for l in rows[2:2 + st.nBeads]])
     assert np.abs(got - xyz).max() < 1e-6
     assert np.allclose(got[0:24:2], grafts[:12], atol=1e-6)   # grafted chains start on their graft points
+
+
+@pytest.mark.gpu
+def test_cli_rdf_option_writes_rdf_py_counts(tmp_path):
+    """`sarw -i pe.in --rdf 2,0.5,38` adds rdf.dat / shapes.dat without touching the reference's output files; the pair counts are
+    the ones the reference's own scripts/rdf.py gave for the same walk (tests/golden/rdf_reference.npz, case 0)."""
+    exe = os.path.join(BIN, "sarw")
+    shutil.copy(os.path.join(GOLDEN, "pe.in"), tmp_path / "pe.in")
+    r = subprocess.run([exe, "-i", "pe.in", "--seed", "1", "--rdf", "2,0.5,38"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    for name in ("polymer.dat", "polymer.xyz", "polymer.xsf", "chains.dat"):
+        assert (tmp_path / name).read_bytes() == open(os.path.join(GOLDEN, "pe_seed1", name), "rb").read(), name
+    rows = np.loadtxt(tmp_path / "rdf.dat")
+    gold = np.load(os.path.join(GOLDEN, "rdf_reference.npz"))
+    assert rows.shape == (38, 6)
+    assert np.abs(rows[:, 2] - gold["intra0"]).sum() <= 2 and np.abs(rows[:, 3] - gold["inter0"]).sum() <= 4
+    shapes = np.loadtxt(tmp_path / "shapes.dat")
+    lengths = np.loadtxt(tmp_path / "chains.dat")
+    assert shapes.shape == (20, 4) and np.array_equal(shapes[:, 1], lengths) and (shapes[:, 2] > 0).all()
