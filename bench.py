@@ -1,9 +1,12 @@
 #!/usr/bin/env python
 """bench.py — accepted beads/s of the chain-growth hot path (BASELINE.json metric) on N B200s of one node.
 
-A step = one complete pass of the hot path over one synthetic melt: SARW::initiateChain + the growth loop of
-main() (sarw.cpp:66-78) for BASELINE.json configs[1] (PE melt, 100 chains x 1000 beads, 0.92 g/cc, ppp,
-minDist 1.0, maxTrials 1000). Every step uses a fresh Philox key, so no work is cached between steps.
+A step = one complete pass of the hot path — SARW::initiateChain + the growth loop of main() (sarw.cpp:66-78) — over one BATCH of
+synthetic melts of BASELINE.json configs[1] (PE melt, 100 chains x 1000 beads, 0.92 g/cc, ppp, minDist 1.0, maxTrials 1000).
+A 100-chain melt grows in one thread-block cluster (13 of the 148 SMs), so the batch is M independent melts grown at the same time,
+one CUDA stream + one host thread each, M = sarw_concurrent_capacity() (7 on B200) — the same thing the reference arm does with the
+host cores (one serial instance per core). `single_melt` in the JSON line is one melt at a time. Every melt uses a fresh Philox
+key, so no work is cached between steps.
 
   value : device-resident throughput — contexts (cell tables) are created before the timed region; a step is
           timed with CUDA events on the stream the kernels run on.
@@ -183,6 +186,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--melts", type=int, default=0, help="independent melts grown concurrently per step (0 = sarw_concurrent_capacity of the device)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary C3 / find_batch measurements")
     args = ap.parse_args()
@@ -208,74 +212,117 @@ def main():
     hbm_peak, peak_src = load_peaks()
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")   # > 126 MB L2
 
-    def one_step_device(ctx):
-        """initiate + grow + terminate on an existing context; device time from CUDA events on the kernels' stream"""
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
+    def one_melt_device(ctx):
+        """initiate + grow + terminate on an existing context (blocking; returns the stats)"""
         ctx.initiate()
         st = ctx.grow(0, -1)
         ctx.terminate()
-        e1.record(stream)
-        e1.synchronize()
-        return e0.elapsed_time(e1), st
+        return st
 
-    def make_ctx(seed):
+    # A melt of <= 256 chains grows in ONE thread-block cluster (13 of 148 SMs for configs[1]); a step is therefore a BATCH of M
+    # independent melts grown at the same time, one CUDA stream + one host thread each, M = sarw_concurrent_capacity (7 on B200).
+    # The reference arm does the same with the host cores (one serial instance per core). M = 1 for the large workloads.
+    probe = sarw_b200.Context(device=local, **ctx_kwargs(w, 1))
+    M = args.melts if args.melts > 0 else probe.concurrent_capacity()
+    probe.close()
+    from concurrent.futures import ThreadPoolExecutor
+    pool = ThreadPoolExecutor(max_workers=M)
+    streams = [stream] if M == 1 else [torch.cuda.Stream() for _ in range(M)]
+
+    def make_ctx(seed, m):
         c = sarw_b200.Context(device=local, **ctx_kwargs(w, seed))
-        c.set_stream(stream.cuda_stream)
+        c.set_stream(streams[m].cuda_stream)
         return c
 
+    def batch_device(ctxs):
+        """one step: M melts at once; CUDA events on the launching streams: start fans out to every stream, the end event waits for all"""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for sm in streams:
+            if sm is not stream: sm.wait_event(e0)
+        def work(m):
+            with torch.cuda.stream(streams[m]):
+                st = one_melt_device(ctxs[m])
+                ev = torch.cuda.Event(); ev.record(streams[m])
+            return st, ev
+        res = list(pool.map(work, range(M)))
+        for _, ev in res: stream.wait_event(ev)
+        e1.record(stream)
+        e1.synchronize()
+        return e0.elapsed_time(e1), [r[0] for r in res]
+
     total = args.warmup + args.steps
-    seeds = rank_seeds(rank, total)
+    seeds = rank_seeds(rank, total * M)
     # -------- device-resident arm
-    ctxs = [make_ctx(s) for s in seeds]
+    ctxs = [[make_ctx(seeds[i * M + m], m) for m in range(M)] for i in range(total)]
     for i in range(args.warmup):
-        flush.fill_(float(i)); one_step_device(ctxs[i])
+        flush.fill_(float(i)); batch_device(ctxs[i])
     torch.cuda.synchronize()
     if dist: dist.barrier()
     sampler = ClockSampler(local); sampler.start()
-    step_ms, beads, queries, trials, rounds, launches, grow_ms, seed_ms, conflicts = [], 0, 0, 0, 0, 0, 0.0, 0.0, 0
+    step_ms, beads, queries, trials, rounds, launches, grow_ms, seed_ms, conflicts, nMelts = [], 0, 0, 0, 0, 0, 0.0, 0.0, 0, 0
     for i in range(args.warmup, total):
         flush.fill_(float(i))          # L2 flush between timed iterations (outside the event pair)
         torch.cuda.synchronize()
-        ms, st = one_step_device(ctxs[i])
+        ms, sts = batch_device(ctxs[i])
         step_ms.append(ms)
-        beads += st.nBeads; queries += st.queries; trials += st.trials; rounds += st.rounds
-        launches += st.growLaunches + st.seedLaunches; grow_ms += st.growMs; seed_ms += st.seedMs; conflicts += st.conflicts
+        for st in sts:
+            beads += st.nBeads; queries += st.queries; trials += st.trials; rounds += st.rounds; nMelts += 1
+            launches += st.growLaunches + st.seedLaunches; grow_ms += st.growMs; seed_ms += st.seedMs; conflicts += st.conflicts
     torch.cuda.synchronize()
     if dist: dist.barrier()
     clocks = sampler.stop()
-    for c in ctxs:
-        c.close()
+    for row in ctxs:
+        for c in row: c.close()
     t_dev = sum(step_ms) / 1e3
 
-    # -------- end-to-end arm through the C ABI with host buffers (results land in pinned host memory)
+    # one melt at a time on an otherwise idle GPU (latency of a melt; what `value` was before batching)
+    single_ms, single_beads = [], 0
+    if M > 1:
+        sc = [sarw_b200.Context(device=local, **ctx_kwargs(w, 900_000 + rank * 1000 + k)) for k in range(args.warmup + args.steps)]
+        for k, c in enumerate(sc):
+            c.set_stream(stream.cuda_stream)
+            flush.fill_(float(k)); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream); st = one_melt_device(c); e1.record(stream); e1.synchronize()
+            if k >= args.warmup: single_ms.append(e0.elapsed_time(e1)); single_beads += st.nBeads
+            c.close()
+
+    # -------- end-to-end arm through the C ABI with host buffers (results land in pinned host memory): the same batch of M melts,
+    # every melt created, grown, downloaded and destroyed inside the timed region
     cap = int(sarw_b200.target_count(w["boxSize"], w["targetMassDensity"]) + w["nChains"] + 16)
-    pinned = {"xyz": torch.empty((cap, 3), dtype=torch.float64, pin_memory=True).numpy(), "chainID": torch.empty(cap, dtype=torch.int32, pin_memory=True).numpy(),
-              "type": torch.empty(cap, dtype=torch.int32, pin_memory=True).numpy(), "bonds": torch.empty((cap, 2), dtype=torch.int64, pin_memory=True).numpy()}
+    pinned = [{"xyz": torch.empty((cap, 3), dtype=torch.float64, pin_memory=True).numpy(), "chainID": torch.empty(cap, dtype=torch.int32, pin_memory=True).numpy(),
+               "type": torch.empty(cap, dtype=torch.int32, pin_memory=True).numpy(), "bonds": torch.empty((cap, 2), dtype=torch.int64, pin_memory=True).numpy()} for _ in range(M)]
     e2e_times, e2e_beads, h2d, d2h, e2e_launch = [], 0, 0, 0, 0
     import gc
+
+    def e2e_melt(args_):
+        m, seed = args_
+        c = sarw_b200.Context(device=local, **ctx_kwargs(w, seed))
+        c.set_stream(streams[m].cuda_stream)
+        c.initiate(); st = c.grow(0, -1); c.terminate()
+        xyz, cid, typ, bonds = c.download(pinned[m])
+        nbytes = xyz.nbytes + cid.nbytes + typ.nbytes + bonds.nbytes
+        c.close()
+        return st, nbytes
+
     for i in range(total):
         gc.collect(); gc.disable()                 # no collector pauses inside the timed call sequence
         flush.fill_(float(i)); torch.cuda.synchronize()
         t0 = time.perf_counter()
-        c = sarw_b200.Context(device=local, **ctx_kwargs(w, seeds[i] + 5_000))
-        c.set_stream(stream.cuda_stream)
-        ta = time.perf_counter()
-        c.initiate(); st = c.grow(0, -1); c.terminate()
-        tb = time.perf_counter()
-        xyz, cid, typ, bonds = c.download(pinned)
+        res = list(pool.map(e2e_melt, [(m, seeds[i * M + m] + 5_000_000) for m in range(M)]))
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        tc = time.perf_counter()
-        c.close()
         gc.enable()
-        if os.environ.get("SARW_BENCH_DEBUG"): print(f"   create {1e3*(ta-t0):.2f} run {1e3*(tb-ta):.2f} download {1e3*(tc-tb):.2f} close {1e3*(time.perf_counter()-tc):.2f}", file=sys.stderr)
-        if os.environ.get("SARW_BENCH_DEBUG"): print(f"e2e step {i}: {dt*1e3:.3f} ms", file=sys.stderr)
+        if os.environ.get("SARW_BENCH_DEBUG"): print(f"e2e step {i}: {dt*1e3:.3f} ms for {M} melts", file=sys.stderr)
         if i >= args.warmup:
-            e2e_times.append(dt); e2e_beads += st.nBeads
-            h2d += sarw_b200.C.sizeof(sarw_b200.Params) + 64                      # parameters + control block
-            d2h += xyz.nbytes + cid.nbytes + typ.nbytes + bonds.nbytes + 3 * 64 + st.growLaunches * 64 + 8   # results + control/stat reads
-            e2e_launch += st.growLaunches + st.seedLaunches + 5                   # + flag, 2x cub scan, gather
+            e2e_times.append(dt)
+            for st, nbytes in res:
+                e2e_beads += st.nBeads
+                h2d += sarw_b200.C.sizeof(sarw_b200.Params) + 64                      # parameters + control block
+                d2h += nbytes + 3 * 64 + st.growLaunches * 64 + 8                     # results + control/stat reads
+                e2e_launch += st.growLaunches + st.seedLaunches + 5                   # + flag, 2x cub scan, gather
+    pool.shutdown()
 
     # -------- aggregate over ranks (max time, summed work)
     t_e2e = sum(e2e_times)
@@ -287,25 +334,32 @@ def main():
         # bytes per bead = T*B_q + B_a with T = trials per accepted bead in the reference's terms (what the serial
         # loop of sarw.cpp:259 evaluates; trials of provably dead chains are decided without memory traffic here)
         alg_bytes = trials * B_QUERY + beads * B_BEAD
-        achieved = alg_bytes / (grow_ms / 1e3) / 1e9
+        achieved = alg_bytes / (grow_ms / 1e3) / 1e9       # per launch: summed bytes / summed launch durations
         line = {
             "metric": "accepted beads/sec", "value": value, "unit": "beads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": w["name"], "seeds": "distinct Philox key per step and rank", "l2": "256 MB flush write between timed steps",
+            "config": {"workload": w["name"], "melts_per_step": M,
+                       "batch": (f"{M} independent melts of the workload grown at the same time (one CUDA stream + one host thread each; a melt of "
+                                 f"{w['nChains']} chains occupies one thread-block cluster, {M} clusters fit the device)") if M > 1 else "one melt per step",
+                       "seeds": "distinct Philox key per melt, step and rank", "l2": "256 MB flush write between timed steps",
                        "multi_gpu": "independent melts per rank, no data-path collective" if world > 1 else "single GPU",
-                       "rounds_per_step": rounds / args.steps, "trials_per_bead": trials / max(1, beads), "conflicts_per_step": conflicts / args.steps},
+                       "rounds_per_melt": rounds / nMelts, "trials_per_bead": trials / max(1, beads), "conflicts_per_melt": conflicts / nMelts},
             "e2e": {"value": e2e_beads_all / t_e2e, "unit": "beads/s", "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps,
                     "ms_per_step": 1e3 * t_e2e / args.steps, "ms_per_step_median": 1e3 * statistics.median(e2e_times), "ms_per_step_max": 1e3 * max(e2e_times),
-                    "includes": "sarw_create (alloc + cell-table init), seeding, growth, terminate, sarw_download to host"},
+                    "includes": "per melt: sarw_create (alloc + cell-table init), seeding, growth, terminate, sarw_download to pinned host memory, sarw_destroy"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": NCU_TRAFFIC.get(args.workload, (None, None))[0], "traffic_source": NCU_TRAFFIC.get(args.workload, (None, None))[1],
                          "kernel": "sarw::grow_cluster_kernel<8> (one thread-block cluster, persistent, one launch per step)" if w["nChains"] <= 128 else "sarw::grow_kernel (persistent cooperative launch)", "peak_source": peak_src,
                          "algorithmic_bytes": f"trials*{B_QUERY:.0f} + beads*{B_BEAD:.0f} (SURVEY §8d, trials in reference terms)",
-                         "trials_per_launch": trials / args.steps, "candidates_evaluated_per_launch": queries / args.steps,
-                         "avg_launch_ms": grow_ms / args.steps, "note": "latency-bound: ~1e2 chains per round, ~1e3 dependent rounds"},
+                         "trials_per_launch": trials / nMelts, "candidates_evaluated_per_launch": queries / nMelts,
+                         "avg_launch_ms": grow_ms / nMelts, "concurrent_launches": M,
+                         "note": "per launch (one melt); latency-bound: ~1e2 chains per round, ~1e3 dependent rounds. M launches run side by side in a step"},
         }
+        if single_ms:
+            line["single_melt"] = {"ms_per_melt": statistics.median(single_ms), "beads_per_s": single_beads / (sum(single_ms) / 1e3),
+                                   "note": "one melt at a time on an otherwise idle GPU, device time (CUDA events)"}
         if not args.no_extra:
             line["extra"] = extra_measurements(sarw_b200, torch, stream, flush, local)
         if not args.no_cpu_baseline and world == 1:

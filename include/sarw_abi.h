@@ -95,6 +95,11 @@ int sarw_propagate_round(sarw_ctx* ctx, int32_t* progressed);
 /* main()'s loop (sarw.cpp:67-78) on the device: rounds until actualCount >= target, a round makes no progress, or
  * maxRounds more rounds were run (maxRounds < 0: unbounded). target <= 0 means SARW::targetCount(). */
 int sarw_grow(sarw_ctx* ctx, int64_t target, int64_t maxRounds, sarw_stats* stats);
+/* How many contexts like this one can run sarw_grow at the same time on the device, each on its own stream (sarw_set_stream) from
+ * its own host thread: a melt of <= 256 chains occupies one thread-block cluster, i.e. a fraction of the SMs (7 melts of
+ * BASELINE configs[1] fit a B200). 1 for larger melts, whose cooperative kernel fills the device. No reference counterpart
+ * (the reference is serial; one runs several processes, one per host core). */
+int32_t sarw_concurrent_capacity(sarw_ctx* ctx);
 /* ---- multi-rank: ONE melt over several GPUs, one context per GPU (rank), every context created with identical
  * parameters, obstacles and grafts. State is replicated; only the proposals of a round are partitioned (chain i is
  * proposed by rank i % nranks). Per round: sarw_mr_propose on every rank writes `recordsPerRank` 32-byte records into a

@@ -184,6 +184,10 @@ int ensure_rounds(sarw_ctx* c, uint32_t rounds)
 
 int read_control(sarw_ctx* c, Control* h)
 {
+	// A device-to-host copy into pageable memory blocks INSIDE the driver until the stream reaches it, and other host threads'
+	// CUDA calls (other melts on the same GPU) queue up behind it for the length of the running kernel (measured: sarw_create
+	// stalled 7.5 ms = one growth kernel). Waiting for the stream first keeps the blocking part outside the driver.
+	CU(c, cudaStreamSynchronize(c->stream));
 	CU(c, cudaMemcpyAsync(h, c->ctl, sizeof(Control), cudaMemcpyDeviceToHost, c->stream));
 	CU(c, cudaStreamSynchronize(c->stream));
 	return 0;
@@ -192,6 +196,7 @@ int read_control(sarw_ctx* c, Control* h)
 int check_overflow(sarw_ctx* c)
 {
 	uint32_t n = 0;
+	CU(c, cudaStreamSynchronize(c->stream));
 	CU(c, cudaMemcpyAsync(&n, c->T.ovfCount, sizeof n, cudaMemcpyDeviceToHost, c->stream));
 	CU(c, cudaStreamSynchronize(c->stream));
 	if (n > c->T.ovfCap) return fail(c, "cell overflow list exhausted (%u beads did not fit their cells; raise cellEdge or lower density)", n);
@@ -228,6 +233,7 @@ int sarw_debug_busy(sarw_ctx* c, unsigned long long* out, int n)
 	for (int k = 0; k < n && k < 256; k++) out[k] = h.busy[k];
 	return 0;
 }
+
 
 int64_t sarw_target_count(const double boxSize[3], double targetMassDensity)
 {
@@ -480,6 +486,7 @@ int sarw_lookup_find_batch(sarw_ctx* c, const double* xyz, const int64_t* ignore
 		CUF(cudaMemcpyAsync(di, ignore, (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
 	}
 	CUF(find_batch_ordered(c, dx, di, n, dh));
+	CUF(cudaStreamSynchronize(c->stream));
 	CUF(cudaMemcpyAsync(hit, dh, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
 	CUF(cudaStreamSynchronize(c->stream));
 #undef CUF
@@ -536,6 +543,17 @@ static cudaError_t launch_grow_auto(sarw_ctx* c, const Geom& g, uint32_t roundEn
 	}
 	return launch_grow(g, c->T, c->chains, c->resTrial, c->origTrial, c->resPos, c->prev, c->ctl, c->roundAcc, c->roundProg, c->dirtyCount,
 		c->dirtyList, roundEnd, blocks, 0, c->stream);
+}
+
+int32_t sarw_concurrent_capacity(sarw_ctx* c)
+{
+	if (!c) return 0;
+	cudaSetDevice(c->device);
+	// small melts grow in ONE thread-block cluster (a fraction of the SMs): several contexts can grow at the same time, each on its
+	// own stream from its own host thread. The cooperative grid kernel of larger melts fills the device by itself.
+	if (!use_cluster(c)) return 1;
+	const int n = cluster_max_active(c->g.nChains);
+	return n < 1 ? 1 : n;
 }
 
 static int grow_impl(sarw_ctx* c, int64_t target, int64_t maxRounds, sarw_stats* stats)
@@ -775,6 +793,7 @@ int sarw_download(sarw_ctx* c, double* xyz, int32_t* chainID, int32_t* type, int
 	if (type) CUF(dev_alloc(c, &dt, N * sizeof(int32_t)));
 	if (bonds && nBonds) CUF(dev_alloc(c, &db, nBonds * 2 * sizeof(int64_t)));
 	CUF(launch_download(c->g, c->T, c->prev, c->chains, nSlots, c->nSeeded, c->terminated ? 1 : 0, flags, scan, tmp, tmpBytes, dx, dc, dt, db, c->stream));
+	CUF(cudaStreamSynchronize(c->stream));   // see read_control
 	if (dx) CUF(cudaMemcpyAsync(xyz, dx, N * 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
 	if (dc) CUF(cudaMemcpyAsync(chainID, dc, N * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
 	if (dt) CUF(cudaMemcpyAsync(type, dt, N * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
@@ -833,6 +852,7 @@ int sarw_rdf(sarw_ctx* c, double rMin, double dr, int32_t nBins, uint64_t* intra
 	CUF(cudaMemcpyAsync(dT, t2.data(), t2.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
 	CUF(cudaMemsetAsync(dh, 0, 2 * (size_t)nBins * sizeof(unsigned long long), c->stream));
 	CUF(launch_rdf(c->g.L, dx, dc, (int64_t)N, dT, nBins, rMin, delta, lastEdge, scratch, dh, dh + nBins, c->stream));
+	CUF(cudaStreamSynchronize(c->stream));
 	CUF(cudaMemcpyAsync(intra, dh, (size_t)nBins * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
 	CUF(cudaMemcpyAsync(inter, dh + nBins, (size_t)nBins * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
 	CUF(cudaStreamSynchronize(c->stream));
@@ -851,6 +871,7 @@ int sarw_chain_shapes(sarw_ctx* c, double* ree2, double* rg2)
 	const size_t n = c->g.nChains;
 	CU(c, dev_alloc(c, &d, 2 * n * sizeof(double)));
 	cudaError_t e = launch_chain_shapes(c->T, c->g.idAtomBase, c->g.nChains, (uint32_t)h.round, d, d + n, c->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
 	if (e == cudaSuccess) e = cudaMemcpyAsync(ree2, d, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
 	if (e == cudaSuccess) e = cudaMemcpyAsync(rg2, d + n, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
 	dev_free(c, d);
@@ -866,6 +887,7 @@ int sarw_chain_lengths(sarw_ctx* c, int32_t* lengths)
 	int32_t* d = nullptr;
 	CU(c, dev_alloc(c, &d, (size_t)c->g.nChains * sizeof(int32_t)));
 	cudaError_t e = launch_chain_lengths(c->chains, c->g.nChains, d, c->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
 	if (e == cudaSuccess) e = cudaMemcpyAsync(lengths, d, (size_t)c->g.nChains * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream);
 	dev_free(c, d);
 	if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);

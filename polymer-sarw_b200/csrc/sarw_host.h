@@ -26,6 +26,7 @@ struct Control {
 cudaError_t launch_find_batch(const Geom& g, const Tables& T, const double* xyz, const int64_t* ignore, int64_t n, uint8_t* hit, int numSMs,
 	void* scratch, cudaStream_t st);
 size_t find_scratch_bytes(const Geom& g, int64_t n);
+int cluster_max_active(uint32_t nChains);
 // analysis (sarw_analysis.cu)
 size_t rdf_scratch_bytes(int64_t n, size_t* cubBytes);
 cudaError_t launch_rdf(const double box[3], const double* d_xyz, const int32_t* d_chain, int64_t n, const double* d_thresh2, int nBins,

@@ -1081,6 +1081,23 @@ static cudaError_t launch_cluster(const GrowArgs& A, cudaStream_t st)
 	return cudaLaunchKernelEx(&cfg, grow_cluster_kernel<WARPS>, A);
 }
 
+// diagnostics: how many clusters of the size launch_cluster would use for nChains chains can be resident at once
+int cluster_max_active(uint32_t nChains)
+{
+	const bool w8 = nChains <= 8u * CL_MAX_CTAS;
+	const int W = w8 ? 8 : 16;
+	int ctas = (int)((nChains + W - 1) / W); if (ctas < 1) ctas = 1;
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3((unsigned)ctas); cfg.blockDim = dim3(W * 32); cfg.dynamicSmemBytes = cluster_smem_bytes(W);
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeClusterDimension;
+	attr[0].val.clusterDim.x = (unsigned)ctas; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+	cfg.attrs = attr; cfg.numAttrs = 1;
+	int n = -1;
+	cudaError_t e = w8 ? cudaOccupancyMaxActiveClusters(&n, grow_cluster_kernel<8>, &cfg) : cudaOccupancyMaxActiveClusters(&n, grow_cluster_kernel<16>, &cfg);
+	return e == cudaSuccess ? n : -(int)e;
+}
+
 cudaError_t launch_grow(const Geom& g, const Tables& T, ChainState* chains, uint32_t* resTrial, uint32_t* origTrial, double* resPos, uint32_t* prev, Control* ctl,
 	uint32_t* roundAcc, uint32_t* roundProg, uint32_t* dirtyCount, uint32_t* dirtyList, uint32_t roundEnd, int blocks, int useCluster, cudaStream_t st)
 {

@@ -23,7 +23,7 @@ ABI_SYMBOLS = [
     "sarw_create", "sarw_destroy", "sarw_last_error", "sarw_set_stream", "sarw_add_obstacles", "sarw_set_grafts",
     "sarw_initiate", "sarw_propagate_round", "sarw_grow", "sarw_terminate", "sarw_get_stats", "sarw_target_count",
     "sarw_download", "sarw_chain_lengths", "sarw_round_counts", "sarw_lookup_add_points", "sarw_lookup_find_batch",
-    "sarw_lookup_find_batch_device", "sarw_lookup_size", "sarw_rdf", "sarw_chain_shapes",
+    "sarw_lookup_find_batch_device", "sarw_lookup_size", "sarw_rdf", "sarw_chain_shapes", "sarw_concurrent_capacity",
     "sarw_mr_setup", "sarw_mr_more", "sarw_mr_propose", "sarw_mr_finish", "sarw_mr_commit",
     "sarw_mr_peer_export", "sarw_mr_peer_connect", "sarw_mr_grow_peer",
 ]
@@ -84,6 +84,8 @@ def load_library(path=LIB_PATH):
     lib.sarw_chain_lengths.argtypes = [vp, vp]
     lib.sarw_rdf.argtypes = [vp, C.c_double, C.c_double, C.c_int32, vp, vp]
     lib.sarw_chain_shapes.argtypes = [vp, vp, vp]
+    lib.sarw_concurrent_capacity.argtypes = [vp]
+    lib.sarw_concurrent_capacity.restype = C.c_int32
     lib.sarw_round_counts.argtypes = [vp, vp, C.c_int64]
     lib.sarw_lookup_add_points.argtypes = [vp, vp, C.c_int64]
     lib.sarw_lookup_find_batch.argtypes = [vp, vp, vp, C.c_int64, vp]
@@ -256,6 +258,9 @@ class Context:
         out = np.zeros(self.nChains, np.int32)
         self._ck(self.lib.sarw_chain_lengths(self.h, out.ctypes.data))
         return out
+
+    def concurrent_capacity(self):
+        return int(self.lib.sarw_concurrent_capacity(self.h))
 
     def rdf(self, rMin=2.0, dr=0.5, nBins=20):
         """scripts/rdf.py:13-20,39-57 on the device: (intra, inter) integer pair counts per bin, bins rMin + k*dr"""
