@@ -255,3 +255,44 @@ def test_obstacle_ignore_quirk_bit_exact(sarw, oracle):
     g = run_gpu(sarw, cfg, 9, obstacles=obst)
     o = oracle.walk(seed=9, trig="portable", obstacles=obst, **cases.oracle_kwargs(cfg))
     assert_same_walk(g, o, exact=True)
+
+
+def test_concurrent_melts_equal_sequential_melts(sarw):
+    """sarw_concurrent_capacity melts grown at the same time (own stream + own host thread each) give, bit for bit, the walks the
+    same seeds give one at a time; three waves so blocks of destroyed contexts are reused while other melts are still running."""
+    import threading
+    import torch
+    cfg = dict(nChains=100, boxSize=(40.0, 40.0, 40.0), minDist=1.0, maxTrials=300)
+    probe = sarw.Context(seed=1, **cfg)
+    M = probe.concurrent_capacity()
+    probe.close()
+    assert M >= 2, M
+
+    def melt(seed, stream=None):
+        c = sarw.Context(seed=seed, **cfg)
+        if stream is not None:
+            c.set_stream(stream.cuda_stream)
+        c.initiate(); st = c.grow(0, -1); c.terminate()
+        out = c.download()
+        c.close()
+        return st.nBeads, out
+
+    want = {seed: melt(seed) for seed in range(50, 50 + 3 * M)}
+    streams = [torch.cuda.Stream() for _ in range(M)]
+    got, errs = {}, []
+
+    def worker(m):
+        try:
+            for wave in range(3):
+                seed = 50 + wave * M + m
+                got[seed] = melt(seed, streams[m])
+        except Exception as e:   # noqa: BLE001
+            errs.append(repr(e))
+
+    th = [threading.Thread(target=worker, args=(m,)) for m in range(M)]
+    for t in th: t.start()
+    for t in th: t.join()
+    assert not errs, errs
+    for seed, (n, (xyz, cid, typ, bonds)) in want.items():
+        gn, (gx, gc, gt, gb) = got[seed]
+        assert gn == n and np.array_equal(gx, xyz) and np.array_equal(gc, cid) and np.array_equal(gt, typ) and np.array_equal(gb, bonds), seed
