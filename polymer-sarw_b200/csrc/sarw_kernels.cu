@@ -731,7 +731,9 @@ __device__ __forceinline__ void round_barrier(Control* ctl)
 	}
 }
 
-template <int WARPS, bool CLUSTER>
+// MR = false: single-GPU instantiation, every multi-rank path is compiled out (they cost the 128-register kernel 170 -> 510 bytes of
+// spill traffic and 13 % of its speed when they were selected at run time); MR = true: the phases of a multi-rank round
+template <int WARPS, bool MR>
 __global__ void __launch_bounds__(WARPS * 32) grow_kernel(GrowArgs A)
 {
 	constexpr int GROW_WARPS = WARPS;
@@ -757,9 +759,10 @@ __global__ void __launch_bounds__(WARPS * 32) grow_kernel(GrowArgs A)
 	unsigned long long nBeads = __ldcg(&A.ctl->nBeads);
 	uint32_t lastProg = __ldcg(&A.ctl->lastProgressed);
 	unsigned long long myTrials = 0, myQueries = 0;
-	bool pendingValid = (A.mrPhase == 1u);   // is there a round whose results are not yet committed? (always possible between phase-1/2 launches)
-	const bool mr = A.mrPhase != 0u;
-	if (A.mrPhase == 3u) {       // multi-rank: commit the last round, nothing else
+	const uint32_t phase = MR ? A.mrPhase : 0u;
+	bool pendingValid = (phase == 1u);   // is there a round whose results are not yet committed? (always possible between phase-1/2 launches)
+	const bool mr = MR && phase != 0u;
+	if (phase == 3u) {       // multi-rank: commit the last round, nothing else
 		for (uint32_t i = gw; i < g.nChains; i += nW) { ChainState cs = load_chain(A.chains + i); commit_pending(A, i, round - 1, cs, lane); }
 		return;
 	}
@@ -776,10 +779,10 @@ __global__ void __launch_bounds__(WARPS * 32) grow_kernel(GrowArgs A)
 		const uint32_t idRound = round_id_base(g, round);
 
 		// ---------------- phase A: commit last round, then propose + tentatively insert
-		if (mr && A.mrPhase != 2u && pendingValid)                   // chains proposed by other ranks: commit only, one thread each
+		if (mr && phase != 2u && pendingValid)                   // chains proposed by other ranks: commit only, one thread each
 			for (uint32_t i = (gw * 32 + lane); i < g.nChains; i += nW * 32)
 				if ((i % A.mrRanks) != A.mrRank) commit_pending_thread(A, i, round - 1);
-		if (A.mrPhase != 2u)
+		if (phase != 2u)
 		for (uint32_t i = mr ? A.mrRank + gw * A.mrRanks : gw; i < g.nChains; i += mr ? nW * A.mrRanks : nW) {
 			ChainState cs = load_chain(A.chains + i);
 			if (pendingValid) commit_pending(A, i, round - 1, cs, lane);
@@ -812,19 +815,19 @@ __global__ void __launch_bounds__(WARPS * 32) grow_kernel(GrowArgs A)
 			}
 		}
 		SUBT(0);
-		if (A.mrPhase == 1u) break;                                  // the host all-gathers the records, then launches phase 2
+		if (phase == 1u) break;                                  // the host all-gathers the records, then launches phase 2
 		const MrRecord* allRec = A.mrAll;
-		if (A.mrPhase == 4u) {                                       // exchange inside the kernel: peer stores + flag handshake
-			round_barrier<CLUSTER>(A.ctl);                            // every record store of this GPU has been issued
+		if (phase == 4u) {                                       // exchange inside the kernel: peer stores + flag handshake
+			round_barrier<false>(A.ctl);                            // every record store of this GPU has been issued
 			SUBT(1);
 			if (gw == 0 && lane == 0 && !mr_peer_meet(A, round)) atomicExch(&A.ctl->abort, 1u);
 			SUBT(2);
-			round_barrier<CLUSTER>(A.ctl);
+			round_barrier<false>(A.ctl);
 			SUBT(3);
 			if (__ldcg(&A.ctl->abort)) break;
 			allRec = A.peerRec[A.mrRank] + (size_t)(round & 1u) * A.mrRanks * A.mrK;
 		}
-		if (A.mrPhase == 2u || A.mrPhase == 4u)                     // tentative beads proposed by the other ranks
+		if (phase == 2u || phase == 4u)                     // tentative beads proposed by the other ranks
 			for (uint32_t i = start + gw * 32 + lane; i < end; i += nW * 32) {
 				if ((i % A.mrRanks) == A.mrRank) continue;
 				const MrRecord* rp_ = allRec + (size_t)(i % A.mrRanks) * A.mrK + i / A.mrRanks;
@@ -839,12 +842,12 @@ __global__ void __launch_bounds__(WARPS * 32) grow_kernel(GrowArgs A)
 			}
 		SUBT(4);
 		pendingValid = true;
-		round_barrier<CLUSTER>(A.ctl);
+		round_barrier<false>(A.ctl);
 		SUBT(5);
 		const long long tk1 = clock64();
 
 		// ---------------- phase V: conflicts with tentative beads of lower-indexed chains of this round
-		const bool splitV = A.mrPhase == 4u && A.mrSplitVerify != 0u;
+		const bool splitV = phase == 4u && A.mrSplitVerify != 0u;
 		{
 			const int sub = lane & 7, grp = lane >> 3;
 			uint32_t acc = 0, prog = 0; unsigned long long tr = 0;
@@ -886,7 +889,7 @@ __global__ void __launch_bounds__(WARPS * 32) grow_kernel(GrowArgs A)
 			}
 		}
 		if (splitV) {   // exchange the conflict lists: block 0 stores this rank's list into every rank's inbox, ranks meet, lists are merged
-			round_barrier<CLUSTER>(A.ctl);
+			round_barrier<false>(A.ctl);
 			if (blockIdx.x == 0) {
 				const uint32_t par = round & 1u, mine = __ldcg(&A.dirtyCount[round]);
 				const size_t slot = ((size_t)par * A.mrRanks + A.mrRank) * (1u + A.mrK);
@@ -910,16 +913,16 @@ __global__ void __launch_bounds__(WARPS * 32) grow_kernel(GrowArgs A)
 				if (threadIdx.x == 0) A.dirtyCount[round] = total;
 			}
 		}
-		round_barrier<CLUSTER>(A.ctl);
+		round_barrier<false>(A.ctl);
 		if (splitV && __ldcg(&A.ctl->abort)) break;
 
 		const long long tk2 = clock64();
 		// ---------------- clean-up (rare): serial re-resolution in chain order
 		if (__ldcg(&A.dirtyCount[round]) != 0u) {
 			cleanup_parallel(A, round, gw, nW, lane);          // independent conflicts, one warp each
-			round_barrier<CLUSTER>(A.ctl);
+			round_barrier<false>(A.ctl);
 			if (gw == 0) cleanup_round(A, round, lane);          // the rest, in chain order
-			round_barrier<CLUSTER>(A.ctl);
+			round_barrier<false>(A.ctl);
 			cleanRounds++;
 		}
 		cycA += tk1 - tk0; cycV += tk2 - tk1; cycC += clock64() - tk2;
@@ -929,7 +932,7 @@ __global__ void __launch_bounds__(WARPS * 32) grow_kernel(GrowArgs A)
 	}
 
 	// commit the last round of this launch (multi-rank: the next phase-1 launch, or phase 3, commits)
-	if (pendingValid && (A.mrPhase == 0u || A.mrPhase == 4u))
+	if (pendingValid && (phase == 0u || phase == 4u))
 		for (uint32_t i = gw; i < g.nChains; i += nW) {
 			ChainState cs = load_chain(A.chains + i);
 			commit_pending(A, i, round - 1, cs, lane);
@@ -1054,6 +1057,7 @@ cudaError_t grow_max_blocks(int numSMs, int* maxBlocks)
 {
 	int perSM = 0;
 	CK(cudaFuncSetAttribute(grow_kernel<GROW_WARPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grow_smem_bytes(GROW_WARPS)));
+	CK(cudaFuncSetAttribute(grow_kernel<GROW_WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grow_smem_bytes(GROW_WARPS)));
 	CK(cudaFuncSetAttribute(grow_cluster_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cluster_smem_bytes(8)));
 	CK(cudaFuncSetAttribute(grow_cluster_kernel<8>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
 	CK(cudaFuncSetAttribute(grow_cluster_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cluster_smem_bytes(16)));
@@ -1127,7 +1131,7 @@ cudaError_t launch_grow_mr(const Geom& g, const Tables& T, ChainState* chains, u
 		A.peerDirty[p] = peerDirty && p < ranks ? (uint32_t*)peerDirty[p] : nullptr;
 	}
 	void* args[] = { &A };
-	return cudaLaunchCooperativeKernel((const void*)grow_kernel<GROW_WARPS, false>, dim3((unsigned)blocks), dim3(GROW_WARPS * 32), args,
+	return cudaLaunchCooperativeKernel((const void*)grow_kernel<GROW_WARPS, true>, dim3((unsigned)blocks), dim3(GROW_WARPS * 32), args,
 		grow_smem_bytes(GROW_WARPS), st);
 }
 

@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libsarw_b200.so")
+LIB_PATH = os.environ.get("SARW_B200_LIB") or os.path.join(_HERE, "lib", "libsarw_b200.so")   # override: A/B builds of the same library
 
 GRAFT = {"file": 0, "z": 1, "zCenter": 2}
 ORDER = {"roundRobin": 0, "grafted": 1}
