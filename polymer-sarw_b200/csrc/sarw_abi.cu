@@ -545,6 +545,15 @@ static cudaError_t launch_grow_auto(sarw_ctx* c, const Geom& g, uint32_t roundEn
 		c->dirtyList, roundEnd, blocks, 0, c->stream);
 }
 
+// diagnostics (not in the ABI header): out[8] = propose cycles and chain-rounds by path (dead, fast, fast->hard, hard) of the cluster kernel
+int sarw_debug_paths(sarw_ctx* c, unsigned long long* out)
+{
+	if (!c) return 1;
+	Control h; if (read_control(c, &h)) return 1;
+	for (int k = 0; k < 4; k++) { out[k] = h.pathCyc[k]; out[4 + k] = h.pathCnt[k]; }
+	return 0;
+}
+
 int32_t sarw_concurrent_capacity(sarw_ctx* c)
 {
 	if (!c) return 0;

@@ -146,8 +146,11 @@ __global__ void __launch_bounds__(RDF_TILE) rdf_pairs_kernel(RdfBox b, const Rdf
 				if (!(r2 >= T0) || r2 >= Tn) continue;
 				int k = (int)((__fsqrt_rn((float)r2) - rMin) * invDr);      // estimate, then settle on the exact thresholds
 				k = k < 0 ? 0 : (k >= nBins ? nBins - 1 : k);
-				while (k > 0 && r2 < sT[k]) --k;
-				while (k + 1 < nBins && r2 >= sT[k + 1]) ++k;
+				{	// settle on the exact thresholds: the estimate is right or off by one, so the usual cost is two loads and two compares
+					const double lo = sT[k], hi = sT[k + 1];
+					if (r2 < lo) { do { --k; } while (k > 0 && r2 < sT[k]); }
+					else if (r2 >= hi) { do { ++k; } while (k + 1 < nBins && r2 >= sT[k + 1]); }
+				}
 				atomicAdd(&hist[(same ? 0 : nBins) + k], 1u);
 			}
 		}

@@ -464,6 +464,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) grow_cluster_kernel(GrowArgs A)
 	const bool timer = (myCta == 0 && threadIdx.x == 0);
 	long long cycA = 0, cycV = 0, cycC = 0; uint32_t cleanRounds = 0;
 	long long sub[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }, ts0 = 0, ts1 = 0;
+	long long pathCyc[4] = { 0, 0, 0, 0 }; uint32_t pathCnt[4] = { 0, 0, 0, 0 };
 #define SUBT(k) do { ts1 = clock64(); sub[k] += ts1 - ts0; ts0 = ts1; } while (0)
 
 	while (round < A.roundEnd && (long long)nBeads < g.target && lastProg) {
@@ -481,10 +482,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) grow_cluster_kernel(GrowArgs A)
 		float offs[3] = { 0, 0, 0 };                       // in-cell offset of the accepted bead (for the slot store)
 		double vAcc[3] = { 0, 0, 0 };                     // its fractional coordinates
 		uint32_t oldCount = 0xFFFFFFFFu;                   // beads its cell held at round start (from the staged copy)
+		int path = 0;
 		if (active && (cs.flags & CHAIN_DEAD)) rec.trial = T_ + 1u;
 		else if (active) {
+			path = hard ? 3 : 1;
 			accepted = propose_chain(g, A.T, A.ctl, A.chains, i, round, idRound, cs, f, rp, hard, raw, nb, NBCAP, arcs, ARCCAP, mbar, tmaParity, lane, cand, vAcc, myQueries);
 			hard = accepted == 0u || accepted > 32u;
+			if (path == 1 && hard) path = 2;
 			rec.trial = accepted ? accepted : T_ + 1u;
 			if (accepted) {
 				rec.x = cand[0]; rec.y = cand[1]; rec.z = cand[2];
@@ -513,6 +517,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) grow_cluster_kernel(GrowArgs A)
 			for (unsigned c = lane; c < nCta; c += 32) *cluster.map_shared_rank(&table[par * CL_MAXCH + i], c) = rec;
 		SUBT(4);
 		myBusy += clock64() - tk0;
+		if (active) { pathCyc[path] += clock64() - tk0; pathCnt[path]++; }
 		cluster_arrive();
 		// in the shadow of the barrier: next round's chain state, frame and region, assuming the tentative bead stands (it almost
 		// always does). The old state is recoverable: old last = new pen, old lastId = new penId; only the old pen is kept aside.
@@ -631,6 +636,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) grow_cluster_kernel(GrowArgs A)
 	if (i == 0 && lane == 0) { A.ctl->round = round; A.ctl->nBeads = nBeads; A.ctl->lastProgressed = lastProg ? 1u : 0u; }
 	if (timer) for (int k = 0; k < 8; k++) A.ctl->cycSub[k] += sub[k];
 	if (lane == 0 && i < 256) A.ctl->busy[i] += (unsigned long long)myBusy;
+	if (lane == 0 && owner) for (int k = 0; k < 4; k++) { atomicAdd(&A.ctl->pathCyc[k], (unsigned long long)pathCyc[k]); atomicAdd(&A.ctl->pathCnt[k], (unsigned long long)pathCnt[k]); }
 	if (timer) { A.ctl->cycPropose += cycA; A.ctl->cycVerify += cycV; A.ctl->cycCleanup += cycC; A.ctl->cleanupRounds += cleanRounds; }
 	cluster_arrive(); cluster_wait();                    // no CTA may exit while others can still write into its shared memory
 }
