@@ -95,6 +95,9 @@ int sarw_propagate_round(sarw_ctx* ctx, int32_t* progressed);
 /* main()'s loop (sarw.cpp:67-78) on the device: rounds until actualCount >= target, a round makes no progress, or
  * maxRounds more rounds were run (maxRounds < 0: unbounded). target <= 0 means SARW::targetCount(). */
 int sarw_grow(sarw_ctx* ctx, int64_t target, int64_t maxRounds, sarw_stats* stats);
+/* The large tables of destroyed contexts are kept per device for the next sarw_create of the same size (up to 24 GB); this hands
+ * them back to the driver. device < 0: every device. */
+int sarw_release_cached_memory(int32_t device);
 /* How many contexts like this one can run sarw_grow at the same time on the device, each on its own stream (sarw_set_stream) from
  * its own host thread: a melt of <= 256 chains occupies one thread-block cluster, i.e. a fraction of the SMs (7 melts of
  * BASELINE configs[1] fit a B200). 1 for larger melts, whose cooperative kernel fills the device. No reference counterpart

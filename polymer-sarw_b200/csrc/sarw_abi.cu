@@ -271,6 +271,8 @@ int sarw_create(const sarw_params* p, sarw_ctx** out)
 	// device facts are queried once per device and process (cudaGetDeviceProperties alone costs milliseconds)
 	struct DevInfo { bool valid; int major, minor, numSMs, coop, growBlocksMax; };
 	static DevInfo devInfo[64] = {};
+	static std::mutex initMutex;                       // contexts may be created from several host threads at once
+	std::unique_lock<std::mutex> initLock(initMutex);
 	DevInfo& di = devInfo[c->device & 63];
 	if (!di.valid) {
 		if (cudaDeviceGetAttribute(&di.major, cudaDevAttrComputeCapabilityMajor, c->device) != cudaSuccess
@@ -281,6 +283,7 @@ int sarw_create(const sarw_params* p, sarw_ctx** out)
 		if (di.major >= 10 && grow_max_blocks(di.numSMs, &di.growBlocksMax) != cudaSuccess) { fail(c, "growth kernels cannot be configured: %s", cudaGetErrorString(cudaGetLastError())); return bail(1); }
 		di.valid = true;
 	}
+	initLock.unlock();
 	if (di.major < 10) { fail(c, "device %d is sm_%d%d; libsarw_b200 is built for sm_100a only", c->device, di.major, di.minor); return bail(1); }
 	c->numSMs = di.numSMs;
 	if (!di.coop) { fail(c, "device lacks cooperative launch"); return bail(1); }
@@ -323,6 +326,8 @@ int sarw_create(const sarw_params* p, sarw_ctx** out)
 		// pool allocations are only reused cheaply by the stream that freed them, so per-context streams would pay the
 		// driver for fresh memory on every sarw_create
 		static cudaStream_t homeStream[64] = {};
+		static std::mutex homeMutex;
+		std::lock_guard<std::mutex> lk(homeMutex);
 		const int d = c->device & 63;
 		if (!homeStream[d] && cudaStreamCreateWithFlags(&homeStream[d], cudaStreamNonBlocking) != cudaSuccess) { fail(c, "cudaStreamCreate failed"); return bail(1); }
 		c->stream = homeStream[d];
@@ -551,6 +556,22 @@ int sarw_debug_paths(sarw_ctx* c, unsigned long long* out)
 	if (!c) return 1;
 	Control h; if (read_control(c, &h)) return 1;
 	for (int k = 0; k < 4; k++) { out[k] = h.pathCyc[k]; out[4 + k] = h.pathCnt[k]; }
+	return 0;
+}
+
+int sarw_release_cached_memory(int32_t device)
+{
+	int cur = 0; cudaGetDevice(&cur);
+	for (int d = 0; d < 64; d++) {
+		if (device >= 0 && d != (device & 63)) continue;
+		BlockCache& bc = g_blocks[d];
+		std::lock_guard<std::mutex> lk(bc.m);
+		if (bc.parked.empty()) continue;
+		cudaSetDevice(d);
+		for (auto& kv : bc.parked) cudaFree(kv.second);   // parked blocks are idle: the synchronous free is safe on any stream
+		bc.parked.clear(); bc.parkedBytes = 0;
+	}
+	cudaSetDevice(cur);
 	return 0;
 }
 

@@ -23,7 +23,7 @@ ABI_SYMBOLS = [
     "sarw_create", "sarw_destroy", "sarw_last_error", "sarw_set_stream", "sarw_add_obstacles", "sarw_set_grafts",
     "sarw_initiate", "sarw_propagate_round", "sarw_grow", "sarw_terminate", "sarw_get_stats", "sarw_target_count",
     "sarw_download", "sarw_chain_lengths", "sarw_round_counts", "sarw_lookup_add_points", "sarw_lookup_find_batch",
-    "sarw_lookup_find_batch_device", "sarw_lookup_size", "sarw_rdf", "sarw_chain_shapes", "sarw_concurrent_capacity",
+    "sarw_lookup_find_batch_device", "sarw_lookup_size", "sarw_rdf", "sarw_chain_shapes", "sarw_concurrent_capacity", "sarw_release_cached_memory",
     "sarw_mr_setup", "sarw_mr_more", "sarw_mr_propose", "sarw_mr_finish", "sarw_mr_commit",
     "sarw_mr_peer_export", "sarw_mr_peer_connect", "sarw_mr_grow_peer",
 ]
@@ -85,6 +85,7 @@ def load_library(path=LIB_PATH):
     lib.sarw_rdf.argtypes = [vp, C.c_double, C.c_double, C.c_int32, vp, vp]
     lib.sarw_chain_shapes.argtypes = [vp, vp, vp]
     lib.sarw_concurrent_capacity.argtypes = [vp]
+    lib.sarw_release_cached_memory.argtypes = [C.c_int32]
     lib.sarw_concurrent_capacity.restype = C.c_int32
     lib.sarw_round_counts.argtypes = [vp, vp, C.c_int64]
     lib.sarw_lookup_add_points.argtypes = [vp, vp, C.c_int64]
@@ -106,6 +107,11 @@ def load_library(path=LIB_PATH):
 def target_count(boxSize, targetMassDensity):
     b = (C.c_double * 3)(*boxSize)
     return load_library().sarw_target_count(b, targetMassDensity)
+
+
+def release_cached_memory(device=-1):
+    """hand the parked tables of destroyed contexts back to the driver"""
+    return load_library().sarw_release_cached_memory(device)
 
 
 def _f64(a):

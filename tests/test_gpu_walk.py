@@ -296,3 +296,18 @@ def test_concurrent_melts_equal_sequential_melts(sarw):
     for seed, (n, (xyz, cid, typ, bonds)) in want.items():
         gn, (gx, gc, gt, gb) = got[seed]
         assert gn == n and np.array_equal(gx, xyz) and np.array_equal(gc, cid) and np.array_equal(gt, typ) and np.array_equal(gb, bonds), seed
+
+
+def test_release_cached_memory_and_reuse(sarw):
+    """destroyed contexts park their tables; releasing them and creating again still gives the same walk"""
+    cfg = cases.SMALL_DEFAULTS
+    def one():
+        s = sarw.SARW(cfg["nChains"], cfg["boxSize"], cfg["minDist"], seed=9, **{k: v for k, v in cfg.items() if k not in ("nChains", "boxSize", "minDist")})
+        s.run(); out = s.ctx.download(); s.close()
+        return out
+    a = one()
+    assert sarw.release_cached_memory(-1) == 0
+    b = one()
+    c = one()
+    for x, y, z in zip(a, b, c):
+        assert np.array_equal(x, y) and np.array_equal(x, z)
