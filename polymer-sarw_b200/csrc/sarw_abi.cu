@@ -550,6 +550,9 @@ static cudaError_t launch_grow_auto(sarw_ctx* c, const Geom& g, uint32_t roundEn
 		c->dirtyList, roundEnd, blocks, 0, c->stream);
 }
 
+// diagnostics (not in the ABI header): fast-path step cycles of a -DSARW_PROF build
+int sarw_debug_prof(unsigned long long* out, int n, int reset) { cudaDeviceSynchronize(); return prof_read(out, n, reset != 0) == cudaSuccess ? 0 : 1; }
+
 // diagnostics (not in the ABI header): out[8] = propose cycles and chain-rounds by path (dead, fast, fast->hard, hard) of the cluster kernel
 int sarw_debug_paths(sarw_ctx* c, unsigned long long* out)
 {

@@ -294,6 +294,21 @@ __device__ __forceinline__ int region_consume(const Geom& g, const RegionPlan& r
 // No global writes except marking a chain dead. Fast path: the exact candidates of trials 1..32 are prepared lane-parallel
 // while the region is being staged, then tested lane-per-trial; chains that found nothing there (`hard`) go through the
 // blocked-arc classification of all remaining trials.
+// -DSARW_PROF: cycles between the steps of the fast path, summed over every chain-round (slot k), and a histogram of the whole
+// propose time per chain-round in 512-cycle bins (slots 16..47); read back with sarw_debug_prof. Off in the shipped library.
+#ifdef SARW_PROF
+constexpr int PROF_ROWS = 4096;                         // one row of 64 counters per warp (mod 4096): no contention between warps
+__device__ unsigned long long g_prof[64 * PROF_ROWS];
+#define PROF_ROW() (g_prof + 64 * ((blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) & (PROF_ROWS - 1)))
+#define PROF_BEGIN() long long prof_t0_ = clock64(), prof_tp_ = prof_t0_
+#define PROF_MARK(k) do { const long long t_ = clock64(); if (lane == 0) atomicAdd(PROF_ROW() + (k), (unsigned long long)(t_ - prof_tp_)); prof_tp_ = t_; } while (0)
+#define PROF_END() do { if (lane == 0) { long long d_ = (clock64() - prof_t0_) >> 9; d_ = d_ > 31 ? 31 : d_; atomicAdd(PROF_ROW() + 16 + d_, 1ull); atomicAdd(PROF_ROW() + 15, 1ull); } } while (0)
+#else
+#define PROF_BEGIN() do { } while (0)
+#define PROF_MARK(k) do { } while (0)
+#define PROF_END() do { } while (0)
+#endif
+
 __device__ __forceinline__ uint32_t propose_chain(const Geom& g, const Tables& T, Control* ctl, ChainState* chains, uint32_t i, uint32_t round,
 	uint32_t idRound, ChainState& cs, const Frame& f, const RegionPlan& rp, bool hard, Cell* raw, float4* nb, int nbCap, float4* arcs, int arcCap, void* mbar,
 	unsigned& tmaParity, int lane, double cand[3], double vAcc[3], unsigned long long& queries)
@@ -302,11 +317,13 @@ __device__ __forceinline__ uint32_t propose_chain(const Geom& g, const Tables& T
 	uint32_t accepted = 0;
 	bool regionOvf = false; int nnb = -1; int narcs = -1;
 	const bool canStage = rp.ncell <= CL_REGION_CELLS;
+	PROF_BEGIN();
 #ifndef SARW_STAGE_LDGSTS
 	if (canStage) region_issue_tma(g, T, rp, raw, mbar, lane);   // bulk copies in flight ...
 #else
 	if (canStage) region_issue_ldgsts(g, T, rp, raw, lane);      // async copies in flight ...
 #endif
+	PROF_MARK(0);   // copies issued
 	// ... while every lane prepares the exact candidate of trial lane+1 (reference arithmetic)
 	double candL[3], vL[3]; bool okL = false; float rel[3] = { 0, 0, 0 };
 	if (!hard) {
@@ -316,15 +333,25 @@ __device__ __forceinline__ uint32_t propose_chain(const Geom& g, const Tables& T
 		to_frac(g, candL, vL);
 		rel[0] = (float)(candL[0] - cs.last[0]); rel[1] = (float)(candL[1] - cs.last[1]); rel[2] = (float)(candL[2] - cs.last[2]);
 	}
+	PROF_MARK(1);   // candidates of trials 1..32 computed
 	if (canStage) {
 #ifndef SARW_STAGE_LDGSTS
 		mbar_wait(mbar, tmaParity); tmaParity ^= 1u;
 #else
 		region_wait_ldgsts();
 #endif
+		PROF_MARK(2);   // waited for the copies
 		nnb = region_consume(g, rp, raw, idRound, cs.lastId, nb, nbCap, lane, regionOvf);
+		PROF_MARK(3);   // neighbour list compacted
+#ifdef SARW_PROF
+		if (lane == 0) { atomicAdd(PROF_ROW() + 8, (unsigned long long)(nnb > 0 ? nnb : 0)); atomicAdd(PROF_ROW() + 9, (unsigned long long)rp.ncell); atomicAdd(PROF_ROW() + 10, (unsigned long long)(rp.nn[1] * rp.nn[2])); }
+#endif
 	} else regionOvf = true;
 	const uint32_t novf = regionOvf ? __ldcg(T.ovfCount) : 0u;
+#ifdef SARW_PROF
+	if (lane == 0 && regionOvf) atomicAdd(PROF_ROW() + 12, 1ull);
+	PROF_MARK(5);
+#endif
 	if (!hard) {
 		// fast path: lane-per-trial exact test of trials 1..32 against the staged neighbourhood
 		if (okL) {
@@ -339,6 +366,9 @@ __device__ __forceinline__ uint32_t propose_chain(const Geom& g, const Tables& T
 					inBand += (d2 <= g.hi2);
 					if (d2 < dmin) { dmin = d2; jmin = j; }
 				}
+#ifdef SARW_PROF
+				{ const unsigned anyBand = __ballot_sync(__activemask(), inBand && !(dmin < g.lo2)); if (anyBand && lane == (__ffs(__activemask()) - 1)) atomicAdd(PROF_ROW() + 11, 1ull); }
+#endif
 				if (dmin < g.lo2) okL = false;
 				else if (inBand) {   // some bead within the undecided band (rare): exact reference arithmetic on those
 					for (int j = 0; j < nnb && okL; ++j) {
@@ -360,6 +390,7 @@ __device__ __forceinline__ uint32_t propose_chain(const Geom& g, const Tables& T
 			} else okL = !probe_cells<1>(g, T, vL, 0u, idRound, cs.lastId, 0);
 		}
 		const unsigned m = __ballot_sync(FULL, okL);
+		PROF_MARK(4);   // 32 trials tested
 		queries += (lane == 0) ? (T_ < 32u ? T_ : 32u) : 0u;
 		if (m) {
 			const int first = __ffs(m) - 1;
@@ -418,6 +449,7 @@ __device__ __forceinline__ uint32_t propose_chain(const Geom& g, const Tables& T
 			if (lane == 0) { chains[i].flags = cs.flags; atomicAdd(&ctl->deadChains, 1u); }
 		}
 	}
+	PROF_END();
 	return accepted;
 }
 

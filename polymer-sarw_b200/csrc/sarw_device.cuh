@@ -318,12 +318,15 @@ __device__ __forceinline__ bool probe_cells(const Geom& g, const Tables& T, cons
 		int ix = ci % n[0], rest = ci / n[0];
 		int iy = rest % n[1], iz = rest / n[1];
 		const Cell* cell = T.cells + cell_index(g, wrap_cell(c0[0] + ix, g.S[0]), wrap_cell(c0[1] + iy, g.S[1]), wrap_cell(c0[2] + iz, g.S[2]));
-		const uint2 hdr = __ldcg(reinterpret_cast<const uint2*>(cell));
-		uint32_t cnt = hdr.x + 1u;
-		anyOvf |= (hdr.y != ID_NONE);
+		// header and first slot share the first 32-byte sector of the cell's line: one 256-bit load, one round trip for cells with <= 1 bead
+		uint32_t w[8];
+		asm volatile("ld.global.cg.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+			: "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(cell));
+		uint32_t cnt = w[0] + 1u;
+		anyOvf |= (w[1] != ID_NONE);
 		if (cnt > (uint32_t)g.cap) cnt = (uint32_t)g.cap;
 		for (uint32_t s = 0; s < cnt; ++s) {
-			float4 b = __ldcg(&cell->slot[s]);
+			float4 b = s == 0 ? make_float4(__uint_as_float(w[4]), __uint_as_float(w[5]), __uint_as_float(w[6]), __uint_as_float(w[7])) : __ldcg(&cell->slot[s]);
 			uint32_t id = __float_as_uint(b.w);
 			if (id < idLo || id >= idHi || id == ignoreId) continue;
 			float dx = q[0][ix] + b.x, dy = q[1][iy] + b.y, dz = q[2][iz] + b.z;

@@ -28,6 +28,7 @@ cudaError_t launch_find_batch(const Geom& g, const Tables& T, const double* xyz,
 	void* scratch, cudaStream_t st);
 size_t find_scratch_bytes(const Geom& g, int64_t n);
 int cluster_max_active(uint32_t nChains);
+cudaError_t prof_read(unsigned long long* out, int n, bool reset);   // -DSARW_PROF builds only
 // analysis (sarw_analysis.cu)
 size_t rdf_scratch_bytes(int64_t n, size_t* cubBytes);
 cudaError_t launch_rdf(const double box[3], const double* d_xyz, const int32_t* d_chain, int64_t n, const double* d_thresh2, int nBins,

@@ -17,6 +17,8 @@
 #include "sarw_host.h"
 #include <cub/device/device_scan.cuh>
 #include <cooperative_groups.h>
+#include <vector>
+#include <algorithm>
 
 namespace sarw {
 
@@ -577,6 +579,42 @@ __device__ __forceinline__ ChainState load_chain(const ChainState* p)
 	return cs;
 }
 
+// Prefetch of everything phase A needs to open a chain: one 32-bit word per lane (lanes 0-15 the chain state, 16-21 the position
+// the last round settled on, 22 its trial), issued while the previous chain of this warp is processed, so the two dependent
+// round trips to L2/HBM (state + trial, then position: 2.7k cycles per chain, measured) disappear from the per-chain latency.
+__device__ __forceinline__ uint32_t chain_prefetch(const GrowArgs& A, uint32_t i, int lane)
+{
+	const uint32_t* p = lane < 16 ? reinterpret_cast<const uint32_t*>(A.chains + i) + lane
+		: lane < 22 ? reinterpret_cast<const uint32_t*>(A.resPos + 3 * (size_t)i) + (lane - 16)
+		: reinterpret_cast<const uint32_t*>(A.resTrial + i);
+	return lane < 23 ? __ldcg(p) : 0u;
+}
+__device__ __forceinline__ double pf_double(uint32_t pf, int w)
+{	return __hiloint2double((int)__shfl_sync(FULL, pf, w + 1), (int)__shfl_sync(FULL, pf, w));
+}
+// state of chain i from its prefetched words, with the pending result of `pendingRound` committed (commit_pending's effect)
+__device__ __forceinline__ ChainState chain_open(const GrowArgs& A, uint32_t i, uint32_t pf, bool pendingValid, uint32_t pendingRound, int lane)
+{
+	const Geom& g = A.g;
+	ChainState cs;
+#pragma unroll
+	for (int k = 0; k < 3; k++) { cs.last[k] = pf_double(pf, 2 * k); cs.pen[k] = pf_double(pf, 6 + 2 * k); }
+	cs.lastId = __shfl_sync(FULL, pf, 12); cs.penId = __shfl_sync(FULL, pf, 13); cs.length = __shfl_sync(FULL, pf, 14); cs.flags = __shfl_sync(FULL, pf, 15);
+	if (pendingValid) {
+		const uint32_t t = __shfl_sync(FULL, pf, 22);
+		if (t >= 1u && t <= (uint32_t)g.maxTrials) {
+			const uint32_t id = round_id_base(g, pendingRound) + i;
+#pragma unroll
+			for (int k = 0; k < 3; k++) { cs.pen[k] = cs.last[k]; cs.last[k] = pf_double(pf, 16 + 2 * k); }
+			if (lane == 0) A.prev[id - g.idAtomBase] = cs.lastId;
+			cs.penId = cs.lastId; cs.lastId = id; cs.length += 1;
+			if (lane == 0) A.chains[i] = cs;
+		}
+		if (t != 0 && lane == 0) A.resTrial[i] = 0;
+	}
+	return cs;
+}
+
 // ------------------------------------------------------------------ same-round conflict resolution
 // re-resolve ONE conflicting chain with the whole warp: drop its current bead, search from the trial phase A stopped at
 // against the beads of the previous rounds plus this round's beads of LOWER chains, insert the new bead, report the
@@ -783,9 +821,16 @@ __global__ void __launch_bounds__(WARPS * 32) grow_kernel(GrowArgs A)
 			for (uint32_t i = (gw * 32 + lane); i < g.nChains; i += nW * 32)
 				if ((i % A.mrRanks) != A.mrRank) commit_pending_thread(A, i, round - 1);
 		if (phase != 2u)
-		for (uint32_t i = mr ? A.mrRank + gw * A.mrRanks : gw; i < g.nChains; i += mr ? nW * A.mrRanks : nW) {
-			ChainState cs = load_chain(A.chains + i);
-			if (pendingValid) commit_pending(A, i, round - 1, cs, lane);
+		{
+		const uint32_t iFirst = mr ? A.mrRank + gw * A.mrRanks : gw, iStride = mr ? nW * A.mrRanks : nW;
+		uint32_t pf = iFirst < g.nChains ? chain_prefetch(A, iFirst, lane) : 0u;
+		for (uint32_t i = iFirst; i < g.nChains; i += iStride) {
+#ifdef SARW_PROF
+			long long prof_tp_ = clock64();
+#endif
+			ChainState cs = chain_open(A, i, pf, pendingValid, round - 1, lane);
+			if (i + iStride < g.nChains) pf = chain_prefetch(A, i + iStride, lane);   // in flight while this chain is worked on
+			PROF_MARK(48);   // state opened, last round committed
 			if (i < start || i >= end) continue;
 			if (cs.flags & CHAIN_DEAD) {   // permanently blocked: the reference burns maxTrials here every round
 				if (lane == 0) {
@@ -796,11 +841,13 @@ __global__ void __launch_bounds__(WARPS * 32) grow_kernel(GrowArgs A)
 			}
 			Frame f; RegionPlan rp;
 			prepare_chain(g, cs, f, rp);
+			PROF_MARK(49);   // frame + region plan
 			const bool hard = (cs.flags & CHAIN_HARD) != 0u;
 			double cand[3] = { 0, 0, 0 }, vAcc[3] = { 0, 0, 0 };
 			const uint32_t flagsBefore = cs.flags;
 			const uint32_t accepted = propose_chain(g, A.T, A.ctl, A.chains, i, round, idRound, cs, f, rp, hard, raw, nb, GROW_NB_CAP, arcs, GROW_ARC_CAP, mbar, tmaParity, lane,
 				cand, vAcc, myQueries);
+			PROF_MARK(50);   // propose_chain
 			const bool hardNow = accepted == 0u || accepted > 32u;
 			cs.flags = (cs.flags & ~CHAIN_HARD) | (hardNow ? CHAIN_HARD : 0u);
 			if (lane == 0) {
@@ -813,6 +860,9 @@ __global__ void __launch_bounds__(WARPS * 32) grow_kernel(GrowArgs A)
 				A.origTrial[i] = accepted ? accepted : T_ + 1u;
 				if (mr) { MrRecord r; r.x = cand[0]; r.y = cand[1]; r.z = cand[2]; r.trial = accepted ? accepted : T_ + 1u; r.pad = 0; mr_publish(A, i, round, r); }
 			}
+			__syncwarp();
+			PROF_MARK(51);   // tentative insert + result stores (lane 0)
+		}
 		}
 		SUBT(0);
 		if (phase == 1u) break;                                  // the host all-gathers the records, then launches phase 2
@@ -863,8 +913,10 @@ __global__ void __launch_bounds__(WARPS * 32) grow_kernel(GrowArgs A)
 				bool h = false; uint32_t t = 0;
 				if (i < end) {
 					t = __ldcg(&A.resTrial[i]);
+					// position loaded together with the trial (always in bounds; garbage when there is no bead, then unused): one round trip, not two
+					double pos[3] = { __ldcg(&A.resPos[3 * (size_t)i]), __ldcg(&A.resPos[3 * (size_t)i + 1]), __ldcg(&A.resPos[3 * (size_t)i + 2]) };
 					if (t <= T_ && i > start) {
-						double pos[3] = { __ldcg(&A.resPos[3 * (size_t)i]), __ldcg(&A.resPos[3 * (size_t)i + 1]), __ldcg(&A.resPos[3 * (size_t)i + 2]) }, v[3];
+						double v[3];
 						to_frac(g, pos, v);
 						h = probe_cells<8>(g, A.T, v, idRound, idRound + i, ID_NONE, sub);
 					}
@@ -1084,6 +1136,19 @@ static cudaError_t launch_cluster(const GrowArgs& A, cudaStream_t st)
 	cfg.attrs = attr; cfg.numAttrs = 1;
 	return cudaLaunchKernelEx(&cfg, grow_cluster_kernel<WARPS>, A);
 }
+
+#ifdef SARW_PROF
+cudaError_t prof_read(unsigned long long* out, int n, bool reset)
+{
+	std::vector<unsigned long long> h((size_t)64 * PROF_ROWS);
+	CK(cudaMemcpyFromSymbol(h.data(), g_prof, h.size() * sizeof(unsigned long long)));
+	for (int k = 0; k < n && k < 64; k++) { unsigned long long s = 0; for (int r = 0; r < PROF_ROWS; r++) s += h[(size_t)64 * r + k]; out[k] = s; }
+	if (reset) { std::fill(h.begin(), h.end(), 0ull); CK(cudaMemcpyToSymbol(g_prof, h.data(), h.size() * sizeof(unsigned long long))); }
+	return cudaSuccess;
+}
+#else
+cudaError_t prof_read(unsigned long long*, int, bool) { return cudaErrorNotSupported; }
+#endif
 
 // diagnostics: how many clusters of the size launch_cluster would use for nChains chains can be resident at once
 int cluster_max_active(uint32_t nChains)
