@@ -772,7 +772,7 @@ __device__ __forceinline__ void round_barrier(Control* ctl)
 // MR = false: single-GPU instantiation, every multi-rank path is compiled out (they cost the 128-register kernel 170 -> 510 bytes of
 // spill traffic and 13 % of its speed when they were selected at run time); MR = true: the phases of a multi-rank round
 template <int WARPS, bool MR>
-__global__ void __launch_bounds__(WARPS * 32) grow_kernel(GrowArgs A)
+__global__ void __launch_bounds__(WARPS * 32, 2) grow_kernel(GrowArgs A)
 {
 	constexpr int GROW_WARPS = WARPS;
 	extern __shared__ __align__(128) unsigned char growSmem[];
@@ -823,13 +823,20 @@ __global__ void __launch_bounds__(WARPS * 32) grow_kernel(GrowArgs A)
 		if (phase != 2u)
 		{
 		const uint32_t iFirst = mr ? A.mrRank + gw * A.mrRanks : gw, iStride = mr ? nW * A.mrRanks : nW;
-		uint32_t pf = iFirst < g.nChains ? chain_prefetch(A, iFirst, lane) : 0u;
+		// (the prefetch is left out of the multi-rank instantiation: there it costs more in spills than it hides in latency)
+		uint32_t pf = (!MR && iFirst < g.nChains) ? chain_prefetch(A, iFirst, lane) : 0u;
 		for (uint32_t i = iFirst; i < g.nChains; i += iStride) {
 #ifdef SARW_PROF
 			long long prof_tp_ = clock64();
 #endif
-			ChainState cs = chain_open(A, i, pf, pendingValid, round - 1, lane);
-			if (i + iStride < g.nChains) pf = chain_prefetch(A, i + iStride, lane);   // in flight while this chain is worked on
+			ChainState cs;
+			if (MR) {
+				cs = load_chain(A.chains + i);
+				if (pendingValid) commit_pending(A, i, round - 1, cs, lane);
+			} else {
+				cs = chain_open(A, i, pf, pendingValid, round - 1, lane);
+				if (i + iStride < g.nChains) pf = chain_prefetch(A, i + iStride, lane);   // in flight while this chain is worked on
+			}
 			PROF_MARK(48);   // state opened, last round committed
 			if (i < start || i >= end) continue;
 			if (cs.flags & CHAIN_DEAD) {   // permanently blocked: the reference burns maxTrials here every round
