@@ -2,6 +2,7 @@
 // No CPU fallback anywhere: every entry point needs a CUDA device and fails with an error text otherwise.
 #include "sarw_abi.h"
 #include "sarw_host.h"
+#include <cuda.h>
 #include <cmath>
 #include <cstdio>
 #include <cstdarg>
@@ -30,6 +31,7 @@ struct sarw_ctx {
 	Tables T{};
 	int device = 0, numSMs = 0, growBlocksMax = 0;
 	cudaStream_t stream = nullptr; bool ownStream = false;
+	alignas(64) CUtensorMap tmapHost;     // tensor map of the cell table (copied into the kernel parameters of every growth launch)
 	cudaStream_t allocStream = nullptr;   // all pool allocations / frees go through the device's home stream (cheap reuse)
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	std::string err;
@@ -347,6 +349,33 @@ int sarw_create(const sarw_params* p, sarw_ctx** out)
 	CUB_(dev_alloc(c, &c->T.cells, nCells * sizeof(Cell)));
 	mark("cells alloc");
 	CUB_(cudaMemsetAsync(c->T.cells, 0xFF, nCells * sizeof(Cell), c->stream));
+	c->T.tmapHost = nullptr; g.useTmap = 0;
+	if (g.S[0] >= 4 && g.S[1] >= 4 && g.S[2] >= 4 && !(getenv("SARW_NO_TMAP") && atoi(getenv("SARW_NO_TMAP")))) {
+		// 3-D tensor map over the cell table (x in 4-byte elements, 32 per cell; y; z), box = 4 x 4 x 4 cells: a chain's whole
+		// neighbourhood is staged by ONE TMA instruction instead of one bulk copy per x-row (each costs ~100 issue cycles).
+		// The map travels in the kernel parameters (__grid_constant__): no device copy, nothing to upload in sarw_create.
+		typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+			const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+		static EncodeFn encode = nullptr; static bool looked = false; static std::mutex encMutex;
+		{	std::lock_guard<std::mutex> lk(encMutex);
+			if (!looked) {
+				void* fn = nullptr; cudaDriverEntryPointQueryResult qr;
+				if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess) encode = (EncodeFn)fn;
+				else cudaGetLastError();
+				looked = true;
+			}
+		}
+		if (encode) {
+			const cuuint64_t dims[3] = { (cuuint64_t)g.S[0] * (sizeof(Cell) / 4), (cuuint64_t)g.S[1], (cuuint64_t)g.S[2] };
+			const cuuint64_t strides[2] = { (cuuint64_t)g.S[0] * sizeof(Cell), (cuuint64_t)g.S[0] * g.S[1] * sizeof(Cell) };
+			const cuuint32_t box[3] = { 4 * (cuuint32_t)(sizeof(Cell) / 4), 4, 4 }, es[3] = { 1, 1, 1 };
+			if (encode(&c->tmapHost, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, c->T.cells, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+					CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
+				static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap is copied into a 128-byte kernel parameter");
+				c->T.tmapHost = &c->tmapHost; g.useTmap = 1;
+			}
+		}
+	}
 	c->T.ovfCap = 1u << 20;
 	CUB_(dev_alloc(c, &c->T.ovf, (size_t)c->T.ovfCap * sizeof(uint4)));
 	CUB_(dev_alloc(c, &c->T.ovfCount, sizeof(uint32_t)));

@@ -155,7 +155,13 @@ __device__ __forceinline__ bool arcs_cs_cover_circle(const float4* arcs, int nar
 // TMA staging: the region (<= 4x4x4 cells, x-rows contiguous in memory) is copied row by row into the warp's shared
 // memory with cp.async.bulk (one lane per row, completion on a per-warp mbarrier). The copies cost no registers and
 // no issue slots while in flight, so the warp prepares its exact candidates meanwhile.
-struct RegionPlan { int lo[3], nn[3], ncell; float base[3]; };
+// tile != 0: the region lies inside the table without crossing the periodic boundary and spans <= 4 cells per dimension: it is staged
+// by ONE 3-D tensor copy as a fixed 4 x 4 x 4 box (row stride 4, layer stride 16); otherwise compact (row stride nn0, layer nn0*nn1)
+struct RegionPlan { int lo[3], nn[3], ncell; float base[3]; int tile; };
+constexpr int REGION_BOX = 4;
+__device__ __forceinline__ int region_index(const RegionPlan& rp, int ix, int iy, int iz)
+{	return rp.tile ? (iz * REGION_BOX + iy) * REGION_BOX + ix : (iz * rp.nn[1] + iy) * rp.nn[0] + ix;
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(void* mbar, unsigned count)
@@ -175,6 +181,11 @@ __device__ __forceinline__ void tma_load_1d(void* dstSmem, const void* srcGlobal
 		:: "r"(smem_u32(dstSmem)), "l"(srcGlobal), "r"(bytes), "r"(smem_u32(mbar)) : "memory");
 }
 
+// one instruction for the whole region: 3-D tiled tensor copy (coordinates: x in 4-byte elements, 32 per cell; y, z in cells)
+__device__ __forceinline__ void tma_load_box3d(void* dstSmem, const void* tmap, int c0, int c1, int c2, void* mbar)
+{	asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+		:: "r"(smem_u32(dstSmem)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(mbar)) : "memory");
+}
 __device__ __forceinline__ int wrap_near(int c, int S)   // c is normally within one period of [0,S): no integer division
 {	c += (c < 0) ? S : 0;
 	c -= (c >= S) ? S : 0;
@@ -201,13 +212,23 @@ __device__ __forceinline__ void prepare_chain(const Geom& g, const ChainState& c
 		rp.ncell *= rp.nn[k];
 		rp.base[k] = (float)((double)rp.lo[k] * g.a[k] - lw);
 	}
+	rp.tile = g.useTmap && rp.nn[0] <= REGION_BOX && rp.nn[1] <= REGION_BOX && rp.nn[2] <= REGION_BOX
+		&& rp.lo[0] >= 0 && rp.lo[1] >= 0 && rp.lo[2] >= 0 && rp.lo[0] + rp.nn[0] <= g.S[0] && rp.lo[1] + rp.nn[1] <= g.S[1] && rp.lo[2] + rp.nn[2] <= g.S[2];
 }
 
 // one lane per x-row: bulk-copy its nn0 cells (split in two when the row crosses the periodic boundary)
-__device__ __forceinline__ void region_issue_tma(const Geom& g, const Tables& T, const RegionPlan& rp, Cell* raw, void* mbar, int lane)
+__device__ __forceinline__ void region_issue_tma(const Geom& g, const Tables& T, const void* tmap, const RegionPlan& rp, Cell* raw, void* mbar, int lane)
 {
 	// (the generic-proxy reads of `raw` from the previous round completed long ago: their results were consumed and two
 	// cluster barriers lie in between, so the async-proxy writes issued here cannot overtake them)
+	if (rp.tile) {   // the usual case: one tensor copy of the 4 x 4 x 4 box (cells beyond the table edge arrive as zeros and are never read)
+		if (lane == 0) {
+			mbar_expect_tx(mbar, (unsigned)(REGION_BOX * REGION_BOX * REGION_BOX) * (unsigned)sizeof(Cell));
+			tma_load_box3d(raw, tmap, rp.lo[0] * (int)(sizeof(Cell) / 4), rp.lo[1], rp.lo[2], mbar);
+		}
+		__syncwarp();
+		return;
+	}
 	if (lane == 0) mbar_expect_tx(mbar, (unsigned)rp.ncell * (unsigned)sizeof(Cell));
 	__syncwarp();
 	const int rows = rp.nn[1] * rp.nn[2];
@@ -256,13 +277,16 @@ __device__ __forceinline__ int region_consume(const Geom& g, const RegionPlan& r
 	float4* nb, int nbCap, int lane, bool& regionOvf)
 {
 	const float inv0 = 1.0f / (float)rp.nn[0], inv1 = 1.0f / (float)rp.nn[1];
-	uint32_t cnt[2] = { 0, 0 }; float sh[2][3]; bool ovf = false;
+	uint32_t cnt[2] = { 0, 0 }; float sh[2][3]; bool ovf = false; int at_[2] = { 0, 0 };
 #pragma unroll
 	for (int q = 0; q < 2; q++) {
 		const int ci = lane + 32 * q;
 		sh[q][0] = sh[q][1] = sh[q][2] = 0.f;
 		if (ci < rp.ncell) {
-			const uint2 hdr = *reinterpret_cast<const uint2*>(raw + ci);
+			const int rest_ = (int)(((float)ci + 0.5f) * inv0), ix_ = ci - rest_ * rp.nn[0];
+			const int iz_ = (int)(((float)rest_ + 0.5f) * inv1), iy_ = rest_ - iz_ * rp.nn[1];
+			at_[q] = region_index(rp, ix_, iy_, iz_);
+			const uint2 hdr = *reinterpret_cast<const uint2*>(raw + at_[q]);
 			cnt[q] = hdr.x + 1u; if (cnt[q] > (uint32_t)g.cap) cnt[q] = (uint32_t)g.cap;
 			ovf |= (hdr.y != ID_NONE);
 			const int rest = (int)(((float)ci + 0.5f) * inv0), ix = ci - rest * rp.nn[0];
@@ -281,7 +305,7 @@ __device__ __forceinline__ int region_consume(const Geom& g, const RegionPlan& r
 #pragma unroll
 	for (int q = 0; q < 2; q++)
 		for (uint32_t k = 0; k < cnt[q]; ++k) {
-			const float4 b = raw[lane + 32 * q].slot[k];
+			const float4 b = raw[at_[q]].slot[k];
 			const uint32_t id = __float_as_uint(b.w);
 			nb[at++] = (id >= idLimit || id == ignoreId) ? make_float4(1e30f, 1e30f, 1e30f, __uint_as_float(ID_NONE))
 				: make_float4(sh[q][0] + b.x, sh[q][1] + b.y, sh[q][2] + b.z, b.w);
@@ -309,7 +333,7 @@ __device__ unsigned long long g_prof[64 * PROF_ROWS];
 #define PROF_END() do { } while (0)
 #endif
 
-__device__ __forceinline__ uint32_t propose_chain(const Geom& g, const Tables& T, Control* ctl, ChainState* chains, uint32_t i, uint32_t round,
+__device__ __forceinline__ uint32_t propose_chain(const Geom& g, const Tables& T, const void* tmap, Control* ctl, ChainState* chains, uint32_t i, uint32_t round,
 	uint32_t idRound, ChainState& cs, const Frame& f, const RegionPlan& rp, bool hard, Cell* raw, float4* nb, int nbCap, float4* arcs, int arcCap, void* mbar,
 	unsigned& tmaParity, int lane, double cand[3], double vAcc[3], unsigned long long& queries)
 {
@@ -319,7 +343,7 @@ __device__ __forceinline__ uint32_t propose_chain(const Geom& g, const Tables& T
 	const bool canStage = rp.ncell <= CL_REGION_CELLS;
 	PROF_BEGIN();
 #ifndef SARW_STAGE_LDGSTS
-	if (canStage) region_issue_tma(g, T, rp, raw, mbar, lane);   // bulk copies in flight ...
+	if (canStage) region_issue_tma(g, T, tmap, rp, raw, mbar, lane);   // bulk copies in flight ...
 #else
 	if (canStage) region_issue_ldgsts(g, T, rp, raw, lane);      // async copies in flight ...
 #endif
@@ -454,7 +478,7 @@ __device__ __forceinline__ uint32_t propose_chain(const Geom& g, const Tables& T
 }
 
 template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 1) grow_cluster_kernel(GrowArgs A)
+__global__ void __launch_bounds__(WARPS * 32, 1) grow_cluster_kernel(const __grid_constant__ GrowArgs A)
 {
 	extern __shared__ __align__(128) unsigned char clSmem[];
 	Cell* rawAll = reinterpret_cast<Cell*>(clSmem);
@@ -518,7 +542,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) grow_cluster_kernel(GrowArgs A)
 		if (active && (cs.flags & CHAIN_DEAD)) rec.trial = T_ + 1u;
 		else if (active) {
 			path = hard ? 3 : 1;
-			accepted = propose_chain(g, A.T, A.ctl, A.chains, i, round, idRound, cs, f, rp, hard, raw, nb, NBCAP, arcs, ARCCAP, mbar, tmaParity, lane, cand, vAcc, myQueries);
+			accepted = propose_chain(g, A.T, A.tmap, A.ctl, A.chains, i, round, idRound, cs, f, rp, hard, raw, nb, NBCAP, arcs, ARCCAP, mbar, tmaParity, lane, cand, vAcc, myQueries);
 			hard = accepted == 0u || accepted > 32u;
 			if (path == 1 && hard) path = 2;
 			rec.trial = accepted ? accepted : T_ + 1u;
@@ -537,7 +561,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) grow_cluster_kernel(GrowArgs A)
 				if (rp.ncell <= CL_REGION_CELLS) {   // count of the bead's cell at round start, from the staged copy (the cell lies inside the region)
 					const int ix = wrap_near(cc[0] - rp.lo[0], g.S[0]), iy = wrap_near(cc[1] - rp.lo[1], g.S[1]), iz = wrap_near(cc[2] - rp.lo[2], g.S[2]);
 					if (ix < rp.nn[0] && iy < rp.nn[1] && iz < rp.nn[2]) {
-						uint32_t c0 = raw[(iz * rp.nn[1] + iy) * rp.nn[0] + ix].countMinus1 + 1u;
+						uint32_t c0 = raw[region_index(rp, ix, iy, iz)].countMinus1 + 1u;
 						oldCount = c0 > (uint32_t)g.cap ? (uint32_t)g.cap : c0;
 					}
 				}

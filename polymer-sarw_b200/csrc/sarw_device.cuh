@@ -53,6 +53,7 @@ struct Geom {
 	double dSinPhi, dCosPhi;  // BondLength*sin(phi), BondLength*cos(phi)   (sarw.cpp:165,178-180)
 	double bias[3];
 	int biased;
+	int useTmap;              // the launch carries a CUtensorMap of the cell table (3-D, box 4 x 4 x 4 cells): regions are staged with one tensor copy where possible
 	int boundary, graftLoc, growthOrder;
 	int maxTrials;
 	uint32_t key0, key1;
@@ -69,6 +70,7 @@ struct Tables {
 	uint4* ovf;               // overflow list: {cell x, cell y, cell z, lookup index} of beads whose cell was full
 	uint32_t* ovfCount;
 	uint32_t ovfCap;
+	const void* tmapHost;     // HOST pointer to the 128-byte CUtensorMap of the cell table (launch wrappers copy it into the kernel parameters), or nullptr
 };
 
 // ------------------------------------------------------------------ Philox4x32-10 (independent of oracle/philox.h)

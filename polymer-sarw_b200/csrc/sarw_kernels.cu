@@ -18,6 +18,7 @@
 #include <cub/device/device_scan.cuh>
 #include <cooperative_groups.h>
 #include <vector>
+#include <cstring>
 #include <algorithm>
 
 namespace sarw {
@@ -459,6 +460,7 @@ struct GrowArgs {
 	uint32_t* peerFlags[8];       // [r]: rank r's arrival flags: 2 parities x 8 words for the records, then 2 x 8 for the conflict lists
 	uint32_t* peerDirty[8];       // [r]: rank r's conflict-list inbox, 2 parities x mrRanks x (1 + mrK) words (count, chains...)
 	uint32_t mrSplitVerify;       // phase 4: each rank verifies only the chains it proposed and the conflict lists are exchanged
+	alignas(64) unsigned char tmap[128];   // CUtensorMap of the cell table (valid when g.useTmap); read by TMA straight from the kernel parameters
 };
 
 __device__ __forceinline__ uint32_t round_id_base(const Geom& g, uint32_t round)
@@ -772,7 +774,7 @@ __device__ __forceinline__ void round_barrier(Control* ctl)
 // MR = false: single-GPU instantiation, every multi-rank path is compiled out (they cost the 128-register kernel 170 -> 510 bytes of
 // spill traffic and 13 % of its speed when they were selected at run time); MR = true: the phases of a multi-rank round
 template <int WARPS, bool MR>
-__global__ void __launch_bounds__(WARPS * 32, 2) grow_kernel(GrowArgs A)
+__global__ void __launch_bounds__(WARPS * 32, 2) grow_kernel(const __grid_constant__ GrowArgs A)
 {
 	constexpr int GROW_WARPS = WARPS;
 	extern __shared__ __align__(128) unsigned char growSmem[];
@@ -852,7 +854,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) grow_kernel(GrowArgs A)
 			const bool hard = (cs.flags & CHAIN_HARD) != 0u;
 			double cand[3] = { 0, 0, 0 }, vAcc[3] = { 0, 0, 0 };
 			const uint32_t flagsBefore = cs.flags;
-			const uint32_t accepted = propose_chain(g, A.T, A.ctl, A.chains, i, round, idRound, cs, f, rp, hard, raw, nb, GROW_NB_CAP, arcs, GROW_ARC_CAP, mbar, tmaParity, lane,
+			const uint32_t accepted = propose_chain(g, A.T, A.tmap, A.ctl, A.chains, i, round, idRound, cs, f, rp, hard, raw, nb, GROW_NB_CAP, arcs, GROW_ARC_CAP, mbar, tmaParity, lane,
 				cand, vAcc, myQueries);
 			PROF_MARK(50);   // propose_chain
 			const bool hardNow = accepted == 0u || accepted > 32u;
@@ -1177,7 +1179,8 @@ int cluster_max_active(uint32_t nChains)
 cudaError_t launch_grow(const Geom& g, const Tables& T, ChainState* chains, uint32_t* resTrial, uint32_t* origTrial, double* resPos, uint32_t* prev, Control* ctl,
 	uint32_t* roundAcc, uint32_t* roundProg, uint32_t* dirtyCount, uint32_t* dirtyList, uint32_t roundEnd, int blocks, int useCluster, cudaStream_t st)
 {
-	GrowArgs A{ g, T, chains, resTrial, origTrial, resPos, prev, ctl, roundAcc, roundProg, dirtyCount, dirtyList, roundEnd, 0u, 1u, 0u, 0u, nullptr, nullptr, {}, {}, {}, 0u };
+	GrowArgs A{ g, T, chains, resTrial, origTrial, resPos, prev, ctl, roundAcc, roundProg, dirtyCount, dirtyList, roundEnd, 0u, 1u, 0u, 0u, nullptr, nullptr, {}, {}, {}, 0u, {} };
+	if (g.useTmap && T.tmapHost) memcpy(A.tmap, T.tmapHost, sizeof A.tmap); else A.g.useTmap = 0;
 	if (useCluster) {
 		// the whole launch is one thread-block cluster: CTAs are co-scheduled by the hardware, synchronise with
 		// barrier.cluster and exchange tentative beads through distributed shared memory. 8 warps per CTA (255
@@ -1197,7 +1200,8 @@ cudaError_t launch_grow_mr(const Geom& g, const Tables& T, ChainState* chains, u
 {
 	const uint32_t K = (g.nChains + ranks - 1) / ranks;
 	GrowArgs A{ g, T, chains, resTrial, origTrial, resPos, prev, ctl, roundAcc, roundProg, dirtyCount, dirtyList, roundEnd, rank, ranks, phase, K,
-		(MrRecord*)localRec, (const MrRecord*)allRec, {}, {}, {}, splitVerify };
+		(MrRecord*)localRec, (const MrRecord*)allRec, {}, {}, {}, splitVerify, {} };
+	if (g.useTmap && T.tmapHost) memcpy(A.tmap, T.tmapHost, sizeof A.tmap); else A.g.useTmap = 0;
 	for (uint32_t p = 0; p < 8; ++p) {
 		A.peerRec[p] = peerRec && p < ranks ? (MrRecord*)peerRec[p] : nullptr; A.peerFlags[p] = peerFlags && p < ranks ? (uint32_t*)peerFlags[p] : nullptr;
 		A.peerDirty[p] = peerDirty && p < ranks ? (uint32_t*)peerDirty[p] : nullptr;
