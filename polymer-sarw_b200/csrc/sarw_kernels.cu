@@ -825,20 +825,13 @@ __global__ void __launch_bounds__(WARPS * 32, 2) grow_kernel(const __grid_consta
 		if (phase != 2u)
 		{
 		const uint32_t iFirst = mr ? A.mrRank + gw * A.mrRanks : gw, iStride = mr ? nW * A.mrRanks : nW;
-		// (the prefetch is left out of the multi-rank instantiation: there it costs more in spills than it hides in latency)
-		uint32_t pf = (!MR && iFirst < g.nChains) ? chain_prefetch(A, iFirst, lane) : 0u;
+		uint32_t pf = iFirst < g.nChains ? chain_prefetch(A, iFirst, lane) : 0u;
 		for (uint32_t i = iFirst; i < g.nChains; i += iStride) {
 #ifdef SARW_PROF
 			long long prof_tp_ = clock64();
 #endif
-			ChainState cs;
-			if (MR) {
-				cs = load_chain(A.chains + i);
-				if (pendingValid) commit_pending(A, i, round - 1, cs, lane);
-			} else {
-				cs = chain_open(A, i, pf, pendingValid, round - 1, lane);
-				if (i + iStride < g.nChains) pf = chain_prefetch(A, i + iStride, lane);   // in flight while this chain is worked on
-			}
+			ChainState cs = chain_open(A, i, pf, pendingValid, round - 1, lane);
+			if (i + iStride < g.nChains) pf = chain_prefetch(A, i + iStride, lane);   // in flight while this chain is worked on
 			PROF_MARK(48);   // state opened, last round committed
 			if (i < start || i >= end) continue;
 			if (cs.flags & CHAIN_DEAD) {   // permanently blocked: the reference burns maxTrials here every round
