@@ -283,14 +283,12 @@ __device__ __forceinline__ int region_consume(const Geom& g, const RegionPlan& r
 		const int ci = lane + 32 * q;
 		sh[q][0] = sh[q][1] = sh[q][2] = 0.f;
 		if (ci < rp.ncell) {
-			const int rest_ = (int)(((float)ci + 0.5f) * inv0), ix_ = ci - rest_ * rp.nn[0];
-			const int iz_ = (int)(((float)rest_ + 0.5f) * inv1), iy_ = rest_ - iz_ * rp.nn[1];
-			at_[q] = region_index(rp, ix_, iy_, iz_);
+			const int rest = (int)(((float)ci + 0.5f) * inv0), ix = ci - rest * rp.nn[0];
+			const int iz = (int)(((float)rest + 0.5f) * inv1), iy = rest - iz * rp.nn[1];
+			at_[q] = region_index(rp, ix, iy, iz);
 			const uint2 hdr = *reinterpret_cast<const uint2*>(raw + at_[q]);
 			cnt[q] = hdr.x + 1u; if (cnt[q] > (uint32_t)g.cap) cnt[q] = (uint32_t)g.cap;
 			ovf |= (hdr.y != ID_NONE);
-			const int rest = (int)(((float)ci + 0.5f) * inv0), ix = ci - rest * rp.nn[0];
-			const int iz = (int)(((float)rest + 0.5f) * inv1), iy = rest - iz * rp.nn[1];
 			sh[q][0] = rp.base[0] + (float)ix * (float)g.a[0]; sh[q][1] = rp.base[1] + (float)iy * (float)g.a[1]; sh[q][2] = rp.base[2] + (float)iz * (float)g.a[2];
 		}
 	}
@@ -593,18 +591,36 @@ __global__ void __launch_bounds__(WARPS * 32, 1) grow_cluster_kernel(const __gri
 		// ---------------- phase V from the local table: round totals, conflicts with lower chains, slot rank
 		uint32_t acc = 0, prog = 0, rank = 0, tot = 0; bool conflict = false;
 		{
-			for (uint32_t jb = start; jb < end; jb += 32) {
-				const uint32_t j = jb + lane;
-				if (j >= end) continue;
-				const TentRec r = table[par * CL_MAXCH + j];
-				const bool has = r.trial >= 1u && r.trial <= T_;
-				acc += has; prog += (has && r.trial < T_);
-				if (!accepted || !has || j == i) continue;
-				int dx = abs(r.cx - rec.cx), dy = abs(r.cy - rec.cy), dz = abs(r.cz - rec.cz);
-				if (dx == 0 && dy == 0 && dz == 0) { tot++; rank += (j < i); }
-				if (j < i) {   // only beads in the same or an adjacent cell (periodic) can be within thresh
-					dx = min(dx, g.S[0] - dx); dy = min(dy, g.S[1] - dy); dz = min(dz, g.S[2] - dz);
-					if (dx <= 1 && dy <= 1 && dz <= 1) { const double pj[3] = { r.x, r.y, r.z }; conflict = conflict || exact_pair_reg(g, vAcc, pj); }
+			// two records per lane and iteration, the small half of a record first (trial + cell): the position is read only for the rare
+			// record in an adjacent cell. Independent loads in flight instead of one dependent 40-byte read per iteration.
+			for (uint32_t jb = start; jb < end; jb += 64) {
+				uint32_t jj[2] = { jb + (uint32_t)lane, jb + 32u + (uint32_t)lane };
+				uint2 tc[2], cyz[2];
+#pragma unroll
+				for (int u = 0; u < 2; u++) {
+					const TentRec* rp_ = &table[par * CL_MAXCH + (jj[u] < end ? jj[u] : start)];
+					tc[u] = *reinterpret_cast<const uint2*>(&rp_->trial);      // {trial, cx}
+					cyz[u] = *reinterpret_cast<const uint2*>(&rp_->cy);        // {cy, cz}
+				}
+#pragma unroll
+				for (int u = 0; u < 2; u++) {
+					const uint32_t j = jj[u];
+					if (j >= end) continue;
+					const uint32_t trial = tc[u].x;
+					const int rcx = (int)tc[u].y, rcy = (int)cyz[u].x, rcz = (int)cyz[u].y;
+					const bool has = trial >= 1u && trial <= T_;
+					acc += has; prog += (has && trial < T_);
+					if (!accepted || !has || j == i) continue;
+					int dx = abs(rcx - rec.cx), dy = abs(rcy - rec.cy), dz = abs(rcz - rec.cz);
+					if (dx == 0 && dy == 0 && dz == 0) { tot++; rank += (j < i); }
+					if (j < i) {   // only beads in the same or an adjacent cell (periodic) can be within thresh
+						dx = min(dx, g.S[0] - dx); dy = min(dy, g.S[1] - dy); dz = min(dz, g.S[2] - dz);
+						if (dx <= 1 && dy <= 1 && dz <= 1) {
+							const TentRec& r = table[par * CL_MAXCH + j];
+							const double pj[3] = { r.x, r.y, r.z };
+							conflict = conflict || exact_pair_reg(g, vAcc, pj);
+						}
+					}
 				}
 			}
 			// one hardware warp reduction over packed counters (each <= 256 chains: 10 bits are plenty)
@@ -613,6 +629,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) grow_cluster_kernel(const __gri
 			tot = __reduce_add_sync(FULL, tot);
 			conflict = __any_sync(FULL, conflict);
 		}
+		SUBT(0);   // table scan + reductions
 		// ---------------- insert with plain stores: slot = count seen while staging + rank among this round's beads of the cell
 		if (active) {
 			if (accepted && lane == 0) {
@@ -645,7 +662,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) grow_cluster_kernel(const __gri
 				for (unsigned c = lane; c < nCta; c += 32) *cluster.map_shared_rank(const_cast<uint32_t*>(&dirtyWord[par]), c) = 1u;
 		}
 		if (i == 0 && lane == 0) { A.roundAcc[round] = acc; A.roundProg[round] = prog; }
+		SUBT(1);   // insert + result stores
 		cluster_arrive(); cluster_wait();
+		SUBT(2);   // second barrier
 		const long long tk2 = clock64();
 
 		// ---------------- clean-up (rare): the shared serial path through global memory

@@ -12,7 +12,7 @@ for seed in (1, 2, 3):
     pp = (C.c_ulonglong * 8)(); s.ctx.lib.sarw_debug_paths(s.ctx.h, pp); pp = list(pp)
     s.close()
     r = max(1, d["rounds"])
-    names = ["frame", "stage", "arcs", "classify", "evaluate", "publish", "barrier", "-"]
+    names = ["V:scan", "V:insert", "V:barrier2", "A:propose", "A:publish", "A:shadow", "A:barrier1", "-"] if cfg["nChains"] <= 256 else ["frame", "stage", "arcs", "classify", "evaluate", "publish", "barrier", "-"]
     sub = d["cycSub"]
     print(name, seed, f"growMs {d['growMs']:.3f} rounds {r} A {d['cycPropose']/r:.0f} V {d['cycVerify']/r:.0f} C {d['cycCleanup']/r:.0f} | " +
           " ".join(f"{n} {v/r:.0f}" for n, v in zip(names, sub)) + " | paths " + " ".join(f"{n}: {pp[4+k]/max(1,d['rounds']):.1f}/round x {pp[k]/max(1,pp[4+k]):.0f} cyc" for k, n in enumerate(["dead", "fast", "fast->hard", "hard"])) + f" | trials/bead {d['trials']/d['nBeads']:.1f} dead {d['deadChains']} arcFallbacks {d['arcFallbacks']} stageFallbacks {d['stageFallbacks']}")
