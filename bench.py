@@ -39,7 +39,7 @@ WORKLOADS = {
                nChains=10000, boxSize=(632.2, 632.2, 632.2), minDist=1.0, maxTrials=1000, boundary="ppp", targetMassDensity=0.92),
 }
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full capture
-NCU_TRAFFIC = {"C2": (33.65e6, "profiles/r1_grow_cluster_kernel_C2_raw.csv")}
+NCU_TRAFFIC = {"C2": (36.86e6, "profiles/r1_grow_cluster_kernel_C2_raw.csv")}
 # algorithmic bytes per overlap query and per accepted bead
 B_QUERY = 121.0
 B_BEAD = 108.0
