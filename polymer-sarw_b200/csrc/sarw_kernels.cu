@@ -177,9 +177,10 @@ __global__ void __launch_bounds__(256, 3) find_batch_kernel(Geom g, Tables T, co
 		}
 		if (!h && cntPack) {
 #pragma unroll 1
-			for (int ci = 0; ci < 8 && !h; ci++) {
+			while (cntPack && !h) {   // only the cells that hold more than one bead (usually one of the eight)
+				const int ci = (__ffs((int)cntPack) - 1) >> 2;
 				const uint32_t extra = (cntPack >> (4 * ci)) & 15u;
-				if (!extra) continue;
+				cntPack &= ~(15u << (4 * ci));
 				const bool ix = ci & 1, iy = (ci >> 1) & 1, iz = ci >> 2;
 				const Cell* cell = T.cells + cell_index(g, ix ? c[0][1] : c[0][0], iy ? c[1][1] : c[1][0], iz ? c[2][1] : c[2][0]);
 				const float ox = ix ? qo[0][1] : qo[0][0], oy = iy ? qo[1][1] : qo[1][0], oz = iz ? qo[2][1] : qo[2][0];
