@@ -38,6 +38,15 @@ WORKLOADS = {
     "C3": dict(name="PE melt 1e4 chains x 1000 beads, 0.92 g/cc, ppp, minDist 1.0, maxTrials 1000 (BASELINE configs[2])",
                nChains=10000, boxSize=(632.2, 632.2, 632.2), minDist=1.0, maxTrials=1000, boundary="ppp", targetMassDensity=0.92),
 }
+# ONE melt over all N GPUs (strong scaling): not the headline workload, selected with --workload
+ONE_MELT = {
+    "ONE_MELT_1E7": dict(name="ONE PE melt of 1e5 chains, 1.0e7 beads (tip density of a 1000-bead melt), grown by all N GPUs together", nChains=100000,
+                         boxSize=(1362.107287789021,) * 3, minDist=1.0, maxTrials=1000, boundary="ppp", targetMassDensity=0.092),
+    "ONE_MELT_2E8": dict(name="ONE PE melt of 2e5 chains x 1000 beads (2.0e8 beads, 0.92 g/cc), grown by all N GPUs together", nChains=200000,
+                         boxSize=(1716.1476441006014,) * 3, minDist=1.0, maxTrials=1000, boundary="ppp", targetMassDensity=0.92),
+    "ONE_MELT_3E8": dict(name="ONE PE melt of 3e5 chains x 1000 beads (3.0e8 beads, 0.92 g/cc; 121 GB of cells per GPU), grown by all N GPUs together", nChains=300000,
+                         boxSize=(1964.4986505263048,) * 3, minDist=1.0, maxTrials=1000, boundary="ppp", targetMassDensity=0.92),
+}
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full capture
 NCU_TRAFFIC = {"C2": (36.86e6, "profiles/r1_grow_cluster_kernel_C2_raw.csv")}
 # algorithmic bytes per overlap query and per accepted bead
@@ -179,17 +188,76 @@ def aggregate_ranks(dist, device, t_dev, t_e2e, beads, e2e_beads):
     return t[0].item(), t[1].item(), w[0].item(), w[1].item()
 
 
+def run_one_melt(args, w):
+    """Strong scaling: every step grows ONE melt with all N GPUs (replicated state, partitioned proposals and verification, records and
+    conflict lists exchanged inside the persistent kernel over NVLink peer memory). N = 1 runs the single-GPU kernel."""
+    import torch
+    import sarw_b200
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    stream = torch.cuda.current_stream()
+    hbm_peak, peak_src = load_peaks()
+    times, beads, stats = [], 0, None
+    sampler = None
+    for s in range(args.warmup + args.steps):
+        c = sarw_b200.Context(device=local, launchMode=1, **ctx_kwargs(w, 31_000 + s))
+        c.set_stream(stream.cuda_stream)
+        c.initiate()
+        if world > 1:
+            sarw_b200.connect_peers(c, dist, rank, world)
+        torch.cuda.synchronize()
+        if dist: dist.barrier()
+        if s == args.warmup and rank == 0:
+            sampler = ClockSampler(local); sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        st = c.mr_grow_peer(-1) if world > 1 else c.grow(0, -1)
+        e1.record(stream); e1.synchronize()
+        ms = e0.elapsed_time(e1) + st.seedMs
+        if dist:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = t.item()
+        if s >= args.warmup:
+            times.append(ms); beads += st.nBeads; stats = st
+        c.close()
+    if rank == 0:
+        clocks = sampler.stop() if sampler else None
+        t_dev = sum(times) / 1e3
+        line = {"metric": "accepted beads/sec", "value": beads / t_dev, "unit": "beads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": w["name"], "multi_gpu": "one melt over all GPUs: replicated state, partitioned proposals + verification, in-kernel peer-memory exchange"
+                           if world > 1 else "single GPU", "rounds_per_melt": stats.rounds, "trials_per_bead": stats.trials / max(1, stats.nBeads),
+                           "conflicts_per_melt": stats.conflicts, "l2": "tables far larger than L2"},
+                "e2e": None, "gpu_launches": int(args.steps * (1 + 4)), "clocks": clocks,
+                "roofline": {"bound": "hbm", "achieved": (stats.trials * B_QUERY + stats.nBeads * B_BEAD) / (times[-1] / 1e3) / 1e9 / world, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": (stats.trials * B_QUERY + stats.nBeads * B_BEAD) / (times[-1] / 1e3) / 1e9 / world / hbm_peak, "traffic": None,
+                             "kernel": "sarw::grow_kernel (persistent cooperative launch per GPU)", "peak_source": peak_src,
+                             "algorithmic_bytes": f"(trials*{B_QUERY:.0f} + beads*{B_BEAD:.0f}) / N GPUs"},
+                "note": "optional strong-scaling workload; the headline is the default workload"}
+        print(json.dumps(line))
+    if dist:
+        dist.barrier(); dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS) + sorted(ONE_MELT))
     ap.add_argument("--melts", type=int, default=0, help="independent melts grown concurrently per step (0 = sarw_concurrent_capacity of the device)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary C3 / find_batch measurements")
     args = ap.parse_args()
+    if args.workload in ONE_MELT:
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "the one-melt strong-scaling workloads have no CPU arm (hours per melt on one core)"}))
+            return
+        return run_one_melt(args, ONE_MELT[args.workload])
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
         return run_reference(args, w)
