@@ -20,6 +20,7 @@ struct Control {
 	unsigned long long cycPropose, cycVerify, cycCleanup;   // SM cycles of block 0 per phase (incl. the closing barrier)
 	unsigned cleanupRounds, deadChains;
 	unsigned long long cycSub[8];       // finer split of the propose phase of block 0 / warp 0 (diagnostics)
+	unsigned int needOrdered[2];        // by round parity: the parallel clean-up left work for the ordered pass (else that pass and its barrier are skipped)
 	unsigned long long pathCyc[4], pathCnt[4];   // cluster kernel: propose cycles / chain-rounds by path: dead, fast, fast->hard, hard (diagnostics)
 	unsigned long long busy[256];       // cluster kernel: per-warp cycles from round start to the first barrier arrive, summed (diagnostics)
 };

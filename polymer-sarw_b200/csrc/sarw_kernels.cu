@@ -721,8 +721,9 @@ __device__ void cleanup_parallel(const GrowArgs& A, uint32_t round, uint32_t gw,
 			const uint32_t other = __ldcg(&A.dirtyList[j]) & ~DONE_BIT;
 			if (other < chain && tip_dist2(A, chain, other) <= R2) dep = true;
 		}
-		if (__any_sync(FULL, dep)) continue;
-		resolve_dirty_chain(A, round, chain, lane, [&](uint32_t c) { const uint32_t at = atomicAdd(&A.ctl->dirty2Count, 1u); A.dirtyList[A.g.nChains + at] = c; });
+		if (__any_sync(FULL, dep)) { if (lane == 0) A.ctl->needOrdered[round & 1u] = 1u; continue; }
+		resolve_dirty_chain(A, round, chain, lane, [&](uint32_t c) { const uint32_t at = atomicAdd(&A.ctl->dirty2Count, 1u); A.dirtyList[A.g.nChains + at] = c;
+			A.ctl->needOrdered[round & 1u] = 1u; });
 		if (lane == 0) A.dirtyList[e] = chain | DONE_BIT;
 		__syncwarp();
 	}
@@ -976,8 +977,12 @@ __global__ void __launch_bounds__(WARPS * 32, 2) grow_kernel(const __grid_consta
 		if (__ldcg(&A.dirtyCount[round]) != 0u) {
 			cleanup_parallel(A, round, gw, nW, lane);          // independent conflicts, one warp each
 			round_barrier<false>(A.ctl);
-			if (gw == 0) cleanup_round(A, round, lane);          // the rest, in chain order
-			round_barrier<false>(A.ctl);
+			// the ordered pass and its barrier only when the parallel part left something (a flag nobody writes after the barrier)
+			if (gw == 0 && lane == 0) A.ctl->needOrdered[(round + 1u) & 1u] = 0u;
+			if (__ldcg(&A.ctl->needOrdered[round & 1u]) != 0u) {
+				if (gw == 0) cleanup_round(A, round, lane);      // the rest, in chain order
+				round_barrier<false>(A.ctl);
+			}
 			cleanRounds++;
 		}
 		cycA += tk1 - tk0; cycV += tk2 - tk1; cycC += clock64() - tk2;
