@@ -311,3 +311,28 @@ def test_release_cached_memory_and_reuse(sarw):
     c = one()
     for x, y, z in zip(a, b, c):
         assert np.array_equal(x, y) and np.array_equal(x, z)
+
+
+def test_row_copy_staging_equals_tensor_copy_staging(sarw, tmp_path):
+    """SARW_NO_TMAP=1 forces the per-row bulk copies (the fallback for regions that cross the periodic boundary) everywhere: the walk
+    must not change. Checked in a child process (the switch is read at sarw_create) for a cluster-kernel and a grid-kernel config."""
+    import hashlib
+    import subprocess
+    import sys
+    code = (
+        "import sys, hashlib, numpy as np\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import sarw_b200, cases\n"
+        "for name in ('MID', 'SMALL_DEFAULTS'):\n"
+        "    cfg = getattr(cases, name)\n"
+        "    s = sarw_b200.SARW(cfg['nChains'], cfg['boxSize'], cfg['minDist'], seed=4, **{k: v for k, v in cfg.items() if k not in ('nChains', 'boxSize', 'minDist')})\n"
+        "    s.run(); xyz, cid, typ, bonds = s.ctx.download(); s.close()\n"
+        "    print(name, hashlib.sha256(xyz.tobytes() + bonds.tobytes() + typ.tobytes()).hexdigest())\n"
+    ) % (os.path.dirname(sarw.__file__), os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for flag in ("0", "1"):
+        env = dict(os.environ, SARW_NO_TMAP=flag)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+        assert r.returncode == 0, r.stderr
+        outs.append(r.stdout)
+    assert outs[0] == outs[1] and outs[0].count("\n") == 2, outs
