@@ -42,9 +42,10 @@ __device__ __forceinline__ int zbin_of(const Geom& g, const double* __restrict__
 	const int cz = (int)floor((t - floor(t)) * g.sOverL[2]);
 	return cz >= g.S[2] ? g.S[2] - 1 : (cz < 0 ? 0 : cz);
 }
-// block b owns the candidates [b*chunk, (b+1)*chunk) in both passes: per-block histogram in shared memory, one global atomic per
-// (block, non-empty layer)
-__global__ void __launch_bounds__(512) zbin_count_kernel(Geom g, const double* __restrict__ xyz, int64_t n, int64_t chunk, uint32_t* __restrict__ counts)
+// Counting sort by layer. Block b owns the candidates [b*chunk, (b+1)*chunk) in both passes. Pass 1 leaves its histogram in
+// blockHist[layer * nBlocks + b]; zbin_rows_kernel (one warp per layer) turns every layer's row into exclusive prefixes over the blocks
+// and records the layer total; zbin_scan_kernel turns the totals into layer offsets; pass 2 reads its cursors and scatters in ONE pass.
+__global__ void __launch_bounds__(512) zbin_count_kernel(Geom g, const double* __restrict__ xyz, int64_t n, int64_t chunk, uint32_t* __restrict__ blockHist)
 {
 	extern __shared__ uint32_t hist[];
 	for (int i = threadIdx.x; i < g.S[2]; i += blockDim.x) hist[i] = 0;
@@ -52,7 +53,24 @@ __global__ void __launch_bounds__(512) zbin_count_kernel(Geom g, const double* _
 	const int64_t lo = (int64_t)blockIdx.x * chunk, hi = lo + chunk < n ? lo + chunk : n;
 	for (int64_t q = lo + threadIdx.x; q < hi; q += blockDim.x) atomicAdd(&hist[zbin_of(g, xyz, q)], 1u);
 	__syncthreads();
-	for (int i = threadIdx.x; i < g.S[2]; i += blockDim.x) if (hist[i]) atomicAdd(&counts[i], hist[i]);
+	for (int i = threadIdx.x; i < g.S[2]; i += blockDim.x) blockHist[(size_t)i * gridDim.x + blockIdx.x] = hist[i];
+}
+__global__ void __launch_bounds__(256) zbin_rows_kernel(uint32_t* __restrict__ blockHist, uint32_t* __restrict__ layerTotal, int nLayers, int nBlocks)
+{
+	const int layer = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+	if (layer >= nLayers) return;
+	uint32_t* row = blockHist + (size_t)layer * nBlocks;
+	uint32_t carry = 0;
+	for (int base = 0; base < nBlocks; base += 32) {
+		const int b = base + lane;
+		const uint32_t v = b < nBlocks ? row[b] : 0u;
+		uint32_t incl = v;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += y; }
+		if (b < nBlocks) row[b] = carry + incl - v;
+		carry += __shfl_sync(FULL, incl, 31);
+	}
+	if (lane == 0) layerTotal[layer] = carry;
 }
 __global__ void zbin_scan_kernel(uint32_t* __restrict__ counts, int nb)   // one block: exclusive scan in place (counts -> cursors)
 {
@@ -85,16 +103,12 @@ __global__ void zbin_scan_kernel(uint32_t* __restrict__ counts, int nb)   // one
 // candidate in processing order: position, ignore index, original index
 struct __align__(32) SortedCand { double x, y, z; int64_t ignore; };
 __global__ void __launch_bounds__(512) zbin_scatter_kernel(Geom g, const double* __restrict__ xyz, const int64_t* __restrict__ ignore, int64_t n, int64_t chunk,
-	uint32_t* __restrict__ cursors, SortedCand* __restrict__ rec, uint32_t* __restrict__ perm)
+	const uint32_t* __restrict__ blockHist, const uint32_t* __restrict__ layerBase, SortedCand* __restrict__ rec, uint32_t* __restrict__ perm)
 {
-	extern __shared__ uint32_t hist[];
-	for (int i = threadIdx.x; i < g.S[2]; i += blockDim.x) hist[i] = 0;
+	extern __shared__ uint32_t hist[];   // this block's cursor into every layer
+	for (int i = threadIdx.x; i < g.S[2]; i += blockDim.x) hist[i] = layerBase[i] + blockHist[(size_t)i * gridDim.x + blockIdx.x];
 	__syncthreads();
 	const int64_t lo = (int64_t)blockIdx.x * chunk, hi = lo + chunk < n ? lo + chunk : n;
-	for (int64_t q = lo + threadIdx.x; q < hi; q += blockDim.x) atomicAdd(&hist[zbin_of(g, xyz, q)], 1u);
-	__syncthreads();
-	for (int i = threadIdx.x; i < g.S[2]; i += blockDim.x) { const uint32_t h = hist[i]; hist[i] = h ? atomicAdd(&cursors[i], h) : 0u; }
-	__syncthreads();
 	for (int64_t q = lo + threadIdx.x; q < hi; q += blockDim.x) {
 		const double x = xyz[3 * q], y = xyz[3 * q + 1], z = xyz[3 * q + 2];
 		const double t = z * g.Linv[2];
@@ -1053,8 +1067,9 @@ __global__ void fill_u32_kernel(uint32_t* p, uint64_t n, uint32_t v)
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
 
 // `scratch`: find_scratch_bytes(g, n) bytes of device scratch for the layer-ordered processing of large batches, or nullptr
+constexpr unsigned FIND_SORT_BLOCKS = 592;   // blocks of the two sort passes (4 per SM on B200); any number works
 size_t find_scratch_bytes(const Geom& g, int64_t n)
-{	return ((size_t)n * sizeof(SortedCand)) + (((size_t)n + (size_t)g.S[2]) * sizeof(uint32_t));
+{	return ((size_t)n * sizeof(SortedCand)) + (((size_t)n + (size_t)g.S[2] * (1 + FIND_SORT_BLOCKS)) * sizeof(uint32_t));
 }
 cudaError_t launch_find_batch(const Geom& g, const Tables& T, const double* xyz, const int64_t* ignore, int64_t n, uint8_t* hit, int numSMs,
 	void* scratch, cudaStream_t st)
@@ -1066,14 +1081,15 @@ cudaError_t launch_find_batch(const Geom& g, const Tables& T, const double* xyz,
 	if (scratch) {
 		SortedCand* r = static_cast<SortedCand*>(scratch);
 		uint32_t* p = reinterpret_cast<uint32_t*>(r + n);
-		uint32_t* cursors = p + n;
-		CK(cudaMemsetAsync(cursors, 0, (size_t)g.S[2] * sizeof(uint32_t), st));
-		const unsigned cb = (unsigned)numSMs * 4;
+		uint32_t* layerBase = p + n;
+		const unsigned cb = FIND_SORT_BLOCKS;
+		uint32_t* blockHist = layerBase + g.S[2];
 		const int64_t chunk = (n + cb - 1) / cb;
 		const size_t sm = (size_t)g.S[2] * sizeof(uint32_t);
-		zbin_count_kernel<<<cb, 512, sm, st>>>(g, xyz, n, chunk, cursors);
-		zbin_scan_kernel<<<1, 1024, 0, st>>>(cursors, g.S[2]);
-		zbin_scatter_kernel<<<cb, 512, sm, st>>>(g, xyz, ignore, n, chunk, cursors, r, p);
+		zbin_count_kernel<<<cb, 512, sm, st>>>(g, xyz, n, chunk, blockHist);
+		zbin_rows_kernel<<<(unsigned)((g.S[2] + 7) / 8), 256, 0, st>>>(blockHist, layerBase, g.S[2], (int)cb);
+		zbin_scan_kernel<<<1, 1024, 0, st>>>(layerBase, g.S[2]);
+		zbin_scatter_kernel<<<cb, 512, sm, st>>>(g, xyz, ignore, n, chunk, blockHist, layerBase, r, p);
 		rec = r; perm = p;
 	}
 	find_batch_kernel<<<(unsigned)blocks, 256, 0, st>>>(g, T, xyz, ignore, n, hit, rec, perm);
