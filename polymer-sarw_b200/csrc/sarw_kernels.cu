@@ -4,9 +4,13 @@
 //   K2-K4 grow_kernel     SARW::propagateChain / randomConePos / checkCollision sarw.cpp:220-283, 159-214
 //                         + PeriodicLookup::find / addPoint                     PeriodicLookup.h:37-75
 //                         + main()'s while loop                                 sarw.cpp:67-78
+//         <8,false> one GPU, cooperative grid; <8,true> the phases of one melt over several GPUs;
+//         grow_cluster_kernel (sarw_cluster.cuh) for <= 256 chains: one thread-block cluster, DSMEM, hardware barrier
 //   K5  find_batch_kernel PeriodicLookup::find on caller-supplied candidates    PeriodicLookup.h:51-75
+//       zbin_*            layer order for large batches (counting sort)
 //       add_points_kernel PeriodicLookup::addPoint                              PeriodicLookup.h:37-47
 //   K7  download kernels  terminateChain's type flip (sarw.cpp:359-368) + compaction into acceptance order
+//   K8  (sarw_analysis.cu) scripts/rdf.py pair histograms, chain shapes
 //
 // Exact sequential semantics in a parallel round (DESIGN.md "Round protocol"): every chain of the round proposes
 // against the beads present at round start and inserts its first passing candidate tentatively (phase A); after a
