@@ -321,34 +321,40 @@ def main():
 
     total = args.warmup + args.steps
     seeds = rank_seeds(rank, total * M)
-    # -------- device-resident arm
-    ctxs = [[make_ctx(seeds[i * M + m], m) for m in range(M)] for i in range(total)]
+    # -------- device-resident arm: the contexts (cell tables) of a step exist before its timed region starts and are destroyed after it,
+    # so memory does not grow with --steps
+    def step_contexts(i):
+        return [make_ctx(seeds[i * M + m], m) for m in range(M)]
+
+    def close_all(row):
+        for c in row: c.close()
+
     for i in range(args.warmup):
-        flush.fill_(float(i)); batch_device(ctxs[i])
+        row = step_contexts(i); flush.fill_(float(i)); batch_device(row); close_all(row)
     torch.cuda.synchronize()
     if dist: dist.barrier()
     sampler = ClockSampler(local); sampler.start()
     step_ms, beads, queries, trials, rounds, launches, grow_ms, seed_ms, conflicts, nMelts = [], 0, 0, 0, 0, 0, 0.0, 0.0, 0, 0
     for i in range(args.warmup, total):
+        row = step_contexts(i)
         flush.fill_(float(i))          # L2 flush between timed iterations (outside the event pair)
         torch.cuda.synchronize()
-        ms, sts = batch_device(ctxs[i])
+        ms, sts = batch_device(row)
         step_ms.append(ms)
         for st in sts:
             beads += st.nBeads; queries += st.queries; trials += st.trials; rounds += st.rounds; nMelts += 1
             launches += st.growLaunches + st.seedLaunches; grow_ms += st.growMs; seed_ms += st.seedMs; conflicts += st.conflicts
+        close_all(row)
     torch.cuda.synchronize()
     if dist: dist.barrier()
     clocks = sampler.stop()
-    for row in ctxs:
-        for c in row: c.close()
     t_dev = sum(step_ms) / 1e3
 
     # one melt at a time on an otherwise idle GPU (latency of a melt; what `value` was before batching)
     single_ms, single_beads = [], 0
     if M > 1:
-        sc = [sarw_b200.Context(device=local, **ctx_kwargs(w, 900_000 + rank * 1000 + k)) for k in range(args.warmup + args.steps)]
-        for k, c in enumerate(sc):
+        for k in range(args.warmup + args.steps):
+            c = sarw_b200.Context(device=local, **ctx_kwargs(w, 900_000 + rank * 1000 + k))
             c.set_stream(stream.cuda_stream)
             flush.fill_(float(k)); torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
