@@ -329,11 +329,15 @@ def main():
     def close_all(row):
         for c in row: c.close()
 
+    # clocks / throttle reasons are sampled by rank 0 only, from before the warm-up (nvidia-smi takes a moment to start) to the end of the
+    # timed region: one poller per rank (8 on a full node) holds the driver long enough to stretch the steps of every rank (measured at
+    # N = 8: 15.8 ms per step against 9.6 ms end to end)
+    sampler = ClockSampler(local)
+    if rank == 0: sampler.start()
     for i in range(args.warmup):
         row = step_contexts(i); flush.fill_(float(i)); batch_device(row); close_all(row)
     torch.cuda.synchronize()
     if dist: dist.barrier()
-    sampler = ClockSampler(local); sampler.start()
     step_ms, beads, queries, trials, rounds, launches, grow_ms, seed_ms, conflicts, nMelts = [], 0, 0, 0, 0, 0, 0.0, 0.0, 0, 0
     for i in range(args.warmup, total):
         row = step_contexts(i)
@@ -347,7 +351,7 @@ def main():
         close_all(row)
     torch.cuda.synchronize()
     if dist: dist.barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop() if rank == 0 else None
     t_dev = sum(step_ms) / 1e3
 
     # one melt at a time on an otherwise idle GPU (latency of a melt; what `value` was before batching)
