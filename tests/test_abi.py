@@ -52,3 +52,29 @@ def test_product_never_imports_oracle():
                 code = line.split("//")[0].split("#include")[-1] if "#include" in line else line.split("//")[0]
                 if re.search(r"#include|^\s*(import|from)\s|dlopen|CDLL", line):
                     assert "oracle" not in code.lower(), (f, line)
+
+
+def test_header_compiles_as_c_and_cpp(tmp_path):
+    """include/sarw_abi.h is the drop-in boundary: it must be usable from plain C (cgo/ctypes-style bindings) and from C++."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src_c = tmp_path / "t.c"; src_cpp = tmp_path / "t.cpp"
+    body = '#include "sarw_abi.h"\nint main(void) { sarw_params p; sarw_stats s; (void)p; (void)s; return (int)sizeof(sarw_params) == 0; }\n'
+    src_c.write_text(body); src_cpp.write_text(body)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-I", os.path.join(root, "include"), str(src_c)], check=True)
+    subprocess.run(["g++", "-std=c++11", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(root, "include"), str(src_cpp)], check=True)
+
+
+def test_python_struct_layouts_match_the_header(sarw, tmp_path):
+    """sizeof / field offsets of sarw_params and sarw_stats as the C compiler sees them == the ctypes mirrors"""
+    import subprocess
+    import ctypes as C
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "l.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "sarw_abi.h"\nint main(void) { printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(sarw_params), '
+                   'offsetof(sarw_params, seed), offsetof(sarw_params, launchMode), sizeof(sarw_stats), offsetof(sarw_stats, growMs), offsetof(sarw_stats, cycSub)); return 0; }\n')
+    exe = tmp_path / "l"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(root, "include"), "-o", str(exe), str(src)], check=True)
+    out = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    P, S = sarw.Params, sarw.Stats
+    assert out == [C.sizeof(P), P.seed.offset, P.launchMode.offset, C.sizeof(S), S.growMs.offset, S.cycSub.offset]
