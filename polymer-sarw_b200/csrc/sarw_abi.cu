@@ -888,6 +888,7 @@ int sarw_rdf(sarw_ctx* c, double rMin, double dr, int32_t nBins, uint64_t* intra
 	const uint64_t N = h.nBeads;
 	for (int32_t k = 0; k < nBins; k++) { intra[k] = 0; inter[k] = 0; }
 	if (N == 0) return 0;
+	if (N > 0x7FFFFFF0ull) return fail(c, "sarw_rdf: more than 2^31 beads are not supported");
 	// bin edges as numpy.arange fills them (rdf.py:19): start + k*((start + dr) - start)
 	std::vector<double> t2((size_t)nBins + 1);
 	volatile double second = rMin + dr;
