@@ -6,6 +6,9 @@
 #ifdef SARW_HOSTTEST
 #include "input_map.h"
 #include "polymer_io.h"
+#include "fast_format.h"
+#include <cmath>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -39,6 +42,30 @@ int main(int argc, char** argv)
 			|| !export_xyz(p, d + "/polymer.xyz", threads, err) || !export_xsf(p, d + "/polymer.xsf", threads, err)) { fputs(err.c_str(), stderr); return 5; }
 		printf("%lld %lld %lld %lld\n", (long long)p.nAtoms(), (long long)p.nBonds(), (long long)p.nAngles(), (long long)p.nDihedrals());
 		return 0;
+	}
+	if (argc >= 3 && !strcmp(argv[1], "fmtcheck")) {
+		// put_fixed6 / put_int against snprintf on argv[2] pseudo-random doubles per family + ties + edge cases; prints the mismatch count
+		const long n = atol(argv[2]);
+		unsigned long long st = 0x9E3779B97F4A7C15ull, bad = 0, total = 0;
+		auto rnd = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return st; };
+		auto check = [&](double x) {
+			char a[64], b[64];
+			*put_fixed6(a, x) = 0; snprintf(b, sizeof b, "%lf", x);
+			total++;
+			if (strcmp(a, b)) { if (bad < 5) fprintf(stderr, "mismatch %.17g: '%s' vs '%s'\n", x, a, b); bad++; }
+		};
+		const double edge[] = { 0.0, -0.0, 1e-7, -1e-7, 5e-7, 4.9999999999999996e-7, 5.0000000000000004e-7, 0.0078125, 0.0234375, 1.0, -1.0, 0.9999995, 0.99999949999999994,
+			999999.9999995, 123456.7890125, 8589934591.9999990, 8589934592.0, 1e15, -1e30, 4.9e-324, 2.2250738585072014e-308, INFINITY, -INFINITY, NAN };
+		for (double x : edge) check(x);
+		for (long i = 0; i < n; i++) {
+			const double u = (double)(rnd() >> 11) * (1.0 / 9007199254740992.0);
+			check(u * 632.2); check(-u * 3000.0); check((u - 0.5) * 1e-4); check(std::ldexp((double)(rnd() >> 11), -(int)(rnd() % 80)));   // incl. many exact ties
+			check((double)(long long)(rnd() % 20000000) / 128.0 + 1.0 / 256.0);                                                          // k/128 + 1/256: ties at 6 decimals
+			char a[32], b[32]; const long long v = (long long)rnd() >> (rnd() % 63);
+			*put_int(a, v) = 0; snprintf(b, sizeof b, "%lld", v); total++; if (strcmp(a, b)) bad++;
+		}
+		printf("%llu %llu\n", bad, total);
+		return bad ? 1 : 0;
 	}
 	fprintf(stderr, "usage: sarw_hosttest parse <input> | export <atoms.bin> <outdir> [polymer] [threads]\n");
 	return 64;

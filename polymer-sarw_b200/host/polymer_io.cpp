@@ -1,4 +1,5 @@
 #include "polymer_io.h"
+#include "fast_format.h"
 #include <algorithm>
 #include <cstdio>
 #include <fstream>
@@ -97,23 +98,34 @@ bool export_lammps(const Polymer& p, const std::string& path, int nThreads, std:
 	fprintf(fp, "%d\t%lf\n", 2, 14.0);
 	fprintf(fp, "\n");
 	fprintf(fp, "Atoms\n\n");                                                   // sarw.cpp:458-464
-	ok = ok && write_rows(fp, p.nAtoms(), 160, nThreads, [&](int64_t i, char* b) {
-		return snprintf(b, 160, "%lld\t%d\t%d\t%lf\t%lf\t%lf\n", (long long)(i + 1), p.chainID[(size_t)i], p.type[(size_t)i],
-			p.xyz[3 * (size_t)i], p.xyz[3 * (size_t)i + 1], p.xyz[3 * (size_t)i + 2]); });
+	ok = ok && write_rows(fp, p.nAtoms(), 160, nThreads, [&](int64_t i, char* b) {   // "%d\t%d\t%d\t%lf\t%lf\t%lf\n"
+		char* q = put_int(b, (long long)(i + 1)); *q++ = '\t';
+		q = put_int(q, p.chainID[(size_t)i]); *q++ = '\t';
+		q = put_int(q, p.type[(size_t)i]);
+		for (int k = 0; k < 3; k++) { *q++ = '\t'; q = put_fixed6(q, p.xyz[3 * (size_t)i + k]); }
+		*q++ = '\n';
+		return (int)(q - b); });
 	fprintf(fp, "\n");
 	fprintf(fp, "Bonds\n\n");                                                   // sarw.cpp:466-470
-	ok = ok && write_rows(fp, p.nBonds(), 96, nThreads, [&](int64_t i, char* b) {
-		return snprintf(b, 96, "%lld\t%d\t%lld\t%lld\n", (long long)(i + 1), 1, (long long)p.bonds[2 * (size_t)i], (long long)p.bonds[2 * (size_t)i + 1]); });
+	ok = ok && write_rows(fp, p.nBonds(), 96, nThreads, [&](int64_t i, char* b) {      // "%d\t%d\t%d\t%d\n"
+		char* q = put_int(b, (long long)(i + 1)); *q++ = '\t'; *q++ = '1';
+		for (int k = 0; k < 2; k++) { *q++ = '\t'; q = put_int(q, (long long)p.bonds[2 * (size_t)i + k]); }
+		*q++ = '\n';
+		return (int)(q - b); });
 	fprintf(fp, "\n");
 	fprintf(fp, "Angles\n\n");                                                  // sarw.cpp:472-476
 	ok = ok && write_rows(fp, p.nAngles(), 120, nThreads, [&](int64_t i, char* b) {
-		return snprintf(b, 120, "%lld\t%d\t%lld\t%lld\t%lld\n", (long long)(i + 1), 1, (long long)p.angles[3 * (size_t)i],
-			(long long)p.angles[3 * (size_t)i + 1], (long long)p.angles[3 * (size_t)i + 2]); });
+		char* q = put_int(b, (long long)(i + 1)); *q++ = '\t'; *q++ = '1';
+		for (int k = 0; k < 3; k++) { *q++ = '\t'; q = put_int(q, (long long)p.angles[3 * (size_t)i + k]); }
+		*q++ = '\n';
+		return (int)(q - b); });
 	fprintf(fp, "\n");
 	fprintf(fp, "Dihedrals\n\n");                                               // sarw.cpp:478-485 (trailing tab on every row)
 	ok = ok && write_rows(fp, p.nDihedrals(), 140, nThreads, [&](int64_t i, char* b) {
-		return snprintf(b, 140, "%lld\t%d\t%lld\t%lld\t%lld\t%lld\t\n", (long long)(i + 1), 1, (long long)p.dihedrals[4 * (size_t)i],
-			(long long)p.dihedrals[4 * (size_t)i + 1], (long long)p.dihedrals[4 * (size_t)i + 2], (long long)p.dihedrals[4 * (size_t)i + 3]); });
+		char* q = put_int(b, (long long)(i + 1)); *q++ = '\t'; *q++ = '1';
+		for (int k = 0; k < 4; k++) { *q++ = '\t'; q = put_int(q, (long long)p.dihedrals[4 * (size_t)i + k]); }
+		*q++ = '\t'; *q++ = '\n';
+		return (int)(q - b); });
 	fprintf(fp, "\n");
 	if (fclose(fp) != 0) ok = false;
 	if (!ok) error = "write to " + path + " failed";
@@ -121,7 +133,10 @@ bool export_lammps(const Polymer& p, const std::string& path, int nThreads, std:
 }
 
 static int xyz_row(const Polymer& p, int64_t i, char* b)
-{	return snprintf(b, 120, "C\t%lf\t%lf\t%lf\n", p.xyz[3 * (size_t)i], p.xyz[3 * (size_t)i + 1], p.xyz[3 * (size_t)i + 2]);
+{	char* q = b; *q++ = 'C';                                                   // "C\t%lf\t%lf\t%lf\n"
+	for (int k = 0; k < 3; k++) { *q++ = '\t'; q = put_fixed6(q, p.xyz[3 * (size_t)i + k]); }
+	*q++ = '\n';
+	return (int)(q - b);
 }
 
 bool export_xyz(const Polymer& p, const std::string& path, int nThreads, std::string& error)

@@ -156,3 +156,12 @@ def test_cli_rdf_option_writes_rdf_py_counts(tmp_path):
     shapes = np.loadtxt(tmp_path / "shapes.dat")
     lengths = np.loadtxt(tmp_path / "chains.dat")
     assert shapes.shape == (20, 4) and np.array_equal(shapes[:, 1], lengths) and (shapes[:, 2] > 0).all()
+
+
+def test_fast_format_equals_printf(hosttest):
+    """The exporters' own number formatting (host/fast_format.h) against snprintf("%lf") / ("%lld") on 3e5 x 5 pseudo-random doubles
+    (coordinates, negatives, tiny values, dyadic rationals that hit exact ties at six decimals) plus edge cases: zero mismatches."""
+    r = subprocess.run([hosttest, "fmtcheck", "300000"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    bad, total = (int(x) for x in r.stdout.split())
+    assert bad == 0 and total > 1_500_000
