@@ -7,6 +7,7 @@
 #include "input_map.h"
 #include "polymer_io.h"
 #include "fast_format.h"
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstdio>
@@ -35,11 +36,17 @@ int main(int argc, char** argv)
 			|| fread(p.bonds.data(), 8, 2 * nB, fp) != 2 * nB || fread(p.chainLengths.data(), 4, (size_t)p.nChains, fp) != (size_t)p.nChains) return 4;
 		fclose(fp);
 		p.name = argc >= 5 ? argv[4] : "Polyethylene";
+		auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+		const double t0 = now();
 		build_topology(p);
+		const double t1 = now();
 		std::string d = argv[3], err;
 		const int threads = argc >= 6 ? atoi(argv[5]) : 0;
-		if (!export_chain_lengths(p, d + "/chains.dat", err) || !export_lammps(p, d + "/polymer.dat", threads, err)
-			|| !export_xyz(p, d + "/polymer.xyz", threads, err) || !export_xsf(p, d + "/polymer.xsf", threads, err)) { fputs(err.c_str(), stderr); return 5; }
+		if (!export_chain_lengths(p, d + "/chains.dat", err) || !export_lammps(p, d + "/polymer.dat", threads, err)) { fputs(err.c_str(), stderr); return 5; }
+		const double t2 = now();
+		if (!export_xyz(p, d + "/polymer.xyz", threads, err) || !export_xsf(p, d + "/polymer.xsf", threads, err)) { fputs(err.c_str(), stderr); return 5; }
+		const double t3 = now();
+		if (getenv("SARW_HOSTTEST_TIMING")) fprintf(stderr, "topology %.2f s, polymer.dat %.2f s, xyz + xsf %.2f s\n", t1 - t0, t2 - t1, t3 - t2);
 		printf("%lld %lld %lld %lld\n", (long long)p.nAtoms(), (long long)p.nBonds(), (long long)p.nAngles(), (long long)p.nDihedrals());
 		return 0;
 	}

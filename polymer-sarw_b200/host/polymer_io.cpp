@@ -43,7 +43,8 @@ void build_topology(Polymer& p)
 
 namespace {
 
-// format rows [0,n) with `row(i, buf)` (returns bytes written, < maxRow) on nThreads threads, write them in order
+// format rows [0,n) with `row(i, buf)` (returns bytes written, < maxRow) on nThreads threads, write them in order; the next batch of
+// chunks is formatted while the current one is being written (two sets of buffers)
 bool write_rows(FILE* fp, int64_t n, size_t maxRow, int nThreads, const std::function<int(int64_t, char*)>& row)
 {
 	if (n <= 0) return true;
@@ -51,24 +52,36 @@ bool write_rows(FILE* fp, int64_t n, size_t maxRow, int nThreads, const std::fun
 	const int64_t chunk = 1 << 16;
 	const int64_t nChunks = (n + chunk - 1) / chunk;
 	nThreads = (int)std::min<int64_t>(nThreads, nChunks);
-	std::vector<std::vector<char>> bufs((size_t)nThreads);
-	std::vector<size_t> lens((size_t)nThreads);
-	for (int64_t c0 = 0; c0 < nChunks; c0 += nThreads) {
-		const int nb = (int)std::min<int64_t>(nThreads, nChunks - c0);
+	struct Batch { std::vector<std::vector<char>> bufs; std::vector<size_t> lens; int nb = 0; };
+	Batch sets[2];
+	for (Batch& s : sets) { s.bufs.resize((size_t)nThreads); s.lens.resize((size_t)nThreads); }
+	auto format_batch = [&](Batch& s, int64_t c0) {
+		s.nb = (int)std::min<int64_t>(nThreads, nChunks - c0);
 		auto work = [&](int t) {
 			const int64_t lo = (c0 + t) * chunk, hi = std::min(n, lo + chunk);
-			std::vector<char>& b = bufs[(size_t)t];
+			std::vector<char>& b = s.bufs[(size_t)t];
 			b.resize((size_t)(hi - lo) * maxRow);
 			size_t at = 0;
 			for (int64_t i = lo; i < hi; i++) at += (size_t)row(i, b.data() + at);
-			lens[(size_t)t] = at;
+			s.lens[(size_t)t] = at;
 		};
 		std::vector<std::thread> th;
-		for (int t = 1; t < nb; t++) th.emplace_back(work, t);
+		for (int t = 1; t < s.nb; t++) th.emplace_back(work, t);
 		work(0);
 		for (auto& x : th) x.join();
-		for (int t = 0; t < nb; t++)
-			if (fwrite(bufs[(size_t)t].data(), 1, lens[(size_t)t], fp) != lens[(size_t)t]) return false;
+	};
+	int cur = 0;
+	format_batch(sets[cur], 0);
+	for (int64_t c0 = 0; c0 < nChunks; c0 += nThreads) {
+		const int64_t next = c0 + nThreads;
+		std::thread ahead;
+		if (next < nChunks) ahead = std::thread(format_batch, std::ref(sets[cur ^ 1]), next);
+		bool ok = true;
+		for (int t = 0; t < sets[cur].nb && ok; t++)
+			ok = fwrite(sets[cur].bufs[(size_t)t].data(), 1, sets[cur].lens[(size_t)t], fp) == sets[cur].lens[(size_t)t];
+		if (ahead.joinable()) ahead.join();
+		if (!ok) return false;
+		cur ^= 1;
 	}
 	return true;
 }
