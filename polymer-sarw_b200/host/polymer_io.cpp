@@ -19,26 +19,35 @@ void build_topology(Polymer& p)
 	for (int64_t c = 0; c < nC; c++) start[(size_t)c + 1] += start[(size_t)c];   // chain id c+1 now occupies [start[c], start[c+1])
 	std::vector<int64_t> order((size_t)N), fill(start.begin(), start.end() - 1);
 	for (int64_t i = 0; i < N; i++) order[(size_t)fill[(size_t)p.chainID[(size_t)i] - 1]++] = i;
-	int64_t nAng = 0, nDih = 0;
+	// per-chain output offsets (prefix sums), then the chains are written by several threads: every chain owns its slice of the output
+	std::vector<int64_t> angAt((size_t)nC + 1, 0), dihAt((size_t)nC + 1, 0);
 	for (int64_t c = 0; c < nC; c++) {
 		const int64_t len = start[(size_t)c + 1] - start[(size_t)c];
 		// sarw.cpp:406: the reference starts each chain at atom 2*iChain-2, i.e. it assumes the seeds of all chains exist
-		if (len > 0 && order[(size_t)start[(size_t)c]] != 2 * c) continue;
-		if (len >= 3) nAng += len - 2;
-		if (len >= 4) nDih += len - 3;
+		const bool skip = len > 0 && order[(size_t)start[(size_t)c]] != 2 * c;
+		angAt[(size_t)c + 1] = angAt[(size_t)c] + ((!skip && len >= 3) ? len - 2 : 0);
+		dihAt[(size_t)c + 1] = dihAt[(size_t)c] + ((!skip && len >= 4) ? len - 3 : 0);
 	}
-	p.angles.resize((size_t)nAng * 3); p.dihedrals.resize((size_t)nDih * 4);
-	int64_t ia = 0, id = 0;
-	for (int64_t c = 0; c < nC; c++) {
-		const int64_t b = start[(size_t)c], len = start[(size_t)c + 1] - b;
-		if (len > 0 && order[(size_t)b] != 2 * c) continue;
-		for (int64_t k = 2; k < len; k++) {                                      // sarw.cpp:410
-			p.angles[(size_t)ia++] = order[(size_t)(b + k - 2)] + 1; p.angles[(size_t)ia++] = order[(size_t)(b + k - 1)] + 1;
-			p.angles[(size_t)ia++] = order[(size_t)(b + k)] + 1;
+	p.angles.resize((size_t)angAt[(size_t)nC] * 3); p.dihedrals.resize((size_t)dihAt[(size_t)nC] * 4);
+	auto emit = [&](int64_t c0, int64_t c1) {
+		for (int64_t c = c0; c < c1; c++) {
+			const int64_t b = start[(size_t)c], len = start[(size_t)c + 1] - b;
+			if (len > 0 && order[(size_t)b] != 2 * c) continue;
+			int64_t ia = angAt[(size_t)c] * 3, id = dihAt[(size_t)c] * 4;
+			for (int64_t k = 2; k < len; k++) {                                      // sarw.cpp:410
+				p.angles[(size_t)ia++] = order[(size_t)(b + k - 2)] + 1; p.angles[(size_t)ia++] = order[(size_t)(b + k - 1)] + 1;
+				p.angles[(size_t)ia++] = order[(size_t)(b + k)] + 1;
+			}
+			for (int64_t k = 3; k < len; k++)                                        // sarw.cpp:412
+				for (int64_t q = 3; q >= 0; q--) p.dihedrals[(size_t)id++] = order[(size_t)(b + k - q)] + 1;
 		}
-		for (int64_t k = 3; k < len; k++)                                        // sarw.cpp:412
-			for (int64_t q = 3; q >= 0; q--) p.dihedrals[(size_t)id++] = order[(size_t)(b + k - q)] + 1;
-	}
+	};
+	int nT = (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()));
+	if (N < (1 << 20)) nT = 1;
+	std::vector<std::thread> th;
+	for (int t = 1; t < nT; t++) th.emplace_back(emit, nC * t / nT, nC * (t + 1) / nT);
+	emit(0, nC / nT);
+	for (auto& x : th) x.join();
 }
 
 namespace {
