@@ -78,3 +78,27 @@ def test_python_struct_layouts_match_the_header(sarw, tmp_path):
     out = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     P, S = sarw.Params, sarw.Stats
     assert out == [C.sizeof(P), P.seed.offset, P.launchMode.offset, C.sizeof(S), S.growMs.offset, S.cycSub.offset]
+
+
+def test_c_example_compiles_and_links_against_the_library(tmp_path):
+    """examples/minimal.c: a plain-C99 program over include/sarw_abi.h links against libsarw_b200.so (it is run by the GPU suite)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = os.path.join(root, "polymer-sarw_b200", "lib")
+    exe = tmp_path / "minimal"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "minimal.c"),
+                    "-L", lib, "-lsarw_b200", "-Wl,-rpath," + lib, "-o", str(exe)], check=True)
+    assert exe.exists()
+
+
+@pytest.mark.gpu
+def test_c_example_runs(tmp_path):
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = os.path.join(root, "polymer-sarw_b200", "lib")
+    exe = tmp_path / "minimal"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "minimal.c"),
+                    "-L", lib, "-lsarw_b200", "-Wl,-rpath," + lib, "-o", str(exe)], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.startswith("176 beads, 156 bonds in 7 rounds (target 158)"), r.stdout
