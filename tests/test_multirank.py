@@ -82,3 +82,27 @@ def test_record_layout_after_all_gather_with_gloo(tmp_path):
     assert r.returncode == 0, r.stderr[-2000:]
     got = json.loads([l for l in r.stdout.splitlines() if l.startswith("[")][-1])
     assert got == list(range(11))
+
+
+def test_committed_bench_line_has_every_contract_key():
+    """profiles/r1_bench_final.json is a line bench.py printed on a B200: the keys the measurement contract names are all there."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    line = json.loads(open(os.path.join(root, "profiles", "r1_bench_final.json")).read().strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+              "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert k in line, k
+    assert line["metric"] == "accepted beads/sec" and line["unit"] == "beads/s" and line["vs_baseline"] is None and line["dtype"] == "f64"
+    assert "workload" in line["config"] and "model" not in line["config"]
+    for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
+        assert k in line["e2e"], k
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert k in line["roofline"], k
+    assert abs(line["roofline"]["frac"] - line["roofline"]["achieved"] / line["roofline"]["peak"]) < 1e-12
+    for k in ("value", "unit", "cores", "kind", "sample"):
+        assert k in line["cpu_baseline"], k
+    for k in ("sm_mhz", "sm_max_mhz", "reasons"):
+        assert k in line["clocks"], k
+    assert line["gpu_launches"] > 0 and line["e2e"]["value"] != line["value"]
+    ref = json.loads(open(os.path.join(root, "profiles", "r1_bench_reference_arm.json")).read().strip().splitlines()[-1])
+    assert ref["impl"] == "reference" and ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["cpu_baseline"]["kind"] == "reference"

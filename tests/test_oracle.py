@@ -134,3 +134,18 @@ def test_chain_shapes_oracle_matches_numpy(oracle):
     ree2, rg2 = oracle.chain_shapes(w["xyz"], w["chainID"], nChains)
     ree2n, rg2n, _ = stats.chain_shapes(w["xyz"], w["chainID"], nChains)
     assert np.allclose(ree2, ree2n, rtol=1e-12, atol=0) and np.allclose(rg2, rg2n, rtol=1e-10, atol=0)
+
+
+def test_rdf_oracle_counts_every_ordered_pair_once(oracle):
+    """Properties of the rdf.py accumulation the device kernel is held to: with rMin = 0 and a range beyond |L/2| every ordered pair
+    (self pairs included) lands in exactly one bin, and inter-chain counts are even (each unordered pair is counted twice)."""
+    w = np.load(os.path.join(GOLDEN, "walk_dense_tiny_seed1.npz"))
+    box = (14.0, 14.0, 14.0)
+    n = len(w["xyz"])
+    nBins = int(np.ceil(np.sqrt(3) * 7.0 / 0.25)) + 2
+    intra, inter = oracle.rdf(box, w["xyz"], w["chainID"], 0.0, 0.25, nBins)
+    assert int(intra.sum() + inter.sum()) == n * n
+    assert int(intra[0]) >= n                      # the self pairs sit in the first bin
+    assert (inter % 2 == 0).all()
+    lengths = np.bincount(w["chainID"])[1:]
+    assert int(intra.sum()) == int((lengths.astype(np.int64) ** 2).sum())
