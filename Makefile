@@ -15,6 +15,12 @@ $(LIB): $(PKG)/csrc/sarw_kernels.cu $(PKG)/csrc/sarw_abi.cu $(PKG)/csrc/sarw_ana
 	mkdir -p $(PKG)/lib
 	$(NVCC) $(NVFLAGS) -Xptxas -v -shared -o $@ $(PKG)/csrc/sarw_kernels.cu $(PKG)/csrc/sarw_abi.cu $(PKG)/csrc/sarw_analysis.cu 2> $(PKG)/lib/ptxas.log || (cat $(PKG)/lib/ptxas.log; exit 1)
 
+# same library with per-step cycle counters in the growth kernels (scripts/prof_fastpath.py; load it with SARW_B200_LIB=...)
+prof: $(PKG)/lib/libsarw_prof.so
+$(PKG)/lib/libsarw_prof.so: $(PKG)/csrc/sarw_kernels.cu $(PKG)/csrc/sarw_abi.cu $(PKG)/csrc/sarw_analysis.cu $(PKG)/csrc/sarw_device.cuh $(PKG)/csrc/sarw_cluster.cuh $(PKG)/csrc/sarw_host.h include/sarw_abi.h
+	mkdir -p $(PKG)/lib
+	$(NVCC) $(NVFLAGS) -DSARW_PROF -shared -o $@ $(PKG)/csrc/sarw_kernels.cu $(PKG)/csrc/sarw_abi.cu $(PKG)/csrc/sarw_analysis.cu
+
 HOSTSRC := $(PKG)/host/input_map.cpp $(PKG)/host/polymer_io.cpp
 cli: $(CLI) $(PKG)/bin/sarw_hosttest
 $(CLI): $(HOSTSRC) $(PKG)/host/main.cpp $(wildcard $(PKG)/host/*.h) include/sarw_abi.h $(LIB)
@@ -31,4 +37,4 @@ oracle:
 clean:
 	rm -rf $(PKG)/lib $(PKG)/bin
 	$(MAKE) -C oracle clean
-.PHONY: all lib cli oracle clean
+.PHONY: all lib cli oracle prof clean
