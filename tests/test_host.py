@@ -165,3 +165,37 @@ def test_fast_format_equals_printf(hosttest):
     assert r.returncode == 0, r.stdout + r.stderr
     bad, total = (int(x) for x in r.stdout.split())
     assert bad == 0 and total > 1_500_000
+
+
+def test_exporters_large_multithreaded_equals_single_thread(hosttest, tmp_path):
+    """1.1e6 beads: the parallel topology emission (N >= 2^20) and the pipelined multi-batch writer (more chunks than threads) must
+    write exactly the bytes the single-threaded path writes."""
+    import hashlib
+    nC, per = 1100, 1000
+    N = nC * per
+    rng = np.random.default_rng(3)
+    chainID = np.concatenate([np.repeat(np.arange(1, nC + 1), 2), np.tile(np.arange(1, nC + 1), per - 2)]).astype(np.int32)
+    xyz = (rng.random((N, 3)) - 0.25) * 300.0                     # negative coordinates too
+    xyz[::1000] = np.round(xyz[::1000] * 128) / 128 + 1.0 / 256   # exact ties at the sixth decimal
+    typ = np.where(rng.random(N) < 0.01, 1, 2).astype(np.int32)
+    bonds = np.zeros((N - nC, 2), np.int64)
+    last = 2 * np.arange(1, nC + 1)
+    bonds[:nC, 0] = last - 1; bonds[:nC, 1] = last
+    b = nC
+    for r in range(per - 2):
+        ids = 2 * nC + r * nC + np.arange(1, nC + 1)
+        bonds[b:b + nC, 0] = last; bonds[b:b + nC, 1] = ids; last = ids; b += nC
+    write_atoms_bin(tmp_path / "a.bin", nC, (300, 300, 300), xyz, chainID, typ, bonds, np.full(nC, per, np.int32))
+    digests = []
+    for threads in ("1", "4"):
+        out = tmp_path / f"o{threads}"; out.mkdir()
+        r = subprocess.run([hosttest, "export", str(tmp_path / "a.bin"), str(out), "Polyethylene", threads], capture_output=True, text=True, check=True, timeout=300)
+        assert [int(x) for x in r.stdout.split()] == [N, N - nC, N - 2 * nC, N - 3 * nC]
+        digests.append([hashlib.md5((out / f).read_bytes()).hexdigest() for f in ("polymer.dat", "polymer.xyz", "polymer.xsf", "chains.dat")])
+        if threads == "4":   # the text itself against Python's exactly rounded "%f" (same rule as glibc's printf), ties included
+            rows = (out / "polymer.xyz").read_text().split("\n")[2:2 + 60000]
+            want = ["C\t%f\t%f\t%f" % tuple(p) for p in xyz[:60000]]
+            assert rows == want
+        for f in ("polymer.dat", "polymer.xyz", "polymer.xsf"):
+            (out / f).unlink()
+    assert digests[0] == digests[1]
