@@ -42,11 +42,12 @@ typedef struct sarw_params {
 	double growthBias[3];       /* README.md:33 only (no reference code): a trial whose step has bias.step < 0 fails */
 	uint64_t seed;              /* extension: Philox key; the reference is unseeded (sarw.cpp:16) */
 	int32_t device;             /* CUDA device ordinal; < 0 = current device */
-	int32_t cellCapacity;       /* 0 = default (7 beads inline per cell); 1..7 = test hook forcing overflow handling */
+	int32_t cellCapacity;       /* 0 = default (3 beads inline per 32-byte cell); 1..2 = test hook forcing overflow handling */
 	double cellEdge;            /* 0 = default; minimum cell edge in Angstrom (>= 2.002*minDist is always enforced) */
 	int64_t reserveRounds;      /* 0 = auto; growth rounds to pre-allocate bead storage for */
 	int32_t launchMode;         /* 0 = auto (one thread-block cluster when nChains <= 256, else cooperative grid); 1 = force grid */
-	int32_t reserved;
+	int32_t maxBlocks;          /* 0 = auto; cap on the thread blocks of the cooperative growth launch, so that several contexts can grow on one
+	                               device at the same time (tests run the ranks of a multi-rank melt side by side on one GPU this way) */
 } sarw_params;
 
 typedef struct sarw_stats {
@@ -95,6 +96,12 @@ int sarw_propagate_round(sarw_ctx* ctx, int32_t* progressed);
 /* main()'s loop (sarw.cpp:67-78) on the device: rounds until actualCount >= target, a round makes no progress, or
  * maxRounds more rounds were run (maxRounds < 0: unbounded). target <= 0 means SARW::targetCount(). */
 int sarw_grow(sarw_ctx* ctx, int64_t target, int64_t maxRounds, sarw_stats* stats);
+/* The same without waiting: sarw_grow_async enqueues seeding (if sarw_initiate was not called yet; main()'s sequence sarw.cpp:66-78)
+ * and the growth loop on the context's stream and returns at once; sarw_wait blocks until it finished (ONE synchronisation per melt),
+ * continues the loop if the walk needs more rounds than bead storage was reserved for, and fills the stats. One host thread can keep
+ * several contexts growing on their own streams this way. No other call on the context in between. */
+int sarw_grow_async(sarw_ctx* ctx, int64_t target, int64_t maxRounds);
+int sarw_wait(sarw_ctx* ctx, sarw_stats* stats);
 /* The large tables of destroyed contexts are kept per device for the next sarw_create of the same size (up to 24 GB); this hands
  * them back to the driver. device < 0: every device. */
 int sarw_release_cached_memory(int32_t device);
@@ -124,6 +131,11 @@ int sarw_mr_commit(sarw_ctx* ctx);
 int sarw_mr_peer_export(sarw_ctx* ctx, void* handle64);
 int sarw_mr_peer_connect(sarw_ctx* ctx, const void* allHandles);
 int sarw_mr_grow_peer(sarw_ctx* ctx, int64_t maxRounds, sarw_stats* stats);
+/* Same exchange for contexts that live in ONE process (several ranks side by side on one GPU with sarw_params.maxBlocks, or several
+ * GPUs with peer access enabled): after sarw_mr_peer_export, sarw_mr_peer_local_base returns the rank's exchange buffer and
+ * sarw_mr_peer_connect_local takes the buffers of all ranks (rank order) instead of IPC handles. */
+int sarw_mr_peer_local_base(sarw_ctx* ctx, void** base);
+int sarw_mr_peer_connect_local(sarw_ctx* ctx, void* const* bases);
 
 /* SARW::terminateChain (sarw.cpp:359-368) */
 int sarw_terminate(sarw_ctx* ctx);

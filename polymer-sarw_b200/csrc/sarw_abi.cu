@@ -33,7 +33,7 @@ struct sarw_ctx {
 	cudaStream_t stream = nullptr; bool ownStream = false;
 	alignas(64) CUtensorMap tmapHost;     // tensor map of the cell table (copied into the kernel parameters of every growth launch)
 	cudaStream_t allocStream = nullptr;   // all pool allocations / frees go through the device's home stream (cheap reuse)
-	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr, evS0 = nullptr, evS1 = nullptr;   // growth launch / seeding, on the context's stream
 	std::string err;
 
 	// lookup index space: [0, nObstacles) obstacles / added points, then atom slots
@@ -44,6 +44,12 @@ struct sarw_ctx {
 	uint32_t roundCap = 0;        // growth rounds storage is allocated for
 
 	Control* ctl = nullptr;
+	Control* hctl = nullptr;      // pinned host mirror of *ctl, refreshed by read_control after every launch sequence (never stale between ABI calls)
+	bool seedTimed = true;        // seedMs / initiated / nSeeded have been taken from the events and the mirror
+	bool growTimed = true;        // the last growth launch's event pair has been added to growMs
+	bool mirrorStale = false;     // work that changes *ctl was enqueued after the last read_control
+	bool asyncPending = false;    // sarw_grow_async enqueued work whose result has not been read yet (sarw_wait)
+	int64_t asyncTarget = 0, asyncRoundsLeft = 0; uint32_t asyncRoundBefore = 0;
 	ChainState* chains = nullptr;
 	uint32_t* resTrial = nullptr; uint32_t* origTrial = nullptr; double* resPos = nullptr;
 	uint32_t* prev = nullptr; uint64_t prevCap = 0;
@@ -53,7 +59,7 @@ struct sarw_ctx {
 	double seedMs = 0, growMs = 0; int64_t growLaunches = 0, seedLaunches = 0;
 	uint32_t mrRank = 0, mrRanks = 1; bool mrPending = false;   // multi-rank mode (sarw_mr_*)
 	void* xbuf = nullptr; size_t xbufRecBytes = 0;               // peer-memory exchange buffer (plain cudaMalloc: IPC-exportable)
-	void* peerRec[8] = {}; void* peerFlags[8] = {}; void* peerDirty[8] = {}; bool peersOpen = false;
+	void* peerRec[8] = {}; void* peerFlags[8] = {}; void* peerDirty[8] = {}; bool peersOpen = false, peersLocal = false;
 };
 
 namespace {
@@ -184,24 +190,51 @@ int ensure_rounds(sarw_ctx* c, uint32_t rounds)
 	return 0;
 }
 
-int read_control(sarw_ctx* c, Control* h)
+// Pinned control-block mirrors are recycled between contexts (cudaHostAlloc costs far more than a melt's launch).
+struct PinnedPool { std::mutex m; std::vector<Control*> idle; };
+static PinnedPool g_pinned;
+Control* pinned_get()
 {
-	// A device-to-host copy into pageable memory blocks INSIDE the driver until the stream reaches it, and other host threads'
-	// CUDA calls (other melts on the same GPU) queue up behind it for the length of the running kernel (measured: sarw_create
-	// stalled 7.5 ms = one growth kernel). Waiting for the stream first keeps the blocking part outside the driver.
-	CU(c, cudaStreamSynchronize(c->stream));
-	CU(c, cudaMemcpyAsync(h, c->ctl, sizeof(Control), cudaMemcpyDeviceToHost, c->stream));
-	CU(c, cudaStreamSynchronize(c->stream));
-	return 0;
+	{	std::lock_guard<std::mutex> lk(g_pinned.m);
+		if (!g_pinned.idle.empty()) { Control* p = g_pinned.idle.back(); g_pinned.idle.pop_back(); return p; }
+	}
+	Control* p = nullptr;
+	if (cudaHostAlloc((void**)&p, sizeof(Control), cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+	return p;
+}
+void pinned_put(Control* p)
+{
+	if (!p) return;
+	std::lock_guard<std::mutex> lk(g_pinned.m);
+	g_pinned.idle.push_back(p);
 }
 
+// ONE synchronisation: the control block (progress, counters, overflow-table fill) lands in the context's pinned mirror. A copy into
+// pinned memory is truly asynchronous, so the driver lock is not held while the stream drains (with a pageable destination every other
+// host thread's CUDA call queued up behind it for the length of the running kernel: sarw_create stalled 7.5 ms, measured in round 1).
+int read_control(sarw_ctx* c, Control* h)
+{
+	CU(c, cudaMemcpyAsync(c->hctl, c->ctl, sizeof(Control), cudaMemcpyDeviceToHost, c->stream));
+	CU(c, cudaStreamSynchronize(c->stream));
+	c->mirrorStale = false;
+	if (!c->seedTimed) {   // first read after the seeding kernels: what sarw_initiate reports
+		float ms = 0; cudaEventElapsedTime(&ms, c->evS0, c->evS1);
+		c->seedMs += ms; c->seedTimed = true;
+		c->initiated = c->hctl->initiated != 0;
+		c->nSeeded = (uint32_t)(c->hctl->nBeads / 2);
+	}
+	if (!c->growTimed) { float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); c->growMs += ms; c->growTimed = true; }
+	if (h && h != c->hctl) *h = *c->hctl;
+	return 0;
+}
+// the mirror as of now: a read only when something was launched since the last one
+int fresh(sarw_ctx* c) { return c->mirrorStale ? read_control(c, nullptr) : 0; }
+
+// after read_control: did the overflow table run out of room?
 int check_overflow(sarw_ctx* c)
 {
-	uint32_t n = 0;
-	CU(c, cudaStreamSynchronize(c->stream));
-	CU(c, cudaMemcpyAsync(&n, c->T.ovfCount, sizeof n, cudaMemcpyDeviceToHost, c->stream));
-	CU(c, cudaStreamSynchronize(c->stream));
-	if (n > c->T.ovfCap) return fail(c, "cell overflow list exhausted (%u beads did not fit their cells; raise cellEdge or lower density)", n);
+	const uint32_t n = c->hctl->ovfCount;
+	if (n > c->T.ovfLimit) return fail(c, "cell overflow table exhausted (%u beads did not fit their cells; raise cellEdge or lower density)", n);
 	return 0;
 }
 
@@ -220,6 +253,7 @@ void fill_stats(sarw_ctx* c, const Control& h, sarw_stats* s)
 	s->cycPropose = h.cycPropose; s->cycVerify = h.cycVerify; s->cycCleanup = h.cycCleanup;
 	s->cleanupRounds = h.cleanupRounds; s->deadChains = h.deadChains;
 	s->stageFallbacks = h.stageFallbacks; s->arcFallbacks = h.arcFallbacks;
+	s->overflowBeads = h.ovfCount;
 	for (int k = 0; k < 8; k++) s->cycSub[k] = h.cycSub[k];
 }
 
@@ -231,7 +265,8 @@ extern "C" {
 int sarw_debug_busy(sarw_ctx* c, unsigned long long* out, int n)
 {
 	if (!c || !out) return 1;
-	Control h; if (read_control(c, &h)) return 1;
+	if (fresh(c)) return 1;
+	Control& h = *c->hctl;
 	for (int k = 0; k < n && k < 256; k++) out[k] = h.busy[k];
 	return 0;
 }
@@ -299,16 +334,21 @@ int sarw_create(const sarw_params* p, sarw_ctx** out)
 		g.L[k] = p->boxSize[k]; g.Linv[k] = 1. / p->boxSize[k];
 		int S = (int)floor(p->boxSize[k] / edgeMin); if (S < 1) S = 1;
 		g.S[k] = S; g.a[k] = p->boxSize[k] / S; g.ainv[k] = S / p->boxSize[k]; g.sOverL[k] = (double)S;
-		g.reachCells[k] = (p->minDist / g.a[k]) * (1 + 1e-9) + 1e-7;
+		// query half-width in cells, strictly below 0.5: a sphere touches at most 2 cells per dimension. The clamp can only bite when
+		// S == 1 (a = L < 2.002 minDist), where every bead lives in the one cell that is visited anyway.
+		g.reachCells[k] = std::min((p->minDist / g.a[k]) * (1 + 1e-9) + 1e-7, 0.4999999);
+		g.qs[k] = (float)(g.a[k] / 65536.0);
 		amax = std::max(amax, g.a[k]);
 	}
 	g.cap = (p->cellCapacity >= 1 && p->cellCapacity <= MAX_CAP) ? p->cellCapacity : MAX_CAP;
-	{	// fp32 pre-filter bounds; the undecided band covers fp32 storage + arithmetic error with a wide margin
-		double band = 4e-6 * (p->minDist + amax + 2 * BOND_LENGTH);
+	{	// fp32 pre-filter bounds. The undecided band covers the half quantisation step of the stored in-cell offsets (edge / 131072 per
+		// coordinate), fp32 storage and arithmetic error, all with a wide margin; whatever falls inside is decided in fp64 from lpos.
+		double band = 4e-6 * (p->minDist + amax + 2 * BOND_LENGTH) + 1.5 * sqrt(3.0) * amax / 131072.0;
 		double lo = std::max(0.0, p->minDist - band), hi = p->minDist + band;
 		g.lo2 = nextafterf((float)(lo * lo * (1 - 1e-6)), 0.f);
 		g.hi2 = nextafterf((float)(hi * hi * (1 + 1e-6)), INFINITY);
 		g.regionReach = p->minDist * (1 + 1e-9) + 1e-6 * amax + band;
+		g.arcShrink = 1e-5 + 1.5 * sqrt(3.0) * amax / 131072.0;
 	}
 	{	double phi = (180 - 109.5) * M_PI / 180, sp, cp;   // sarw.cpp:165
 		sincos_portable(phi, sp, cp);
@@ -341,7 +381,7 @@ int sarw_create(const sarw_params* p, sarw_ctx** out)
 		if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
 	}
 	mark("device+stream");
-	cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
+	cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1); cudaEventCreate(&c->evS0); cudaEventCreate(&c->evS1);
 	mark("events");
 
 	const size_t nCells = (size_t)g.S[0] * g.S[1] * g.S[2];
@@ -376,12 +416,22 @@ int sarw_create(const sarw_params* p, sarw_ctx** out)
 			}
 		}
 	}
-	c->T.ovfCap = 1u << 20;
-	CUB_(dev_alloc(c, &c->T.ovf, (size_t)c->T.ovfCap * sizeof(uint4)));
-	CUB_(dev_alloc(c, &c->T.ovfCount, sizeof(uint32_t)));
-	CUB_(cudaMemsetAsync(c->T.ovfCount, 0, sizeof(uint32_t), c->stream));
+	{	// overflow hash table: a power of two >= nCells / 16 entries (>= 2^16); at most half of it is ever used
+		uint64_t want = std::max<uint64_t>((uint64_t)1 << 16, nCells / 16);
+		if (p->cellCapacity >= 1 && p->cellCapacity < MAX_CAP) want = std::max<uint64_t>(want, nCells * 4);   // test hook: most beads overflow
+		uint64_t size = (uint64_t)1 << 16;
+		while (size < want && size < ((uint64_t)1 << 31)) size <<= 1;
+		c->T.ovfMask = (uint32_t)(size - 1); c->T.ovfLimit = (uint32_t)(size / 2);
+		CUB_(dev_alloc(c, &c->T.ovf, (size_t)size * sizeof(uint4)));
+		CUB_(cudaMemsetAsync(c->T.ovf, 0xFF, (size_t)size * sizeof(uint4), c->stream));
+	}
 	CUB_(dev_alloc(c, &c->ctl, sizeof(Control)));
-	CUB_(cudaMemsetAsync(c->ctl, 0, sizeof(Control), c->stream));
+	c->hctl = pinned_get();
+	if (!c->hctl) { fail(c, "cudaHostAlloc of the control-block mirror failed"); return bail(1); }
+	memset(c->hctl, 0, sizeof(Control));
+	c->hctl->seedFailChain = ID_NONE; c->hctl->lastProgressed = 1;
+	CUB_(cudaMemcpyAsync(c->ctl, c->hctl, sizeof(Control), cudaMemcpyHostToDevice, c->stream));
+	c->T.ovfCount = &c->ctl->ovfCount;
 	CUB_(dev_alloc(c, &c->chains, (size_t)g.nChains * sizeof(ChainState)));
 	CUB_(cudaMemsetAsync(c->chains, 0, (size_t)g.nChains * sizeof(ChainState), c->stream));
 	CUB_(dev_alloc(c, &c->resTrial, (size_t)g.nChains * sizeof(uint32_t)));
@@ -414,15 +464,18 @@ void sarw_destroy(sarw_ctx* c)
 	if (c->stream) cudaStreamSynchronize(c->stream);
 	if (c->stream) {
 		if (c->allocStream != c->stream) cudaStreamSynchronize(c->allocStream);   // both streams idle: the blocks may be parked
-		dev_park(c, c->T.cells); dev_park(c, c->T.lpos); dev_park(c, c->T.ovf); dev_free(c, c->T.ovfCount);
+		dev_park(c, c->T.cells); dev_park(c, c->T.lpos); dev_park(c, c->T.ovf);
 		dev_free(c, c->ctl); dev_park(c, c->chains); dev_park(c, c->resTrial); dev_park(c, c->origTrial); dev_park(c, c->resPos); dev_park(c, c->prev);
 		dev_park(c, c->roundAcc); dev_park(c, c->roundProg); dev_park(c, c->dirtyCount); dev_park(c, c->dirtyList); dev_park(c, c->grafts);
 	}
-	if (c->peersOpen) for (uint32_t p = 0; p < c->mrRanks; ++p) if (p != c->mrRank && c->peerRec[p]) cudaIpcCloseMemHandle(c->peerRec[p]);
+	if (c->peersOpen && !c->peersLocal) for (uint32_t p = 0; p < c->mrRanks; ++p) if (p != c->mrRank && c->peerRec[p]) cudaIpcCloseMemHandle(c->peerRec[p]);
 	if (c->xbuf) cudaFree(c->xbuf);
 	if (c->ev0) cudaEventDestroy(c->ev0);
 	if (c->ev1) cudaEventDestroy(c->ev1);
+	if (c->evS0) cudaEventDestroy(c->evS0);
+	if (c->evS1) cudaEventDestroy(c->evS1);
 	if (c->ownStream && c->stream) cudaStreamDestroy(c->stream);
+	pinned_put(c->hctl);
 	delete c;
 }
 
@@ -447,9 +500,9 @@ int sarw_lookup_add_points(sarw_ctx* c, const double* xyz, int64_t n)
 	CU(c, dev_alloc(c, &d, (size_t)n * 3 * sizeof(double)));
 	CU(c, cudaMemcpyAsync(d, xyz, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
 	cudaError_t e = launch_add_points(c->g, c->T, d, n, c->nextId, c->stream);
+	if (e != cudaSuccess) { dev_free(c, d); return fail(c, "add_points failed: %s", cudaGetErrorString(e)); }
+	if (read_control(c, nullptr)) { dev_free(c, d); return 1; }
 	dev_free(c, d);
-	cudaError_t e2 = cudaStreamSynchronize(c->stream);
-	if (e != cudaSuccess || e2 != cudaSuccess) return fail(c, "add_points failed: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
 	c->nextId += (uint32_t)n;
 	return check_overflow(c);
 }
@@ -460,7 +513,8 @@ int64_t sarw_lookup_size(sarw_ctx* c)
 {
 	if (!c) return -1;
 	if (!c->initiateCalled) return c->nextId;
-	Control h; if (read_control(c, &h)) return -1;
+	if (fresh(c)) return -1;
+	Control& h = *c->hctl;
 	return (int64_t)c->g.idAtomBase + (int64_t)h.nBeads;
 }
 
@@ -528,9 +582,9 @@ int sarw_lookup_find_batch(sarw_ctx* c, const double* xyz, const int64_t* ignore
 	return 0;
 }
 
-int sarw_initiate(sarw_ctx* c, int32_t* ok)
+// the seeding kernels on the context's stream, no synchronisation
+static int initiate_enqueue(sarw_ctx* c)
 {
-	if (!c) return 1;
 	if (c->initiateCalled) return fail(c, "sarw_initiate was already called on this context");
 	cudaSetDevice(c->device);
 	Geom& g = c->g;
@@ -542,19 +596,20 @@ int sarw_initiate(sarw_ctx* c, int32_t* ok)
 	if (ensure_rounds(c, std::max<uint32_t>(c->roundCap, 1))) return 1;
 	if (ensure_ids(c, (uint64_t)g.idAtomBase + slots_for_rounds(c, c->roundCap))) return 1;   // obstacles shift the atom index space
 
-	Control h0; memset(&h0, 0, sizeof h0);
-	h0.seedFailChain = ID_NONE; h0.lastProgressed = 1;
-	CU(c, cudaMemcpyAsync(c->ctl, &h0, sizeof h0, cudaMemcpyHostToDevice, c->stream));
-	CU(c, cudaEventRecord(c->ev0, c->stream));
+	CU(c, cudaEventRecord(c->evS0, c->stream));
 	int launches = 0;
 	CU(c, launch_seed(g, c->T, c->chains, c->resTrial, c->prev, c->grafts, c->ctl, c->dirtyList, c->numSMs, c->stream, &launches));
-	CU(c, cudaEventRecord(c->ev1, c->stream));
-	Control h; if (read_control(c, &h)) return 1;
-	float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
-	c->seedMs += ms; c->seedLaunches += launches;
-	c->initiateCalled = true;
-	c->initiated = h.initiated != 0;
-	c->nSeeded = (uint32_t)(h.nBeads / 2);
+	CU(c, cudaEventRecord(c->evS1, c->stream));
+	c->seedLaunches += launches;
+	c->initiateCalled = true; c->mirrorStale = true; c->seedTimed = false;
+	return 0;
+}
+
+int sarw_initiate(sarw_ctx* c, int32_t* ok)
+{
+	if (!c) return 1;
+	if (initiate_enqueue(c)) return 1;
+	if (read_control(c, nullptr)) return 1;
 	if (ok) *ok = c->initiated ? 1 : 0;
 	return check_overflow(c);
 }
@@ -586,7 +641,8 @@ int sarw_debug_prof(unsigned long long* out, int n, int reset) { cudaDeviceSynch
 int sarw_debug_paths(sarw_ctx* c, unsigned long long* out)
 {
 	if (!c) return 1;
-	Control h; if (read_control(c, &h)) return 1;
+	if (fresh(c)) return 1;
+	Control& h = *c->hctl;
 	for (int k = 0; k < 4; k++) { out[k] = h.pathCyc[k]; out[4 + k] = h.pathCnt[k]; }
 	return 0;
 }
@@ -618,33 +674,54 @@ int32_t sarw_concurrent_capacity(sarw_ctx* c)
 	return n < 1 ? 1 : n;
 }
 
-static int grow_impl(sarw_ctx* c, int64_t target, int64_t maxRounds, sarw_stats* stats)
+// CTAs of a cooperative growth launch: enough for one warp per chain, at most what fits the device (or the caller's cap)
+static int grow_blocks(const sarw_ctx* c, int64_t chains)
 {
-	if (!c->initiateCalled) return fail(c, "sarw_initiate must be called before growing");
-	cudaSetDevice(c->device);
-	Geom g = c->g;
-	if (target > 0) g.target = target;
-	Control h; if (read_control(c, &h)) return 1;
-	int64_t roundsLeft = maxRounds < 0 ? INT64_MAX : maxRounds;
+	int64_t cap = c->growBlocksMax;
+	if (c->p.maxBlocks > 0 && c->p.maxBlocks < cap) cap = c->p.maxBlocks;
+	const int blocks = (int)std::min<int64_t>(cap, (chains + 7) / 8);
+	return blocks < 1 ? 1 : blocks;
+}
+
+// one growth launch on the context's stream covering as many rounds as bead storage is allocated for; no synchronisation
+static int grow_enqueue(sarw_ctx* c, const Geom& g, uint32_t roundNow, int64_t roundsLeft)
+{
+	if (roundNow >= c->roundCap && ensure_rounds(c, roundNow + 1)) return 1;
+	uint32_t roundEnd = c->roundCap;
+	if ((int64_t)(roundEnd - roundNow) > roundsLeft) roundEnd = roundNow + (uint32_t)roundsLeft;
+	CU(c, cudaEventRecord(c->ev0, c->stream));
+	CU(c, launch_grow_auto(c, g, roundEnd, grow_blocks(c, g.nChains)));
+	CU(c, cudaEventRecord(c->ev1, c->stream));
+	c->mirrorStale = true; c->growTimed = false; c->growLaunches += 1;
+	return 0;
+}
+
+// main()'s loop: launch, read the control block (ONE synchronisation per launch), repeat only if round storage ran out
+static int grow_loop(sarw_ctx* c, const Geom& g, int64_t roundsLeft)
+{
+	Control& h = *c->hctl;
 	// main() only enters the loop when initiateChain succeeded (sarw.cpp:66)
 	while (c->initiated && roundsLeft > 0 && (int64_t)h.nBeads < g.target && h.lastProgressed) {
-		if (h.round >= c->roundCap && ensure_rounds(c, h.round + 1)) return 1;
-		uint32_t roundEnd = c->roundCap;
-		if ((int64_t)(roundEnd - h.round) > roundsLeft) roundEnd = h.round + (uint32_t)roundsLeft;
-		int blocks = (int)std::min<int64_t>(c->growBlocksMax, ((int64_t)g.nChains + 7) / 8);
-		if (blocks < 1) blocks = 1;
-		CU(c, cudaEventRecord(c->ev0, c->stream));
-		CU(c, launch_grow_auto(c, g, roundEnd, blocks));
-		CU(c, cudaEventRecord(c->ev1, c->stream));
-		uint32_t before = h.round;
-		if (read_control(c, &h)) return 1;
-		float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
-		c->growMs += ms; c->growLaunches += 1;
+		const uint32_t before = h.round;
+		if (grow_enqueue(c, g, before, roundsLeft)) return 1;
+		if (read_control(c, nullptr)) return 1;
 		roundsLeft -= (int64_t)(h.round - before);
 		if (check_overflow(c)) return 1;
 		if (h.round == before) break;
 	}
-	if (stats) fill_stats(c, h, stats);
+	return 0;
+}
+
+static int grow_impl(sarw_ctx* c, int64_t target, int64_t maxRounds, sarw_stats* stats)
+{
+	if (!c->initiateCalled) return fail(c, "sarw_initiate must be called before growing");
+	if (c->asyncPending) return fail(c, "sarw_wait must be called before another growth call");
+	cudaSetDevice(c->device);
+	Geom g = c->g;
+	if (target > 0) g.target = target;
+	if (fresh(c)) return 1;
+	if (grow_loop(c, g, maxRounds < 0 ? INT64_MAX : maxRounds)) return 1;
+	if (stats) fill_stats(c, *c->hctl, stats);
 	return 0;
 }
 
@@ -654,26 +731,57 @@ int sarw_grow(sarw_ctx* c, int64_t target, int64_t maxRounds, sarw_stats* stats)
 	return grow_impl(c, target, maxRounds, stats);
 }
 
+int sarw_grow_async(sarw_ctx* c, int64_t target, int64_t maxRounds)
+{
+	if (!c) return 1;
+	if (c->asyncPending) return fail(c, "sarw_wait must be called before another growth call");
+	cudaSetDevice(c->device);
+	// main()'s sequence (sarw.cpp:66-78): initiateChain, then the loop. Whether seeding succeeded is checked by the growth kernel
+	// itself (it reads `initiated` from the control block), so nothing has to come back to the host in between.
+	if (!c->initiateCalled) { if (initiate_enqueue(c)) return 1; }
+	else if (fresh(c)) return 1;
+	Geom g = c->g;
+	if (target > 0) g.target = target;
+	c->asyncTarget = g.target; c->asyncRoundsLeft = maxRounds < 0 ? INT64_MAX : maxRounds; c->asyncRoundBefore = c->hctl->round;
+	if (c->asyncRoundsLeft > 0 && grow_enqueue(c, g, c->asyncRoundBefore, c->asyncRoundsLeft)) return 1;
+	c->asyncPending = true;
+	return 0;
+}
+
+int sarw_wait(sarw_ctx* c, sarw_stats* stats)
+{
+	if (!c) return 1;
+	cudaSetDevice(c->device);
+	if (c->asyncPending) {
+		c->asyncPending = false;
+		if (read_control(c, nullptr)) return 1;
+		if (check_overflow(c)) return 1;
+		Control& h = *c->hctl;
+		Geom g = c->g; g.target = c->asyncTarget;
+		const int64_t left = c->asyncRoundsLeft - (int64_t)(h.round - c->asyncRoundBefore);
+		// the launch stops at the last round bead storage was allocated for: continue (synchronously) if the walk needs more
+		if (h.round > c->asyncRoundBefore && grow_loop(c, g, left)) return 1;
+	} else if (fresh(c)) return 1;
+	if (stats) fill_stats(c, *c->hctl, stats);
+	return 0;
+}
+
 int sarw_propagate_round(sarw_ctx* c, int32_t* progressed)
 {
 	if (!c) return 1;
 	if (!c->initiateCalled) return fail(c, "sarw_initiate must be called before sarw_propagate_round");
-	if (!c->initiated) return fail(c, "initiateChain failed; the reference never propagates in that case (sarw.cpp:66)");
+	if (c->asyncPending) return fail(c, "sarw_wait must be called before another growth call");
 	// one unconditional round, like a direct call of SARW::propagateChain
 	cudaSetDevice(c->device);
-	Control h; if (read_control(c, &h)) return 1;
-	if (h.round >= c->roundCap && ensure_rounds(c, h.round + 1)) return 1;
+	if (fresh(c)) return 1;
+	if (!c->initiated) return fail(c, "initiateChain failed; the reference never propagates in that case (sarw.cpp:66)");
+	Control& h = *c->hctl;
 	Geom g = c->g;
 	g.target = INT64_MAX;
-	unsigned one = 1;
-	CU(c, cudaMemcpyAsync(&c->ctl->lastProgressed, &one, sizeof one, cudaMemcpyHostToDevice, c->stream));
-	int blocks = (int)std::min<int64_t>(c->growBlocksMax, ((int64_t)g.nChains + 7) / 8);
-	CU(c, cudaEventRecord(c->ev0, c->stream));
-	CU(c, launch_grow_auto(c, g, h.round + 1, blocks));
-	CU(c, cudaEventRecord(c->ev1, c->stream));
-	if (read_control(c, &h)) return 1;
-	float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
-	c->growMs += ms; c->growLaunches += 1;
+	h.lastProgressed = 1;   // one unconditional round
+	CU(c, cudaMemcpyAsync(&c->ctl->lastProgressed, &h.lastProgressed, sizeof(unsigned), cudaMemcpyHostToDevice, c->stream));   // source is pinned
+	if (grow_enqueue(c, g, h.round, 1)) return 1;
+	if (read_control(c, nullptr)) return 1;
 	if (progressed) *progressed = (int32_t)h.lastProgressed;
 	return check_overflow(c);
 }
@@ -689,22 +797,21 @@ int sarw_mr_setup(sarw_ctx* c, int32_t rank, int32_t nranks, int64_t* recordsPer
 	return 0;
 }
 
-static int mr_launch(sarw_ctx* c, uint32_t phase, void* localRec, const void* allRec, Control* hOut)
+static int mr_launch(sarw_ctx* c, uint32_t phase, void* localRec, const void* allRec, bool readBack)
 {
 	if (!c->initiateCalled) return fail(c, "sarw_initiate must be called before the multi-rank rounds");
 	cudaSetDevice(c->device);
-	Control h; if (read_control(c, &h)) return 1;
+	if (phase != 2u && fresh(c)) return 1;   // phase 2 follows phase 1 of the same round: the round number in the mirror is still right
+	Control& h = *c->hctl;
 	if (h.round >= c->roundCap && ensure_rounds(c, h.round + 1)) return 1;
-	int blocks = (int)std::min<int64_t>(c->growBlocksMax, ((int64_t)c->g.nChains + 7) / 8);
-	if (blocks < 1) blocks = 1;
 	CU(c, cudaEventRecord(c->ev0, c->stream));
 	CU(c, launch_grow_mr(c->g, c->T, c->chains, c->resTrial, c->origTrial, c->resPos, c->prev, c->ctl, c->roundAcc, c->roundProg, c->dirtyCount, c->dirtyList,
-		h.round + 1, blocks, c->mrRank, c->mrRanks, phase, localRec, allRec, nullptr, nullptr, nullptr, 0u, c->stream));
+		h.round + 1, grow_blocks(c, c->g.nChains), c->mrRank, c->mrRanks, phase, localRec, allRec, nullptr, nullptr, nullptr, 0u, c->stream));
 	CU(c, cudaEventRecord(c->ev1, c->stream));
-	c->growLaunches += 1;
-	if (hOut) {
-		if (read_control(c, hOut)) return 1;
-		float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); c->growMs += ms;
+	c->growLaunches += 1; c->mirrorStale = true;
+	if (readBack) {
+		c->growTimed = false;
+		if (read_control(c, nullptr)) return 1;
 		return check_overflow(c);
 	}
 	return 0;
@@ -713,7 +820,8 @@ static int mr_launch(sarw_ctx* c, uint32_t phase, void* localRec, const void* al
 int sarw_mr_more(sarw_ctx* c, int32_t* more)
 {
 	if (!c || !more) return 1;
-	Control h; if (read_control(c, &h)) return 1;
+	if (fresh(c)) return 1;
+	Control& h = *c->hctl;
 	*more = (c->initiated && (int64_t)h.nBeads < c->g.target && h.lastProgressed) ? 1 : 0;
 	return 0;
 }
@@ -721,7 +829,7 @@ int sarw_mr_more(sarw_ctx* c, int32_t* more)
 int sarw_mr_propose(sarw_ctx* c, void* d_localRecords)
 {
 	if (!c || !d_localRecords) return 1;
-	if (mr_launch(c, 1u, d_localRecords, nullptr, nullptr)) return 1;
+	if (mr_launch(c, 1u, d_localRecords, nullptr, false)) return 1;
 	c->mrPending = true;
 	return 0;
 }
@@ -729,8 +837,8 @@ int sarw_mr_propose(sarw_ctx* c, void* d_localRecords)
 int sarw_mr_finish(sarw_ctx* c, const void* d_allRecords, int32_t* more)
 {
 	if (!c || !d_allRecords) return 1;
-	Control h;
-	if (mr_launch(c, 2u, nullptr, d_allRecords, &h)) return 1;
+	if (mr_launch(c, 2u, nullptr, d_allRecords, true)) return 1;
+	Control& h = *c->hctl;
 	if (more) *more = (c->initiated && (int64_t)h.nBeads < c->g.target && h.lastProgressed) ? 1 : 0;
 	return 0;
 }
@@ -739,8 +847,7 @@ int sarw_mr_commit(sarw_ctx* c)
 {
 	if (!c) return 1;
 	if (!c->mrPending) return 0;
-	Control h;
-	if (mr_launch(c, 3u, nullptr, nullptr, &h)) return 1;
+	if (mr_launch(c, 3u, nullptr, nullptr, true)) return 1;
 	c->mrPending = false;
 	return 0;
 }
@@ -780,29 +887,50 @@ int sarw_mr_peer_connect(sarw_ctx* c, const void* allHandles)
 	return 0;
 }
 
+// contexts of ONE process (ranks emulated on one GPU, or several GPUs of one process with peer access enabled): the exchange
+// buffers are plain device pointers, no IPC. bases[r] = sarw_mr_peer_local_base of rank r's context.
+int sarw_mr_peer_local_base(sarw_ctx* c, void** base)
+{
+	if (!c || !base) return 1;
+	if (!c->xbuf) return fail(c, "sarw_mr_peer_local_base: call sarw_mr_peer_export first");
+	*base = c->xbuf;
+	return 0;
+}
+
+int sarw_mr_peer_connect_local(sarw_ctx* c, void* const* bases)
+{
+	if (!c || !bases) return 1;
+	if (!c->xbuf) return fail(c, "sarw_mr_peer_connect_local: call sarw_mr_peer_export first");
+	for (uint32_t p = 0; p < c->mrRanks; ++p) {
+		char* base = (char*)(p == c->mrRank ? c->xbuf : bases[p]);
+		if (!base) return fail(c, "sarw_mr_peer_connect_local: no buffer for rank %u", p);
+		c->peerRec[p] = base; c->peerFlags[p] = base + c->xbufRecBytes; c->peerDirty[p] = base + c->xbufRecBytes + 256;
+	}
+	c->peersOpen = true; c->peersLocal = true;
+	return 0;
+}
+
 int sarw_mr_grow_peer(sarw_ctx* c, int64_t maxRounds, sarw_stats* stats)
 {
 	if (!c) return 1;
 	if (!c->peersOpen) return fail(c, "sarw_mr_grow_peer: peers are not connected");
 	if (!c->initiateCalled) return fail(c, "sarw_initiate must be called before growing");
 	cudaSetDevice(c->device);
-	Control h; if (read_control(c, &h)) return 1;
+	if (fresh(c)) return 1;
+	Control& h = *c->hctl;
 	int64_t roundsLeft = maxRounds < 0 ? INT64_MAX : maxRounds;
 	while (c->initiated && roundsLeft > 0 && (int64_t)h.nBeads < c->g.target && h.lastProgressed) {
 		if (h.round >= c->roundCap && ensure_rounds(c, h.round + 1)) return 1;
 		uint32_t roundEnd = c->roundCap;
 		if ((int64_t)(roundEnd - h.round) > roundsLeft) roundEnd = h.round + (uint32_t)roundsLeft;
-		int blocks = (int)std::min<int64_t>(c->growBlocksMax, ((int64_t)c->g.nChains / c->mrRanks + 7) / 8);
-		if (blocks < 1) blocks = 1;
 		CU(c, cudaEventRecord(c->ev0, c->stream));
 		CU(c, launch_grow_mr(c->g, c->T, c->chains, c->resTrial, c->origTrial, c->resPos, c->prev, c->ctl, c->roundAcc, c->roundProg, c->dirtyCount, c->dirtyList,
-			roundEnd, blocks, c->mrRank, c->mrRanks, 4u, nullptr, nullptr, c->peerRec, c->peerFlags, c->peerDirty,
+			roundEnd, grow_blocks(c, (int64_t)c->g.nChains / c->mrRanks), c->mrRank, c->mrRanks, 4u, nullptr, nullptr, c->peerRec, c->peerFlags, c->peerDirty,
 			(c->p.launchMode & 2) ? 0u : 1u, c->stream));   // launchMode bit 1: keep the verification replicated (diagnostics)
 		CU(c, cudaEventRecord(c->ev1, c->stream));
-		uint32_t before = h.round;
-		if (read_control(c, &h)) return 1;
-		float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
-		c->growMs += ms; c->growLaunches += 1;
+		c->mirrorStale = true; c->growTimed = false; c->growLaunches += 1;
+		const uint32_t before = h.round;
+		if (read_control(c, nullptr)) return 1;
 		roundsLeft -= (int64_t)(h.round - before);
 		if (h.abort) return fail(c, "multi-rank growth aborted: a peer stopped answering (round %u)", h.round);
 		if (check_overflow(c)) return 1;
@@ -824,11 +952,9 @@ int sarw_get_stats(sarw_ctx* c, sarw_stats* s)
 {
 	if (!c || !s) return 1;
 	cudaSetDevice(c->device);
-	Control h; if (read_control(c, &h)) return 1;
+	if (fresh(c)) return 1;
+	Control& h = *c->hctl;
 	fill_stats(c, h, s);
-	uint32_t n = 0;
-	cudaMemcpy(&n, c->T.ovfCount, sizeof n, cudaMemcpyDeviceToHost);
-	s->overflowBeads = n;
 	return 0;
 }
 
@@ -837,7 +963,8 @@ int sarw_download(sarw_ctx* c, double* xyz, int32_t* chainID, int32_t* type, int
 	if (!c) return 1;
 	if (!c->initiateCalled) return fail(c, "nothing to download before sarw_initiate");
 	cudaSetDevice(c->device);
-	Control h; if (read_control(c, &h)) return 1;
+	if (fresh(c)) return 1;
+	Control& h = *c->hctl;
 	const uint64_t N = h.nBeads, nBonds = N > c->nSeeded ? N - c->nSeeded : 0;
 	if (N == 0) return 0;
 	const uint64_t nSlots = slots_for_rounds(c, h.round);
@@ -884,7 +1011,8 @@ int sarw_rdf(sarw_ctx* c, double rMin, double dr, int32_t nBins, uint64_t* intra
 	if (!intra || !inter || nBins < 1 || nBins > 4096 || !(dr > 0) || !std::isfinite(rMin)) return fail(c, "sarw_rdf: bad arguments (1 <= nBins <= 4096, dr > 0)");
 	if (!c->initiateCalled) return fail(c, "nothing to analyse before sarw_initiate");
 	cudaSetDevice(c->device);
-	Control h; if (read_control(c, &h)) return 1;
+	if (fresh(c)) return 1;
+	Control& h = *c->hctl;
 	const uint64_t N = h.nBeads;
 	for (int32_t k = 0; k < nBins; k++) { intra[k] = 0; inter[k] = 0; }
 	if (N == 0) return 0;
@@ -929,7 +1057,8 @@ int sarw_chain_shapes(sarw_ctx* c, double* ree2, double* rg2)
 	if (!c || !ree2 || !rg2) return 1;
 	if (!c->initiateCalled) return fail(c, "nothing to analyse before sarw_initiate");
 	cudaSetDevice(c->device);
-	Control h; if (read_control(c, &h)) return 1;
+	if (fresh(c)) return 1;
+	Control& h = *c->hctl;
 	double* d = nullptr;
 	const size_t n = c->g.nChains;
 	CU(c, dev_alloc(c, &d, 2 * n * sizeof(double)));
@@ -963,7 +1092,8 @@ int sarw_round_counts(sarw_ctx* c, int64_t* counts, int64_t n)
 	if (!c || (n > 0 && !counts)) return 1;
 	if (!c->initiateCalled) return fail(c, "sarw_initiate must be called first");
 	cudaSetDevice(c->device);
-	Control h; if (read_control(c, &h)) return 1;
+	if (fresh(c)) return 1;
+	Control& h = *c->hctl;
 	int64_t m = std::min<int64_t>(n, h.round);
 	if (m <= 0) return 0;
 	std::vector<uint32_t> acc((size_t)m);

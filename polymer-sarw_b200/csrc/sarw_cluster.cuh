@@ -8,8 +8,9 @@
 //   * every warp broadcasts its tentative bead {xyz, trial, cell} into the shared memory of EVERY CTA of the cluster
 //     (distributed shared memory), so after the hardware cluster barrier each warp checks conflicts with lower chains and
 //     counts the round's accepted beads from its own CTA's copy, without global loads or atomics;
-//   * beads enter the cell list AFTER that barrier with plain stores: the slot is old count (seen while staging) + rank
-//     among this round's beads of the same cell, which every warp derives from the same table — no atomic round trip;
+//   * beads enter the cell list AFTER that barrier with plain stores: the slot is the rank-th free slot of the cell as seen while
+//     staging, rank = position among this round's beads of the same cell, which every warp derives from the same table — no
+//     atomic round trip;
 //   * the second cluster barrier publishes the stores and the (rare) conflict flag; conflicts fall back to the shared
 //     serial clean-up (cleanup_round) through global memory.
 #pragma once
@@ -18,7 +19,7 @@ namespace cgx = ::cooperative_groups;
 
 constexpr int CL_MAX_CTAS = 16;         // non-portable cluster size
 constexpr int CL_MAXCH = 16 * CL_MAX_CTAS;   // table capacity: 16 warps per CTA x 16 CTAs (the 8-warp variant uses half of it)
-constexpr int CL_REGION_CELLS = 64;     // staged region: at most 4 x 4 x 4 cells of 128 bytes
+constexpr int CL_REGION_CELLS = 64;     // staged region: at most 4 x 4 x 4 cells of 32 bytes (2 KB per chain)
 
 
 // tentative bead of one chain in one round, as broadcast to every CTA
@@ -37,16 +38,17 @@ constexpr size_t cluster_smem_bytes(int warps)
 		+ 2 * (size_t)CL_MAXCH * sizeof(TentRec) + (size_t)warps * 8 + 16;
 }
 
-__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_arrive() { fence_cells_for_tma(); asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
 // Blocked arcs as (cos alpha, sin alpha, kappa): a trial angle theta is CERTAINLY rejected by the bead iff
-// cos(alpha) cos(theta) + sin(alpha) sin(theta) >= kappa. kappa carries margins (1e-5 A in distance, 3e-5 in cos) that
+// cos(alpha) cos(theta) + sin(alpha) sin(theta) >= kappa. kappa carries margins (g.arcShrink = 1e-5 A + the quantisation error of
+// the staged positions in distance, 3e-5 in cos) that
 // dominate the fp32 evaluation error of both sides; arcs only ever skip trials, the exact test decides everything else.
 __device__ __forceinline__ int build_arcs_cs(const Geom& g, const Frame& f, const double last[3], const float4* nb, int nnb, float4* arcs, int arcCap, int lane)
 {
 	const double rho = g.dSinPhi, h = g.dCosPhi;
-	const double ts = g.thresh - 1e-5;
+	const double ts = g.thresh - g.arcShrink;
 	const float halfInvRho = (float)(0.5 / rho);
 	int narcs = 0;
 	for (int jb = 0; jb < nnb; jb += 32) {
@@ -246,7 +248,7 @@ __device__ __forceinline__ void region_issue_tma(const Geom& g, const Tables& T,
 	}
 }
 
-// Alternative staging with per-lane 16-byte cp.async (LDGSTS): lane handles cells lane, lane+32 (8 chunks of 16 B each).
+// Alternative staging with per-lane 16-byte cp.async (LDGSTS): lane handles cells lane, lane+32 (2 chunks of 16 B each).
 // Kept because the issue cost of bulk copies matters here: 16 row copies issued by 16 lanes measured ~1.7k cycles
 // of issue time per round, against ~0.3k for 16 LDGSTS per lane (profiles/).
 __device__ __forceinline__ void region_issue_ldgsts(const Geom& g, const Tables& T, const RegionPlan& rp, Cell* raw, int lane)
@@ -261,7 +263,7 @@ __device__ __forceinline__ void region_issue_ldgsts(const Geom& g, const Tables&
 			const Cell* src = T.cells + cell_index(g, wrap_near(rp.lo[0] + ix, g.S[0]), wrap_near(rp.lo[1] + iy, g.S[1]), wrap_near(rp.lo[2] + iz, g.S[2]));
 			const uint32_t dst = smem_u32(raw + ci);
 #pragma unroll
-			for (int k = 0; k < 8; k++)
+			for (int k = 0; k < (int)(sizeof(Cell) / 16); k++)
 				asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + 16u * k), "l"(reinterpret_cast<const char*>(src) + 16 * k) : "memory");
 		}
 	}
@@ -272,12 +274,14 @@ __device__ __forceinline__ void region_wait_ldgsts()
 	__syncwarp();
 }
 
-// compaction of the staged cells into the warp's neighbour list, positions relative to the (wrapped) last bead
-__device__ __forceinline__ int region_consume(const Geom& g, const RegionPlan& rp, const Cell* raw, uint32_t idLimit, uint32_t ignoreId,
-	float4* nb, int nbCap, int lane, bool& regionOvf)
+// compaction of the staged cells into the warp's neighbour list, positions relative to the (wrapped) last bead. Only beads that
+// count (older than this round, not the bonded neighbour) are listed; the overflow-table beads of flagged cells are appended,
+// so the list is complete and no later step looks at the table again. Returns the list length or -1 if it does not fit.
+__device__ __forceinline__ int region_consume(const Geom& g, const Tables& T, const RegionPlan& rp, const Cell* raw, uint32_t idLimit, uint32_t ignoreId,
+	float4* nb, int nbCap, int lane)
 {
 	const float inv0 = 1.0f / (float)rp.nn[0], inv1 = 1.0f / (float)rp.nn[1];
-	uint32_t cnt[2] = { 0, 0 }; float sh[2][3]; bool ovf = false; int at_[2] = { 0, 0 };
+	uint32_t vm[2] = { 0, 0 }; float sh[2][3]; bool flg[2] = { false, false }; int at_[2] = { 0, 0 };
 #pragma unroll
 	for (int q = 0; q < 2; q++) {
 		const int ci = lane + 32 * q;
@@ -286,29 +290,56 @@ __device__ __forceinline__ int region_consume(const Geom& g, const RegionPlan& r
 			const int rest = (int)(((float)ci + 0.5f) * inv0), ix = ci - rest * rp.nn[0];
 			const int iz = (int)(((float)rest + 0.5f) * inv1), iy = rest - iz * rp.nn[1];
 			at_[q] = region_index(rp, ix, iy, iz);
-			const uint2 hdr = *reinterpret_cast<const uint2*>(raw + at_[q]);
-			cnt[q] = hdr.x + 1u; if (cnt[q] > (uint32_t)g.cap) cnt[q] = (uint32_t)g.cap;
-			ovf |= (hdr.y != ID_NONE);
+			const Cell& sc = raw[at_[q]];
+#pragma unroll
+			for (int k = 0; k < MAX_CAP; k++) { const uint32_t id = sc.id[k]; vm[q] |= (id < idLimit && id != ignoreId ? 1u : 0u) << k; }
+			flg[q] = sc.ovfInv != 0xFFFFu;
 			sh[q][0] = rp.base[0] + (float)ix * (float)g.a[0]; sh[q][1] = rp.base[1] + (float)iy * (float)g.a[1]; sh[q][2] = rp.base[2] + (float)iz * (float)g.a[2];
 		}
 	}
-	const uint32_t mine = cnt[0] + cnt[1];                 // <= 14
+	const uint32_t mine = (uint32_t)(__popc(vm[0]) + __popc(vm[1]));                 // <= 6
 	const unsigned lt = (1u << lane) - 1u;
 	uint32_t excl = 0, total = 0;
 #pragma unroll
-	for (int b = 0; b < 4; b++) { const unsigned m = __ballot_sync(FULL, (mine >> b) & 1u); excl += (uint32_t)__popc(m & lt) << b; total += (uint32_t)__popc(m) << b; }
-	regionOvf = __any_sync(FULL, ovf);
+	for (int b = 0; b < 3; b++) { const unsigned m = __ballot_sync(FULL, (mine >> b) & 1u); excl += (uint32_t)__popc(m & lt) << b; total += (uint32_t)__popc(m) << b; }
+	unsigned flagged = __ballot_sync(FULL, flg[0] || flg[1]);
 	if (total > (uint32_t)nbCap) return -1;
 	uint32_t at = excl;
 #pragma unroll
-	for (int q = 0; q < 2; q++)
-		for (uint32_t k = 0; k < cnt[q]; ++k) {
-			const float4 b = raw[at_[q]].slot[k];
-			const uint32_t id = __float_as_uint(b.w);
-			nb[at++] = (id >= idLimit || id == ignoreId) ? make_float4(1e30f, 1e30f, 1e30f, __uint_as_float(ID_NONE))
-				: make_float4(sh[q][0] + b.x, sh[q][1] + b.y, sh[q][2] + b.z, b.w);
+	for (int q = 0; q < 2; q++) {
+		const Cell& sc = raw[at_[q]];
+#pragma unroll
+		for (int k = 0; k < MAX_CAP; k++)
+			if ((vm[q] >> k) & 1u)
+				nb[at++] = make_float4(sh[q][0] + dec_off(g, sc.off[k][0], 0), sh[q][1] + dec_off(g, sc.off[k][1], 1), sh[q][2] + dec_off(g, sc.off[k][2], 2),
+					__uint_as_float(sc.id[k]));
+	}
+	while (flagged) {   // rare: one lane at a time walks the hash table for its flagged cells and appends what it finds
+		const int src = __ffs(flagged) - 1;
+		uint32_t add = 0;
+		if (lane == src) {
+#pragma unroll 1
+			for (int q = 0; q < 2; q++) {
+				if (!flg[q]) continue;
+				const int ci = lane + 32 * q;
+				const int rest = (int)(((float)ci + 0.5f) * inv0), ix = ci - rest * rp.nn[0];
+				const int iz = (int)(((float)rest + 0.5f) * inv1), iy = rest - iz * rp.nn[1];
+				const int64_t cidx = cell_index(g, wrap_near(rp.lo[0] + ix, g.S[0]), wrap_near(rp.lo[1] + iy, g.S[1]), wrap_near(rp.lo[2] + iz, g.S[2]));
+				ovf_for_cell(T, cidx, [&](uint32_t id, uint32_t o0, uint32_t o1, uint32_t o2) {
+					if (id < idLimit && id != ignoreId) {
+						if (total + add < (uint32_t)nbCap)
+							nb[total + add] = make_float4(sh[q][0] + dec_off(g, o0, 0), sh[q][1] + dec_off(g, o1, 1), sh[q][2] + dec_off(g, o2, 2), __uint_as_float(id));
+						add++;
+					}
+					return false;
+				});
+			}
 		}
+		total += __shfl_sync(FULL, add, src);
+		flagged &= flagged - 1u;
+	}
 	__syncwarp();
+	if (total > (uint32_t)nbCap) return -1;
 	return (int)total;
 }
 
@@ -337,7 +368,7 @@ __device__ __forceinline__ uint32_t propose_chain(const Geom& g, const Tables& T
 {
 	const uint32_t T_ = (uint32_t)g.maxTrials;
 	uint32_t accepted = 0;
-	bool regionOvf = false; int nnb = -1; int narcs = -1;
+	int nnb = -1; int narcs = -1;
 	const bool canStage = rp.ncell <= CL_REGION_CELLS;
 	PROF_BEGIN();
 #ifndef SARW_STAGE_LDGSTS
@@ -363,15 +394,13 @@ __device__ __forceinline__ uint32_t propose_chain(const Geom& g, const Tables& T
 		region_wait_ldgsts();
 #endif
 		PROF_MARK(2);   // waited for the copies
-		nnb = region_consume(g, rp, raw, idRound, cs.lastId, nb, nbCap, lane, regionOvf);
+		nnb = region_consume(g, T, rp, raw, idRound, cs.lastId, nb, nbCap, lane);
 		PROF_MARK(3);   // neighbour list compacted
 #ifdef SARW_PROF
 		if (lane == 0) { atomicAdd(PROF_ROW() + 8, (unsigned long long)(nnb > 0 ? nnb : 0)); atomicAdd(PROF_ROW() + 9, (unsigned long long)rp.ncell); atomicAdd(PROF_ROW() + 10, (unsigned long long)(rp.nn[1] * rp.nn[2])); }
 #endif
-	} else regionOvf = true;
-	const uint32_t novf = regionOvf ? __ldcg(T.ovfCount) : 0u;
+	}
 #ifdef SARW_PROF
-	if (lane == 0 && regionOvf) atomicAdd(PROF_ROW() + 12, 1ull);
 	PROF_MARK(5);
 #endif
 	if (!hard) {
@@ -401,14 +430,6 @@ __device__ __forceinline__ uint32_t propose_chain(const Geom& g, const Tables& T
 					}
 				}
 				(void)jmin;
-				if (okL && novf) {
-					const uint32_t m = novf > T.ovfCap ? T.ovfCap : novf;
-					int cq[3]; cell_of_frac(g, vL, cq);
-					for (uint32_t j = 0; j < m && okL; ++j) {
-						const uint4 e = __ldcg(T.ovf + j);
-						if (e.w < idRound && e.w != cs.lastId && ovf_entry_near(g, e, cq) && exact_pair(g, vL, T.lpos + 3 * (size_t)e.w)) okL = false;
-					}
-				}
 			} else okL = !probe_cells<1>(g, T, vL, 0u, idRound, cs.lastId, 0);
 		}
 		const unsigned m = __ballot_sync(FULL, okL);
@@ -456,7 +477,7 @@ __device__ __forceinline__ uint32_t propose_chain(const Geom& g, const Tables& T
 				const uint32_t word = __shfl_sync(FULL, wj[0], l) * (j == 0) + __shfl_sync(FULL, wj[1], l) * (j == 1)
 					+ __shfl_sync(FULL, wj[2], l) * (j == 2) + __shfl_sync(FULL, wj[3], l) * (j == 3);
 				queries += (lane == 0);
-				if (eval_trial_coop(g, T, f, cs, (double)word * (1.0 / 4294967296.0), nb, nnb, idRound, novf, lane, cand)) {
+				if (eval_trial_coop(g, T, f, cs, (double)word * (1.0 / 4294967296.0), nb, nnb, idRound, lane, cand)) {
 					accepted = base + 4 * l + j + 1;
 					to_frac(g, cand, vAcc);
 					break;
@@ -514,6 +535,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) grow_cluster_kernel(const __gri
 	uint32_t round = __ldcg(&A.ctl->round);
 	unsigned long long nBeads = __ldcg(&A.ctl->nBeads);
 	uint32_t lastProg = __ldcg(&A.ctl->lastProgressed);
+	const bool go = __ldcg(&A.ctl->initiated) != 0u;   // sarw.cpp:66 (see grow_kernel)
 	unsigned long long myTrials = 0, myQueries = 0; long long myBusy = 0;
 	const bool timer = (myCta == 0 && threadIdx.x == 0);
 	long long cycA = 0, cycV = 0, cycC = 0; uint32_t cleanRounds = 0;
@@ -521,7 +543,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) grow_cluster_kernel(const __gri
 	long long pathCyc[4] = { 0, 0, 0, 0 }; uint32_t pathCnt[4] = { 0, 0, 0, 0 };
 #define SUBT(k) do { ts1 = clock64(); sub[k] += ts1 - ts0; ts0 = ts1; } while (0)
 
-	while (round < A.roundEnd && (long long)nBeads < g.target && lastProg) {
+	while (go && round < A.roundEnd && (long long)nBeads < g.target && lastProg) {
 		const long long tk0 = clock64();
 		ts0 = tk0;
 		uint32_t start, end;
@@ -533,9 +555,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) grow_cluster_kernel(const __gri
 		// ---------------- phase A: no global writes
 		uint32_t accepted = 0; double cand[3] = { 0, 0, 0 };
 		TentRec rec; rec.x = rec.y = rec.z = 0; rec.trial = 0; rec.cx = rec.cy = rec.cz = 0;
-		float offs[3] = { 0, 0, 0 };                       // in-cell offset of the accepted bead (for the slot store)
+		uint32_t q16[3] = { 0, 0, 0 };                     // quantised in-cell offset of the accepted bead (for the slot store)
 		double vAcc[3] = { 0, 0, 0 };                     // its fractional coordinates
-		uint32_t oldCount = 0xFFFFFFFFu;                   // beads its cell held at round start (from the staged copy)
+		uint32_t freeMask = 0x80000000u;                   // free slots of its cell at round start (from the staged copy); top bit = unknown
 		int path = 0;
 		if (active && (cs.flags & CHAIN_DEAD)) rec.trial = T_ + 1u;
 		else if (active) {
@@ -547,20 +569,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) grow_cluster_kernel(const __gri
 			if (accepted) {
 				rec.x = cand[0]; rec.y = cand[1]; rec.z = cand[2];
 				int cc[3];
-#pragma unroll
-				for (int k = 0; k < 3; k++) {
-					const double s = vAcc[k] * g.sOverL[k];
-					int ci = (int)floor(s);
-					if (ci >= g.S[k]) ci = g.S[k] - 1;
-					if (ci < 0) ci = 0;
-					cc[k] = ci; offs[k] = (float)((s - (double)ci) * g.a[k]);
-				}
+				bead_cell(g, vAcc, q16, cc);
 				rec.cx = cc[0]; rec.cy = cc[1]; rec.cz = cc[2];
-				if (rp.ncell <= CL_REGION_CELLS) {   // count of the bead's cell at round start, from the staged copy (the cell lies inside the region)
+				if (rp.ncell <= CL_REGION_CELLS) {   // free slots of the bead's cell at round start, from the staged copy (the cell lies inside the region)
 					const int ix = wrap_near(cc[0] - rp.lo[0], g.S[0]), iy = wrap_near(cc[1] - rp.lo[1], g.S[1]), iz = wrap_near(cc[2] - rp.lo[2], g.S[2]);
 					if (ix < rp.nn[0] && iy < rp.nn[1] && iz < rp.nn[2]) {
-						uint32_t c0 = raw[region_index(rp, ix, iy, iz)].countMinus1 + 1u;
-						oldCount = c0 > (uint32_t)g.cap ? (uint32_t)g.cap : c0;
+						const Cell& sc = raw[region_index(rp, ix, iy, iz)];
+						freeMask = (sc.id[0] == ID_NONE ? 1u : 0u) | (sc.id[1] == ID_NONE ? 2u : 0u) | (sc.id[2] == ID_NONE ? 4u : 0u);
 					}
 				}
 			}
@@ -589,7 +604,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) grow_cluster_kernel(const __gri
 		const long long tk1 = clock64();
 
 		// ---------------- phase V from the local table: round totals, conflicts with lower chains, slot rank
-		uint32_t acc = 0, prog = 0, rank = 0, tot = 0; bool conflict = false;
+		uint32_t acc = 0, prog = 0, rank = 0; bool conflict = false;
 		{
 			// two records per lane and iteration, the small half of a record first (trial + cell): the position is read only for the rare
 			// record in an adjacent cell. Independent loads in flight instead of one dependent 40-byte read per iteration.
@@ -612,7 +627,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) grow_cluster_kernel(const __gri
 					acc += has; prog += (has && trial < T_);
 					if (!accepted || !has || j == i) continue;
 					int dx = abs(rcx - rec.cx), dy = abs(rcy - rec.cy), dz = abs(rcz - rec.cz);
-					if (dx == 0 && dy == 0 && dz == 0) { tot++; rank += (j < i); }
+					if (dx == 0 && dy == 0 && dz == 0) rank += (j < i);
 					if (j < i) {   // only beads in the same or an adjacent cell (periodic) can be within thresh
 						dx = min(dx, g.S[0] - dx); dy = min(dy, g.S[1] - dy); dz = min(dz, g.S[2] - dz);
 						if (dx <= 1 && dy <= 1 && dz <= 1) {
@@ -626,7 +641,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) grow_cluster_kernel(const __gri
 			// one hardware warp reduction over packed counters (each <= 256 chains: 10 bits are plenty)
 			const unsigned packed = __reduce_add_sync(FULL, acc | (prog << 10) | (rank << 20));
 			acc = packed & 1023u; prog = (packed >> 10) & 1023u; rank = packed >> 20;
-			tot = __reduce_add_sync(FULL, tot);
 			conflict = __any_sync(FULL, conflict);
 		}
 		SUBT(0);   // table scan + reductions
@@ -634,22 +648,24 @@ __global__ void __launch_bounds__(WARPS * 32, 1) grow_cluster_kernel(const __gri
 		if (active) {
 			if (accepted && lane == 0) {
 				const uint32_t id = idRound + i;
-				Cell* cell = A.T.cells + cell_index(g, rec.cx, rec.cy, rec.cz);
-				uint32_t old = oldCount;
-				if (old == 0xFFFFFFFFu) { old = __ldcg(&cell->countMinus1) + 1u; if (old > (uint32_t)g.cap) old = (uint32_t)g.cap; }
+				const int64_t cidx = cell_index(g, rec.cx, rec.cy, rec.cz);
+				Cell* cell = A.T.cells + cidx;
+				uint32_t fm = freeMask;
+				if (fm & 0x80000000u) {   // the cell was not staged (crowded region): its ids as of round start from global memory
+					const uint4 w = __ldcg(reinterpret_cast<const uint4*>(cell));
+					fm = (w.x == ID_NONE ? 1u : 0u) | (w.y == ID_NONE ? 2u : 0u) | (w.z == ID_NONE ? 4u : 0u);
+				}
+				fm &= (1u << g.cap) - 1u;
 				double* lp = A.T.lpos + 3 * (size_t)id;
 				lp[0] = cand[0]; lp[1] = cand[1]; lp[2] = cand[2];
-				const uint32_t slot = old + rank;
-				if (slot < (uint32_t)g.cap) {
-					__stcg(&cell->slot[slot], make_float4(offs[0], offs[1], offs[2], __uint_as_float(id)));
-					if (rank == 0) {   // one writer per cell: the new count of this round
-						uint32_t nc = old + tot + 1u; if (nc > (uint32_t)g.cap) nc = (uint32_t)g.cap;
-						cell->countMinus1 = nc - 1u;
-					}
-				} else {           // cell full: overflow list (rare); the header count is written by the rank-0 bead, if it fits
-					atomicExch(&cell->ovfFlagInv, 0u);
-					const uint32_t at = atomicAdd(A.T.ovfCount, 1u);
-					if (at < A.T.ovfCap) A.T.ovf[at] = make_uint4((uint32_t)rec.cx, (uint32_t)rec.cy, (uint32_t)rec.cz, id);
+				for (uint32_t r = 0; r < rank && fm; ++r) fm &= fm - 1u;   // the rank-th free slot: every warp derives the same assignment
+				if (fm) {
+					const int k = __ffs((int)fm) - 1;
+					st_off16(cell, k, q16);
+					__stcg(&cell->id[k], id);
+				} else {           // cell full: overflow table (rare)
+					cell->ovfInv = 0;
+					ovf_insert(A.T, cidx, id, q16);
 				}
 				for (int k = 0; k < 3; k++) A.resPos[3 * (size_t)i + k] = cand[k];
 			}

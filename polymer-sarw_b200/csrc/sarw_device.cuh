@@ -11,21 +11,30 @@
 namespace sarw {
 
 // ------------------------------------------------------------------ data layout in HBM
-// One 128-byte line per cell: header + up to 7 beads inline. slot = (ox, oy, oz, id): Cartesian offset of the
-// bead from the cell's low corner in fp32 (|error| <= edge * 2^-24) and the bead's lookup index (bit-cast).
-// The header word holds count-1 (so that a memset to 0xFF yields "empty cell, all ids invalid, not overflowed").
-// Beads that do not fit (more than `cap` in one cell) go to a global overflow list and flag their cell; a query
-// scans that list only when one of the cells it visits is flagged.
-struct __align__(16) Cell {
-	uint32_t countMinus1;
-	uint32_t ovfFlagInv;      // 0xFFFFFFFF = no bead of this cell lives in the overflow list (memset state); anything else = some do
-	uint32_t pad[2];
-	float4 slot[7];
+// One 32-byte record per cell (one DRAM sector; four x-adjacent cells share a 128-byte line): up to 3 beads inline.
+//   id[k]     lookup index of the bead in slot k, ID_NONE = free. A slot is claimed with one atomicCAS on its id word, so there
+//             is no count to keep consistent and a removed bead simply leaves a free slot behind.
+//   off[k][d] position of bead k inside the cell along d in units of edge/65536 (the fp32 pre-filter works on the centre of the
+//             quantisation step; its undecided band covers the half step, everything inside the band is re-evaluated exactly
+//             from lpos in the reference's fp64 arithmetic).
+//   ovfInv    0xFFFF = no bead of this cell lives in the overflow table (the memset state), anything else = some do (or did).
+// A memset to 0xFF yields "empty cell, not overflowed". Beads that do not fit (more than `cap` in one cell: ~1e-4 of the beads
+// at melt density with 2 A cells) go to an open-addressing hash table keyed by the cell index; a query probes it only for
+// the visited cells that are flagged.
+// Round-1 format for comparison: 128 bytes per cell (header + 7 fp32 slots), 0.32 beads per cell on average: 400 B of table
+// per bead, one 128-byte line per visited cell of which 32 bytes were useful (ncu: 1.95x wasted DRAM traffic in K5).
+struct __align__(32) Cell {
+	uint32_t id[3];
+	uint16_t off[3][3];
+	uint16_t ovfInv;
 };
-static_assert(sizeof(Cell) == 128, "cell record must be one 128-byte line");
+static_assert(sizeof(Cell) == 32, "cell record must be one 32-byte sector");
+constexpr int CELL_WORDS = 8;
 
 constexpr uint32_t ID_NONE = 0xFFFFFFFFu;
-constexpr int MAX_CAP = 7;
+constexpr uint32_t ID_TOMB = 0xFFFFFFFEu;   // overflow-table entry whose bead was removed again (probing continues past it)
+constexpr uint32_t ID_BUSY = 0xFFFFFFFDu;   // overflow-table entry claimed, record not yet published
+constexpr int MAX_CAP = 3;
 
 // Per-chain growth state (sarw.h:81-83 lastIndices / penultimateIndices / chainLengths, plus the two tip
 // positions so that a round needs one 64-byte read per chain).
@@ -47,9 +56,11 @@ struct Geom {
 	double sOverL[3];         // S as double (cell-space scale for fractional coordinates)
 	double reachCells[3];     // conservative query half-width in cell units (< 0.5)
 	int S[3];
-	int cap;                  // inline capacity in use (<= 7)
+	int cap;                  // inline capacity in use (<= 3)
+	float qs[3];              // edge / 65536: quantisation step of the in-cell offsets
 	float lo2, hi2;           // fp32 pre-filter: d2 < lo2 => certainly within thresh, d2 > hi2 => certainly outside
 	double regionReach;       // thresh + margin, Angstrom: halo around the cone circle when staging
+	double arcShrink;         // blocked arcs are built for thresh - arcShrink: dominates the error of the staged fp32 positions (quantised offsets)
 	double dSinPhi, dCosPhi;  // BondLength*sin(phi), BondLength*cos(phi)   (sarw.cpp:165,178-180)
 	double bias[3];
 	int biased;
@@ -67,9 +78,11 @@ struct Geom {
 struct Tables {
 	Cell* cells;
 	double* lpos;             // Cartesian position by lookup index, 3 doubles each; all-ones bit pattern = never accepted
-	uint4* ovf;               // overflow list: {cell x, cell y, cell z, lookup index} of beads whose cell was full
-	uint32_t* ovfCount;
-	uint32_t ovfCap;
+	uint4* ovf;               // overflow hash table (open addressing, linear probing), entry = {cell index low word, lookup index,
+	                          //   off0 | off1 << 16, off2 | cell index high bits << 16}; all ones = never used
+	uint32_t* ovfCount;       // entries ever claimed (monotonic)
+	uint32_t ovfMask;         // table size - 1 (power of two)
+	uint32_t ovfLimit;        // at most this many entries are claimed (half the table): probing always terminates; beyond it the host fails the call
 	const void* tmapHost;     // HOST pointer to the 128-byte CUtensorMap of the cell table (launch wrappers copy it into the kernel parameters), or nullptr
 };
 
@@ -259,8 +272,8 @@ __device__ __forceinline__ int64_t cell_index(const Geom& g, int wx, int wy, int
 {	return wx + (int64_t)g.S[0] * (wy + (int64_t)g.S[1] * wz);
 }
 
-// cell + in-cell offset of a bead from its fractional coordinates
-__device__ __forceinline__ int64_t bead_cell(const Geom& g, const double v[3], float o[3], int c[3])
+// cell + quantised in-cell offset of a bead from its fractional coordinates
+__device__ __forceinline__ int64_t bead_cell(const Geom& g, const double v[3], uint32_t q16[3], int c[3])
 {
 #pragma unroll
 	for (int k = 0; k < 3; k++) {
@@ -269,36 +282,79 @@ __device__ __forceinline__ int64_t bead_cell(const Geom& g, const double v[3], f
 		if (ci >= g.S[k]) ci = g.S[k] - 1;
 		if (ci < 0) ci = 0;
 		c[k] = ci;
-		o[k] = (float)((s - (double)ci) * g.a[k]);
+		int q = (int)((s - (double)ci) * 65536.0);
+		q16[k] = (uint32_t)(q < 0 ? 0 : (q > 65535 ? 65535 : q));
 	}
 	return cell_index(g, c[0], c[1], c[2]);
 }
-__device__ __forceinline__ int64_t bead_cell(const Geom& g, const double v[3], float o[3])
+__device__ __forceinline__ int64_t bead_cell(const Geom& g, const double v[3], uint32_t q16[3])
 {	int c[3];
-	return bead_cell(g, v, o, c);
+	return bead_cell(g, v, q16, c);
 }
 
-// wrapped cell coordinates of a point given by its fractional coordinates
-__device__ __forceinline__ void cell_of_frac(const Geom& g, const double v[3], int c[3])
+// the whole 32-byte record with one 256-bit load (SASS LDG.E.256), straight from L2
+__device__ __forceinline__ void ld_cell(const Cell* cell, uint32_t (&w)[CELL_WORDS])
 {
-#pragma unroll
-	for (int k = 0; k < 3; k++) {
-		int ci = (int)floor(v[k] * g.sOverL[k]);
-		c[k] = ci >= g.S[k] ? g.S[k] - 1 : (ci < 0 ? 0 : ci);
+	asm volatile("ld.global.cg.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+		: "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(cell));
+}
+// quantised offset of slot k along d from the record's words (k, d compile-time constants after unrolling)
+__device__ __forceinline__ uint32_t cell_off(const uint32_t (&w)[CELL_WORDS], int k, int d)
+{	const int e = 3 * k + d;
+	return (w[3 + (e >> 1)] >> (16 * (e & 1))) & 0xFFFFu;
+}
+__device__ __forceinline__ bool cell_flagged(const uint32_t (&w)[CELL_WORDS]) { return (w[7] >> 16) != 0xFFFFu; }
+// centre of the quantisation step, in Angstrom from the cell's low corner
+__device__ __forceinline__ float dec_off(const Geom& g, uint32_t q, int d) { return ((float)q + 0.5f) * g.qs[d]; }
+
+// ------------------------------------------------------------------ overflow table (beads whose cell was full)
+__device__ __forceinline__ uint32_t ovf_hash(int64_t cidx)
+{	unsigned long long x = (unsigned long long)cidx * 0x9E3779B97F4A7C15ull;
+	return (uint32_t)(x >> 32);
+}
+// visit every published entry of cell `cidx`: fn(id, q0, q1, q2) returns true to stop early
+template <typename F>
+__device__ __forceinline__ void ovf_for_cell(const Tables& T, int64_t cidx, F&& fn)
+{
+	const uint32_t lo = (uint32_t)cidx, hi = (uint32_t)((unsigned long long)cidx >> 32);
+	uint32_t h = ovf_hash(cidx) & T.ovfMask;
+	for (uint32_t n = 0; n <= T.ovfMask; ++n, h = (h + 1u) & T.ovfMask) {
+		const uint4 e = __ldcg(T.ovf + h);
+		if (e.y == ID_NONE) return;                 // never used: end of every probe sequence through here
+		if (e.y >= ID_BUSY) continue;               // being written (a bead of the running round: nobody needs it yet) or removed
+		if (e.x == lo && (e.w >> 16) == hi && fn(e.y, e.z & 0xFFFFu, e.z >> 16, e.w & 0xFFFFu)) return;
 	}
 }
-// can an overflow-list entry be within thresh of a point in cell c? (cells are wider than 2*thresh: same or adjacent cell, periodic)
-__device__ __forceinline__ bool ovf_entry_near(const Geom& g, const uint4& e, const int c[3])
+__device__ inline void ovf_insert(const Tables& T, int64_t cidx, uint32_t id, const uint32_t q16[3])
 {
-	int dx = abs((int)e.x - c[0]), dy = abs((int)e.y - c[1]), dz = abs((int)e.z - c[2]);
-	dx = min(dx, g.S[0] - dx); dy = min(dy, g.S[1] - dy); dz = min(dz, g.S[2] - dz);
-	return dx <= 1 && dy <= 1 && dz <= 1;
+	if (atomicAdd(T.ovfCount, 1u) >= T.ovfLimit) return;   // the host sees ovfCount > ovfLimit and fails the call
+	uint32_t h = ovf_hash(cidx) & T.ovfMask;
+	while (atomicCAS(&T.ovf[h].y, ID_NONE, ID_BUSY) != ID_NONE) h = (h + 1u) & T.ovfMask;
+	// published with ONE 16-byte store: a concurrent reader sees either the busy entry or the complete one
+	__stcg(T.ovf + h, make_uint4((uint32_t)cidx, id, q16[0] | (q16[1] << 16), q16[2] | ((uint32_t)((unsigned long long)cidx >> 32) << 16)));
+}
+__device__ inline void ovf_remove(const Tables& T, int64_t cidx, uint32_t id)
+{
+	uint32_t h = ovf_hash(cidx) & T.ovfMask;
+	for (uint32_t n = 0; n <= T.ovfMask; ++n, h = (h + 1u) & T.ovfMask) {
+		const uint32_t y = __ldcg(&T.ovf[h].y);
+		if (y == ID_NONE) return;
+		if (y == id) { atomicExch(&T.ovf[h].y, ID_TOMB); return; }   // tombstone: entries are never moved, so concurrent probes stay valid
+	}
 }
 
 // ------------------------------------------------------------------ overlap query against the cell list
+// fp32 pre-filter + exact fall-back for one stored bead; (dx, dy, dz) = bead - candidate in fp32
+__device__ __forceinline__ bool pair_hits(const Geom& g, const Tables& T, const double v[3], float dx, float dy, float dz, uint32_t id)
+{
+	const float d2 = dx * dx + dy * dy + dz * dz;
+	if (d2 < g.lo2) return true;
+	return d2 <= g.hi2 && exact_pair(g, v, T.lpos + 3 * (size_t)id);
+}
+
 // Does any stored bead with lookup index in [idLo, idHi) and != ignoreId lie within thresh of the candidate?
 // GROUP lanes share the (<= 8) cells of the query: lane `sub` takes cells sub, sub+GROUP, ... ; the caller ORs
-// the per-lane results. The overflow list is scanned by the same striding.
+// the per-lane results.
 template <int GROUP>
 __device__ __forceinline__ bool probe_cells(const Geom& g, const Tables& T, const double v[3],
 	uint32_t idLo, uint32_t idHi, uint32_t ignoreId, int sub)
@@ -310,99 +366,80 @@ __device__ __forceinline__ bool probe_cells(const Geom& g, const Tables& T, cons
 		double s = v[k] * g.sOverL[k];
 		int lo = (int)floor(s - g.reachCells[k]);
 		int hi = (int)floor(s + g.reachCells[k]);
-		c0[k] = lo; n[k] = hi - lo + 1;   // 1 or 2
+		c0[k] = lo; n[k] = hi - lo + 1;   // 1 or 2 (reachCells < 0.5)
 		q[k][0] = (float)(((double)lo - s) * g.a[k]);
 		q[k][1] = (float)(((double)(lo + 1) - s) * g.a[k]);
 	}
-	bool hit = false, anyOvf = false;
+	bool hit = false;
 	const int total = n[0] * n[1] * n[2];
 	for (int ci = sub; ci < total && !hit; ci += GROUP) {
-		int ix = ci % n[0], rest = ci / n[0];
-		int iy = rest % n[1], iz = rest / n[1];
-		const Cell* cell = T.cells + cell_index(g, wrap_cell(c0[0] + ix, g.S[0]), wrap_cell(c0[1] + iy, g.S[1]), wrap_cell(c0[2] + iz, g.S[2]));
-		// header and first slot share the first 32-byte sector of the cell's line: one 256-bit load, one round trip for cells with <= 1 bead
-		uint32_t w[8];
-		asm volatile("ld.global.cg.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-			: "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(cell));
-		uint32_t cnt = w[0] + 1u;
-		anyOvf |= (w[1] != ID_NONE);
-		if (cnt > (uint32_t)g.cap) cnt = (uint32_t)g.cap;
-		for (uint32_t s = 0; s < cnt; ++s) {
-			float4 b = s == 0 ? make_float4(__uint_as_float(w[4]), __uint_as_float(w[5]), __uint_as_float(w[6]), __uint_as_float(w[7])) : __ldcg(&cell->slot[s]);
-			uint32_t id = __float_as_uint(b.w);
-			if (id < idLo || id >= idHi || id == ignoreId) continue;
-			float dx = q[0][ix] + b.x, dy = q[1][iy] + b.y, dz = q[2][iz] + b.z;
-			float d2 = dx * dx + dy * dy + dz * dz;
-			if (d2 < g.lo2) { hit = true; break; }
-			if (d2 <= g.hi2 && exact_pair(g, v, T.lpos + 3 * (size_t)id)) { hit = true; break; }
+		const int ix = ci % n[0], rest = ci / n[0];
+		const int iy = rest % n[1], iz = rest / n[1];
+		const int64_t cidx = cell_index(g, wrap_cell(c0[0] + ix, g.S[0]), wrap_cell(c0[1] + iy, g.S[1]), wrap_cell(c0[2] + iz, g.S[2]));
+		uint32_t w[CELL_WORDS];
+		ld_cell(T.cells + cidx, w);
+		const float qx = q[0][ix], qy = q[1][iy], qz = q[2][iz];
+#pragma unroll
+		for (int s = 0; s < MAX_CAP; ++s) {
+			const uint32_t id = w[s];
+			if (hit || id < idLo || id >= idHi || id == ignoreId) continue;   // idHi <= 0xFFFFFFF0: free slots never pass
+			hit = pair_hits(g, T, v, qx + dec_off(g, cell_off(w, s, 0), 0), qy + dec_off(g, cell_off(w, s, 1), 1), qz + dec_off(g, cell_off(w, s, 2), 2), id);
 		}
-	}
-	if (!hit && anyOvf) {   // only lanes whose own cells overflowed scan the list: the overflowed beads of a cell are in range of it
-		uint32_t novf = __ldcg(T.ovfCount);
-		if (novf > T.ovfCap) novf = T.ovfCap;
-		int cq[3]; cell_of_frac(g, v, cq);
-		for (uint32_t j = 0; j < novf && !hit; ++j) {
-			const uint4 e = __ldcg(T.ovf + j);
-			const uint32_t id = e.w;
-			if (id < idLo || id >= idHi || id == ignoreId || !ovf_entry_near(g, e, cq)) continue;
-			hit = exact_pair(g, v, T.lpos + 3 * (size_t)id);
-		}
+		if (!hit && cell_flagged(w))
+			ovf_for_cell(T, cidx, [&](uint32_t id, uint32_t o0, uint32_t o1, uint32_t o2) {
+				if (id < idLo || id >= idHi || id == ignoreId) return false;
+				hit = pair_hits(g, T, v, qx + dec_off(g, o0, 0), qy + dec_off(g, o1, 1), qz + dec_off(g, o2, 2), id);
+				return hit;
+			});
 	}
 	return hit;
 }
 
-// insert a bead (PeriodicLookup.h:37-47 + the atom store of sarw.h:123-126); any number of threads may insert concurrently
+__device__ __forceinline__ void st_off16(Cell* cell, int k, const uint32_t q16[3])
+{
+	unsigned short* o = reinterpret_cast<unsigned short*>(&cell->off[k][0]);
+	o[0] = (unsigned short)q16[0]; o[1] = (unsigned short)q16[1]; o[2] = (unsigned short)q16[2];
+}
+
+// insert a bead (PeriodicLookup.h:37-47 + the atom store of sarw.h:123-126); any number of threads may insert concurrently.
+// The slot is claimed by a compare-and-swap on its id word; the offsets follow with plain stores: a bead inserted in the running
+// round is never read before the next grid-wide barrier (readers filter on id < first id of the round).
 __device__ __forceinline__ void insert_bead(const Geom& g, const Tables& T, const double pos[3], uint32_t id)
 {
-	double v[3]; float o[3]; int cc[3];
+	double v[3]; uint32_t q16[3];
 	to_frac(g, pos, v);
-	int64_t ci = bead_cell(g, v, o, cc);
+	const int64_t ci = bead_cell(g, v, q16);
 	double* lp = T.lpos + 3 * (size_t)id;
 	lp[0] = pos[0]; lp[1] = pos[1]; lp[2] = pos[2];
 	Cell* cell = T.cells + ci;
-	uint32_t k = atomicAdd(&cell->countMinus1, 1u) + 1u;
-	if (k < (uint32_t)g.cap) {
-		__stcg(&cell->slot[k], make_float4(o[0], o[1], o[2], __uint_as_float(id)));
-	} else {
-		atomicSub(&cell->countMinus1, 1u);
-		atomicExch(&cell->ovfFlagInv, 0u);
-		uint32_t j = atomicAdd(T.ovfCount, 1u);
-		if (j < T.ovfCap) T.ovf[j] = make_uint4((uint32_t)cc[0], (uint32_t)cc[1], (uint32_t)cc[2], id);   // beyond ovfCap the host sees ovfCount > ovfCap and fails the call
-	}
+	for (int k = 0; k < g.cap; ++k)
+		if (atomicCAS(&cell->id[k], ID_NONE, id) == ID_NONE) { st_off16(cell, k, q16); return; }
+	cell->ovfInv = 0;              // idempotent plain store: every writer stores the same value
+	ovf_insert(T, ci, id, q16);
 }
 
-// remove a bead again (only ever called from the single-threaded conflict clean-up, nobody else is touching cells)
+// remove a bead again (conflict clean-up; several warps may do this at once for beads of different chains)
 __device__ inline void remove_bead(const Geom& g, const Tables& T, uint32_t id)
 {
 	double* lp = T.lpos + 3 * (size_t)id;
 	double pos[3] = { __ldcg(lp), __ldcg(lp + 1), __ldcg(lp + 2) };
-	double v[3]; float o[3];
+	double v[3]; uint32_t q16[3];
 	to_frac(g, pos, v);
-	Cell* cell = T.cells + bead_cell(g, v, o);
-	uint32_t cnt = __ldcg(&cell->countMinus1) + 1u;
-	uint32_t cc = cnt > (uint32_t)g.cap ? (uint32_t)g.cap : cnt;
+	const int64_t ci = bead_cell(g, v, q16);
+	Cell* cell = T.cells + ci;
 	bool found = false;
-	for (uint32_t s = 0; s < cc; ++s) {
-		float4 b = __ldcg(&cell->slot[s]);
-		if (__float_as_uint(b.w) == id) {
-			float4 lastSlot = __ldcg(&cell->slot[cc - 1]);
-			__stcg(&cell->slot[s], lastSlot);
-			__stcg(&cell->slot[cc - 1], make_float4(0.f, 0.f, 0.f, __uint_as_float(ID_NONE)));
-			cell->countMinus1 = cc - 2u;   // (cc-1) beads remain
-			found = true;
-			break;
-		}
-	}
-	if (!found) {
-		uint32_t novf = __ldcg(T.ovfCount);
-		if (novf > T.ovfCap) novf = T.ovfCap;
-		for (uint32_t j = 0; j < novf; ++j)
-			if (__ldcg(T.ovf + j).w == id) { T.ovf[j] = __ldcg(T.ovf + novf - 1); *T.ovfCount = novf - 1; break; }
-	}
+	for (int k = 0; k < MAX_CAP && !found; ++k)
+		if (__ldcg(&cell->id[k]) == id) { atomicExch(&cell->id[k], ID_NONE); found = true; }   // the slot is free for the next insert
+	if (!found) ovf_remove(T, ci, id);
 	unsigned long long ones = ~0ull;
 	lp[0] = __longlong_as_double((long long)ones); lp[1] = lp[0]; lp[2] = lp[0];
 	__threadfence();
 }
+
+// Writes made through the generic proxy (the inserts above) are read in later rounds by bulk / tensor copies, i.e. through the
+// async proxy; the PTX memory model orders the two only across a proxy fence. Every thread that may have written cells issues
+// it before the round's barrier. (The LDGSTS staging variant reads through the generic proxy and needs none.)
+__device__ __forceinline__ void fence_cells_for_tma() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
 // ------------------------------------------------------------------ grid-wide barrier for the persistent kernel
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p)
@@ -410,6 +447,7 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p)
 }
 __device__ __forceinline__ void grid_barrier(unsigned* count, unsigned* gen, unsigned nBlocks)
 {
+	fence_cells_for_tma();
 	__syncthreads();
 	if (threadIdx.x == 0) {
 		unsigned my = ld_acquire_u32(gen);

@@ -13,7 +13,8 @@ struct Control {
 	unsigned seedFailChain;           // first chain whose seeding failed, ID_NONE if none
 	unsigned seedDirtyCount;
 	unsigned abort;                   // set when a peer stopped answering in the peer-memory multi-rank loop
-	unsigned dirty2Count, padA;       // chains put in conflict by the parallel clean-up (second list)
+	unsigned dirty2Count;             // chains put in conflict by the parallel clean-up (second list)
+	unsigned ovfCount;                // entries claimed in the overflow table (Tables::ovfCount points here: one read returns it with the rest)
 	unsigned long long stageFallbacks, arcFallbacks;   // chain-rounds whose neighbourhood / arcs did not fit the shared-memory buffers
 	unsigned long long nBeads;        // SARW::actualCount()
 	unsigned long long trials, queries, conflicts, seedTrials;

@@ -125,15 +125,10 @@ __global__ void __launch_bounds__(512) zbin_scatter_kernel(Geom g, const double*
 	}
 }
 
-// One lane per candidate. The (up to) 8 cells a candidate's sphere touches are fetched with eight independent 256-bit loads
-// (header + first slot = the first 32-byte sector of the cell's line) issued back to back, so a warp keeps 256 sectors in flight:
-// the kernel is bound by HBM/L2 bandwidth, not by the latency of a chain of dependent loads. Cells holding more than one bead
-// (a few per cent at melt density) are finished in a second, rarely taken loop.
-__device__ __forceinline__ void ld_cell_head(const Cell* cell, uint32_t (&w)[8])
-{
-	asm volatile("ld.global.cg.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-		: "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(cell));
-}
+// One lane per candidate. The (up to) 8 cells a candidate's sphere touches are fetched with eight independent 256-bit loads (one
+// 32-byte cell record = one DRAM sector each) issued back to back, so a warp keeps 256 sectors in flight: the kernel is bound by
+// HBM/L2 bandwidth, not by the latency of a chain of dependent loads. Four x-adjacent cells share a 128-byte line, so the two
+// cells a sphere touches along x usually arrive with one line fill.
 __global__ void __launch_bounds__(256, 3) find_batch_kernel(Geom g, Tables T, const double* __restrict__ xyz,
 	const int64_t* __restrict__ ignore, int64_t n, uint8_t* __restrict__ hit, const SortedCand* __restrict__ rec, const uint32_t* __restrict__ perm)
 {
@@ -167,61 +162,40 @@ __global__ void __launch_bounds__(256, 3) find_batch_kernel(Geom g, Tables T, co
 			qo[k][0] = d * af;
 			qo[k][1] = (d + 1.0f) * af;
 		}
-		uint32_t w[8][8];
+		uint32_t w[8][CELL_WORDS];
 #pragma unroll
 		for (int ci = 0; ci < 8; ci++) {
 			const int ix = ci & 1, iy = (ci >> 1) & 1, iz = ci >> 2;
 			const bool valid = (ix == 0 || two[0]) && (iy == 0 || two[1]) && (iz == 0 || two[2]);
-			if (valid) ld_cell_head(T.cells + cell_index(g, c[0][ix], c[1][iy], c[2][iz]), w[ci]);
-			else { w[ci][0] = ID_NONE; w[ci][1] = ID_NONE; }   // count-1 = all ones: empty, not overflowed
+			if (valid) ld_cell(T.cells + cell_index(g, c[0][ix], c[1][iy], c[2][iz]), w[ci]);
+			else { w[ci][0] = ID_NONE; w[ci][1] = ID_NONE; w[ci][2] = ID_NONE; w[ci][7] = ID_NONE; }   // empty, not flagged
 		}
-		bool h = false, anyOvf = false;
-		uint32_t cntPack = 0;   // 4 bits per cell: beads beyond the first
+		bool h = false;
+		unsigned flagged = 0;   // bit ci: the cell has beads in the overflow table
 #pragma unroll
 		for (int ci = 0; ci < 8; ci++) {
 			const int ix = ci & 1, iy = (ci >> 1) & 1, iz = ci >> 2;
-			const uint32_t cnt = w[ci][0] + 1u;
-			anyOvf |= (w[ci][1] != ID_NONE);
-			if (cnt > 1u) cntPack |= ((cnt > (uint32_t)g.cap ? (uint32_t)g.cap : cnt) - 1u) << (4 * ci);
-			if (cnt >= 1u && !h) {
-				const uint32_t id = w[ci][7];
-				if (id != ignoreId) {
-					const float dx = qo[0][ix] + __uint_as_float(w[ci][4]), dy = qo[1][iy] + __uint_as_float(w[ci][5]), dz = qo[2][iz] + __uint_as_float(w[ci][6]);
-					const float d2 = dx * dx + dy * dy + dz * dz;
-					if (d2 < g.lo2) h = true;
-					else if (d2 <= g.hi2 && exact_pair(g, v, T.lpos + 3 * (size_t)id)) h = true;
-				}
+			flagged |= (cell_flagged(w[ci]) ? 1u : 0u) << ci;
+#pragma unroll
+			for (int s = 0; s < MAX_CAP; ++s) {
+				const uint32_t id = w[ci][s];
+				if (h || id == ID_NONE || id == ignoreId) continue;
+				h = pair_hits(g, T, v, qo[0][ix] + dec_off(g, cell_off(w[ci], s, 0), 0), qo[1][iy] + dec_off(g, cell_off(w[ci], s, 1), 1),
+					qo[2][iz] + dec_off(g, cell_off(w[ci], s, 2), 2), id);
 			}
 		}
-		if (!h && cntPack) {
 #pragma unroll 1
-			while (cntPack && !h) {   // only the cells that hold more than one bead (usually one of the eight)
-				const int ci = (__ffs((int)cntPack) - 1) >> 2;
-				const uint32_t extra = (cntPack >> (4 * ci)) & 15u;
-				cntPack &= ~(15u << (4 * ci));
-				const bool ix = ci & 1, iy = (ci >> 1) & 1, iz = ci >> 2;
-				const Cell* cell = T.cells + cell_index(g, ix ? c[0][1] : c[0][0], iy ? c[1][1] : c[1][0], iz ? c[2][1] : c[2][0]);
-				const float ox = ix ? qo[0][1] : qo[0][0], oy = iy ? qo[1][1] : qo[1][0], oz = iz ? qo[2][1] : qo[2][0];
-				for (uint32_t s = 1; s <= extra; ++s) {
-					const float4 b = __ldcg(&cell->slot[s]);
-					const uint32_t id = __float_as_uint(b.w);
-					if (id == ignoreId) continue;
-					const float dx = ox + b.x, dy = oy + b.y, dz = oz + b.z;
-					const float d2 = dx * dx + dy * dy + dz * dz;
-					if (d2 < g.lo2) { h = true; break; }
-					if (d2 <= g.hi2 && exact_pair(g, v, T.lpos + 3 * (size_t)id)) { h = true; break; }
-				}
-			}
-		}
-		if (!h && anyOvf) {   // a visited cell overflowed: its extra beads are in the overflow list
-			uint32_t novf = __ldcg(T.ovfCount);
-			if (novf > T.ovfCap) novf = T.ovfCap;
-			int cq[3]; cell_of_frac(g, v, cq);
-			for (uint32_t j = 0; j < novf && !h; ++j) {
-				const uint4 e = __ldcg(T.ovf + j);
-				if (e.w == ignoreId || !ovf_entry_near(g, e, cq)) continue;
-				h = exact_pair(g, v, T.lpos + 3 * (size_t)e.w);
-			}
+		while (flagged && !h) {   // a visited cell overflowed (rare): its other beads are in the hash table
+			const int ci = __ffs((int)flagged) - 1;
+			flagged &= flagged - 1u;
+			const bool ix = ci & 1, iy = (ci >> 1) & 1, iz = ci >> 2;
+			const float ox = ix ? qo[0][1] : qo[0][0], oy = iy ? qo[1][1] : qo[1][0], oz = iz ? qo[2][1] : qo[2][0];
+			ovf_for_cell(T, cell_index(g, ix ? c[0][1] : c[0][0], iy ? c[1][1] : c[1][0], iz ? c[2][1] : c[2][0]),
+				[&](uint32_t id, uint32_t o0, uint32_t o1, uint32_t o2) {
+					if (id == ignoreId) return false;
+					h = pair_hits(g, T, v, ox + dec_off(g, o0, 0), oy + dec_off(g, o1, 1), oz + dec_off(g, o2, 2), id);
+					return h;
+				});
 		}
 		hit[q] = h ? 1 : 0;
 	}
@@ -236,13 +210,12 @@ __global__ void add_points_kernel(Geom g, Tables T, const double* __restrict__ x
 }
 
 // enumerate beads with id in (idLo, idHi) within thresh of the candidate (clean-up only); lane `sub` of GROUP takes
-// cells sub, sub+GROUP, ... and, when one of its cells is flagged, the overflow list
+// cells sub, sub+GROUP, ... including the overflow entries of those cells
 template <int GROUP, typename F>
 __device__ void enumerate_hits(const Geom& g, const Tables& T, const double v[3], uint32_t idLoExcl, uint32_t idHi, int sub, F&& fn)
 {
 	int c0[3], n[3];
 	float q[3][2];
-	bool anyOvf = false;
 	for (int k = 0; k < 3; k++) {
 		double s = v[k] * g.sOverL[k];
 		int lo = (int)floor(s - g.reachCells[k]), hi = (int)floor(s + g.reachCells[k]);
@@ -254,29 +227,21 @@ __device__ void enumerate_hits(const Geom& g, const Tables& T, const double v[3]
 	for (int ci = sub; ci < total; ci += GROUP) {
 		const int ix = ci % n[0], rest = ci / n[0];
 		const int iy = rest % n[1], iz = rest / n[1];
-		const Cell* cell = T.cells + cell_index(g, wrap_cell(c0[0] + ix, g.S[0]), wrap_cell(c0[1] + iy, g.S[1]), wrap_cell(c0[2] + iz, g.S[2]));
-		const uint2 hdr = __ldcg(reinterpret_cast<const uint2*>(cell));
-		uint32_t cnt = hdr.x + 1u;
-		anyOvf |= (hdr.y != ID_NONE);
-		if (cnt > (uint32_t)g.cap) cnt = (uint32_t)g.cap;
-		for (uint32_t s = 0; s < cnt; ++s) {
-			float4 b = __ldcg(&cell->slot[s]);
-			uint32_t id = __float_as_uint(b.w);
+		const int64_t cidx = cell_index(g, wrap_cell(c0[0] + ix, g.S[0]), wrap_cell(c0[1] + iy, g.S[1]), wrap_cell(c0[2] + iz, g.S[2]));
+		uint32_t w[CELL_WORDS];
+		ld_cell(T.cells + cidx, w);
+		const float qx = q[0][ix], qy = q[1][iy], qz = q[2][iz];
+#pragma unroll
+		for (int s = 0; s < MAX_CAP; ++s) {
+			const uint32_t id = w[s];
 			if (id <= idLoExcl || id >= idHi) continue;
-			float dx = q[0][ix] + b.x, dy = q[1][iy] + b.y, dz = q[2][iz] + b.z;
-			float d2 = dx * dx + dy * dy + dz * dz;
-			if (d2 < g.lo2 || (d2 <= g.hi2 && exact_pair(g, v, T.lpos + 3 * (size_t)id))) fn(id);
+			if (pair_hits(g, T, v, qx + dec_off(g, cell_off(w, s, 0), 0), qy + dec_off(g, cell_off(w, s, 1), 1), qz + dec_off(g, cell_off(w, s, 2), 2), id)) fn(id);
 		}
-	}
-	if (!anyOvf) return;
-	uint32_t novf = __ldcg(T.ovfCount);
-	if (novf > T.ovfCap) novf = T.ovfCap;
-	int cq[3]; cell_of_frac(g, v, cq);
-	for (uint32_t j = 0; j < novf; ++j) {
-		const uint4 e = __ldcg(T.ovf + j);
-		const uint32_t id = e.w;
-		if (id <= idLoExcl || id >= idHi || !ovf_entry_near(g, e, cq)) continue;
-		if (exact_pair(g, v, T.lpos + 3 * (size_t)id)) fn(id);
+		if (cell_flagged(w))
+			ovf_for_cell(T, cidx, [&](uint32_t id, uint32_t o0, uint32_t o1, uint32_t o2) {
+				if (id > idLoExcl && id < idHi && pair_hits(g, T, v, qx + dec_off(g, o0, 0), qy + dec_off(g, o1, 1), qz + dec_off(g, o2, 2), id)) fn(id);
+				return false;
+			});
 	}
 }
 
@@ -495,9 +460,10 @@ __device__ __forceinline__ void round_range(const Geom& g, unsigned long long nB
 	}
 }
 
-// exact evaluation of one trial by the whole warp (reference arithmetic; neighbours split across lanes)
+// exact evaluation of one trial by the whole warp (reference arithmetic; neighbours split across lanes). The neighbour list
+// is complete: region_consume appended the overflow-table beads of the staged cells.
 __device__ __forceinline__ bool eval_trial_coop(const Geom& g, const Tables& T, const Frame& f, const ChainState& cs, double u01,
-	const float4* nb, int nnb, uint32_t idRound, uint32_t novf, int lane, double cand[3])
+	const float4* nb, int nnb, uint32_t idRound, int lane, double cand[3])
 {
 	cone_candidate(g, f, cs.last, u01, cand);
 	if (growth_rules_reject(g, cand, cs.last)) return false;
@@ -512,14 +478,6 @@ __device__ __forceinline__ bool eval_trial_coop(const Geom& g, const Tables& T, 
 			const float d2 = dx * dx + dy * dy + dz * dz;
 			if (d2 < g.lo2) hit = true;
 			else if (d2 <= g.hi2) hit = exact_pair(g, v, T.lpos + 3 * (size_t)__float_as_uint(b.w));
-		}
-		if (novf) {   // beads that did not fit their cell live in the overflow list
-			const uint32_t m = novf > T.ovfCap ? T.ovfCap : novf;
-			int cq[3]; cell_of_frac(g, v, cq);
-			for (uint32_t j = lane; j < m && !hit; j += 32) {
-				const uint4 e = __ldcg(T.ovf + j);
-				if (e.w < idRound && e.w != cs.lastId && ovf_entry_near(g, e, cq)) hit = exact_pair(g, v, T.lpos + 3 * (size_t)e.w);
-			}
 		}
 	} else {   // region too crowded for the staging buffer: query the cell list directly (8 cells over 8 lanes)
 		if (lane < 8) hit = probe_cells<8>(g, T, v, 0u, idRound, cs.lastId, lane);
@@ -688,11 +646,12 @@ __device__ void resolve_dirty_chain(const GrowArgs& A, uint32_t round, uint32_t 
 	__syncwarp();
 	if (found) {   // higher-indexed chains of this round whose tentative bead now collides with the new position
 		uint32_t hits[8]; int nh = 0;
-		if (lane < 8) enumerate_hits<8>(g, A.T, v, myId, idEnd, lane, [&](uint32_t id) { if (nh < 8) hits[nh++] = id; });
+		if (lane < 8) enumerate_hits<8>(g, A.T, v, myId, idEnd, lane, [&](uint32_t id) { if (nh < 8) hits[nh] = id; nh++; });
 		unsigned pending = __ballot_sync(FULL, nh > 0);
+		unsigned spilled = __ballot_sync(FULL, nh > 8);   // more hits than the register list holds (tentative beads of one round may pile up)
 		while (pending) {
 			const int src = __ffs(pending) - 1;
-			const int cnt = __shfl_sync(FULL, nh, src);
+			const int cnt = min(__shfl_sync(FULL, nh, src), 8);
 			for (int q = 0; q < cnt; ++q) {
 				uint32_t id = 0;
 #pragma unroll
@@ -701,6 +660,12 @@ __device__ void resolve_dirty_chain(const GrowArgs& A, uint32_t round, uint32_t 
 				if (lane == 0) push(id - idRound);
 			}
 			pending &= pending - 1;
+		}
+		while (spilled) {   // the lane enumerates again and reports what did not fit, one lane at a time (push is not re-entrant)
+			const int src = __ffs(spilled) - 1;
+			if (lane == src) { int k = 0; enumerate_hits<8>(g, A.T, v, myId, idEnd, lane, [&](uint32_t id) { if (k++ >= 8) push(id - idRound); }); }
+			__syncwarp();
+			spilled &= spilled - 1;
 		}
 		__syncwarp();
 	}
@@ -818,6 +783,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) grow_kernel(const __grid_consta
 	uint32_t round = __ldcg(&A.ctl->round);
 	unsigned long long nBeads = __ldcg(&A.ctl->nBeads);
 	uint32_t lastProg = __ldcg(&A.ctl->lastProgressed);
+	const bool go = __ldcg(&A.ctl->initiated) != 0u;   // main() only enters the loop when initiateChain succeeded (sarw.cpp:66); checked here so that seeding and growth can be enqueued back to back
 	unsigned long long myTrials = 0, myQueries = 0;
 	const uint32_t phase = MR ? A.mrPhase : 0u;
 	bool pendingValid = (phase == 1u);   // is there a round whose results are not yet committed? (always possible between phase-1/2 launches)
@@ -831,7 +797,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) grow_kernel(const __grid_consta
 	long long cycA = 0, cycV = 0, cycC = 0; uint32_t cleanRounds = 0;
 	long long sub[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }, ts0 = 0, ts1 = 0;
 #define SUBT(k) do { ts1 = clock64(); sub[k] += ts1 - ts0; ts0 = ts1; } while (0)
-	while (round < A.roundEnd && (long long)nBeads < g.target && lastProg) {
+	while (go && round < A.roundEnd && (long long)nBeads < g.target && lastProg) {
 		const long long tk0 = clock64();
 		ts0 = tk0;
 		uint32_t start, end;

@@ -25,7 +25,8 @@ ABI_SYMBOLS = [
     "sarw_download", "sarw_chain_lengths", "sarw_round_counts", "sarw_lookup_add_points", "sarw_lookup_find_batch",
     "sarw_lookup_find_batch_device", "sarw_lookup_size", "sarw_rdf", "sarw_chain_shapes", "sarw_concurrent_capacity", "sarw_release_cached_memory",
     "sarw_mr_setup", "sarw_mr_more", "sarw_mr_propose", "sarw_mr_finish", "sarw_mr_commit",
-    "sarw_mr_peer_export", "sarw_mr_peer_connect", "sarw_mr_grow_peer",
+    "sarw_mr_peer_export", "sarw_mr_peer_connect", "sarw_mr_grow_peer", "sarw_mr_peer_local_base", "sarw_mr_peer_connect_local",
+    "sarw_grow_async", "sarw_wait",
 ]
 
 
@@ -39,7 +40,7 @@ class Params(C.Structure):
                 ("graftLoc", C.c_int32), ("growthOrder", C.c_int32), ("boundary", C.c_int32),
                 ("growthBias", C.c_double * 3), ("seed", C.c_uint64), ("device", C.c_int32),
                 ("cellCapacity", C.c_int32), ("cellEdge", C.c_double), ("reserveRounds", C.c_int64),
-                ("launchMode", C.c_int32), ("reserved", C.c_int32)]
+                ("launchMode", C.c_int32), ("maxBlocks", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -100,6 +101,10 @@ def load_library(path=LIB_PATH):
     lib.sarw_mr_peer_export.argtypes = [vp, vp]
     lib.sarw_mr_peer_connect.argtypes = [vp, vp]
     lib.sarw_mr_grow_peer.argtypes = [vp, C.c_int64, C.POINTER(Stats)]
+    lib.sarw_mr_peer_local_base.argtypes = [vp, C.POINTER(vp)]
+    lib.sarw_mr_peer_connect_local.argtypes = [vp, C.POINTER(vp)]
+    lib.sarw_grow_async.argtypes = [vp, C.c_int64, C.c_int64]
+    lib.sarw_wait.argtypes = [vp, C.POINTER(Stats)]
     _lib = lib
     return lib
 
@@ -123,7 +128,7 @@ class Context:
 
     def __init__(self, nChains=1, boxSize=(10, 10, 10), minDist=2.0, targetMassDensity=0.92, maxTrials=100,
                  boundary="ppp", nGraftChains=0, graftLoc="file", growthOrder="roundRobin", growthBias=(0, 0, 0),
-                 seed=1, device=-1, cellCapacity=0, cellEdge=0.0, reserveRounds=0, launchMode=0):
+                 seed=1, device=-1, cellCapacity=0, cellEdge=0.0, reserveRounds=0, launchMode=0, maxBlocks=0):
         self.lib = load_library()
         p = Params()
         p.nChains = nChains; p.boxSize = (C.c_double * 3)(*boxSize); p.minDist = minDist
@@ -131,7 +136,7 @@ class Context:
         p.graftLoc = GRAFT.get(graftLoc, 3); p.growthOrder = ORDER.get(growthOrder, 0)
         p.boundary = BOUNDARY.get(boundary, 0)   # only exact ppf/pfp/fpp act, anything else == ppp (sarw.cpp:201-203)
         p.growthBias = (C.c_double * 3)(*growthBias); p.seed = seed; p.device = device
-        p.cellCapacity = cellCapacity; p.cellEdge = cellEdge; p.reserveRounds = reserveRounds; p.launchMode = launchMode
+        p.cellCapacity = cellCapacity; p.cellEdge = cellEdge; p.reserveRounds = reserveRounds; p.launchMode = launchMode; p.maxBlocks = maxBlocks
         self.params = p
         self.nChains = nChains
         h = C.c_void_p()
@@ -203,6 +208,15 @@ class Context:
         self._ck(self.lib.sarw_grow(self.h, target, maxRounds, C.byref(s)))
         return s
 
+    def grow_async(self, target=0, maxRounds=-1):
+        """seeding (unless initiate() was called) + the growth loop enqueued on the context's stream; returns at once"""
+        self._ck(self.lib.sarw_grow_async(self.h, target, maxRounds))
+
+    def wait(self):
+        s = Stats()
+        self._ck(self.lib.sarw_wait(self.h, C.byref(s)))
+        return s
+
     # ---- one melt over several GPUs (replicated state, partitioned proposals; include/sarw_abi.h "multi-rank")
     def mr_setup(self, rank, nranks):
         k, b = C.c_int64(), C.c_int64()
@@ -234,6 +248,15 @@ class Context:
         raw = b"".join(all_handles)
         buf = (C.c_ubyte * len(raw)).from_buffer_copy(raw)
         self._ck(self.lib.sarw_mr_peer_connect(self.h, buf))
+
+    def mr_peer_local_base(self):
+        b = C.c_void_p()
+        self._ck(self.lib.sarw_mr_peer_local_base(self.h, C.byref(b)))
+        return b.value
+
+    def mr_peer_connect_local(self, bases):
+        arr = (C.c_void_p * len(bases))(*bases)
+        self._ck(self.lib.sarw_mr_peer_connect_local(self.h, arr))
 
     def mr_grow_peer(self, maxRounds=-1):
         s = Stats()
@@ -375,6 +398,37 @@ def connect_peers(ctx, dist, rank, nranks):
     dist.all_gather_object(handles, mine)
     ctx.mr_peer_connect(handles)
     dist.barrier()
+
+
+def connect_peers_local(ctxs):
+    """All ranks' contexts live in this process (ranks side by side on one GPU, each created with maxBlocks so that their cooperative
+    grids are resident together): exchange buffers are shared as plain device pointers."""
+    R = len(ctxs)
+    for r, c in enumerate(ctxs):
+        c.mr_setup(r, R)
+        c.mr_peer_export()
+    bases = [c.mr_peer_local_base() for c in ctxs]
+    for c in ctxs:
+        c.mr_peer_connect_local(bases)
+
+
+def grow_peer_local(ctxs):
+    """sarw_mr_grow_peer on every rank at the same time, one host thread per rank (the kernels meet inside the launch)."""
+    import threading
+    out, errs = [None] * len(ctxs), []
+
+    def work(r):
+        try:
+            out[r] = ctxs[r].mr_grow_peer(-1)
+        except Exception as e:   # noqa: BLE001
+            errs.append(f"rank {r}: {e!r}")
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(len(ctxs))]
+    for t in th: t.start()
+    for t in th: t.join()
+    if errs:
+        raise SarwError("; ".join(errs))
+    return out
 
 
 def grow_multirank_peer(ctx, dist, rank, nranks, connected=False):

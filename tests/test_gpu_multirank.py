@@ -89,3 +89,89 @@ def test_ranks_c2_full_size_matches_oracle(sarw, oracle):
     xyz, chainID, typ, bonds, lengths, st = outs[2]
     assert np.array_equal(xyz, o.xyz) and np.array_equal(bonds, o.bonds) and np.array_equal(typ, o.type)
     assert st["trials"] == o.trials
+
+
+# ------------------------------------------------------------------ the peer-memory kernel (sarw_mr_grow_peer)
+# The whole loop of every rank runs in ONE persistent launch; records and conflict lists are stored straight into the other
+# ranks' buffers and the ranks meet on flags (st.release.sys / ld.acquire.sys). Here the R ranks are R contexts of this process
+# on ONE GPU, each on its own stream and host thread, with maxBlocks small enough that all R cooperative grids are resident at
+# the same time (sarw_mr_peer_connect_local shares the exchange buffers as plain device pointers instead of CUDA IPC handles).
+def run_ranks_peer(sarw, cfg, seed, R, split_verify=True, grafts=None, obstacles=None, maxBlocks=24):
+    import torch
+    streams = [torch.cuda.Stream() for _ in range(R)]
+    ctxs = []
+    for r in range(R):
+        c = sarw.Context(seed=seed, launchMode=1 if split_verify else 3, maxBlocks=maxBlocks, **cfg)
+        c.set_stream(streams[r].cuda_stream)
+        if obstacles is not None: c.add_obstacles(obstacles)
+        if grafts is not None: c.set_grafts(grafts)
+        assert c.initiate()
+        ctxs.append(c)
+    sarw.connect_peers_local(ctxs)
+    torch.cuda.synchronize()
+    stats = sarw.grow_peer_local(ctxs)
+    outs = []
+    for c, st in zip(ctxs, stats):
+        c.terminate()
+        xyz, chainID, typ, bonds = c.download()
+        outs.append((xyz, chainID, typ, bonds, c.chain_lengths(), c.stats().as_dict()))
+        c.close()
+    return outs
+
+
+@pytest.mark.parametrize("split_verify", [True, False])
+@pytest.mark.parametrize("R", [2, 3, 4])
+@pytest.mark.parametrize("name,cfg", [("mid", cases.MID), ("dense", cases.DENSE_TINY)])
+def test_peer_kernel_gives_the_single_gpu_walk_bit_for_bit(sarw, name, cfg, R, split_verify):
+    ref = run_single(sarw, cfg, 13)
+    outs = run_ranks_peer(sarw, cfg, 13, R, split_verify)
+    for o in outs:                                      # every rank holds the complete, identical result
+        for a, b in zip(o[:5], ref[:5]):
+            assert np.array_equal(a, b)
+        assert (o[5]["rounds"], o[5]["nBeads"], o[5]["trials"], o[5]["conflicts"]) == (ref[5]["rounds"], ref[5]["nBeads"], ref[5]["trials"], ref[5]["conflicts"])
+    if name == "mid":
+        assert ref[5]["conflicts"] > 0
+
+
+@pytest.mark.parametrize("R,split_verify", [(2, True), (4, True), (3, False)])
+def test_peer_kernel_c2_full_size_matches_oracle(sarw, oracle, R, split_verify):
+    outs = run_ranks_peer(sarw, cases.C2, 3, R, split_verify)
+    o = oracle.walk(seed=3, trig="portable", **cases.oracle_kwargs(cases.C2))
+    for xyz, chainID, typ, bonds, lengths, st in outs:
+        assert st["rounds"] == o.rounds and st["trials"] == o.trials
+        assert np.array_equal(xyz, o.xyz) and np.array_equal(bonds, o.bonds) and np.array_equal(typ, o.type)
+
+
+def test_peer_kernel_many_chains_and_conflicts(sarw, oracle):
+    """4000 chains in a 100 A box (about 10 same-round conflicts per round): partitioned verification, conflict-list exchange, the
+    parallel and the ordered clean-up all run on every rank; == oracle."""
+    cfg = dict(nChains=4000, boxSize=(100.0, 100.0, 100.0), minDist=1.0, maxTrials=300, targetMassDensity=0.92)
+    outs = run_ranks_peer(sarw, cfg, 17, 3, True, maxBlocks=64)
+    o = oracle.walk(seed=17, trig="portable", **cases.oracle_kwargs(cfg))
+    for xyz, chainID, typ, bonds, lengths, st in outs:
+        assert st["conflicts"] > 20 and st["trials"] == o.trials
+        assert np.array_equal(xyz, o.xyz) and np.array_equal(bonds, o.bonds) and np.array_equal(typ, o.type)
+
+
+def test_peer_kernel_with_grafts_obstacles_growth_order(sarw):
+    cfg = dict(nChains=24, boxSize=(24.0, 24.0, 30.0), minDist=1.0, maxTrials=200, boundary="ppf", nGraftChains=12, graftLoc="file", growthOrder="grafted")
+    grafts = cases.make_grafts(12, cfg["boxSize"], seed=5)
+    obst = cases.make_obstacles(30, cfg["boxSize"], seed=2)
+    ref = run_single(sarw, cfg, 4, grafts=grafts, obstacles=obst)
+    for o in run_ranks_peer(sarw, cfg, 4, 2, True, grafts=grafts, obstacles=obst):
+        for a, b in zip(o[:5], ref[:5]):
+            assert np.array_equal(a, b)
+
+
+def test_peer_kernel_under_torchrun_two_gpus():
+    """the real thing: one process per GPU, CUDA IPC handles, NVLink. Skipped on boxes with fewer than 2 GPUs."""
+    import json, os, subprocess, sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29631",
+                        os.path.join(root, "scripts", "mr_run.py"), "4000", "100"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["nccl_identical_on_all_ranks"] and line["peer_identical_on_all_ranks"]
