@@ -21,6 +21,11 @@ $(PKG)/lib/libsarw_prof.so: $(PKG)/csrc/sarw_kernels.cu $(PKG)/csrc/sarw_abi.cu 
 	mkdir -p $(PKG)/lib
 	$(NVCC) $(NVFLAGS) -DSARW_PROF -shared -o $@ $(PKG)/csrc/sarw_kernels.cu $(PKG)/csrc/sarw_abi.cu $(PKG)/csrc/sarw_analysis.cu
 
+# A/B variants of the library for measurements: make variant NAME=nofence DEFS="-DSARW_NO_PROXY_FENCE"; load with SARW_B200_LIB=...
+variant:
+	mkdir -p $(PKG)/lib
+	$(NVCC) $(NVFLAGS) $(DEFS) -shared -o $(PKG)/lib/libsarw_$(NAME).so $(PKG)/csrc/sarw_kernels.cu $(PKG)/csrc/sarw_abi.cu $(PKG)/csrc/sarw_analysis.cu
+
 HOSTSRC := $(PKG)/host/input_map.cpp $(PKG)/host/polymer_io.cpp
 cli: $(CLI) $(PKG)/bin/sarw_hosttest
 $(CLI): $(HOSTSRC) $(PKG)/host/main.cpp $(wildcard $(PKG)/host/*.h) include/sarw_abi.h $(LIB)
@@ -37,4 +42,4 @@ oracle:
 clean:
 	rm -rf $(PKG)/lib $(PKG)/bin
 	$(MAKE) -C oracle clean
-.PHONY: all lib cli oracle prof clean
+.PHONY: all lib cli oracle prof clean variant

@@ -148,6 +148,20 @@ int64_t sarw_target_count(const double boxSize[3], double targetMassDensity);
  * xyz[3*nBeads] (polymerChains[i].pos), chainID[nBeads], type[nBeads], bonds[2*nBonds] (1-based species, listBonds).
  * Any pointer may be NULL. */
 int sarw_download(sarw_ctx* ctx, double* xyz, int32_t* chainID, int32_t* type, int64_t* bonds);
+/* ---- checks that do not need the whole walk on the host (1e9 beads are 48 GB of state vectors) ----
+ * Order-independent checksum of the walk, computed on the device over bead slots (slot = 2*chain + {0,1} for the two seed beads,
+ * 2*nChains + round*nChains + chain for the bead a chain accepted in a round): out[0] = sum and out[1] = xor of a 64-bit hash of
+ * (slot, bit patterns of x, y, z), out[2] = beads, out[3] = sum of a hash of (bead, slot of its bonded predecessor). A function of the
+ * walk alone: one GPU, N GPUs and the CPU oracle give the same four words iff every coordinate and bond is identical
+ * (tests/stats.py walk_checksum is the numpy restatement). */
+int sarw_walk_checksum(sarw_ctx* ctx, uint64_t out[4]);
+/* Beads whose WRAPPED position lies in the axis-aligned box [lo, hi) (0 <= lo < hi <= boxSize), for brute-force verification of samples
+ * of a walk too large to download: wrapped xyz[3*cap], ids[cap] (bead slot), prevIds[cap] (slot of the bonded predecessor, -1 for a
+ * chain's first bead), chainID[cap] (1-based); arbitrary order. *count = beads found (if > cap the output is truncated). */
+int sarw_download_box(sarw_ctx* ctx, const double lo[3], const double hi[3], int64_t cap, int64_t* count, double* xyz, int64_t* ids, int64_t* prevIds, int32_t* chainID);
+/* After growth: free the cell table (the analysis and download calls do not need it; at 1e9 beads it is 100 GB). No growth or
+ * overlap query on the context afterwards. */
+int sarw_release_lookup(sarw_ctx* ctx);
 /* chainLengths (sarw.h:83): lengths[nChains] */
 int sarw_chain_lengths(sarw_ctx* ctx, int32_t* lengths);
 /* actualCount() after each completed round, for the PROGRESS log of sarw.cpp:70-76: counts[min(n, rounds)] */

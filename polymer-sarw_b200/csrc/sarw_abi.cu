@@ -45,6 +45,7 @@ struct sarw_ctx {
 
 	Control* ctl = nullptr;
 	Control* hctl = nullptr;      // pinned host mirror of *ctl, refreshed by read_control after every launch sequence (never stale between ABI calls)
+	bool lookupReleased = false;  // sarw_release_lookup was called: no cell table any more
 	bool seedTimed = true;        // seedMs / initiated / nSeeded have been taken from the events and the mirror
 	bool growTimed = true;        // the last growth launch's event pair has been added to growMs
 	bool mirrorStale = false;     // work that changes *ctl was enqueued after the last read_control
@@ -551,6 +552,7 @@ int sarw_lookup_find_batch_device(sarw_ctx* c, const double* d_xyz, const int64_
 {
 	if (!c) return 1;
 	if (n < 0 || (n > 0 && (!d_xyz || !d_hit))) return fail(c, "sarw_lookup_find_batch_device: bad arguments");
+	if (c->lookupReleased) return fail(c, "the lookup was released (sarw_release_lookup)");
 	cudaSetDevice(c->device);
 	CU(c, find_batch_ordered(c, d_xyz, d_ignore, n, d_hit));
 	return 0;
@@ -560,6 +562,7 @@ int sarw_lookup_find_batch(sarw_ctx* c, const double* xyz, const int64_t* ignore
 {
 	if (!c) return 1;
 	if (n < 0 || (n > 0 && (!xyz || !hit))) return fail(c, "sarw_lookup_find_batch: bad arguments");
+	if (c->lookupReleased) return fail(c, "the lookup was released (sarw_release_lookup)");
 	if (n == 0) return 0;
 	cudaSetDevice(c->device);
 	double* dx = nullptr; int64_t* di = nullptr; uint8_t* dh = nullptr;
@@ -686,6 +689,7 @@ static int grow_blocks(const sarw_ctx* c, int64_t chains)
 // one growth launch on the context's stream covering as many rounds as bead storage is allocated for; no synchronisation
 static int grow_enqueue(sarw_ctx* c, const Geom& g, uint32_t roundNow, int64_t roundsLeft)
 {
+	if (c->lookupReleased) return fail(c, "the lookup was released (sarw_release_lookup): no more growth on this context");
 	if (roundNow >= c->roundCap && ensure_rounds(c, roundNow + 1)) return 1;
 	uint32_t roundEnd = c->roundCap;
 	if ((int64_t)(roundEnd - roundNow) > roundsLeft) roundEnd = roundNow + (uint32_t)roundsLeft;
@@ -1069,6 +1073,75 @@ int sarw_chain_shapes(sarw_ctx* c, double* ree2, double* rg2)
 	dev_free(c, d);
 	if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
 	if (e != cudaSuccess) return fail(c, "sarw_chain_shapes: %s", cudaGetErrorString(e));
+	return 0;
+}
+
+int sarw_walk_checksum(sarw_ctx* c, uint64_t out[4])
+{
+	if (!c || !out) return 1;
+	if (!c->initiateCalled) return fail(c, "nothing to sum before sarw_initiate");
+	cudaSetDevice(c->device);
+	if (fresh(c)) return 1;
+	unsigned long long* d = nullptr;
+	CU(c, dev_alloc(c, &d, 4 * sizeof(unsigned long long)));
+	cudaError_t e = launch_walk_checksum(c->T, c->prev, c->g.idAtomBase, slots_for_rounds(c, c->hctl->round), d, c->numSMs, c->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(out, d, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+	dev_free(c, d);
+	if (e != cudaSuccess) return fail(c, "sarw_walk_checksum: %s", cudaGetErrorString(e));
+	return 0;
+}
+
+int sarw_download_box(sarw_ctx* c, const double lo[3], const double hi[3], int64_t cap, int64_t* count, double* xyz, int64_t* ids, int64_t* prevIds, int32_t* chainID)
+{
+	if (!c || !lo || !hi || !count || cap < 0) return 1;
+	if (cap > 0 && (!xyz || !ids || !prevIds || !chainID)) return fail(c, "sarw_download_box: null output buffer");
+	if (!c->initiateCalled) return fail(c, "nothing to download before sarw_initiate");
+	for (int k = 0; k < 3; k++) if (!(lo[k] >= 0 && lo[k] < hi[k] && hi[k] <= c->g.L[k])) return fail(c, "sarw_download_box: need 0 <= lo < hi <= boxSize in every dimension");
+	cudaSetDevice(c->device);
+	if (fresh(c)) return 1;
+	const uint64_t nSlots = slots_for_rounds(c, c->hctl->round);
+	const size_t n = (size_t)std::max<int64_t>(cap, 1);
+	unsigned long long* dCount = nullptr; double* dx = nullptr; int64_t *di = nullptr, *dp = nullptr; int32_t* dc = nullptr;
+	int rc = 0;
+	auto cleanup = [&]() { dev_free(c, dCount); dev_free(c, dx); dev_free(c, di); dev_free(c, dp); dev_free(c, dc); };
+#define CUF(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { rc = fail(c, "%s: %s", #x, cudaGetErrorString(e_)); cleanup(); return rc; } } while (0)
+	CUF(dev_alloc(c, &dCount, sizeof(unsigned long long)));
+	CUF(dev_alloc(c, &dx, n * 3 * sizeof(double)));
+	CUF(dev_alloc(c, &di, n * sizeof(int64_t)));
+	CUF(dev_alloc(c, &dp, n * sizeof(int64_t)));
+	CUF(dev_alloc(c, &dc, n * sizeof(int32_t)));
+	CUF(launch_gather_box(c->g, c->T, c->prev, nSlots, lo, hi, (uint64_t)cap, dCount, dx, di, dp, dc, c->stream));
+	CUF(cudaStreamSynchronize(c->stream));
+	unsigned long long found = 0;
+	CUF(cudaMemcpyAsync(&found, dCount, sizeof found, cudaMemcpyDeviceToHost, c->stream));
+	CUF(cudaStreamSynchronize(c->stream));
+	*count = (int64_t)found;
+	const size_t m = (size_t)std::min<unsigned long long>(found, (unsigned long long)cap);
+	if (m) {
+		CUF(cudaMemcpyAsync(xyz, dx, m * 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+		CUF(cudaMemcpyAsync(ids, di, m * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+		CUF(cudaMemcpyAsync(prevIds, dp, m * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+		CUF(cudaMemcpyAsync(chainID, dc, m * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+		CUF(cudaStreamSynchronize(c->stream));
+	}
+#undef CUF
+	cleanup();
+	return 0;
+}
+
+// growth is over and no more overlap queries will be made: hand the cell table and the overflow table back (at 1e9 beads they are
+// 100 GB that the analysis calls need for their own buffers). sarw_lookup_find_batch / growth calls fail afterwards.
+int sarw_release_lookup(sarw_ctx* c)
+{
+	if (!c) return 1;
+	cudaSetDevice(c->device);
+	if (fresh(c)) return 1;
+	if (c->stream) cudaStreamSynchronize(c->stream);
+	dev_free(c, c->T.cells); dev_free(c, c->T.ovf);
+	c->T.cells = nullptr; c->T.ovf = nullptr; c->lookupReleased = true;
+	cudaStreamSynchronize(c->allocStream);
 	return 0;
 }
 

@@ -38,7 +38,7 @@ constexpr size_t cluster_smem_bytes(int warps)
 		+ 2 * (size_t)CL_MAXCH * sizeof(TentRec) + (size_t)warps * 8 + 16;
 }
 
-__device__ __forceinline__ void cluster_arrive() { fence_cells_for_tma(); asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
 // Blocked arcs as (cos alpha, sin alpha, kappa): a trial angle theta is CERTAINLY rejected by the bead iff
@@ -282,6 +282,7 @@ __device__ __forceinline__ int region_consume(const Geom& g, const Tables& T, co
 {
 	const float inv0 = 1.0f / (float)rp.nn[0], inv1 = 1.0f / (float)rp.nn[1];
 	uint32_t vm[2] = { 0, 0 }; float sh[2][3]; bool flg[2] = { false, false }; int at_[2] = { 0, 0 };
+	uint32_t w[2][CELL_WORDS];
 #pragma unroll
 	for (int q = 0; q < 2; q++) {
 		const int ci = lane + 32 * q;
@@ -290,10 +291,12 @@ __device__ __forceinline__ int region_consume(const Geom& g, const Tables& T, co
 			const int rest = (int)(((float)ci + 0.5f) * inv0), ix = ci - rest * rp.nn[0];
 			const int iz = (int)(((float)rest + 0.5f) * inv1), iy = rest - iz * rp.nn[1];
 			at_[q] = region_index(rp, ix, iy, iz);
-			const Cell& sc = raw[at_[q]];
+			const uint4* sp = reinterpret_cast<const uint4*>(raw + at_[q]);   // the record in registers: two 128-bit shared loads
+			const uint4 lo = sp[0], hi = sp[1];
+			w[q][0] = lo.x; w[q][1] = lo.y; w[q][2] = lo.z; w[q][3] = lo.w; w[q][4] = hi.x; w[q][5] = hi.y; w[q][6] = hi.z; w[q][7] = hi.w;
 #pragma unroll
-			for (int k = 0; k < MAX_CAP; k++) { const uint32_t id = sc.id[k]; vm[q] |= (id < idLimit && id != ignoreId ? 1u : 0u) << k; }
-			flg[q] = sc.ovfInv != 0xFFFFu;
+			for (int k = 0; k < MAX_CAP; k++) { const uint32_t id = w[q][k]; vm[q] |= (id < idLimit && id != ignoreId ? 1u : 0u) << k; }
+			flg[q] = cell_flagged(w[q]);
 			sh[q][0] = rp.base[0] + (float)ix * (float)g.a[0]; sh[q][1] = rp.base[1] + (float)iy * (float)g.a[1]; sh[q][2] = rp.base[2] + (float)iz * (float)g.a[2];
 		}
 	}
@@ -307,12 +310,11 @@ __device__ __forceinline__ int region_consume(const Geom& g, const Tables& T, co
 	uint32_t at = excl;
 #pragma unroll
 	for (int q = 0; q < 2; q++) {
-		const Cell& sc = raw[at_[q]];
 #pragma unroll
 		for (int k = 0; k < MAX_CAP; k++)
 			if ((vm[q] >> k) & 1u)
-				nb[at++] = make_float4(sh[q][0] + dec_off(g, sc.off[k][0], 0), sh[q][1] + dec_off(g, sc.off[k][1], 1), sh[q][2] + dec_off(g, sc.off[k][2], 2),
-					__uint_as_float(sc.id[k]));
+				nb[at++] = make_float4(sh[q][0] + dec_off(g, cell_off(w[q], k, 0), 0), sh[q][1] + dec_off(g, cell_off(w[q], k, 1), 1),
+					sh[q][2] + dec_off(g, cell_off(w[q], k, 2), 2), __uint_as_float(w[q][k]));
 	}
 	while (flagged) {   // rare: one lane at a time walks the hash table for its flagged cells and appends what it finds
 		const int src = __ffs(flagged) - 1;
@@ -667,6 +669,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) grow_cluster_kernel(const __gri
 					cell->ovfInv = 0;
 					ovf_insert(A.T, cidx, id, q16);
 				}
+				fence_cells_for_tma();
 				for (int k = 0; k < 3; k++) A.resPos[3 * (size_t)i + k] = cand[k];
 			}
 			if (lane == 0) {

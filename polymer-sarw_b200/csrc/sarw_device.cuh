@@ -395,6 +395,17 @@ __device__ __forceinline__ bool probe_cells(const Geom& g, const Tables& T, cons
 	return hit;
 }
 
+// Cells are written through the generic proxy (the inserts below) and read in later rounds by bulk / tensor copies, i.e. through the
+// async proxy; the PTX memory model orders the two only across a proxy fence. Every thread that wrote a cell issues it right after
+// its stores; the round's barrier (release / acquire) then carries the ordering to the thread that issues the copy. (The LDGSTS
+// staging variant reads through the generic proxy and needs none.)
+__device__ __forceinline__ void fence_cells_for_tma()
+{
+#ifndef SARW_NO_PROXY_FENCE
+	asm volatile("fence.proxy.async.global;" ::: "memory");
+#endif
+}
+
 __device__ __forceinline__ void st_off16(Cell* cell, int k, const uint32_t q16[3])
 {
 	unsigned short* o = reinterpret_cast<unsigned short*>(&cell->off[k][0]);
@@ -413,9 +424,10 @@ __device__ __forceinline__ void insert_bead(const Geom& g, const Tables& T, cons
 	lp[0] = pos[0]; lp[1] = pos[1]; lp[2] = pos[2];
 	Cell* cell = T.cells + ci;
 	for (int k = 0; k < g.cap; ++k)
-		if (atomicCAS(&cell->id[k], ID_NONE, id) == ID_NONE) { st_off16(cell, k, q16); return; }
+		if (atomicCAS(&cell->id[k], ID_NONE, id) == ID_NONE) { st_off16(cell, k, q16); fence_cells_for_tma(); return; }
 	cell->ovfInv = 0;              // idempotent plain store: every writer stores the same value
 	ovf_insert(T, ci, id, q16);
+	fence_cells_for_tma();
 }
 
 // remove a bead again (conflict clean-up; several warps may do this at once for beads of different chains)
@@ -434,12 +446,8 @@ __device__ inline void remove_bead(const Geom& g, const Tables& T, uint32_t id)
 	unsigned long long ones = ~0ull;
 	lp[0] = __longlong_as_double((long long)ones); lp[1] = lp[0]; lp[2] = lp[0];
 	__threadfence();
+	fence_cells_for_tma();
 }
-
-// Writes made through the generic proxy (the inserts above) are read in later rounds by bulk / tensor copies, i.e. through the
-// async proxy; the PTX memory model orders the two only across a proxy fence. Every thread that may have written cells issues
-// it before the round's barrier. (The LDGSTS staging variant reads through the generic proxy and needs none.)
-__device__ __forceinline__ void fence_cells_for_tma() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
 // ------------------------------------------------------------------ grid-wide barrier for the persistent kernel
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p)
@@ -447,7 +455,6 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p)
 }
 __device__ __forceinline__ void grid_barrier(unsigned* count, unsigned* gen, unsigned nBlocks)
 {
-	fence_cells_for_tma();
 	__syncthreads();
 	if (threadIdx.x == 0) {
 		unsigned my = ld_acquire_u32(gen);

@@ -51,6 +51,9 @@ cudaError_t download_scan_bytes(uint64_t nSlots, size_t* bytes);
 cudaError_t launch_download(const Geom& g, const Tables& T, const uint32_t* prev, const ChainState* chains, uint64_t nSlots, uint32_t nSeeded,
 	int terminated, uint32_t* flags, uint32_t* scan, void* cubTemp, size_t cubBytes,
 	double* xyz, int32_t* chainID, int32_t* type, int64_t* bonds, cudaStream_t st);
+cudaError_t launch_walk_checksum(const Tables& T, const uint32_t* prev, uint32_t idAtomBase, uint64_t nSlots, unsigned long long* out4, int numSMs, cudaStream_t st);
+cudaError_t launch_gather_box(const Geom& g, const Tables& T, const uint32_t* prev, uint64_t nSlots, const double lo[3], const double hi[3], uint64_t cap,
+	unsigned long long* count, double* xyz, int64_t* ids, int64_t* prevIds, int32_t* chainID, cudaStream_t st);
 cudaError_t launch_chain_lengths(const ChainState* chains, uint32_t n, int32_t* out, cudaStream_t st);
 cudaError_t launch_fill_u32(uint32_t* p, uint64_t n, uint32_t v, cudaStream_t st);
 

@@ -129,7 +129,10 @@ __global__ void __launch_bounds__(512) zbin_scatter_kernel(Geom g, const double*
 // 32-byte cell record = one DRAM sector each) issued back to back, so a warp keeps 256 sectors in flight: the kernel is bound by
 // HBM/L2 bandwidth, not by the latency of a chain of dependent loads. Four x-adjacent cells share a 128-byte line, so the two
 // cells a sphere touches along x usually arrive with one line fill.
-__global__ void __launch_bounds__(256, 3) find_batch_kernel(Geom g, Tables T, const double* __restrict__ xyz,
+#ifndef SARW_FIND_MINBLOCKS
+#define SARW_FIND_MINBLOCKS 3
+#endif
+__global__ void __launch_bounds__(256, SARW_FIND_MINBLOCKS) find_batch_kernel(Geom g, Tables T, const double* __restrict__ xyz,
 	const int64_t* __restrict__ ignore, int64_t n, uint8_t* __restrict__ hit, const SortedCand* __restrict__ rec, const uint32_t* __restrict__ perm)
 {
 	// one block per 256 consecutive candidates, no grid-stride loop: blocks are dispatched in order, so the candidates in flight at
@@ -1022,6 +1025,57 @@ __global__ void gather_atoms_kernel(Geom g, const double* __restrict__ lpos, con
 	}
 }
 
+// ------------------------------------------------------------------ size-independent checks of large walks
+// Order-independent checksum of the whole walk in slot space (slot = 2*chain + {0,1} for seeds, 2n + round*n + chain for grown
+// beads: a function of the walk alone, so one GPU, several GPUs and the CPU oracle must all give the same four words):
+//   out[0] = sum, out[1] = xor of h(slot, x, y, z bits) over accepted slots; out[2] = accepted slots; out[3] = sum of h2(h, slot of the bonded predecessor)
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z)
+{	z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull; z ^= z >> 27; z *= 0x94D049BB133111EBull; z ^= z >> 31; return z;
+}
+__global__ void __launch_bounds__(256) walk_checksum_kernel(const double* __restrict__ lpos, const uint32_t* __restrict__ prev, uint32_t idAtomBase, uint64_t nSlots,
+	unsigned long long* __restrict__ out)
+{
+	unsigned long long sum = 0, x = 0, cnt = 0, bsum = 0;
+	for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < nSlots; s += (uint64_t)gridDim.x * blockDim.x) {
+		const double* p = lpos + 3 * (size_t)(idAtomBase + s);
+		const unsigned long long bx = (unsigned long long)__double_as_longlong(p[0]);
+		if (bx == ~0ull) continue;   // never accepted
+		unsigned long long h = mix64(s + 0x9E3779B97F4A7C15ull);
+		h = mix64(h ^ bx); h = mix64(h ^ (unsigned long long)__double_as_longlong(p[1])); h = mix64(h ^ (unsigned long long)__double_as_longlong(p[2]));
+		const uint32_t pv = prev[s];
+		sum += h; x ^= h; cnt += 1;
+		bsum += mix64(h ^ (pv == ID_NONE ? ~0ull : (unsigned long long)(pv - idAtomBase)));
+	}
+#pragma unroll
+	for (int d = 16; d > 0; d >>= 1) {
+		sum += __shfl_xor_sync(FULL, sum, d); x ^= __shfl_xor_sync(FULL, x, d); cnt += __shfl_xor_sync(FULL, cnt, d); bsum += __shfl_xor_sync(FULL, bsum, d);
+	}
+	if ((threadIdx.x & 31) == 0) { atomicAdd(&out[0], sum); atomicXor(&out[1], x); atomicAdd(&out[2], cnt); atomicAdd(&out[3], bsum); }
+}
+
+// beads whose wrapped position lies inside the axis-aligned box [lo, hi) (0 <= lo < hi <= L): position, lookup index, lookup index of the
+// bonded predecessor (-1 for a chain's first bead) and chain; order is arbitrary. *count is the number found (may exceed cap: then truncated).
+__global__ void __launch_bounds__(256) gather_box_kernel(Geom g, const double* __restrict__ lpos, const uint32_t* __restrict__ prev, uint64_t nSlots,
+	double lo0, double lo1, double lo2, double hi0, double hi1, double hi2, unsigned long long cap, unsigned long long* __restrict__ count,
+	double* __restrict__ xyz, int64_t* __restrict__ ids, int64_t* __restrict__ prevIds, int32_t* __restrict__ chainID)
+{
+	const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= nSlots) return;
+	const double* p = lpos + 3 * (size_t)(g.idAtomBase + s);
+	const double x = p[0], y = p[1], z = p[2];
+	if (__double_as_longlong(x) == -1ll) return;
+	const double wx = x - floor(x * g.Linv[0]) * g.L[0], wy = y - floor(y * g.Linv[1]) * g.L[1], wz = z - floor(z * g.Linv[2]) * g.L[2];
+	if (wx < lo0 || wx >= hi0 || wy < lo1 || wy >= hi1 || wz < lo2 || wz >= hi2) return;
+	const unsigned long long at = atomicAdd(count, 1ull);
+	if (at >= cap) return;
+	xyz[3 * at] = wx; xyz[3 * at + 1] = wy; xyz[3 * at + 2] = wz;
+	ids[at] = (int64_t)s;
+	const uint32_t pv = prev[s];
+	prevIds[at] = pv == ID_NONE ? -1 : (int64_t)(pv - g.idAtomBase);
+	const uint64_t nSeedSlots = 2ull * g.nChains;
+	chainID[at] = (int32_t)(s < nSeedSlots ? (s >> 1) : ((s - nSeedSlots) % g.nChains)) + 1;
+}
+
 __global__ void chain_lengths_kernel(const ChainState* __restrict__ chains, uint32_t n, int32_t* __restrict__ out)
 {
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1212,6 +1266,26 @@ cudaError_t download_scan_bytes(uint64_t nSlots, size_t* bytes)
 {
 	*bytes = 0;
 	return cub::DeviceScan::ExclusiveSum(nullptr, *bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int64_t)nSlots, 0);
+}
+
+cudaError_t launch_walk_checksum(const Tables& T, const uint32_t* prev, uint32_t idAtomBase, uint64_t nSlots, unsigned long long* out4, int numSMs, cudaStream_t st)
+{
+	CK(cudaMemsetAsync(out4, 0, 4 * sizeof(unsigned long long), st));
+	if (!nSlots) return cudaSuccess;
+	uint64_t blocks = (nSlots + 255) / 256; if (blocks > (uint64_t)numSMs * 16) blocks = (uint64_t)numSMs * 16;
+	walk_checksum_kernel<<<(unsigned)blocks, 256, 0, st>>>(T.lpos, prev, idAtomBase, nSlots, out4);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_gather_box(const Geom& g, const Tables& T, const uint32_t* prev, uint64_t nSlots, const double lo[3], const double hi[3], uint64_t cap,
+	unsigned long long* count, double* xyz, int64_t* ids, int64_t* prevIds, int32_t* chainID, cudaStream_t st)
+{
+	CK(cudaMemsetAsync(count, 0, sizeof(unsigned long long), st));
+	if (!nSlots) return cudaSuccess;
+	const uint64_t blocks = (nSlots + 255) / 256;
+	if (blocks > 0x7FFFFFFFull) return cudaErrorInvalidValue;
+	gather_box_kernel<<<(unsigned)blocks, 256, 0, st>>>(g, T.lpos, prev, nSlots, lo[0], lo[1], lo[2], hi[0], hi[1], hi[2], cap, count, xyz, ids, prevIds, chainID);
+	return cudaGetLastError();
 }
 
 cudaError_t launch_chain_lengths(const ChainState* chains, uint32_t n, int32_t* out, cudaStream_t st)

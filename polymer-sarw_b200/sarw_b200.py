@@ -26,7 +26,7 @@ ABI_SYMBOLS = [
     "sarw_lookup_find_batch_device", "sarw_lookup_size", "sarw_rdf", "sarw_chain_shapes", "sarw_concurrent_capacity", "sarw_release_cached_memory",
     "sarw_mr_setup", "sarw_mr_more", "sarw_mr_propose", "sarw_mr_finish", "sarw_mr_commit",
     "sarw_mr_peer_export", "sarw_mr_peer_connect", "sarw_mr_grow_peer", "sarw_mr_peer_local_base", "sarw_mr_peer_connect_local",
-    "sarw_grow_async", "sarw_wait",
+    "sarw_grow_async", "sarw_wait", "sarw_walk_checksum", "sarw_download_box", "sarw_release_lookup",
 ]
 
 
@@ -105,6 +105,9 @@ def load_library(path=LIB_PATH):
     lib.sarw_mr_peer_connect_local.argtypes = [vp, C.POINTER(vp)]
     lib.sarw_grow_async.argtypes = [vp, C.c_int64, C.c_int64]
     lib.sarw_wait.argtypes = [vp, C.POINTER(Stats)]
+    lib.sarw_walk_checksum.argtypes = [vp, vp]
+    lib.sarw_download_box.argtypes = [vp, vp, vp, C.c_int64, C.POINTER(C.c_int64), vp, vp, vp, vp]
+    lib.sarw_release_lookup.argtypes = [vp]
     _lib = lib
     return lib
 
@@ -282,6 +285,26 @@ class Context:
             xyz, chainID, typ, bonds = out["xyz"][:s.nBeads], out["chainID"][:s.nBeads], out["type"][:s.nBeads], out["bonds"][:s.nBonds]
         self._ck(self.lib.sarw_download(self.h, xyz.ctypes.data, chainID.ctypes.data, typ.ctypes.data, bonds.ctypes.data))
         return xyz, chainID, typ, bonds
+
+    def walk_checksum(self):
+        """four 64-bit words that identify the walk (every coordinate and bond), computed on the device"""
+        out = np.zeros(4, np.uint64)
+        self._ck(self.lib.sarw_walk_checksum(self.h, out.ctypes.data))
+        return tuple(int(x) for x in out)
+
+    def download_box(self, lo, hi, cap=1 << 22):
+        """beads with wrapped position in [lo, hi): (wrapped xyz, slot ids, slot ids of the bonded predecessors, chainID)"""
+        lo_ = (C.c_double * 3)(*lo); hi_ = (C.c_double * 3)(*hi)
+        xyz = np.empty((cap, 3), np.float64); ids = np.empty(cap, np.int64); prev = np.empty(cap, np.int64); cid = np.empty(cap, np.int32)
+        n = C.c_int64()
+        self._ck(self.lib.sarw_download_box(self.h, lo_, hi_, cap, C.byref(n), xyz.ctypes.data, ids.ctypes.data, prev.ctypes.data, cid.ctypes.data))
+        if n.value > cap:
+            return self.download_box(lo, hi, int(n.value))
+        m = n.value
+        return xyz[:m], ids[:m], prev[:m], cid[:m]
+
+    def release_lookup(self):
+        self._ck(self.lib.sarw_release_lookup(self.h))
 
     def chain_lengths(self):
         out = np.zeros(self.nChains, np.int32)

@@ -76,3 +76,39 @@ def verify_structure(xyz, chainID, typ, bonds, box, minDist, nChains, check_pair
 # 1e5 chains, ~100 beads each, in the box of a 1000-bead melt (same chain-tip density as BASELINE configs[2..4]): the size at
 # which several same-round conflicts happen every round (scripts/mr_run.py, profiles/r1_multigpu_scaling.md)
 BIG = dict(nChains=100000, boxSize=(1362.107287789021,) * 3, minDist=1.0, maxTrials=1000, targetMassDensity=0.092)
+
+
+# BASELINE configs[3] (the grafted brush) as it can be run: 1e4 chains in the 632.2 A box of configs[2], graftFraction 0.5 = the first
+# 5000 chains grafted on z = 0 from a graft file, growthBias 0,0,1, boundary ppf. BASELINE.md's recipe spaces the graft points 1.0 A
+# (= minDist) apart; with that spacing the UNMODIFIED reference fails its own seeding (an earlier chain's second bead lands within
+# minDist of a later graft point: initiateChain returns false, sarw.cpp:313-314,353 - checked with oracle/_ref). 2.6 A (> bond +
+# minDist) cannot be blocked that way, so that is the spacing used everywhere (tests, bench.py, golden hashes).
+C4 = dict(nChains=10000, boxSize=(632.2, 632.2, 632.2), minDist=1.0, maxTrials=1000, boundary="ppf", nGraftChains=5000, graftLoc="file",
+          growthBias=(0.0, 0.0, 1.0))
+C4_GRAFT_SEP = 2.6
+
+
+def brush_grafts(n=5000, L=632.2, seed=2024, sep=C4_GRAFT_SEP):
+    """x,y ~ U(0,L), z = 0, numpy default_rng(seed); a point within `sep` (min image in x,y) of an earlier point is rejected."""
+    from scipy.spatial import cKDTree
+    rng = np.random.default_rng(seed)
+    pts = np.zeros((0, 2))
+    while len(pts) < n:
+        cand = rng.uniform(0, L, (2 * (n - len(pts)) + 16, 2))
+        allp = np.concatenate([pts, cand])
+        tree = cKDTree(allp, boxsize=(L, L))
+        pairs = tree.query_pairs(sep, output_type="ndarray")
+        bad = set(pairs[:, 1][pairs[:, 1] >= len(pts)].tolist())          # the later point of each close pair goes
+        keep = [i for i in range(len(pts), len(allp)) if i not in bad]
+        pts = np.concatenate([pts, allp[keep]])[:n]
+    return np.concatenate([pts, np.zeros((n, 1))], axis=1)
+
+
+def walk_digest(xyz, bonds, typ):
+    """SHA-256 over the bytes of the walk's three output arrays (float64 xyz, int64 bonds, int32 type), as the golden hashes store it."""
+    import hashlib
+    h = hashlib.sha256()
+    h.update(np.ascontiguousarray(xyz, dtype=np.float64).tobytes())
+    h.update(np.ascontiguousarray(bonds, dtype=np.int64).tobytes())
+    h.update(np.ascontiguousarray(typ, dtype=np.int32).tobytes())
+    return h.hexdigest()

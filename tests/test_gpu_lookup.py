@@ -22,6 +22,21 @@ def test_find_matches_golden_reference_truth_tables(sarw):
         lk.close()
 
 
+def test_find_matches_reference_on_sparse_adversarial_tables(sarw):
+    """1e6 candidates ON the threshold sphere of isolated points (0/1/4/64 ulp either side, axis-aligned, unwrapped images, S = 2 and
+    anisotropic boxes, ignoreIndex): answers of the unmodified reference (tests/golden/make_golden_find.py), about half of them hits."""
+    from test_oracle import _sparse_tables
+    total = 0
+    for ti, box, thresh, pts, q, ig, want in _sparse_tables():
+        lk = sarw.PeriodicLookup(box, thresh)
+        lk.addPoint(pts)
+        got = lk.find(q, ig); lk.close()
+        assert np.array_equal(got, want), (ti, int(np.sum(got != want)))
+        assert 0.3 < want.mean() < 0.7
+        total += len(q)
+    assert total >= 1_000_000
+
+
 @pytest.mark.parametrize("cap", [0, 1, 2])
 def test_find_matches_oracle_random_and_overflowing_cells(sarw, oracle, cap):
     """Dense random points (cells overflow into the overflow list when cellCapacity is forced small)."""

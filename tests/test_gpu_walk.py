@@ -336,3 +336,81 @@ def test_row_copy_staging_equals_tensor_copy_staging(sarw, tmp_path):
         assert r.returncode == 0, r.stderr
         outs.append(r.stdout)
     assert outs[0] == outs[1] and outs[0].count("\n") == 2, outs
+
+
+# ------------------------------------------------------------------ large walks pinned by hashes of ONE oracle walk each
+def _golden_big():
+    import json
+    return json.load(open(os.path.join(GOLDEN, "big_walk_hashes.json")))
+
+
+@pytest.mark.parametrize("name", [k for k in ("C3", "C4", "BIG") if k in _golden_big()])
+def test_large_walk_equals_oracle_hash(sarw, name):
+    """BASELINE configs[2] (1e4 x 1000 melt) and configs[3] (1e4-chain brush, graftFraction 0.5, growthBias 0,0,1, ppf) at FULL size, and the
+    1e5-chain melt whose rounds have several same-round conflicts each:
+    SHA-256 of xyz / bonds / type equals the hash of the oracle's Philox-keyed walk (tests/golden/make_golden_big.py), i.e. every one
+    of the ~1e7 beads is bit-identical to what the serial reference algorithm produces with the same random numbers."""
+    gold = _golden_big()[name]
+    cfg = getattr(cases, name)
+    g = run_gpu(sarw, cfg, gold["seed"], grafts=cases.brush_grafts() if name == "C4" else None)
+    st = g["st"]
+    assert (st["nBeads"], st["nBonds"], st["rounds"], st["trials"], st["seedTrials"], st["initiated"], st["lastProgressed"]) == \
+        (gold["nAtoms"], gold["nBonds"], gold["rounds"], gold["trials"], gold["seedTrials"], gold["initiated"], gold["lastProgressed"])
+    assert cases.walk_digest(g["xyz"], g["bonds"], g["type"]) == gold["sha256"]
+    import hashlib
+    assert hashlib.sha256(np.ascontiguousarray(g["chainLengths"], dtype=np.int32).tobytes()).hexdigest() == gold["chainLengths_sha256"]
+    if name == "C4":
+        assert g["xyz"][:, 2].min() >= 0.0 and g["xyz"][:, 2].max() <= cfg["boxSize"][2]
+
+
+def test_walk_checksum_matches_numpy_restatement_of_oracle_walk(sarw, oracle):
+    """sarw_walk_checksum (the device-side identity of a walk, used where a download is impossible) equals the numpy restatement
+    evaluated on the ORACLE's walk, for a melt with conflicts and for the jammed-seeding case."""
+    import stats
+    for cfg, seed in ((cases.MID, 9), (cases.PE_IN, 2), (dict(nChains=400, boxSize=(8.0, 8.0, 8.0), minDist=1.5, maxTrials=20), 1)):
+        s = sarw.SARW(cfg["nChains"], cfg["boxSize"], cfg["minDist"], seed=seed, **{k: v for k, v in cfg.items() if k not in ("nChains", "boxSize", "minDist")})
+        s.run()
+        got = s.ctx.walk_checksum()
+        s.close()
+        o = oracle.walk(seed=seed, trig="portable", **cases.oracle_kwargs(cfg))
+        want = stats.walk_checksum(o.xyz, o.chainID, o.bonds, o.countAfterRound, cfg["nChains"])
+        assert got == want, (got, want)
+
+
+def test_download_box_sample_and_verifier(sarw):
+    """sarw_download_box returns exactly the beads of the full download whose wrapped position lies in the box; the sample verifier
+    finds no minDist violation; after sarw_release_lookup the walk can still be read but not queried."""
+    import stats
+    cfg = cases.MID
+    s = sarw.SARW(cfg["nChains"], cfg["boxSize"], cfg["minDist"], seed=5, maxTrials=cfg["maxTrials"])
+    s.run()
+    xyz, cid, typ, bonds = s.ctx.download()
+    lo, hi = (10.0, 5.0, 20.0), (40.0, 35.0, 55.0)
+    bx, ids, prev, bc = s.ctx.download_box(lo, hi, cap=1000)        # cap too small on purpose: the binding retries with the reported count
+    L = np.array(cfg["boxSize"]); w = xyz - np.floor(xyz / L) * L
+    inside = np.all((w >= np.array(lo)) & (w < np.array(hi)), axis=1)
+    assert len(ids) == inside.sum() and len(ids) > 1000
+    assert np.allclose(np.sort(bx[:, 0]), np.sort(w[inside, 0]), rtol=0, atol=0)
+    assert sorted(np.bincount(bc, minlength=401)) == sorted(np.bincount(cid[inside], minlength=401))
+    v = stats.verify_box_sample(bx, ids, prev, cfg["minDist"])
+    assert v["violations"] == 0 and v["closest_nonbonded"] > cfg["minDist"] and abs(v["bond_min"] - 1.54) < 1e-5 and abs(v["bond_max"] - 1.54) < 1e-5
+    before = s.ctx.walk_checksum()
+    s.ctx.release_lookup()
+    assert s.ctx.walk_checksum() == before
+    with pytest.raises(sarw.SarwError):
+        s.ctx.find(xyz[:4])
+    s.close()
+
+
+def test_async_growth_equals_blocking_growth(sarw, oracle):
+    """sarw_grow_async / sarw_wait (seeding + loop enqueued back to back, ONE synchronisation) give the blocking calls' walk, also when
+    bead storage runs out mid-walk (reserveRounds) and when seeding fails (the kernel itself skips the loop, sarw.cpp:66)."""
+    for cfg, extra in ((cases.SMALL_DEFAULTS, dict(reserveRounds=4)), (cases.MID, {}), (dict(nChains=400, boxSize=(8.0, 8.0, 8.0), minDist=1.5, maxTrials=20), {})):
+        kw = {k: v for k, v in cfg.items() if k not in ("nChains", "boxSize", "minDist")}
+        c = sarw.Context(nChains=cfg["nChains"], boxSize=cfg["boxSize"], minDist=cfg["minDist"], seed=6, **kw, **extra)
+        c.grow_async(0, -1)
+        st = c.wait(); c.terminate()
+        xyz, cid, typ, bonds = c.download(); c.close()
+        o = oracle.walk(seed=6, trig="portable", **cases.oracle_kwargs(cfg))
+        assert (st.nBeads, st.rounds, st.trials, st.initiated, st.lastProgressed) == (o.nAtoms, o.rounds, o.trials, o.initiated, o.lastProgressed)
+        assert np.array_equal(xyz, o.xyz) and np.array_equal(bonds, o.bonds) and np.array_equal(typ, o.type)

@@ -91,6 +91,33 @@ def test_oracle_find_matches_golden_reference(oracle):
         lk.close()
 
 
+def _sparse_tables():
+    """the 1e6 adversarial candidates of tests/golden/make_golden_find.py, regenerated from their seeds and checked against the
+    committed SHA-256 (a numpy whose generator streams differ would fail here, loudly, not silently test something else)"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_find", os.path.join(GOLDEN, "make_golden_find.py"))
+    m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+    gold = np.load(os.path.join(GOLDEN, "find_truth_sparse.npz"))
+    for ti in range(int(gold["n"])):
+        box, thresh, _, n = m.TABLES[ti]
+        pts = m.points(ti); q, ig = m.candidates(ti)
+        assert m.digest(q, ig) == str(gold[f"sha{ti}"]), "candidate generator drifted: rerun tests/golden/make_golden_find.py where /root/reference exists"
+        yield ti, box, thresh, pts, q, ig, np.unpackbits(gold[f"hit{ti}"])[:n]
+
+
+def test_oracle_find_matches_reference_on_sparse_adversarial_tables(oracle):
+    """1e6 candidates ON the threshold sphere (0/1/4/64 ulp either side) of isolated points: the near-threshold pair decides, so a
+    table that is half hits / half misses pins the `dist <= thresh` arithmetic of PeriodicLookup.h:67-71."""
+    total = 0
+    for ti, box, thresh, pts, q, ig, want in _sparse_tables():
+        assert 0.3 < want.mean() < 0.7, (ti, want.mean())
+        lk = oracle.lookup(box, thresh); lk.add(pts)
+        got = lk.find(q, ig); lk.close()
+        assert np.array_equal(got, want), (ti, int(np.sum(got != want)))
+        total += len(q)
+    assert total >= 1_000_000
+
+
 def test_oracle_walk_matches_live_reference_c2(oracle, ref):
     """Full BASELINE config 2 (100 x 1000 melt): oracle == unmodified reference, bit for bit."""
     r = ref.walk(seed=5, **cases.oracle_kwargs(cases.C2))
