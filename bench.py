@@ -2,22 +2,27 @@
 """bench.py — accepted beads/s of the chain-growth hot path (BASELINE.json metric) on N B200s of one node.
 
 A step = one complete pass of the hot path — SARW::initiateChain + the growth loop of main() (sarw.cpp:66-78) — over one BATCH of
-synthetic melts of BASELINE.json configs[1] (PE melt, 100 chains x 1000 beads, 0.92 g/cc, ppp, minDist 1.0, maxTrials 1000).
-A 100-chain melt grows in one thread-block cluster (13 of the 148 SMs), so the batch is M independent melts grown at the same time,
-one CUDA stream + one host thread each, M = sarw_concurrent_capacity() (7 on B200) — the same thing the reference arm does with the
-host cores (one serial instance per core). `single_melt` in the JSON line is one melt at a time. Every melt uses a fresh Philox
-key, so no work is cached between steps.
+synthetic melts of the workload. The headline workload is BASELINE.json configs[1] (PE melt, 100 chains x 1000 beads, 0.92 g/cc,
+ppp, minDist 1.0, maxTrials 1000): such a melt grows in ONE thread-block cluster (13 of the 148 SMs), so the batch is M independent
+melts grown at the same time, M = sarw_concurrent_capacity() (7 on B200), all driven by ONE host thread (sarw_grow_async on M
+streams, then sarw_wait) — the same thing the reference arm does with the host cores (one serial instance per core).
+Every melt uses a fresh Philox key, so no work is cached between steps.
 
-  value : device-resident throughput — contexts (cell tables) are created before the timed region; a step is
-          timed with CUDA events on the stream the kernels run on.
-  e2e   : the same metric through the public C ABI with host buffers: sarw_create (allocations + table init),
-          H2D of the inputs, seeding, growth, sarw_terminate and sarw_download of every bead/bond into host memory,
-          wall clock around the calls.
-  N > 1 : one process per GPU (torchrun). The melts of different ranks are independent (no data-path collective yet:
-          spatial decomposition with NCCL halo exchange is the next §8e row); "scaling": "weak".
+  value : device-resident throughput — contexts (cell tables) are created before the timed region; a step is timed with CUDA events
+          on the streams the kernels run on.
+  e2e   : the same metric through the public C ABI with host buffers: sarw_create (allocations + table init), H2D of the inputs,
+          seeding, growth, sarw_terminate and sarw_download of every bead/bond into pinned host memory, sarw_destroy; wall clock.
+  workloads : the same two measurements, as full records of their own (repeated steps, roofline, e2e, clocks), for BASELINE
+          configs[2] (1e4 x 1000 melt, 1e7 beads) and configs[3] (1e4-chain grafted brush); N = 1 only.
+  N > 1 : one process per GPU (torchrun). The headline melts of different ranks are independent ("scaling": "weak", no data-path
+          collective). The record `one_melt` is ONE melt of 1e7*N beads grown by all N GPUs together (sarw_mr_grow_peer: proposals and
+          verification partitioned, records and conflict lists exchanged inside the persistent kernel over NVLink peer memory), with
+          every rank's walk checksum compared with the others' and with the single-GPU walk. At N = 8 the record `C5` is
+          BASELINE configs[4]: one melt of 1e6 chains x 1000 beads (1e9 beads).
   --impl reference : the UNMODIFIED reference (oracle/_ref, built from /root/reference) timed on the host cores.
 """
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -30,6 +35,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "polymer-sarw_b200"))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+C4_GRAFT_SEP = 2.6
 WORKLOADS = {
     # BASELINE.json configs[1] / SURVEY §8d C2
     "C2": dict(name="PE melt 100 chains x 1000 beads, 0.92 g/cc, ppp, minDist 1.0, maxTrials 1000 (BASELINE configs[1])",
@@ -37,18 +43,33 @@ WORKLOADS = {
     # BASELINE.json configs[2] / C3
     "C3": dict(name="PE melt 1e4 chains x 1000 beads, 0.92 g/cc, ppp, minDist 1.0, maxTrials 1000 (BASELINE configs[2])",
                nChains=10000, boxSize=(632.2, 632.2, 632.2), minDist=1.0, maxTrials=1000, boundary="ppp", targetMassDensity=0.92),
+    # BASELINE.json configs[3] / C4. BASELINE.md spaces the graft points 1.0 A (= minDist) apart; with that spacing the UNMODIFIED
+    # reference fails its own seeding (a second bead lands within minDist of a later graft point, sarw.cpp:313-314,353), so the graft
+    # points here are 2.6 A (> bond + minDist) apart — the same recipe as tests/cases.py C4 and the golden hash.
+    "C4": dict(name="grafted brush: 1e4 chains in a 632.2 A box, graftFraction 0.5 (5000 chains grafted on z = 0 from a graft file, points >= 2.6 A apart "
+                    "instead of BASELINE.md's 1.0 A, which the reference itself cannot seed), growthBias 0,0,1, boundary ppf, 0.92 g/cc target (BASELINE configs[3])",
+               nChains=10000, boxSize=(632.2, 632.2, 632.2), minDist=1.0, maxTrials=1000, boundary="ppf", targetMassDensity=0.92,
+               nGraftChains=5000, graftLoc="file", growthBias=(0.0, 0.0, 1.0), grafts="brush"),
 }
-# ONE melt over all N GPUs (strong scaling): not the headline workload, selected with --workload
+
+
+def melt_workload(nChains, what):
+    """a PE melt of nChains x 1000 beads at 0.92 g/cc: the box of BASELINE configs[2] scaled to the chain count"""
+    L = 632.2 * (nChains / 10000.0) ** (1.0 / 3.0)
+    return dict(name=f"ONE PE melt of {nChains} chains x 1000 beads ({nChains * 1000:.1e} beads, 0.92 g/cc, L = {L:.1f} A), {what}",
+                nChains=nChains, boxSize=(L, L, L), minDist=1.0, maxTrials=1000, boundary="ppp", targetMassDensity=0.92)
+
+
+# ONE melt over all N GPUs (strong scaling; DESIGN.md section 6), selected with --workload
 ONE_MELT = {
     "ONE_MELT_1E7": dict(name="ONE PE melt of 1e5 chains, 1.0e7 beads (tip density of a 1000-bead melt), grown by all N GPUs together", nChains=100000,
                          boxSize=(1362.107287789021,) * 3, minDist=1.0, maxTrials=1000, boundary="ppp", targetMassDensity=0.092),
-    "ONE_MELT_2E8": dict(name="ONE PE melt of 2e5 chains x 1000 beads (2.0e8 beads, 0.92 g/cc), grown by all N GPUs together", nChains=200000,
-                         boxSize=(1716.1476441006014,) * 3, minDist=1.0, maxTrials=1000, boundary="ppp", targetMassDensity=0.92),
-    "ONE_MELT_3E8": dict(name="ONE PE melt of 3e5 chains x 1000 beads (3.0e8 beads, 0.92 g/cc; 121 GB of cells per GPU), grown by all N GPUs together", nChains=300000,
-                         boxSize=(1964.4986505263048,) * 3, minDist=1.0, maxTrials=1000, boundary="ppp", targetMassDensity=0.92),
+    "ONE_MELT_2E8": melt_workload(200000, "grown by all N GPUs together"),
+    "ONE_MELT_3E8": melt_workload(300000, "grown by all N GPUs together"),
+    "C5": melt_workload(1000000, "BASELINE configs[4], grown by all N GPUs together"),
 }
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full capture
-NCU_TRAFFIC = {"C2": (36.86e6, "profiles/r1_grow_cluster_kernel_C2_raw.csv")}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full captures
+NCU_TRAFFIC = {"C2": (36.86e6, "profiles/r1_grow_cluster_kernel_C2_raw.csv (128-byte cells; not re-captured for the 32-byte format)")}
 # SURVEY.md §8(d): algorithmic bytes per overlap query and per accepted bead
 B_QUERY = 121.0
 B_BEAD = 108.0
@@ -73,7 +94,7 @@ class ClockSampler:
 
     def start(self):
         if os.environ.get("SARW_BENCH_NOSAMPLER"):
-            return
+            return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -81,6 +102,7 @@ class ClockSampler:
             self.t.start()
         except Exception:
             self.proc = None
+        return self
 
     def _read(self):
         for line in self.proc.stdout:
@@ -108,21 +130,37 @@ class ClockSampler:
 
 
 def ctx_kwargs(w, seed):
-    return dict(nChains=w["nChains"], boxSize=w["boxSize"], minDist=w["minDist"], targetMassDensity=w["targetMassDensity"],
-                maxTrials=w["maxTrials"], boundary=w["boundary"], seed=seed)
+    kw = dict(nChains=w["nChains"], boxSize=w["boxSize"], minDist=w["minDist"], targetMassDensity=w["targetMassDensity"],
+              maxTrials=w["maxTrials"], boundary=w["boundary"], seed=seed)
+    for k in ("nGraftChains", "graftLoc", "growthBias"):
+        if k in w: kw[k] = w[k]
+    return kw
+
+
+_grafts_cache = {}
+
+
+def workload_grafts(w):
+    """graft points of a workload (None for melts); the brush uses the recipe of tests/cases.py (the one the golden hash pins)"""
+    if w.get("grafts") != "brush":
+        return None
+    if "brush" not in _grafts_cache:
+        import cases
+        _grafts_cache["brush"] = cases.brush_grafts(n=w["nGraftChains"], L=w["boxSize"][0], sep=C4_GRAFT_SEP)
+    return _grafts_cache["brush"]
 
 
 # ------------------------------------------------------------------ reference on host cores (oracle/_ref)
 def _ref_one(args):
-    w, seed = args
+    w, seed, rng, maxRounds = args
     import oracle_bindings as ob
     R = ob.RefLib()
     r = R.walk(nChains=w["nChains"], box=w["boxSize"], minDist=w["minDist"], targetMassDensity=w["targetMassDensity"],
-               maxTrials=w["maxTrials"], boundary=w["boundary"], rng="mt", seed=seed)
+               maxTrials=w["maxTrials"], boundary=w["boundary"], rng=rng, seed=seed, maxRounds=maxRounds)
     return r.nAtoms, r.seconds, r.trials, r.rounds
 
 
-def reference_throughput(w, instances, seed0):
+def reference_throughput(w, instances, seed0, rng="mt", maxRounds=-1):
     """`instances` independent melts of the reference, one per host core, run concurrently (the reference itself is
     strictly serial: 1 thread per instance). Returns (beads/s aggregate, wall seconds of the slowest, details)."""
     import multiprocessing as mp
@@ -135,7 +173,7 @@ def reference_throughput(w, instances, seed0):
     ctx = mp.get_context("fork")
     with ctx.Pool(instances) as pool:
         t0 = time.perf_counter()
-        res = pool.map(_ref_one, [(w, seed0 + i) for i in range(instances)])
+        res = pool.map(_ref_one, [(w, seed0 + i, rng, maxRounds) for i in range(instances)])
         wall = time.perf_counter() - t0
     beads = sum(r[0] for r in res)
     slowest = max(r[1] for r in res)
@@ -144,11 +182,19 @@ def reference_throughput(w, instances, seed0):
                 trials_per_bead=sum(r[2] for r in res) / beads, rounds=[r[3] for r in res])
 
 
+def host_cores():
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    return max(1, min(n, 32))
+
+
 def run_reference(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = max(1, min(os.cpu_count() or 1, 32))
+    cores = host_cores()
     times, values = [], []
     last = None
     for s in range(args.warmup + args.steps):
@@ -161,11 +207,15 @@ def run_reference(args, w):
     value = sum(values) / len(values)
     sample = (f"{cores} concurrent instances (1 thread each; the reference is serial) of the full workload per step, unmodified reference "
               f"sources (oracle/_ref) with mt19937_64 re-seeded per trial like upstream; seeding + growth loop timed (sarw.cpp:66-78)")
+    keyed = reference_throughput(w, cores, 5000, rng="keyed")
     line = {"impl": "reference", "metric": "accepted beads/sec", "value": value, "unit": "beads/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": w["name"], "instances": cores},
             "cpu_baseline": {"value": value, "unit": "beads/s", "cores": cores, "kind": "reference", "sample": sample,
-                             "per_core_beads_per_s": last["per_core"], "trials_per_bead": last["trials_per_bead"]},
+                             "per_core_beads_per_s": last["per_core"], "trials_per_bead": last["trials_per_bead"],
+                             "keyed_rng_beads_per_s": keyed["value"] if keyed else None,
+                             "keyed_rng_note": "same unmodified reference with the stand-in's Random::seed reduced to a counter set-up (no mt19937_64 "
+                                               "re-initialisation per trial): upper bound of the reference's speed whatever JDFTx's Random::seed costs"},
             "e2e": {"value": value, "unit": "beads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
 
@@ -188,9 +238,280 @@ def aggregate_ranks(dist, device, t_dev, t_e2e, beads, e2e_beads):
     return t[0].item(), t[1].item(), w[0].item(), w[1].item()
 
 
-def run_one_melt(args, w):
+class Env:
+    """what every measurement needs: the binding, torch, the launching stream, the L2 flush buffer, the device"""
+    def __init__(self, sarw_b200, torch, local):
+        self.sarw, self.torch, self.local = sarw_b200, torch, local
+        self.stream = torch.cuda.current_stream()
+        self.flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")   # > 126 MB L2
+        self.hbm_peak, self.peak_src = load_peaks()
+        self._streams = {}
+
+    def streams(self, M):
+        if M == 1:
+            return [self.stream]
+        if M not in self._streams:
+            self._streams[M] = [self.torch.cuda.Stream() for _ in range(M)]
+        return self._streams[M]
+
+    def l2_flush(self, i):
+        self.flush.fill_(float(i)); self.torch.cuda.synchronize()
+
+
+def make_ctx(env, w, seed, stream):
+    c = env.sarw.Context(device=env.local, **ctx_kwargs(w, seed))
+    c.set_stream(stream.cuda_stream)
+    g = workload_grafts(w)
+    if g is not None: c.set_grafts(g)
+    return c
+
+
+def measure_device(env, w, M, seeds, warmup, steps):
+    """device-resident arm: the contexts (cell tables) of a step exist before its timed region starts and are destroyed after it, so
+    memory does not grow with the step count. ONE host thread: seeding + the growth loop of every melt are enqueued back to back on the
+    melt's stream (sarw_grow_async), then each is waited for (sarw_wait: one synchronisation per melt). CUDA events on the launching
+    streams: the start event fans out to every stream, the end event waits for all of them."""
+    torch, stream, streams = env.torch, env.stream, env.streams(M)
+    step_ms, acc = [], dict(beads=0, queries=0, trials=0, rounds=0, launches=0, grow_ms=0.0, seed_ms=0.0, conflicts=0, melts=0)
+    for i in range(warmup + steps):
+        ctxs = [make_ctx(env, w, seeds[i * M + m], streams[m]) for m in range(M)]
+        env.l2_flush(i)          # L2 flush between timed iterations (outside the event pair)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for sm in streams:
+            if sm is not stream: sm.wait_event(e0)
+        for c in ctxs: c.grow_async(0, -1)
+        for sm in streams:
+            if sm is not stream:
+                ev = torch.cuda.Event(); ev.record(sm); stream.wait_event(ev)
+        e1.record(stream)
+        sts = [c.wait() for c in ctxs]
+        for c in ctxs: c.terminate()
+        e1.synchronize()
+        if i >= warmup:
+            step_ms.append(e0.elapsed_time(e1))
+            for st in sts:
+                acc["beads"] += st.nBeads; acc["queries"] += st.queries; acc["trials"] += st.trials; acc["rounds"] += st.rounds; acc["melts"] += 1
+                acc["launches"] += st.growLaunches + st.seedLaunches; acc["grow_ms"] += st.growMs; acc["seed_ms"] += st.seedMs; acc["conflicts"] += st.conflicts
+        for c in ctxs: c.close()
+    torch.cuda.synchronize()
+    return step_ms, acc
+
+
+def measure_e2e(env, w, M, seeds, warmup, steps):
+    """end-to-end arm through the C ABI with host buffers (results land in pinned host memory): the same batch of M melts, every melt
+    created, seeded, grown, downloaded and destroyed inside the timed region; wall clock, one host thread."""
+    torch, streams = env.torch, env.streams(M)
+    cap = int(env.sarw.target_count(w["boxSize"], w["targetMassDensity"]) + w["nChains"] + 16)
+    pinned = [{"xyz": torch.empty((cap, 3), dtype=torch.float64, pin_memory=True).numpy(), "chainID": torch.empty(cap, dtype=torch.int32, pin_memory=True).numpy(),
+               "type": torch.empty(cap, dtype=torch.int32, pin_memory=True).numpy(), "bonds": torch.empty((cap, 2), dtype=torch.int64, pin_memory=True).numpy()} for _ in range(M)]
+    grafts = workload_grafts(w)
+    times, acc = [], dict(beads=0, h2d=0, d2h=0, launches=0)
+    for i in range(warmup + steps):
+        gc.collect(); gc.disable()                 # no collector pauses inside the timed call sequence
+        env.l2_flush(i)
+        t0 = time.perf_counter()
+        ctxs = []
+        for m in range(M):
+            c = make_ctx(env, w, seeds[i * M + m] + 5_000_000, streams[m])
+            c.grow_async(0, -1)
+            ctxs.append(c)
+        res = []
+        for m, c in enumerate(ctxs):
+            st = c.wait(); c.terminate()
+            xyz, cid, typ, bonds = c.download(pinned[m])
+            res.append((st, xyz.nbytes + cid.nbytes + typ.nbytes + bonds.nbytes))
+            c.close()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        gc.enable()
+        if os.environ.get("SARW_BENCH_DEBUG"): print(f"e2e step {i}: {dt*1e3:.3f} ms for {M} melts", file=sys.stderr)
+        if i >= warmup:
+            times.append(dt)
+            for st, nbytes in res:
+                acc["beads"] += st.nBeads
+                acc["h2d"] += env.sarw.C.sizeof(env.sarw.Params) + 64 + (0 if grafts is None else grafts.nbytes)   # parameters + control block + graft points
+                acc["d2h"] += nbytes + 2 * 64 + st.growLaunches * 64 + 8               # results + control/stat reads
+                acc["launches"] += st.growLaunches + st.seedLaunches + 5               # + flag, 2x cub scan, gather
+    del pinned
+    return times, acc
+
+
+def grow_kernel_name(w):
+    return ("sarw::grow_cluster_kernel<8> (one thread-block cluster, persistent, one launch per melt)" if w["nChains"] <= 128
+            else "sarw::grow_kernel<8,false> (persistent cooperative launch, one per melt)")
+
+
+def roofline_record(env, w, key, acc, M):
+    """dominant kernel = the growth kernel (~all of the step). SURVEY §8d: bytes per bead = T*B_q + B_a with T = trials per accepted
+    bead in the reference's terms (what the serial loop of sarw.cpp:259 evaluates; trials of provably dead chains are decided without
+    memory traffic here). achieved = summed algorithmic bytes / summed launch durations (the kernel's own CUDA-event pair on its stream)."""
+    alg = acc["trials"] * B_QUERY + acc["beads"] * B_BEAD
+    achieved = alg / (acc["grow_ms"] / 1e3) / 1e9
+    traffic, src = NCU_TRAFFIC.get(key, (None, None))
+    return {"bound": "hbm", "achieved": achieved, "peak": env.hbm_peak, "unit": "GB/s", "frac": achieved / env.hbm_peak, "traffic": traffic, "traffic_source": src,
+            "kernel": grow_kernel_name(w), "peak_source": env.peak_src,
+            "algorithmic_bytes": f"trials*{B_QUERY:.0f} + beads*{B_BEAD:.0f} (SURVEY §8d, trials in reference terms)",
+            "algorithmic_bytes_per_launch": alg / acc["melts"], "trials_per_launch": acc["trials"] / acc["melts"],
+            "candidates_evaluated_per_launch": acc["queries"] / acc["melts"], "avg_launch_ms": acc["grow_ms"] / acc["melts"], "concurrent_launches": M,
+            "note": "per launch (one melt); latency-bound (~1e3 dependent rounds per melt), see DESIGN.md section 5. Trials of chains that are provably dead (every "
+                    "torsion blocked: the brush has thousands of them) are counted as the reference burns them (maxTrials per round) but cost no memory traffic here, so "
+                    "frac can exceed 1 for such workloads"}
+
+
+def workload_record(env, key, warmup=2, steps=5):
+    """a first-class record of a single-GPU workload other than the headline: repeated steps, roofline, e2e, clocks"""
+    w = WORKLOADS[key]
+    sampler = ClockSampler(env.local).start()
+    seeds = [77_000 + s for s in range(warmup + steps)]
+    step_ms, acc = measure_device(env, w, 1, seeds, warmup, steps)
+    e2e_t, e2e = measure_e2e(env, w, 1, seeds, 1, steps)
+    clocks = sampler.stop()
+    t = sum(step_ms) / 1e3
+    return {"workload": w["name"], "metric": "accepted beads/sec", "unit": "beads/s", "value": acc["beads"] / t, "steps": steps, "warmup": warmup,
+            "ms_per_step": 1e3 * t / steps, "ms_per_step_median": statistics.median(step_ms), "ms_per_step_min": min(step_ms), "ms_per_step_max": max(step_ms),
+            "beads_per_melt": acc["beads"] / acc["melts"], "rounds_per_melt": acc["rounds"] / acc["melts"], "trials_per_bead": acc["trials"] / max(1, acc["beads"]),
+            "conflicts_per_melt": acc["conflicts"] / acc["melts"], "seed_ms_per_melt": acc["seed_ms"] / acc["melts"], "grow_ms_per_melt": acc["grow_ms"] / acc["melts"],
+            "l2": "256 MB flush write between timed steps; tables far larger than L2",
+            "e2e": {"value": e2e["beads"] / sum(e2e_t), "unit": "beads/s", "h2d_bytes_per_step": e2e["h2d"] // steps, "d2h_bytes_per_step": e2e["d2h"] // steps,
+                    "ms_per_step": 1e3 * sum(e2e_t) / steps, "ms_per_step_median": 1e3 * statistics.median(e2e_t), "ms_per_step_max": 1e3 * max(e2e_t),
+                    "includes": "sarw_create (alloc + cell-table init), graft upload, seeding, growth, terminate, sarw_download of every bead and bond to pinned host memory, sarw_destroy"},
+            "gpu_launches": int(acc["launches"]), "clocks": clocks, "roofline": roofline_record(env, w, key, acc, 1)}
+
+
+# ------------------------------------------------------------------ ONE melt over all GPUs
+def checksum_words(torch, dist, c):
+    """this rank's walk checksum and every rank's (all-gathered as int64 bit patterns)"""
+    import numpy as np
+    mine = np.array(c.walk_checksum(), dtype=np.uint64)
+    if dist is None:
+        return mine, [mine]
+    t = torch.from_numpy(mine.view(np.int64).copy()).cuda()
+    out = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t)
+    return mine, [o.cpu().numpy().view(np.uint64) for o in out]
+
+
+def one_melt_record(env, dist, rank, world, w, warmup, steps, single_gpu_check=True, box_samples=0, rdf=False):
     """Strong scaling: every step grows ONE melt with all N GPUs (replicated state, partitioned proposals and verification, records and
-    conflict lists exchanged inside the persistent kernel over NVLink peer memory). N = 1 runs the single-GPU kernel."""
+    conflict lists exchanged inside the persistent kernel over NVLink peer memory). N = 1 runs the single-GPU kernel. Every rank's walk
+    checksum (sarw_walk_checksum: every coordinate and bond) is compared with the others'; rank 0 then grows the melt of the last step
+    once more on its own and compares that checksum too. Returns the record on rank 0, None elsewhere."""
+    torch, sarw_b200, stream, local = env.torch, env.sarw, env.stream, env.local
+    import numpy as np
+    times, beads, st, agree, sums = [], 0, None, True, None
+    sampler = None
+    extra = {}
+    for s in range(warmup + steps):
+        seed = 31_000 + s
+        c = sarw_b200.Context(device=local, launchMode=1, **ctx_kwargs(w, seed))
+        c.set_stream(stream.cuda_stream)
+        c.initiate()
+        if world > 1:
+            sarw_b200.connect_peers(c, dist, rank, world)
+        torch.cuda.synchronize()
+        if dist: dist.barrier()
+        if s == warmup and rank == 0:
+            sampler = ClockSampler(local).start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        st = c.mr_grow_peer(-1) if world > 1 else c.grow(0, -1)
+        e1.record(stream); e1.synchronize()
+        ms = e0.elapsed_time(e1) + st.seedMs
+        if dist:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = t.item()
+        mine, sums = checksum_words(torch, dist, c)
+        agree = agree and all(np.array_equal(x, sums[0]) for x in sums)
+        if s >= warmup:
+            times.append(ms); beads += st.nBeads
+        last = s == warmup + steps - 1
+        if last and rank == 0 and (box_samples or rdf):
+            extra = verify_large_walk(c, w, box_samples, rdf)
+        c.close()
+    clocks = sampler.stop() if sampler else None
+    single = None
+    if single_gpu_check and world > 1:
+        # the same melt (seed of the last step) on ONE GPU: rank 0 alone, the other ranks wait at the barrier
+        if rank == 0:
+            sarw_b200.release_cached_memory(local)
+            c = sarw_b200.Context(device=local, launchMode=1, **ctx_kwargs(w, 31_000 + warmup + steps - 1))
+            c.set_stream(stream.cuda_stream)
+            c.initiate()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream); st1 = c.grow(0, -1); e1.record(stream); e1.synchronize()
+            one = np.array(c.walk_checksum(), dtype=np.uint64)
+            single = {"ms": e0.elapsed_time(e1) + st1.seedMs, "beads": st1.nBeads, "checksum_equal": bool(np.array_equal(one, sums[0])),
+                      "invariants_equal": (st1.nBeads, st1.rounds, st1.trials, st1.conflicts) == (st.nBeads, st.rounds, st.trials, st.conflicts)}
+            c.close()
+        dist.barrier()
+    if rank != 0:
+        return None
+    t_dev = sum(times) / 1e3
+    alg = (st.trials * B_QUERY + st.nBeads * B_BEAD) / world
+    rounds = max(1, st.rounds)
+    rec = {"workload": w["name"], "metric": "accepted beads/sec", "unit": "beads/s", "value": beads / t_dev, "beads": st.nBeads, "n_gpus": world, "steps": steps, "warmup": warmup,
+           "ms_per_step": 1e3 * t_dev / steps, "ms_per_step_min": min(times), "ms_per_step_max": max(times), "scaling": "strong",
+           "multi_gpu": ("one melt over all GPUs: replicated state, partitioned proposals + verification, records and conflict lists exchanged inside the persistent "
+                         "kernel over NVLink peer memory (st.release.sys / ld.acquire.sys flags)") if world > 1 else "single GPU",
+           "rounds": st.rounds, "trials_per_bead": st.trials / max(1, st.nBeads), "conflicts": st.conflicts, "overflow_beads": st.overflowBeads,
+           "all_ranks_agree": bool(agree), "walk_checksum": [int(x) for x in sums[0]],
+           "matches_single_gpu": None if single is None else bool(single["checksum_equal"] and single["invariants_equal"]),
+           "single_gpu": single, "speedup_vs_single_gpu": None if single is None else single["ms"] / times[-1],
+           "cycles_per_round_rank0": {"propose": st.cycPropose / rounds, "verify": st.cycVerify / rounds, "cleanup": st.cycCleanup / rounds,
+                                      "sub": {n: st.cycSub[k] / rounds for k, n in enumerate(("propose_loop", "barrier_after_propose", "peer_handshake", "barrier_after_handshake",
+                                                                                                "apply_remote", "barrier_after_apply"))}},
+           "clocks": clocks,
+           "roofline": {"bound": "hbm", "achieved": alg / (times[-1] / 1e3) / 1e9, "peak": env.hbm_peak, "unit": "GB/s", "frac": alg / (times[-1] / 1e3) / 1e9 / env.hbm_peak,
+                        "traffic": None, "kernel": "sarw::grow_kernel<8,true> (persistent cooperative launch per GPU)", "peak_source": env.peak_src,
+                        "algorithmic_bytes": f"(trials*{B_QUERY:.0f} + beads*{B_BEAD:.0f}) / N GPUs, per GPU"}}
+    rec.update(extra)
+    return rec
+
+
+def verify_large_walk(c, w, box_samples, rdf):
+    """checks of a walk too large to download (1e9 beads are 48 GB of state vectors): brute-force verifier on sampled sub-boxes
+    (sarw_download_box), and the RDF of the whole melt (sarw_rdf, scripts/rdf.py math) against the reference's C2 melts"""
+    import numpy as np
+    import stats
+    out = {}
+    L = w["boxSize"][0]
+    if box_samples:
+        rng = np.random.default_rng(12345)
+        side = min(100.0, L / 2)
+        samples = []
+        for k in range(box_samples):
+            lo = rng.random(3) * (L - side)
+            xyz, ids, prev, cid = c.download_box(tuple(lo), tuple(lo + side))
+            v = stats.verify_box_sample(xyz, ids, prev, w["minDist"])
+            v.update(lo=[float(x) for x in lo], side=side, density_g_cc=len(ids) * 14.0 / 6.022e23 / (side ** 3 * 1e-24))   # sarw.h:4-6 constants
+            samples.append(v)
+        out["box_samples"] = samples
+        out["minDist_violations"] = int(sum(v["violations"] for v in samples))
+    if rdf:
+        t0 = time.perf_counter()
+        c.release_lookup()
+        intra, inter = c.rdf(2.0, 0.5, 20)
+        st = c.stats()
+        edges = 2.0 + 0.5 * np.arange(21)
+        shell = 4.0 / 3.0 * np.pi * (edges[1:] ** 3 - edges[:-1] ** 3)
+        N = st.nBeads
+        ideal = N * (N - 1) / (L ** 3) * shell
+        g = (intra.astype(np.float64) + inter.astype(np.float64)) / ideal
+        rec = {"seconds": time.perf_counter() - t0, "r": [float(x) for x in 0.5 * (edges[1:] + edges[:-1])], "g_total": [float(x) for x in g]}
+        ref_path = os.path.join(ROOT, "tests", "golden", "stats_c2_reference_mt.npz")
+        if os.path.exists(ref_path):
+            ref = np.load(ref_path)
+            gr = ref["gIntra"] + ref["gInter"]                      # 12 melts of BASELINE configs[1] grown by the unmodified reference (native RNG)
+            mean, se = gr.mean(0), gr.std(0, ddof=1) / np.sqrt(len(gr))
+            tol = 4 * se + 0.01 * np.abs(mean)
+            rec.update(reference_mean=[float(x) for x in mean], tolerance=[float(x) for x in tol], max_dev_over_tol=float(np.max(np.abs(g - mean) / tol)),
+                       within_tolerance=bool(np.all(np.abs(g - mean) <= tol)),
+                       tolerance_def="|g - mean_ref| <= 4 * standard error of the 12 reference melts + 1 % of the reference mean, per 0.5 A bin from 2 to 12 A")
+        out["rdf"] = rec
+    return out
+
+
+def run_one_melt(args, w):
     import torch
     import sarw_b200
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -199,43 +520,15 @@ def run_one_melt(args, w):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    stream = torch.cuda.current_stream()
-    hbm_peak, peak_src = load_peaks()
-    times, beads, stats = [], 0, None
-    sampler = None
-    for s in range(args.warmup + args.steps):
-        c = sarw_b200.Context(device=local, launchMode=1, **ctx_kwargs(w, 31_000 + s))
-        c.set_stream(stream.cuda_stream)
-        c.initiate()
-        if world > 1:
-            sarw_b200.connect_peers(c, dist, rank, world)
-        torch.cuda.synchronize()
-        if dist: dist.barrier()
-        if s == args.warmup and rank == 0:
-            sampler = ClockSampler(local); sampler.start()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        st = c.mr_grow_peer(-1) if world > 1 else c.grow(0, -1)
-        e1.record(stream); e1.synchronize()
-        ms = e0.elapsed_time(e1) + st.seedMs
-        if dist:
-            t = torch.tensor([ms], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = t.item()
-        if s >= args.warmup:
-            times.append(ms); beads += st.nBeads; stats = st
-        c.close()
+    env = Env(sarw_b200, torch, local)
+    big = w["nChains"] >= 500000
+    rec = one_melt_record(env, dist, rank, world, w, args.warmup, args.steps, single_gpu_check=not args.no_single_check,
+                          box_samples=3 if big or args.verify else 0, rdf=args.rdf)
     if rank == 0:
-        clocks = sampler.stop() if sampler else None
-        t_dev = sum(times) / 1e3
-        line = {"metric": "accepted beads/sec", "value": beads / t_dev, "unit": "beads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": w["name"], "multi_gpu": "one melt over all GPUs: replicated state, partitioned proposals + verification, in-kernel peer-memory exchange"
-                           if world > 1 else "single GPU", "rounds_per_melt": stats.rounds, "trials_per_bead": stats.trials / max(1, stats.nBeads),
-                           "conflicts_per_melt": stats.conflicts, "l2": "tables far larger than L2"},
-                "e2e": None, "gpu_launches": int(args.steps * (1 + 4)), "clocks": clocks,
-                "roofline": {"bound": "hbm", "achieved": (stats.trials * B_QUERY + stats.nBeads * B_BEAD) / (times[-1] / 1e3) / 1e9 / world, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": (stats.trials * B_QUERY + stats.nBeads * B_BEAD) / (times[-1] / 1e3) / 1e9 / world / hbm_peak, "traffic": None,
-                             "kernel": "sarw::grow_kernel (persistent cooperative launch per GPU)", "peak_source": peak_src,
-                             "algorithmic_bytes": f"(trials*{B_QUERY:.0f} + beads*{B_BEAD:.0f}) / N GPUs"},
+        line = {"metric": rec["metric"], "value": rec["value"], "unit": rec["unit"], "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": w["name"], "multi_gpu": rec["multi_gpu"], "l2": "tables far larger than L2"},
+                "e2e": None, "gpu_launches": int(args.steps * (1 + 4)), "clocks": rec["clocks"], "roofline": rec["roofline"], "one_melt": rec,
                 "note": "optional strong-scaling workload; the headline is the default workload"}
         print(json.dumps(line))
     if dist:
@@ -251,18 +544,21 @@ def main():
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS) + sorted(ONE_MELT))
     ap.add_argument("--melts", type=int, default=0, help="independent melts grown concurrently per step (0 = sarw_concurrent_capacity of the device)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extra", action="store_true", help="skip the secondary C3 / find_batch measurements")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary records (C3 / C4 / find_batch at N = 1, one_melt / C5 at N > 1)")
+    ap.add_argument("--no-single-check", action="store_true", help="one-melt workloads: skip the single-GPU re-run of the melt on rank 0")
+    ap.add_argument("--verify", action="store_true", help="one-melt workloads: brute-force verifier on sampled sub-boxes")
+    ap.add_argument("--rdf", action="store_true", help="one-melt workloads: RDF of the whole melt against the reference's C2 melts")
     args = ap.parse_args()
     if args.workload in ONE_MELT:
         if args.impl == "reference":
-            print(json.dumps({"impl": "reference", "unavailable": "the one-melt strong-scaling workloads have no CPU arm (hours per melt on one core)"}))
+            if int(os.environ.get("RANK", "0")) == 0:
+                print(json.dumps({"impl": "reference", "unavailable": "the one-melt strong-scaling workloads have no CPU arm (hours per melt on one core)"}))
             return
         return run_one_melt(args, ONE_MELT[args.workload])
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
         return run_reference(args, w)
 
-    import numpy as np
     import torch
     import sarw_b200
 
@@ -276,178 +572,106 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    stream = torch.cuda.current_stream()
-    hbm_peak, peak_src = load_peaks()
-    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")   # > 126 MB L2
-
-    def one_melt_device(ctx):
-        """initiate + grow + terminate on an existing context (blocking; returns the stats)"""
-        ctx.initiate()
-        st = ctx.grow(0, -1)
-        ctx.terminate()
-        return st
+    env = Env(sarw_b200, torch, local)
+    stream = env.stream
 
     # A melt of <= 256 chains grows in ONE thread-block cluster (13 of 148 SMs for configs[1]); a step is therefore a BATCH of M
-    # independent melts grown at the same time, one CUDA stream + one host thread each, M = sarw_concurrent_capacity (7 on B200).
-    # The reference arm does the same with the host cores (one serial instance per core). M = 1 for the large workloads.
-    probe = sarw_b200.Context(device=local, **ctx_kwargs(w, 1))
+    # independent melts grown at the same time on M streams, M = sarw_concurrent_capacity (7 on B200). M = 1 for the large workloads.
+    probe = make_ctx(env, w, 1, stream)
     M = args.melts if args.melts > 0 else probe.concurrent_capacity()
     probe.close()
-    from concurrent.futures import ThreadPoolExecutor
-    pool = ThreadPoolExecutor(max_workers=M)
-    streams = [stream] if M == 1 else [torch.cuda.Stream() for _ in range(M)]
-
-    def make_ctx(seed, m):
-        c = sarw_b200.Context(device=local, **ctx_kwargs(w, seed))
-        c.set_stream(streams[m].cuda_stream)
-        return c
-
-    def batch_device(ctxs):
-        """one step: M melts at once; CUDA events on the launching streams: start fans out to every stream, the end event waits for all"""
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for sm in streams:
-            if sm is not stream: sm.wait_event(e0)
-        def work(m):
-            with torch.cuda.stream(streams[m]):
-                st = one_melt_device(ctxs[m])
-                ev = torch.cuda.Event(); ev.record(streams[m])
-            return st, ev
-        res = list(pool.map(work, range(M)))
-        for _, ev in res: stream.wait_event(ev)
-        e1.record(stream)
-        e1.synchronize()
-        return e0.elapsed_time(e1), [r[0] for r in res]
-
     total = args.warmup + args.steps
     seeds = rank_seeds(rank, total * M)
-    # -------- device-resident arm: the contexts (cell tables) of a step exist before its timed region starts and are destroyed after it,
-    # so memory does not grow with --steps
-    def step_contexts(i):
-        return [make_ctx(seeds[i * M + m], m) for m in range(M)]
-
-    def close_all(row):
-        for c in row: c.close()
 
     # clocks / throttle reasons are sampled by rank 0 only, from before the warm-up (nvidia-smi takes a moment to start) to the end of the
-    # timed region: one poller per rank (8 on a full node) holds the driver long enough to stretch the steps of every rank (measured at
-    # N = 8: 15.8 ms per step against 9.6 ms end to end)
+    # timed region
     sampler = ClockSampler(local)
     if rank == 0: sampler.start()
-    for i in range(args.warmup):
-        row = step_contexts(i); flush.fill_(float(i)); batch_device(row); close_all(row)
-    torch.cuda.synchronize()
     if dist: dist.barrier()
-    step_ms, beads, queries, trials, rounds, launches, grow_ms, seed_ms, conflicts, nMelts = [], 0, 0, 0, 0, 0, 0.0, 0.0, 0, 0
-    for i in range(args.warmup, total):
-        row = step_contexts(i)
-        flush.fill_(float(i))          # L2 flush between timed iterations (outside the event pair)
-        torch.cuda.synchronize()
-        ms, sts = batch_device(row)
-        step_ms.append(ms)
-        for st in sts:
-            beads += st.nBeads; queries += st.queries; trials += st.trials; rounds += st.rounds; nMelts += 1
-            launches += st.growLaunches + st.seedLaunches; grow_ms += st.growMs; seed_ms += st.seedMs; conflicts += st.conflicts
-        close_all(row)
-    torch.cuda.synchronize()
+    step_ms, acc = measure_device(env, w, M, seeds, args.warmup, args.steps)
     if dist: dist.barrier()
     clocks = sampler.stop() if rank == 0 else None
     t_dev = sum(step_ms) / 1e3
 
-    # one melt at a time on an otherwise idle GPU (latency of a melt; what `value` was before batching)
+    # one melt at a time on an otherwise idle GPU (latency of a melt)
     single_ms, single_beads = [], 0
     if M > 1:
-        for k in range(args.warmup + args.steps):
-            c = sarw_b200.Context(device=local, **ctx_kwargs(w, 900_000 + rank * 1000 + k))
-            c.set_stream(stream.cuda_stream)
-            flush.fill_(float(k)); torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream); st = one_melt_device(c); e1.record(stream); e1.synchronize()
-            if k >= args.warmup: single_ms.append(e0.elapsed_time(e1)); single_beads += st.nBeads
-            c.close()
+        s_ms, s_acc = measure_device(env, w, 1, [900_000 + rank * 1000 + k for k in range(total)], args.warmup, args.steps)
+        single_ms, single_beads = s_ms, s_acc["beads"]
 
-    # -------- end-to-end arm through the C ABI with host buffers (results land in pinned host memory): the same batch of M melts,
-    # every melt created, grown, downloaded and destroyed inside the timed region
-    cap = int(sarw_b200.target_count(w["boxSize"], w["targetMassDensity"]) + w["nChains"] + 16)
-    pinned = [{"xyz": torch.empty((cap, 3), dtype=torch.float64, pin_memory=True).numpy(), "chainID": torch.empty(cap, dtype=torch.int32, pin_memory=True).numpy(),
-               "type": torch.empty(cap, dtype=torch.int32, pin_memory=True).numpy(), "bonds": torch.empty((cap, 2), dtype=torch.int64, pin_memory=True).numpy()} for _ in range(M)]
-    e2e_times, e2e_beads, h2d, d2h, e2e_launch = [], 0, 0, 0, 0
-    import gc
-
-    def e2e_melt(args_):
-        m, seed = args_
-        c = sarw_b200.Context(device=local, **ctx_kwargs(w, seed))
-        c.set_stream(streams[m].cuda_stream)
-        c.initiate(); st = c.grow(0, -1); c.terminate()
-        xyz, cid, typ, bonds = c.download(pinned[m])
-        nbytes = xyz.nbytes + cid.nbytes + typ.nbytes + bonds.nbytes
-        c.close()
-        return st, nbytes
-
-    for i in range(total):
-        gc.collect(); gc.disable()                 # no collector pauses inside the timed call sequence
-        flush.fill_(float(i)); torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        res = list(pool.map(e2e_melt, [(m, seeds[i * M + m] + 5_000_000) for m in range(M)]))
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        gc.enable()
-        if os.environ.get("SARW_BENCH_DEBUG"): print(f"e2e step {i}: {dt*1e3:.3f} ms for {M} melts", file=sys.stderr)
-        if i >= args.warmup:
-            e2e_times.append(dt)
-            for st, nbytes in res:
-                e2e_beads += st.nBeads
-                h2d += sarw_b200.C.sizeof(sarw_b200.Params) + 64                      # parameters + control block
-                d2h += nbytes + 3 * 64 + st.growLaunches * 64 + 8                     # results + control/stat reads
-                e2e_launch += st.growLaunches + st.seedLaunches + 5                   # + flag, 2x cub scan, gather
-    pool.shutdown()
+    e2e_times, e2e = measure_e2e(env, w, M, seeds, args.warmup, args.steps)
 
     # -------- aggregate over ranks (max time, summed work)
     t_e2e = sum(e2e_times)
-    t_dev, t_e2e, beads_all, e2e_beads_all = aggregate_ranks(dist, "cuda", t_dev, t_e2e, beads, e2e_beads)
+    t_dev, t_e2e, beads_all, e2e_beads_all = aggregate_ranks(dist, "cuda", t_dev, t_e2e, acc["beads"], e2e["beads"])
 
+    line = None
     if rank == 0:
-        value = beads_all / t_dev
-        # roofline of the dominant kernel (grow_kernel: ~all of the step): algorithmic bytes / its CUDA-event duration
-        # SURVEY §8d: bytes per bead = T*B_q + B_a with T = trials per accepted bead in the reference's terms (what the serial
-        # loop of sarw.cpp:259 evaluates; trials of provably dead chains are decided without memory traffic here)
-        alg_bytes = trials * B_QUERY + beads * B_BEAD
-        achieved = alg_bytes / (grow_ms / 1e3) / 1e9       # per launch: summed bytes / summed launch durations
         line = {
-            "metric": "accepted beads/sec", "value": value, "unit": "beads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": "accepted beads/sec", "value": beads_all / t_dev, "unit": "beads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": w["name"], "melts_per_step": M,
-                       "batch": (f"{M} independent melts of the workload grown at the same time (one CUDA stream + one host thread each; a melt of "
+                       "batch": (f"{M} independent melts of the workload grown at the same time on {M} CUDA streams driven by one host thread (a melt of "
                                  f"{w['nChains']} chains occupies one thread-block cluster, {M} clusters fit the device)") if M > 1 else "one melt per step",
                        "seeds": "distinct Philox key per melt, step and rank", "l2": "256 MB flush write between timed steps",
-                       "multi_gpu": "independent melts per rank, no data-path collective" if world > 1 else "single GPU",
-                       "rounds_per_melt": rounds / nMelts, "trials_per_bead": trials / max(1, beads), "conflicts_per_melt": conflicts / nMelts},
-            "e2e": {"value": e2e_beads_all / t_e2e, "unit": "beads/s", "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps,
+                       "multi_gpu": "independent melts per rank, no data-path collective (the record one_melt is ONE melt over all GPUs)" if world > 1 else "single GPU",
+                       "rounds_per_melt": acc["rounds"] / acc["melts"], "trials_per_bead": acc["trials"] / max(1, acc["beads"]), "conflicts_per_melt": acc["conflicts"] / acc["melts"]},
+            "e2e": {"value": e2e_beads_all / t_e2e, "unit": "beads/s", "h2d_bytes_per_step": e2e["h2d"] // args.steps, "d2h_bytes_per_step": e2e["d2h"] // args.steps,
                     "ms_per_step": 1e3 * t_e2e / args.steps, "ms_per_step_median": 1e3 * statistics.median(e2e_times), "ms_per_step_max": 1e3 * max(e2e_times),
                     "includes": "per melt: sarw_create (alloc + cell-table init), seeding, growth, terminate, sarw_download to pinned host memory, sarw_destroy"},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(acc["launches"]),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": NCU_TRAFFIC.get(args.workload, (None, None))[0], "traffic_source": NCU_TRAFFIC.get(args.workload, (None, None))[1],
-                         "kernel": "sarw::grow_cluster_kernel<8> (one thread-block cluster, persistent, one launch per step)" if w["nChains"] <= 128 else "sarw::grow_kernel (persistent cooperative launch)", "peak_source": peak_src,
-                         "algorithmic_bytes": f"trials*{B_QUERY:.0f} + beads*{B_BEAD:.0f} (SURVEY §8d, trials in reference terms)",
-                         "trials_per_launch": trials / nMelts, "candidates_evaluated_per_launch": queries / nMelts,
-                         "avg_launch_ms": grow_ms / nMelts, "concurrent_launches": M,
-                         "note": "per launch (one melt); latency-bound: ~1e2 chains per round, ~1e3 dependent rounds. M launches run side by side in a step"},
+            "roofline": roofline_record(env, w, args.workload, acc, M),
         }
         if single_ms:
             line["single_melt"] = {"ms_per_melt": statistics.median(single_ms), "beads_per_s": single_beads / (sum(single_ms) / 1e3),
                                    "note": "one melt at a time on an otherwise idle GPU, device time (CUDA events)"}
-        if not args.no_extra:
-            line["extra"] = extra_measurements(sarw_b200, torch, stream, flush, local)
+    if not args.no_extra:
+        if world == 1:
+            line["workloads"] = {}
+            for key in ("C3", "C4"):
+                if key == args.workload: continue
+                try:
+                    line["workloads"][key] = workload_record(env, key)
+                except Exception as e:   # secondary records must never take the headline down
+                    line["workloads"][key] = {"error": repr(e)}
+            line["extra"] = extra_measurements(env)
+        else:
+            # ONE melt of 1e7*N beads over all N GPUs, checked against the other ranks and against the single-GPU walk
+            try:
+                rec = one_melt_record(env, dist, rank, world, melt_workload(10000 * world, "grown by all N GPUs together"), 1, 3)
+            except Exception as e:
+                rec = {"error": repr(e)}
+            if rank == 0: line["one_melt"] = rec
+            if world == 8 and not os.environ.get("SARW_BENCH_NO_C5"):
+                sarw_b200.release_cached_memory(local)
+                try:
+                    rec = one_melt_record(env, dist, rank, world, ONE_MELT["C5"], 1, 2, single_gpu_check=False, box_samples=3, rdf=False)
+                except Exception as e:
+                    rec = {"error": repr(e)}
+                if rank == 0: line["C5"] = rec
+    if rank == 0:
         if not args.no_cpu_baseline and world == 1:
-            cores = max(1, min(os.cpu_count() or 1, 32))
+            cores = host_cores()
             r = reference_throughput(w, cores, 777)
             if r is not None:
+                keyed = reference_throughput(w, cores, 888, rng="keyed")
                 line["cpu_baseline"] = {"value": r["value"], "unit": "beads/s", "cores": cores, "kind": "reference",
                                         "sample": f"{cores} concurrent single-thread instances of the full workload, unmodified reference (oracle/_ref), "
                                                   f"seeding + growth timed; slowest instance {r['slowest']:.2f} s", "per_core_beads_per_s": r["per_core"],
-                                        "trials_per_bead": r["trials_per_bead"]}
+                                        "trials_per_bead": r["trials_per_bead"], "keyed_rng_beads_per_s": keyed["value"],
+                                        "keyed_rng_note": "the same unmodified reference with Random::seed reduced to a counter set-up (no mt19937_64 re-initialisation per "
+                                                          "trial): an upper bound of the reference's speed whatever JDFTx's Random::seed costs"}
+                for key in ("C3",):
+                    if "workloads" in line and key in line["workloads"] and "error" not in line["workloads"][key]:
+                        # the reference's cost per bead depends on density, chain length and maxTrials (trials per bead), not on the box: a bounded
+                        # sample of the big melt itself would have to be its FIRST rounds, which are ~10x cheaper than the average round (no dead chains yet)
+                        line["workloads"][key]["cpu_baseline"] = {
+                            "value": r["value"], "unit": "beads/s", "cores": cores, "kind": "reference", "per_core_beads_per_s": r["per_core"],
+                            "sample": f"{cores} concurrent single-thread instances of BASELINE configs[1] (same density, chain length, minDist and maxTrials, hence the same "
+                                      f"trials per bead: {r['trials_per_bead']:.1f}); a whole configs[2] melt takes one core 253 s (3.95e4 beads/s, SURVEY section 6) - its table no "
+                                      f"longer fits the CPU caches"}
             else:
                 line["cpu_baseline"] = {"value": None, "unit": "beads/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
         print(json.dumps(line))
@@ -455,18 +679,14 @@ def main():
         dist.barrier(); dist.destroy_process_group()
 
 
-def extra_measurements(sarw_b200, torch, stream, flush, local):
-    """Secondary numbers (not the headline): BASELINE configs[2] growth and the overlap-query kernel on its melt."""
-    import numpy as np
+def extra_measurements(env):
+    """Secondary number: the overlap-query kernel (K5) on a finished BASELINE configs[2] melt."""
+    torch, stream = env.torch, env.stream
     out = {}
     w = WORKLOADS["C3"]
     try:
-        c = sarw_b200.Context(device=local, **ctx_kwargs(w, 4242))
-        c.set_stream(stream.cuda_stream)
+        c = make_ctx(env, w, 4242, stream)
         c.initiate(); st = c.grow(0, -1); c.terminate()
-        out["C3_growth"] = {"workload": w["name"], "beads": st.nBeads, "rounds": st.rounds, "grow_ms": st.growMs, "seed_ms": st.seedMs,
-                            "beads_per_s": st.nBeads / ((st.growMs + st.seedMs) / 1e3), "trials_per_bead": st.trials / st.nBeads,
-                            "queries": st.queries, "conflicts": st.conflicts}
         # K5 on the finished melt: 16 Mi random candidates resident in HBM
         n = 1 << 24
         g = torch.Generator(device="cuda"); g.manual_seed(5)
@@ -477,15 +697,14 @@ def extra_measurements(sarw_b200, torch, stream, flush, local):
         torch.cuda.synchronize()
         ms = []
         for i in range(5):
-            flush.fill_(float(i)); torch.cuda.synchronize()
+            env.l2_flush(i)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream); c.find_device(q.data_ptr(), None, n, hit.data_ptr()); e1.record(stream); e1.synchronize()
             ms.append(e0.elapsed_time(e1))
         t = statistics.median(ms) / 1e3
-        hbm_peak, _ = load_peaks()
         bq = 134.0 + 24 + 1   # SURVEY §8d B_q at full density + candidate read + result write
-        out["find_batch"] = {"queries": n, "ms": t * 1e3, "queries_per_s": n / t, "algorithmic_GBps": n * bq / t / 1e9,
-                             "frac_of_hbm_peak": n * bq / t / 1e9 / hbm_peak, "hit_fraction": float(hit.float().mean().item()),
+        out["find_batch"] = {"queries": n, "table_beads": st.nBeads, "ms": t * 1e3, "queries_per_s": n / t, "algorithmic_GBps": n * bq / t / 1e9,
+                             "frac_of_hbm_peak": n * bq / t / 1e9 / env.hbm_peak, "hit_fraction": float(hit.float().mean().item()),
                              "bytes_per_query": bq}
         c.close()
     except Exception as e:   # secondary numbers must never take the headline down

@@ -222,7 +222,7 @@ int read_control(sarw_ctx* c, Control* h)
 		float ms = 0; cudaEventElapsedTime(&ms, c->evS0, c->evS1);
 		c->seedMs += ms; c->seedTimed = true;
 		c->initiated = c->hctl->initiated != 0;
-		c->nSeeded = (uint32_t)(c->hctl->nBeads / 2);
+		c->nSeeded = c->hctl->nSeeded;   // not nBeads / 2: with sarw_grow_async the first read happens after the growth loop
 	}
 	if (!c->growTimed) { float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); c->growMs += ms; c->growTimed = true; }
 	if (h && h != c->hctl) *h = *c->hctl;

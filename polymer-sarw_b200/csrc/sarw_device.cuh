@@ -304,8 +304,10 @@ __device__ __forceinline__ uint32_t cell_off(const uint32_t (&w)[CELL_WORDS], in
 	return (w[3 + (e >> 1)] >> (16 * (e & 1))) & 0xFFFFu;
 }
 __device__ __forceinline__ bool cell_flagged(const uint32_t (&w)[CELL_WORDS]) { return (w[7] >> 16) != 0xFFFFu; }
-// centre of the quantisation step, in Angstrom from the cell's low corner
-__device__ __forceinline__ float dec_off(const Geom& g, uint32_t q, int d) { return ((float)q + 0.5f) * g.qs[d]; }
+// centre of the quantisation step, in Angstrom from the cell's low corner: (q + 0.5) * step. The integer -> float conversion (I2F)
+// issues on the XU pipe (16 lanes/clk/SM; 72 of them per candidate made K5 slower with the compact cells than with fp32 offsets),
+// so q (< 2^16) is placed in the mantissa of 2^23 instead: 2^23 + q - (2^23 - 0.5) = q + 0.5 exactly, one LOP3 and one FADD.
+__device__ __forceinline__ float dec_off(const Geom& g, uint32_t q, int d) { return (__uint_as_float(0x4B000000u | q) - 8388607.5f) * g.qs[d]; }
 
 // ------------------------------------------------------------------ overflow table (beads whose cell was full)
 __device__ __forceinline__ uint32_t ovf_hash(int64_t cidx)

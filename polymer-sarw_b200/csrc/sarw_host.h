@@ -14,6 +14,7 @@ struct Control {
 	unsigned seedDirtyCount;
 	unsigned abort;                   // set when a peer stopped answering in the peer-memory multi-rank loop
 	unsigned dirty2Count;             // chains put in conflict by the parallel clean-up (second list)
+	unsigned nSeeded;                 // chains seeded by initiateChain (all of them, or the index of the first that failed): written once by the seeding kernels
 	unsigned ovfCount;                // entries claimed in the overflow table (Tables::ovfCount points here: one read returns it with the rest)
 	unsigned long long stageFallbacks, arcFallbacks;   // chain-rounds whose neighbourhood / arcs did not fit the shared-memory buffers
 	unsigned long long nBeads;        // SARW::actualCount()

@@ -27,7 +27,13 @@
 
 namespace sarw {
 
-constexpr int GROW_WARPS = 8;            // grid mode: warps per CTA of the cooperative launch
+#ifndef SARW_GROW_WARPS
+#define SARW_GROW_WARPS 8
+#endif
+#ifndef SARW_GROW_MINBLOCKS
+#define SARW_GROW_MINBLOCKS 2
+#endif
+constexpr int GROW_WARPS = SARW_GROW_WARPS;   // grid mode: warps per CTA of the cooperative launch (x SARW_GROW_MINBLOCKS CTAs per SM)
 constexpr int GROW_NB_CAP = 256;    // grid kernel: staged beads per chain (shared memory, 16 B each)
 constexpr int GROW_ARC_CAP = 128;   // grid kernel: blocked arcs per chain
 constexpr uint32_t CHAIN_DEAD = 1u; // ChainState.flags: every torsion angle is permanently blocked
@@ -413,6 +419,7 @@ __global__ void seed_commit_kernel(SeedArgs A)
 	if (myTrials) atomicAdd(&A.ctl->seedTrials, myTrials);
 	if (blockIdx.x == 0 && threadIdx.x == 0) {
 		A.ctl->nBeads = 2ull * nSeeded;
+		A.ctl->nSeeded = nSeeded;
 		A.ctl->initiated = fail == ID_NONE ? 1u : 0u;
 	}
 }
@@ -762,7 +769,7 @@ __device__ __forceinline__ void round_barrier(Control* ctl)
 // MR = false: single-GPU instantiation, every multi-rank path is compiled out (they cost the 128-register kernel 170 -> 510 bytes of
 // spill traffic and 13 % of its speed when they were selected at run time); MR = true: the phases of a multi-rank round
 template <int WARPS, bool MR>
-__global__ void __launch_bounds__(WARPS * 32, 2) grow_kernel(const __grid_constant__ GrowArgs A)
+__global__ void __launch_bounds__(WARPS * 32, SARW_GROW_MINBLOCKS) grow_kernel(const __grid_constant__ GrowArgs A)
 {
 	constexpr int GROW_WARPS = WARPS;
 	extern __shared__ __align__(128) unsigned char growSmem[];
