@@ -36,6 +36,8 @@ namespace sarw {
 constexpr int GROW_WARPS = SARW_GROW_WARPS;   // grid mode: warps per CTA of the cooperative launch (x SARW_GROW_MINBLOCKS CTAs per SM)
 constexpr int GROW_NB_CAP = 256;    // grid kernel: staged beads per chain (shared memory, 16 B each)
 constexpr int GROW_ARC_CAP = 128;   // grid kernel: blocked arcs per chain
+constexpr int GROW_RAW_CELLS = 256; // grid kernel: staged cells per warp = four 4 x 4 x 4 boxes (quad path: four chains per warp at a time)
+constexpr int QUAD_NB_CAP = GROW_NB_CAP / 4;   // quad path: staged beads per chain
 constexpr uint32_t CHAIN_DEAD = 1u; // ChainState.flags: every torsion angle is permanently blocked
 constexpr uint32_t CHAIN_HARD = 2u; // ChainState.flags: none of the first 32 trials passed last round (skip the fast path)
 constexpr unsigned FULL = 0xFFFFFFFFu;
@@ -773,16 +775,18 @@ __global__ void __launch_bounds__(WARPS * 32, SARW_GROW_MINBLOCKS) grow_kernel(c
 {
 	constexpr int GROW_WARPS = WARPS;
 	extern __shared__ __align__(128) unsigned char growSmem[];
+	// per warp: 8 KB of staged cells (four 4 x 4 x 4 boxes: the quad path stages the regions of four chains at once; the one-chain path
+	// uses the first box and keeps its blocked arcs in the second), 4 KB of neighbour lists (4 x 64 or 1 x 256 beads), one mbarrier
 	Cell* rawAll = reinterpret_cast<Cell*>(growSmem);
-	float4* nbAll = reinterpret_cast<float4*>(rawAll + WARPS * CL_REGION_CELLS);
-	float4* arcAll = nbAll + WARPS * GROW_NB_CAP;
-	unsigned long long* mbarAll = reinterpret_cast<unsigned long long*>(arcAll + WARPS * GROW_ARC_CAP);
+	float4* nbAll = reinterpret_cast<float4*>(rawAll + WARPS * GROW_RAW_CELLS);
+	unsigned long long* mbarAll = reinterpret_cast<unsigned long long*>(nbAll + WARPS * GROW_NB_CAP);
 	const Geom& g = A.g;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const uint32_t gw = blockIdx.x * GROW_WARPS + warp, nW = gridDim.x * GROW_WARPS;
-	Cell* raw = rawAll + warp * CL_REGION_CELLS;
+	Cell* raw = rawAll + warp * GROW_RAW_CELLS;
 	float4* nb = nbAll + warp * GROW_NB_CAP;
-	float4* arcs = arcAll + warp * GROW_ARC_CAP;
+	float4* arcs = reinterpret_cast<float4*>(raw + CL_REGION_CELLS);
+	static_assert(GROW_ARC_CAP * sizeof(float4) <= CL_REGION_CELLS * sizeof(Cell), "the arcs alias the second staged box");
 	void* mbar = mbarAll + warp;
 	unsigned tmaParity = 0;
 	if (lane == 0) mbar_init(mbar, 1);
@@ -820,6 +824,7 @@ __global__ void __launch_bounds__(WARPS * 32, SARW_GROW_MINBLOCKS) grow_kernel(c
 				if ((i % A.mrRanks) != A.mrRank) commit_pending_thread(A, i, round - 1);
 		if (phase != 2u)
 		{
+#if defined(SARW_NO_QUAD) || defined(SARW_PROF)
 		const uint32_t iFirst = mr ? A.mrRank + gw * A.mrRanks : gw, iStride = mr ? nW * A.mrRanks : nW;
 		uint32_t pf = iFirst < g.nChains ? chain_prefetch(A, iFirst, lane) : 0u;
 		for (uint32_t i = iFirst; i < g.nChains; i += iStride) {
@@ -861,6 +866,253 @@ __global__ void __launch_bounds__(WARPS * 32, SARW_GROW_MINBLOCKS) grow_kernel(c
 			__syncwarp();
 			PROF_MARK(51);   // tentative insert + result stores (lane 0)
 		}
+#else
+		// FOUR chains per warp at a time, eight lanes (= the first eight trials) each. Per chain-round the work of the one-chain path is
+		// mostly warp-uniform fp64 arithmetic (state, frame, region) that all 32 lanes repeat, and nearly every chain accepts one of its
+		// first trials: with 8 lanes per chain the same instruction stream serves four chains. A chain that is hard, whose region crosses
+		// the periodic boundary or does not fit the staging buffers, or that finds nothing among its first eight trials, goes through
+		// the one-chain path (propose_chain, all trials from the first) right after its quad: same walk, bit for bit.
+		{
+		const int sub = lane & 7, grp = lane >> 3, gbase = lane & 24;
+		const uint32_t unit = mr ? A.mrRanks : 1u, first0 = mr ? A.mrRank : 0u;
+		const uint32_t nOwn = g.nChains > first0 ? (g.nChains - first0 + unit - 1u) / unit : 0u;   // chains this rank proposes
+		Cell* rawq = raw + grp * CL_REGION_CELLS;
+		float4* nbq = nb + grp * QUAD_NB_CAP;
+		auto own_chain = [&](uint32_t q) { return first0 + (4u * q + (uint32_t)grp) * unit; };
+		// prefetch of a chain's state: three 32-bit words per lane (words 0-15 the chain state, 16-21 last round's position, 22 its trial)
+		auto prefetch = [&](uint32_t q, uint32_t& w0, uint32_t& w1, uint32_t& w2) {
+			w0 = w1 = w2 = 0u;
+			if (4u * q + (uint32_t)grp < nOwn) {
+				const uint32_t i = own_chain(q);
+				const uint32_t* st = reinterpret_cast<const uint32_t*>(A.chains + i);
+				w0 = __ldcg(st + sub); w1 = __ldcg(st + 8 + sub);
+				if (sub < 6) w2 = __ldcg(reinterpret_cast<const uint32_t*>(A.resPos + 3 * (size_t)i) + sub);
+				else if (sub == 6) w2 = __ldcg(A.resTrial + i);
+			}
+		};
+		uint32_t pw0, pw1, pw2;
+		prefetch(gw, pw0, pw1, pw2);
+#ifdef SARW_QUAD_STATS
+		long long qt0 = clock64(), qt1, qsec[13] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+#define QMARK(k) do { qt1 = clock64(); qsec[k] += qt1 - qt0; qt0 = qt1; } while (0)
+#else
+#define QMARK(k) do { } while (0)
+#endif
+		for (uint32_t q = gw; 4u * q < nOwn; q += nW) {
+			const bool valid = 4u * q + (uint32_t)grp < nOwn;
+			const uint32_t i = valid ? own_chain(q) : 0u;
+			// ---- open the chain: state from the prefetched words, last round's result committed (commit_pending's effect)
+			ChainState cs;
+#define GSH(v, s) __shfl_sync(FULL, (v), gbase | (s))
+#define GDBL(v, s) __hiloint2double((int)GSH(v, (s) + 1), (int)GSH(v, (s)))
+			cs.last[0] = GDBL(pw0, 0); cs.last[1] = GDBL(pw0, 2); cs.last[2] = GDBL(pw0, 4);
+			cs.pen[0] = GDBL(pw0, 6); cs.pen[1] = GDBL(pw1, 0); cs.pen[2] = GDBL(pw1, 2);
+			cs.lastId = GSH(pw1, 4); cs.penId = GSH(pw1, 5); cs.length = GSH(pw1, 6); cs.flags = GSH(pw1, 7);
+			{
+				const double r0 = GDBL(pw2, 0), r1 = GDBL(pw2, 2), r2 = GDBL(pw2, 4);
+				const uint32_t t = GSH(pw2, 6);
+				if (pendingValid && valid) {
+					if (t >= 1u && t <= T_) {
+						const uint32_t id = round_id_base(g, round - 1) + i;
+						cs.pen[0] = cs.last[0]; cs.pen[1] = cs.last[1]; cs.pen[2] = cs.last[2];
+						cs.last[0] = r0; cs.last[1] = r1; cs.last[2] = r2;
+						if (sub == 0) A.prev[id - g.idAtomBase] = cs.lastId;
+						cs.penId = cs.lastId; cs.lastId = id; cs.length += 1;
+						if (sub == 0) A.chains[i] = cs;
+					}
+					if (t != 0u && sub == 0) A.resTrial[i] = 0;
+				}
+			}
+			prefetch(q + nW, pw0, pw1, pw2);                           // in flight while this quad is worked on
+			QMARK(0);
+			const bool inRange = valid && i >= start && i < end;
+			const bool dead = inRange && (cs.flags & CHAIN_DEAD) != 0u;
+			if (dead && sub == 0) {   // permanently blocked: the reference burns maxTrials here every round
+				A.resTrial[i] = T_ + 1u; A.origTrial[i] = T_ + 1u;
+				if (mr) { MrRecord r; r.x = r.y = r.z = 0; r.trial = T_ + 1u; r.pad = 0; mr_publish(A, i, round, r); }
+			}
+			const bool active = inRange && !dead;
+			Frame f; RegionPlan rp;
+			prepare_chain(g, cs, f, rp);                                  // (harmless arithmetic on the zero state of an invalid group)
+			QMARK(1);
+			// ---- stage the four regions: one tensor copy per chain, one mbarrier phase per warp
+			const bool stage = active && !(cs.flags & CHAIN_HARD) && rp.tile != 0;
+			const unsigned stageMask = __ballot_sync(FULL, stage && sub == 0);
+			if (stageMask) {
+				if (lane == 0) mbar_expect_tx(mbar, (unsigned)__popc(stageMask) * (unsigned)(CL_REGION_CELLS * sizeof(Cell)));
+				__syncwarp();
+				if (stage && sub == 0) tma_load_box3d(rawq, A.tmap, rp.lo[0] * (int)(sizeof(Cell) / 4), rp.lo[1], rp.lo[2], mbar);
+			}
+			// ---- while the copies fly: the exact candidate of trial sub + 1 (reference arithmetic)
+			double candL[3] = { 0, 0, 0 }, vL[3] = { 0, 0, 0 }; float rel[3] = { 0, 0, 0 }; bool okL = false;
+			if (stage) {
+				const uint4 w = philox4x32_10(make_uint4(i, round, (uint32_t)sub >> 2, 0u), g.key0, g.key1);
+				cone_candidate(g, f, cs.last, (double)pick(w, (uint32_t)sub & 3u) * (1.0 / 4294967296.0), candL);
+				okL = (uint32_t)sub < T_ && !growth_rules_reject(g, candL, cs.last);
+				to_frac(g, candL, vL);
+				rel[0] = (float)(candL[0] - cs.last[0]); rel[1] = (float)(candL[1] - cs.last[1]); rel[2] = (float)(candL[2] - cs.last[2]);
+			}
+			int tot = 0; bool fits = stage;
+			QMARK(2);
+			if (stageMask) {
+				mbar_wait(mbar, tmaParity); tmaParity ^= 1u;
+				QMARK(3);
+				// ---- neighbour list of each chain: lane `sub` takes box cells sub, sub + 8, ... (ix = sub & 3, iy = (sub >> 2) + 2 (k & 1), iz = k >> 1)
+				const int ix = sub & 3, iy0 = sub >> 2;
+				const bool xin = stage && ix < rp.nn[0];
+				// pass 1, branch-free: which slots of the lane's eight cells hold a bead that counts (bit 3k + s), which cells are flagged
+				uint32_t vm = 0; unsigned flgMask = 0;
+#pragma unroll
+				for (int k = 0; k < 8; k++) {
+					const int iy = iy0 + 2 * (k & 1), iz = k >> 1;
+					const uint32_t* cw = reinterpret_cast<const uint32_t*>(rawq + (iz * REGION_BOX + iy) * REGION_BOX + ix);
+					const uint4 lo4 = *reinterpret_cast<const uint4*>(cw);
+					const uint32_t w7 = cw[7];
+					const bool in = xin && iy < rp.nn[1] && iz < rp.nn[2];
+					const uint32_t m = (lo4.x < idRound && lo4.x != cs.lastId ? 1u : 0u) | (lo4.y < idRound && lo4.y != cs.lastId ? 2u : 0u) | (lo4.z < idRound && lo4.z != cs.lastId ? 4u : 0u);
+					vm |= (in ? m : 0u) << (3 * k);
+					flgMask |= (in && (w7 >> 16) != 0xFFFFu ? 1u : 0u) << k;
+				}
+				const int cnt = __popc(vm);
+				QMARK(9);
+				int incl = cnt;
+#pragma unroll
+				for (int d = 1; d < 8; d <<= 1) { const int v = __shfl_up_sync(FULL, incl, d, 8); if (sub >= d) incl += v; }
+				tot = __shfl_sync(FULL, incl, 7, 8);
+				fits = stage && tot <= QUAD_NB_CAP;
+				int at = incl - cnt;
+				if (!fits) vm = 0;
+				// pass 2: one bead per iteration (a lane holds 2.5 on average)
+				while (vm) {
+					const int bit = __ffs((int)vm) - 1;
+					vm &= vm - 1u;
+					const int k = (bit * 11) >> 5, s2 = bit - 3 * k;             // bit / 3 for bit < 24
+					const int iy = iy0 + 2 * (k & 1), iz = k >> 1;
+					const Cell* cell = rawq + (iz * REGION_BOX + iy) * REGION_BOX + ix;
+					const uint32_t id = cell->id[s2];
+					const unsigned short* o = &cell->off[s2][0];
+					const float sx = rp.base[0] + (float)ix * (float)g.a[0], sy = rp.base[1] + (float)iy * (float)g.a[1], sz = rp.base[2] + (float)iz * (float)g.a[2];
+					nbq[at++] = make_float4(sx + dec_off(g, o[0], 0), sy + dec_off(g, o[1], 1), sz + dec_off(g, o[2], 2), __uint_as_float(id));
+				}
+				QMARK(10);
+				// beads of flagged cells live in the overflow table: one lane of a group at a time appends them (a region holds a flagged cell in ~10 % of the chain-rounds of a melt)
+				unsigned fm = __ballot_sync(FULL, fits && flgMask != 0u);
+				for (int s2 = 0; s2 < 8 && fm; ++s2) {
+					const unsigned has = fm & (0x01010101u << s2);
+					if (!has) continue;
+					int add = 0;
+					if (fits && flgMask != 0u && sub == s2) {
+#pragma unroll 1
+						for (int k = 0; k < 8; k++) {
+							if (!((flgMask >> k) & 1u)) continue;
+							const int iy = iy0 + 2 * (k & 1), iz = k >> 1;
+							const float sx = rp.base[0] + (float)ix * (float)g.a[0], sy = rp.base[1] + (float)iy * (float)g.a[1], sz = rp.base[2] + (float)iz * (float)g.a[2];
+							ovf_for_cell(A.T, cell_index(g, rp.lo[0] + ix, rp.lo[1] + iy, rp.lo[2] + iz), [&](uint32_t id, uint32_t o0, uint32_t o1, uint32_t o2) {
+								if (id < idRound && id != cs.lastId) {
+									if (tot + add < QUAD_NB_CAP) nbq[tot + add] = make_float4(sx + dec_off(g, o0, 0), sy + dec_off(g, o1, 1), sz + dec_off(g, o2, 2), __uint_as_float(id));
+									add++;
+								}
+								return false;
+							});
+						}
+					}
+					tot += __shfl_sync(FULL, add, s2, 8);
+					fm &= ~has;
+				}
+				fits = stage && tot <= QUAD_NB_CAP;
+				__syncwarp();
+				QMARK(4);
+				// ---- lane-per-trial test against the chain's list (fp32 pre-filter, exact arithmetic inside the undecided band)
+				if (okL && fits) {
+					float dmin = 3.0e38f; int inBand = 0;
+#pragma unroll 4
+					for (int j = 0; j < tot; ++j) {
+						const float4 b = nbq[j];
+						const float dx = rel[0] - b.x, dy = rel[1] - b.y, dz = rel[2] - b.z;
+						const float d2 = dx * dx + dy * dy + dz * dz;
+						inBand += (d2 <= g.hi2);
+						dmin = fminf(dmin, d2);
+					}
+					if (dmin < g.lo2) okL = false;
+					else if (inBand) {
+						for (int j = 0; j < tot && okL; ++j) {
+							const float4 b = nbq[j];
+							const float dx = rel[0] - b.x, dy = rel[1] - b.y, dz = rel[2] - b.z;
+							const float d2 = dx * dx + dy * dy + dz * dz;
+							if (d2 <= g.hi2 && exact_pair(g, vL, A.T.lpos + 3 * (size_t)__float_as_uint(b.w))) okL = false;
+						}
+					}
+				}
+			}
+			const unsigned passMask = __ballot_sync(FULL, okL && fits);
+			QMARK(5);
+			const unsigned gm = (passMask >> gbase) & 0xFFu;
+			const uint32_t accepted = gm ? (uint32_t)__ffs((int)gm) : 0u;       // lowest passing trial of the chain (1-based)
+			const int winner = gbase | (accepted ? (int)accepted - 1 : 0);
+			double cand[3];
+#pragma unroll
+			for (int k = 0; k < 3; k++) cand[k] = __shfl_sync(FULL, candL[k], winner);
+			if (lane == 0) myQueries += (unsigned long long)(8 * __popc(stageMask));
+			if (accepted && sub == 0) {
+				insert_bead(g, A.T, cand, idRound + i);
+				for (int k2 = 0; k2 < 3; k2++) A.resPos[3 * (size_t)i + k2] = cand[k2];
+				A.resTrial[i] = accepted; A.origTrial[i] = accepted;
+				if (mr) { MrRecord r; r.x = cand[0]; r.y = cand[1]; r.z = cand[2]; r.trial = accepted; r.pad = 0; mr_publish(A, i, round, r); }
+			}
+			__syncwarp();
+			QMARK(6);
+			// ---- the chains that need the one-chain path, one after the other with the whole warp
+			unsigned slowMask = __ballot_sync(FULL, active && !accepted && sub == 0);
+#ifdef SARW_QUAD_STATS
+			if (sub == 0 && active && blockIdx.x == 0) {   // diagnostics (block 0 only): why chains leave the quad path (read with sarw_debug_paths)
+				const int why = accepted ? 0 : ((cs.flags & CHAIN_HARD) ? 1 : (!rp.tile ? 2 : (!fits ? 3 : 4)));
+				atomicAdd(&A.ctl->pathCnt[why < 4 ? why : 3], 1ull);
+				if (why == 4) atomicAdd(&A.ctl->pathCyc[0], 1ull);
+			}
+#endif
+			while (slowMask) {
+				const int src = __ffs((int)slowMask) - 1;
+				slowMask &= slowMask - 1u;
+				const uint32_t i1 = __shfl_sync(FULL, i, src);
+				ChainState c1;
+#pragma unroll
+				for (int k = 0; k < 3; k++) { c1.last[k] = __shfl_sync(FULL, cs.last[k], src); c1.pen[k] = __shfl_sync(FULL, cs.pen[k], src); }
+				c1.lastId = __shfl_sync(FULL, cs.lastId, src); c1.penId = __shfl_sync(FULL, cs.penId, src);
+				c1.length = __shfl_sync(FULL, cs.length, src); c1.flags = __shfl_sync(FULL, cs.flags, src);
+				Frame f1; RegionPlan rp1;
+				prepare_chain(g, c1, f1, rp1);
+				const bool hard = (c1.flags & CHAIN_HARD) != 0u;
+				double cand1[3] = { 0, 0, 0 }, vAcc[3] = { 0, 0, 0 };
+				const uint32_t flagsBefore = c1.flags;
+				const uint32_t acc1 = propose_chain(g, A.T, A.tmap, A.ctl, A.chains, i1, round, idRound, c1, f1, rp1, hard, raw, nb, GROW_NB_CAP, arcs, GROW_ARC_CAP, mbar, tmaParity, lane,
+					cand1, vAcc, myQueries);
+				const bool hardNow = acc1 == 0u || acc1 > 32u;
+				c1.flags = (c1.flags & ~CHAIN_HARD) | (hardNow ? CHAIN_HARD : 0u);
+				if (lane == 0) {
+					if (c1.flags != flagsBefore) A.chains[i1].flags = c1.flags;
+					if (acc1) {
+						insert_bead(g, A.T, cand1, idRound + i1);
+						for (int k2 = 0; k2 < 3; k2++) A.resPos[3 * (size_t)i1 + k2] = cand1[k2];
+					}
+					A.resTrial[i1] = acc1 ? acc1 : T_ + 1u;
+					A.origTrial[i1] = acc1 ? acc1 : T_ + 1u;
+					if (mr) { MrRecord r; r.x = cand1[0]; r.y = cand1[1]; r.z = cand1[2]; r.trial = acc1 ? acc1 : T_ + 1u; r.pad = 0; mr_publish(A, i1, round, r); }
+				}
+				__syncwarp();
+			}
+			QMARK(7);
+#ifdef SARW_QUAD_STATS
+			qsec[8] += 1;
+#endif
+#undef GSH
+#undef GDBL
+		}
+#ifdef SARW_QUAD_STATS
+		if (timer) for (int k2 = 0; k2 < 13; k2++) A.ctl->busy[k2] += (unsigned long long)qsec[k2];
+#endif
+#undef QMARK
+		}
+#endif
 		}
 		SUBT(0);
 		if (phase == 1u) break;                                  // the host all-gathers the records, then launches phase 2
@@ -1157,7 +1409,7 @@ cudaError_t launch_seed(const Geom& g, const Tables& T, ChainState* chains, uint
 }
 
 constexpr size_t grow_smem_bytes(int warps)
-{	return (size_t)warps * (CL_REGION_CELLS * sizeof(Cell) + GROW_NB_CAP * sizeof(float4) + GROW_ARC_CAP * sizeof(float4) + 8);
+{	return (size_t)warps * (GROW_RAW_CELLS * sizeof(Cell) + GROW_NB_CAP * sizeof(float4) + 8);
 }
 
 cudaError_t grow_max_blocks(int numSMs, int* maxBlocks)
