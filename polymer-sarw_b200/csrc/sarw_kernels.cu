@@ -1149,7 +1149,6 @@ __global__ void __launch_bounds__(WARPS * 32, SARW_GROW_MINBLOCKS) grow_kernel(c
 		// ---------------- phase V: conflicts with tentative beads of lower-indexed chains of this round
 		const bool splitV = phase == 4u && A.mrSplitVerify != 0u;
 		{
-			const int sub = lane & 7, grp = lane >> 3;
 			uint32_t acc = 0, prog = 0; unsigned long long tr = 0;
 			if (splitV)   // round totals from the trial numbers every rank knows; the probing below covers this rank's chains only
 				for (uint32_t i = start + gw * 32 + lane; i < end; i += nW * 32) {
@@ -1158,6 +1157,11 @@ __global__ void __launch_bounds__(WARPS * 32, SARW_GROW_MINBLOCKS) grow_kernel(c
 				}
 			const uint32_t stride = splitV ? A.mrRanks : 1u;
 			const uint32_t first = splitV ? A.mrRank + ((start > A.mrRank ? start - A.mrRank + stride - 1u : 0u) / stride) * stride : start;   // first chain >= start of this rank
+			// eight lanes per chain (one cell record each), four chains per warp and iteration, in the SAME chain -> warp mapping as the quads of
+			// phase A: the pages of the cell table a warp touches here are the ones its SM touched a moment ago. (One THREAD per chain with its
+			// eight records in flight at once - find_batch_kernel's scheme - measured 2.3x slower here: 32 chains per warp are ~80 distinct
+			// 2 MB pages of the table, and the address-translation misses of one warp are served one after the other.)
+			const int vsub = lane & 7, grp = lane >> 3;
 			for (uint32_t base = first + gw * 4 * stride; base < end; base += nW * 4 * stride) {
 				const uint32_t i = base + grp * stride;
 				bool h = false; uint32_t t = 0;
@@ -1168,11 +1172,11 @@ __global__ void __launch_bounds__(WARPS * 32, SARW_GROW_MINBLOCKS) grow_kernel(c
 					if (t <= T_ && i > start) {
 						double v[3];
 						to_frac(g, pos, v);
-						h = probe_cells<8>(g, A.T, v, idRound, idRound + i, ID_NONE, sub);
+						h = probe_cells<8>(g, A.T, v, idRound, idRound + i, ID_NONE, vsub);
 					}
 				}
 				const unsigned bal = __ballot_sync(FULL, h);
-				if (sub == 0 && i < end) {
+				if (vsub == 0 && i < end) {
 					if (!splitV) { if (t <= T_) { acc++; tr += t; if (t < T_) prog++; } else tr += T_; }
 					if ((bal >> (grp * 8)) & 0xFFu) {
 						uint32_t at = atomicAdd(&A.dirtyCount[round], 1u);
@@ -1189,6 +1193,7 @@ __global__ void __launch_bounds__(WARPS * 32, SARW_GROW_MINBLOCKS) grow_kernel(c
 				if (prog) atomicAdd(&A.roundProg[round], prog);
 				myTrials += tr;
 			}
+			SUBT(6);   // verify work of block 0 / warp 0 (the barrier that follows is in cycVerify)
 		}
 		if (splitV) {   // exchange the conflict lists: block 0 stores this rank's list into every rank's inbox, ranks meet, lists are merged
 			round_barrier<false>(A.ctl);

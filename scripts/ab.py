@@ -4,7 +4,7 @@ import os, sys, time, statistics
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "polymer-sarw_b200")); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch, sarw_b200, cases
-what = sys.argv[1:] or ["c2", "batch", "c3", "find"]
+what = sys.argv[1:] or ["c2", "batch", "c3", "find", "big"]
 tag = os.path.basename(os.environ.get("SARW_B200_LIB", "libsarw_b200.so"))
 stream = torch.cuda.current_stream()
 flush = torch.empty(256 << 18, dtype=torch.float32, device="cuda")
@@ -47,7 +47,7 @@ if "c3" in what or "find" in what:
         t, st = timed(lambda: (c.initiate(), c.grow(0, -1))[1]); ms.append(t)
         d = st.as_dict()
         if k < 2: c.close()
-    print(f"[{tag}] C3 one melt: {['%.2f' % x for x in ms]} ms, {d['nBeads'] / min(ms) * 1e3:.3e} beads/s; ovf {d['overflowBeads']} conflicts {d['conflicts']} cyc/round A {d['cycPropose']/d['rounds']:.0f} V {d['cycVerify']/d['rounds']:.0f} C {d['cycCleanup']/d['rounds']:.0f}", flush=True)
+    print(f"[{tag}] C3 one melt: {['%.2f' % x for x in ms]} ms, {d['nBeads'] / min(ms) * 1e3:.3e} beads/s; ovf {d['overflowBeads']} conflicts {d['conflicts']} cyc/round A {d['cycPropose']/d['rounds']:.0f} V {d['cycVerify']/d['rounds']:.0f} C {d['cycCleanup']/d['rounds']:.0f} sub {[round(x/d['rounds']) for x in d['cycSub']]}", flush=True)
     if "find" in what:
         n = 1 << 24
         g = torch.Generator(device="cuda"); g.manual_seed(5)
@@ -58,3 +58,10 @@ if "c3" in what or "find" in what:
         os.environ["SARW_FIND_ORDER"] = "0"
         print(f"[{tag}] K5 16.8M candidates on the C3 melt: median {statistics.median(ts):.3f} ms = {n / statistics.median(ts) / 1e6:.2f} Gq/s, hit fraction {hit.float().mean().item():.4f}", flush=True)
     c.close()
+if "big" in what:
+    ms = []
+    for k in range(3):
+        c = sarw_b200.Context(seed=77 + k, **cases.BIG); c.set_stream(stream.cuda_stream)
+        t, st = timed(lambda: (c.initiate(), c.grow(0, -1))[1]); ms.append(t)
+        d = st.as_dict(); c.close()
+    print(f"[{tag}] BIG one melt: {['%.2f' % x for x in ms]} ms, {d['nBeads'] / min(ms) * 1e3:.3e} beads/s; conflicts {d['conflicts']} cyc/round A {d['cycPropose']/d['rounds']:.0f} V {d['cycVerify']/d['rounds']:.0f} C {d['cycCleanup']/d['rounds']:.0f} sub {[round(x/d['rounds']) for x in d['cycSub']]}", flush=True)
