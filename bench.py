@@ -404,8 +404,10 @@ def one_melt_record(env, dist, rank, world, w, warmup, steps, single_gpu_check=T
     extra = {}
     for s in range(warmup + steps):
         seed = 31_000 + s
-        c = sarw_b200.Context(device=local, launchMode=1, **ctx_kwargs(w, seed))
+        slab = dict(slabRank=rank, slabRanks=world) if world > 1 and not os.environ.get("SARW_BENCH_REPLICATED") else {}
+        c = sarw_b200.Context(device=local, launchMode=1, **slab, **ctx_kwargs(w, seed))
         c.set_stream(stream.cuda_stream)
+        cell_bytes = c.cell_table_bytes()
         c.initiate()
         if world > 1:
             sarw_b200.connect_peers(c, dist, rank, world)
@@ -441,7 +443,7 @@ def one_melt_record(env, dist, rank, world, w, warmup, steps, single_gpu_check=T
             e0.record(stream); st1 = c.grow(0, -1); e1.record(stream); e1.synchronize()
             one = np.array(c.walk_checksum(), dtype=np.uint64)
             single = {"ms": e0.elapsed_time(e1) + st1.seedMs, "beads": st1.nBeads, "checksum_equal": bool(np.array_equal(one, sums[0])),
-                      "invariants_equal": (st1.nBeads, st1.rounds, st1.trials, st1.conflicts) == (st.nBeads, st.rounds, st.trials, st.conflicts)}
+                      "invariants_equal": (st1.nBeads, st1.rounds, st1.trials) == (st.nBeads, st.rounds, st.trials), "conflict_resolutions": [st1.conflicts, st.conflicts]}
             c.close()
         dist.barrier()
     if rank != 0:
@@ -451,8 +453,12 @@ def one_melt_record(env, dist, rank, world, w, warmup, steps, single_gpu_check=T
     rounds = max(1, st.rounds)
     rec = {"workload": w["name"], "metric": "accepted beads/sec", "unit": "beads/s", "value": beads / t_dev, "beads": st.nBeads, "n_gpus": world, "steps": steps, "warmup": warmup,
            "ms_per_step": 1e3 * t_dev / steps, "ms_per_step_min": min(times), "ms_per_step_max": max(times), "scaling": "strong",
-           "multi_gpu": ("one melt over all GPUs: replicated state, partitioned proposals + verification, records and conflict lists exchanged inside the persistent "
-                         "kernel over NVLink peer memory (st.release.sys / ld.acquire.sys flags)") if world > 1 else "single GPU",
+           "multi_gpu": (("one melt over all GPUs, box decomposed into z-slabs: each rank holds the cell layers of its slab + halo (rest of the table unbacked), proposes / verifies / "
+                          "re-resolves the chains whose tip is in its slab; bead records, conflict lists and re-resolution results exchanged inside the persistent kernel over "
+                          "NVLink peer memory (st.release.sys / ld.acquire.sys flags); chain states and coordinates replicated") if slab else
+                         ("one melt over all GPUs: replicated state, partitioned proposals + verification, records and conflict lists exchanged inside the persistent "
+                          "kernel over NVLink peer memory (st.release.sys / ld.acquire.sys flags)")) if world > 1 else "single GPU",
+           "cell_table_bytes_rank0": cell_bytes,
            "rounds": st.rounds, "trials_per_bead": st.trials / max(1, st.nBeads), "conflicts": st.conflicts, "overflow_beads": st.overflowBeads,
            "all_ranks_agree": bool(agree), "walk_checksum": [int(x) for x in sums[0]],
            "matches_single_gpu": None if single is None else bool(single["checksum_equal"] and single["invariants_equal"]),

@@ -48,6 +48,13 @@ typedef struct sarw_params {
 	int32_t launchMode;         /* 0 = auto (one thread-block cluster when nChains <= 256, else cooperative grid); 1 = force grid */
 	int32_t maxBlocks;          /* 0 = auto; cap on the thread blocks of the cooperative growth launch, so that several contexts can grow on one
 	                               device at the same time (tests run the ranks of a multi-rank melt side by side on one GPU this way) */
+	/* Slab decomposition of ONE melt over the GPUs of a node (see "multi-rank" below): with slabRanks >= 2 this context is rank slabRank
+	 * of slabRanks and allocates only the cell layers (along z) of its own slab plus slabHalo layers on either side - the memory of the
+	 * cell list is partitioned, which is what lets a box larger than one GPU's memory run. 0 / 1 = the whole box (every other use). */
+	int32_t slabRank;
+	int32_t slabRanks;
+	int32_t slabHalo;           /* cell layers kept beyond the slab on either side; 0 = default (8, at least what a round can reach) */
+	int32_t reserved0;
 } sarw_params;
 
 typedef struct sarw_stats {
@@ -136,6 +143,21 @@ int sarw_mr_grow_peer(sarw_ctx* ctx, int64_t maxRounds, sarw_stats* stats);
  * sarw_mr_peer_connect_local takes the buffers of all ranks (rank order) instead of IPC handles. */
 int sarw_mr_peer_local_base(sarw_ctx* ctx, void** base);
 int sarw_mr_peer_connect_local(sarw_ctx* ctx, void* const* bases);
+/* Slab mode (sarw_params.slabRanks >= 2): the same calls (sarw_mr_setup with the context's slabRank / slabRanks, peer export / connect,
+ * sarw_mr_grow_peer), but the box is decomposed in space. Rank r holds the cell layers of z-slab r plus a halo. Each round a chain is
+ * proposed, verified and - on a same-round conflict - re-resolved by the rank whose slab holds the chain's tip; the 32-byte records of
+ * the accepted beads are stored into every rank's buffer over NVLink and each rank inserts those that fall into its slab or halo;
+ * conflicts are settled by a fixed-point iteration whose results are exchanged the same way. Chain states and bead coordinates stay
+ * replicated (72 bytes per bead and rank against ~100 bytes of cell list per bead, which is partitioned), so every rank can download the
+ * complete walk; it is bit-identical to the single-GPU walk. sarw_lookup_find_batch is not available on a slab context. */
+
+/* The same for contexts of ONE process (what `sarw --gpus N` uses): ctxs[r] = rank r of n, created with identical parameters (slab
+ * contexts: slabRank = r, slabRanks = n) on any devices - several may share a device - and initiated. Enables peer access between the
+ * devices, shares the exchange buffers as device pointers and runs sarw_mr_grow_peer on every rank at once, one host thread each.
+ * stats (may be NULL) receives rank 0's. */
+int sarw_mr_grow_local(sarw_ctx* const* ctxs, int32_t n, int64_t maxRounds, sarw_stats* stats);
+/* number of CUDA devices visible to the process (0 if none) */
+int32_t sarw_device_count(void);
 
 /* SARW::terminateChain (sarw.cpp:359-368) */
 int sarw_terminate(sarw_ctx* ctx);
@@ -187,6 +209,8 @@ int sarw_lookup_find_batch(sarw_ctx* ctx, const double* xyz, const int64_t* igno
 int sarw_lookup_find_batch_device(sarw_ctx* ctx, const double* d_xyz, const int64_t* d_ignore, int64_t n, uint8_t* d_hit);
 /* number of points currently in the lookup (obstacles + beads + added points) */
 int64_t sarw_lookup_size(sarw_ctx* ctx);
+/* bytes of device memory behind this context's cell list (a slab context holds only its layers: about 1/slabRanks of the table plus the halo) */
+int64_t sarw_cell_table_bytes(sarw_ctx* ctx);
 
 #ifdef __cplusplus
 }

@@ -14,6 +14,7 @@
 #include <map>
 #include <mutex>
 #include <unordered_map>
+#include <thread>
 
 using namespace sarw;
 
@@ -59,8 +60,15 @@ struct sarw_ctx {
 
 	double seedMs = 0, growMs = 0; int64_t growLaunches = 0, seedLaunches = 0;
 	uint32_t mrRank = 0, mrRanks = 1; bool mrPending = false;   // multi-rank mode (sarw_mr_*)
-	void* xbuf = nullptr; size_t xbufRecBytes = 0;               // peer-memory exchange buffer (plain cudaMalloc: IPC-exportable)
+	void* xbuf = nullptr; size_t xbufRecBytes = 0, xbufDirtyBytes = 0;               // peer-memory exchange buffer (plain cudaMalloc: IPC-exportable)
 	void* peerRec[8] = {}; void* peerFlags[8] = {}; void* peerDirty[8] = {}; bool peersOpen = false, peersLocal = false;
+	// slab mode (sarw_params.slabRanks >= 2): the cell table is a virtual address range of the full size of which only this rank's
+	// window of z layers is backed by memory (CUDA virtual memory management), so every kernel addresses cells as on a single GPU
+	bool slab = false;
+	bool cellsVm = false; CUdeviceptr vmBase = 0; size_t vmSize = 0;
+	struct VmRange { size_t off, size; CUmemGenericAllocationHandle h; } vmRanges[2] = {}; int nVmRanges = 0;
+	size_t windowBytes = 0;
+	SlabBuffers sb{};
 };
 
 namespace {
@@ -73,6 +81,87 @@ int fail(sarw_ctx* c, const char* fmt, ...)
 	return 1;
 }
 #define CU(c, x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(c, "%s: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+// CUDA virtual memory management through the runtime's driver entry points (no link dependency on libcuda)
+struct VmApi {
+	CUresult (*getGranularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) = nullptr;
+	CUresult (*addressReserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+	CUresult (*addressFree)(CUdeviceptr, size_t) = nullptr;
+	CUresult (*create)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long) = nullptr;
+	CUresult (*release)(CUmemGenericAllocationHandle) = nullptr;
+	CUresult (*map)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+	CUresult (*unmap)(CUdeviceptr, size_t) = nullptr;
+	CUresult (*setAccess)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) = nullptr;
+	bool ok = false;
+};
+const VmApi& vm_api()
+{
+	static VmApi api; static std::once_flag once;
+	std::call_once(once, [] {
+		auto get = [](const char* name, void** fn) {
+			cudaDriverEntryPointQueryResult qr;
+			if (cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) { cudaGetLastError(); *fn = nullptr; }
+			return *fn != nullptr;
+		};
+		bool ok = get("cuMemGetAllocationGranularity", (void**)&api.getGranularity);
+		ok = get("cuMemAddressReserve", (void**)&api.addressReserve) && ok;
+		ok = get("cuMemAddressFree", (void**)&api.addressFree) && ok;
+		ok = get("cuMemCreate", (void**)&api.create) && ok;
+		ok = get("cuMemRelease", (void**)&api.release) && ok;
+		ok = get("cuMemMap", (void**)&api.map) && ok;
+		ok = get("cuMemUnmap", (void**)&api.unmap) && ok;
+		ok = get("cuMemSetAccess", (void**)&api.setAccess) && ok;
+		api.ok = ok;
+	});
+	return api;
+}
+
+void vm_free_cells(sarw_ctx* c)
+{
+	if (!c->cellsVm) return;
+	const VmApi& vm = vm_api();
+	for (int k = 0; k < c->nVmRanges; k++) { vm.unmap(c->vmBase + c->vmRanges[k].off, c->vmRanges[k].size); vm.release(c->vmRanges[k].h); }
+	if (c->vmBase) vm.addressFree(c->vmBase, c->vmSize);
+	c->nVmRanges = 0; c->vmBase = 0; c->vmSize = 0; c->cellsVm = false; c->T.cells = nullptr;
+}
+
+// The cell table of a slab context: the full table's address range, backed only where this rank's layers [winLo, winLo + winLen) (mod S2)
+// lie (a z layer is one contiguous run of S0*S1 cells; the window is one run, or two when it wraps around the periodic boundary).
+int vm_alloc_cells_window(sarw_ctx* c, size_t nCells, size_t layerBytes, int winLo, int winLen, int S2)
+{
+	const VmApi& vm = vm_api();
+	if (!vm.ok) return fail(c, "slab mode needs CUDA virtual memory management (cuMemCreate / cuMemMap), which this driver does not offer");
+	CUmemAllocationProp prop = {};
+	prop.type = CU_MEM_ALLOCATION_TYPE_PINNED; prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE; prop.location.id = c->device;
+	size_t gran = 0;
+	if (vm.getGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_MINIMUM) != CUDA_SUCCESS || gran == 0) return fail(c, "cuMemGetAllocationGranularity failed");
+	const size_t total = ((nCells * sizeof(Cell) + gran - 1) / gran) * gran;
+	if (vm.addressReserve(&c->vmBase, total, 0, 0, 0) != CUDA_SUCCESS) return fail(c, "cuMemAddressReserve of %zu bytes failed", total);
+	c->vmSize = total; c->cellsVm = true; c->T.cells = reinterpret_cast<Cell*>(c->vmBase);
+	// byte ranges of the window, rounded outwards to the mapping granularity and merged when they touch
+	size_t lo[2], hi[2]; int n = 0;
+	const int first = winLo, last = winLo + winLen;   // last may exceed S2: wraps
+	if (last <= S2) { lo[0] = (size_t)first * layerBytes; hi[0] = (size_t)last * layerBytes; n = 1; }
+	else { lo[0] = 0; hi[0] = (size_t)(last - S2) * layerBytes; lo[1] = (size_t)first * layerBytes; hi[1] = (size_t)S2 * layerBytes; n = 2; }
+	for (int k = 0; k < n; k++) { lo[k] = (lo[k] / gran) * gran; hi[k] = std::min(total, ((hi[k] + gran - 1) / gran) * gran); }
+	if (n == 2 && hi[0] >= lo[1]) { hi[0] = hi[1]; n = 1; }
+	CUmemAccessDesc acc = {};
+	acc.location = prop.location; acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+	c->windowBytes = 0;
+	for (int k = 0; k < n; k++) {
+		const size_t size = hi[k] - lo[k];
+		CUmemGenericAllocationHandle h;
+		CUresult r = vm.create(&h, size, &prop, 0);
+		if (r != CUDA_SUCCESS) return fail(c, "cuMemCreate of %zu bytes for the cell layers of this slab failed (%d)", size, (int)r);
+		if (vm.map(c->vmBase + lo[k], size, 0, h, 0) != CUDA_SUCCESS) { vm.release(h); return fail(c, "cuMemMap failed"); }
+		c->vmRanges[c->nVmRanges++] = { lo[k], size, h };
+		if (vm.setAccess(c->vmBase + lo[k], size, &acc, 1) != CUDA_SUCCESS) return fail(c, "cuMemSetAccess failed");
+		cudaError_t e = cudaMemsetAsync(reinterpret_cast<void*>(c->vmBase + lo[k]), 0xFF, size, c->stream);
+		if (e != cudaSuccess) return fail(c, "cudaMemsetAsync of the mapped cell layers: %s", cudaGetErrorString(e));
+		c->windowBytes += size;
+	}
+	return 0;
+}
 
 // Device memory. Transient buffers are stream-ordered allocations from the device's default pool. The large long-lived tables
 // (cell table, bead storage) of a destroyed context are parked in a per-device cache and handed to the next context that asks for
@@ -293,6 +382,8 @@ int sarw_create(const sarw_params* p, sarw_ctx** out)
 		if (!(p->boxSize[k] >= 2 * p->minDist))   // the reference needs S = floor(L/minDist) >= 2 (PeriodicLookup.h:16-22,29)
 			return fail(nullptr, "boxSize[%d] = %g must be at least 2*minDist = %g", k, p->boxSize[k], 2 * p->minDist);
 	if (p->nGraftChains < 0 || p->nGraftChains > p->nChains) return fail(nullptr, "nGraftChains must be in [0, nChains]");
+	if (p->slabRanks > 8 || (p->slabRanks >= 2 && (p->slabRank < 0 || p->slabRank >= p->slabRanks)) || p->slabHalo < 0)
+		return fail(nullptr, "slab decomposition: need 2 <= slabRanks <= 8, 0 <= slabRank < slabRanks, slabHalo >= 0");
 
 	int nDev = 0;
 	cudaError_t e = cudaGetDeviceCount(&nDev);
@@ -341,6 +432,7 @@ int sarw_create(const sarw_params* p, sarw_ctx** out)
 		g.qs[k] = (float)(g.a[k] / 65536.0);
 		amax = std::max(amax, g.a[k]);
 	}
+	g.winLo = 0; g.winLen = g.S[2]; g.slabRank = 0; g.slabRanks = 1; g.winStrict = 0; g.tmapZ0 = 0; g.tmapZn = g.S[2];   // the whole table, unless this is one slab of a decomposed melt (below)
 	g.cap = (p->cellCapacity >= 1 && p->cellCapacity <= MAX_CAP) ? p->cellCapacity : MAX_CAP;
 	{	// fp32 pre-filter bounds. The undecided band covers the half quantisation step of the stored in-cell offsets (edge / 131072 per
 		// coordinate), fp32 storage and arithmetic error, all with a wide margin; whatever falls inside is decided in fp64 from lpos.
@@ -387,9 +479,27 @@ int sarw_create(const sarw_params* p, sarw_ctx** out)
 
 	const size_t nCells = (size_t)g.S[0] * g.S[1] * g.S[2];
 #define CUB_(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fail(c, "%s: %s", #x, cudaGetErrorString(e_)); return bail(1); } } while (0)
-	CUB_(dev_alloc(c, &c->T.cells, nCells * sizeof(Cell)));
-	mark("cells alloc");
-	CUB_(cudaMemsetAsync(c->T.cells, 0xFF, nCells * sizeof(Cell), c->stream));
+	size_t tableCells = nCells;   // cells backed by memory (sizes the overflow table)
+	if (p->slabRanks >= 2) {
+		// this rank's slab of z layers plus a halo that covers what a round can reach from a tip in the slab: the staged 4-layer box, the
+		// +-1-layer verify probe around the new bead, the candidates of a re-resolution (all within reach + 2 layers of the tip's layer)
+		c->slab = true;
+		g.slabRank = p->slabRank; g.slabRanks = p->slabRanks;
+		const int reach = (int)floor((2.0 + p->minDist + 0.1) / g.a[2]) + 1;
+		const int halo = std::max(p->slabHalo > 0 ? p->slabHalo : 8, reach + 2);
+		const int lo = slab_lo(g.S[2], g.slabRanks, g.slabRank), hi = slab_lo(g.S[2], g.slabRanks, g.slabRank + 1);
+		if (hi - lo < 1) { fail(c, "slab decomposition: %d cell layers cannot be split over %d ranks", g.S[2], g.slabRanks); return bail(1); }
+		if (hi - lo + 2 * halo < g.S[2]) { g.winLo = ((lo - halo) % g.S[2] + g.S[2]) % g.S[2]; g.winLen = hi - lo + 2 * halo; }
+		if (g.winLen < g.S[2]) {
+			if (vm_alloc_cells_window(c, nCells, (size_t)g.S[0] * g.S[1] * sizeof(Cell), g.winLo, g.winLen, g.S[2])) return bail(1);
+			tableCells = c->windowBytes / sizeof(Cell);
+		}
+	}
+	if (!c->cellsVm) {
+		CUB_(dev_alloc(c, &c->T.cells, nCells * sizeof(Cell)));
+		mark("cells alloc");
+		CUB_(cudaMemsetAsync(c->T.cells, 0xFF, nCells * sizeof(Cell), c->stream));
+	}
 	c->T.tmapHost = nullptr; g.useTmap = 0;
 	if (g.S[0] >= 4 && g.S[1] >= 4 && g.S[2] >= 4 && !(getenv("SARW_NO_TMAP") && atoi(getenv("SARW_NO_TMAP")))) {
 		// 3-D tensor map over the cell table (x in 4-byte elements, 32 per cell; y; z), box = 4 x 4 x 4 cells: a chain's whole
@@ -407,19 +517,24 @@ int sarw_create(const sarw_params* p, sarw_ctx** out)
 			}
 		}
 		if (encode) {
-			const cuuint64_t dims[3] = { (cuuint64_t)g.S[0] * (sizeof(Cell) / 4), (cuuint64_t)g.S[1], (cuuint64_t)g.S[2] };
+			// An inner slab's window is one run of layers with unbacked address space before it: its tensor map starts at the window (measured:
+			// a tensor copy faults when the map's base address has no memory behind it, even if every element the box touches has).
+			// The windows of the first and last slab wrap around the periodic boundary and include the table's first layers.
+			if (c->cellsVm && g.winLo + g.winLen <= g.S[2]) { g.tmapZ0 = g.winLo; g.tmapZn = g.winLen; }
+			const cuuint64_t dims[3] = { (cuuint64_t)g.S[0] * (sizeof(Cell) / 4), (cuuint64_t)g.S[1], (cuuint64_t)g.tmapZn };
 			const cuuint64_t strides[2] = { (cuuint64_t)g.S[0] * sizeof(Cell), (cuuint64_t)g.S[0] * g.S[1] * sizeof(Cell) };
 			const cuuint32_t box[3] = { 4 * (cuuint32_t)(sizeof(Cell) / 4), 4, 4 }, es[3] = { 1, 1, 1 };
-			if (encode(&c->tmapHost, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, c->T.cells, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+			if (encode(&c->tmapHost, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, c->T.cells + (size_t)g.tmapZ0 * g.S[0] * g.S[1], dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
 					CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
 				static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap is copied into a 128-byte kernel parameter");
 				c->T.tmapHost = &c->tmapHost; g.useTmap = 1;
-			}
+			} else { g.tmapZ0 = 0; g.tmapZn = g.S[2]; }
 		}
 	}
 	{	// overflow hash table: a power of two >= nCells / 16 entries (>= 2^16); at most half of it is ever used
-		uint64_t want = std::max<uint64_t>((uint64_t)1 << 16, nCells / 16);
-		if (p->cellCapacity >= 1 && p->cellCapacity < MAX_CAP) want = std::max<uint64_t>(want, nCells * 4);   // test hook: most beads overflow
+		uint64_t want = std::max<uint64_t>((uint64_t)1 << 16, tableCells / 16);
+		if (p->cellCapacity >= 1 && p->cellCapacity < MAX_CAP) want = std::max<uint64_t>(want, tableCells * 4);   // test hook: most beads overflow
+		if (c->cellsVm) want += 8 * (uint64_t)g.nChains;   // a slab context keeps the seed beads of the layers it does not hold in this table
 		uint64_t size = (uint64_t)1 << 16;
 		while (size < want && size < ((uint64_t)1 << 31)) size <<= 1;
 		c->T.ovfMask = (uint32_t)(size - 1); c->T.ovfLimit = (uint32_t)(size / 2);
@@ -433,6 +548,7 @@ int sarw_create(const sarw_params* p, sarw_ctx** out)
 	c->hctl->seedFailChain = ID_NONE; c->hctl->lastProgressed = 1;
 	CUB_(cudaMemcpyAsync(c->ctl, c->hctl, sizeof(Control), cudaMemcpyHostToDevice, c->stream));
 	c->T.ovfCount = &c->ctl->ovfCount;
+	c->T.oowCount = &c->ctl->oowCount;
 	CUB_(dev_alloc(c, &c->chains, (size_t)g.nChains * sizeof(ChainState)));
 	CUB_(cudaMemsetAsync(c->chains, 0, (size_t)g.nChains * sizeof(ChainState), c->stream));
 	CUB_(dev_alloc(c, &c->resTrial, (size_t)g.nChains * sizeof(uint32_t)));
@@ -465,7 +581,9 @@ void sarw_destroy(sarw_ctx* c)
 	if (c->stream) cudaStreamSynchronize(c->stream);
 	if (c->stream) {
 		if (c->allocStream != c->stream) cudaStreamSynchronize(c->allocStream);   // both streams idle: the blocks may be parked
-		dev_park(c, c->T.cells); dev_park(c, c->T.lpos); dev_park(c, c->T.ovf);
+		if (c->cellsVm) vm_free_cells(c); else dev_park(c, c->T.cells);
+		dev_park(c, c->T.lpos); dev_park(c, c->T.ovf);
+		dev_free(c, c->sb.ownList); dev_free(c, c->sb.ownerOf); dev_free(c, (char*)c->sb.cleanRes); dev_free(c, c->sb.cleanPush);
 		dev_free(c, c->ctl); dev_park(c, c->chains); dev_park(c, c->resTrial); dev_park(c, c->origTrial); dev_park(c, c->resPos); dev_park(c, c->prev);
 		dev_park(c, c->roundAcc); dev_park(c, c->roundProg); dev_park(c, c->dirtyCount); dev_park(c, c->dirtyList); dev_park(c, c->grafts);
 	}
@@ -519,6 +637,12 @@ int64_t sarw_lookup_size(sarw_ctx* c)
 	return (int64_t)c->g.idAtomBase + (int64_t)h.nBeads;
 }
 
+int64_t sarw_cell_table_bytes(sarw_ctx* c)
+{
+	if (!c || c->lookupReleased) return 0;
+	return c->cellsVm ? (int64_t)c->windowBytes : (int64_t)((size_t)c->g.S[0] * c->g.S[1] * c->g.S[2] * sizeof(Cell));
+}
+
 int sarw_set_grafts(sarw_ctx* c, const double* xyz, int64_t n)
 {
 	if (!c) return 1;
@@ -552,6 +676,7 @@ int sarw_lookup_find_batch_device(sarw_ctx* c, const double* d_xyz, const int64_
 {
 	if (!c) return 1;
 	if (n < 0 || (n > 0 && (!d_xyz || !d_hit))) return fail(c, "sarw_lookup_find_batch_device: bad arguments");
+	if (c->cellsVm) return fail(c, "sarw_lookup_find_batch is not available on a slab context (this rank holds only its layers of the cell list)");
 	if (c->lookupReleased) return fail(c, "the lookup was released (sarw_release_lookup)");
 	cudaSetDevice(c->device);
 	CU(c, find_batch_ordered(c, d_xyz, d_ignore, n, d_hit));
@@ -562,6 +687,7 @@ int sarw_lookup_find_batch(sarw_ctx* c, const double* xyz, const int64_t* ignore
 {
 	if (!c) return 1;
 	if (n < 0 || (n > 0 && (!xyz || !hit))) return fail(c, "sarw_lookup_find_batch: bad arguments");
+	if (c->cellsVm) return fail(c, "sarw_lookup_find_batch is not available on a slab context (this rank holds only its layers of the cell list)");
 	if (c->lookupReleased) return fail(c, "the lookup was released (sarw_release_lookup)");
 	if (n == 0) return 0;
 	cudaSetDevice(c->device);
@@ -795,6 +921,7 @@ int sarw_mr_setup(sarw_ctx* c, int32_t rank, int32_t nranks, int64_t* recordsPer
 {
 	if (!c) return 1;
 	if (nranks < 1 || rank < 0 || rank >= nranks) return fail(c, "sarw_mr_setup: rank %d of %d", rank, nranks);
+	if (c->slab && (rank != c->p.slabRank || nranks != c->p.slabRanks)) return fail(c, "sarw_mr_setup: this context was created as slab %d of %d", c->p.slabRank, c->p.slabRanks);
 	c->mrRank = (uint32_t)rank; c->mrRanks = (uint32_t)nranks;
 	if (recordsPerRank) *recordsPerRank = ((int64_t)c->g.nChains + nranks - 1) / nranks;
 	if (recordBytes) *recordBytes = 32;
@@ -804,13 +931,14 @@ int sarw_mr_setup(sarw_ctx* c, int32_t rank, int32_t nranks, int64_t* recordsPer
 static int mr_launch(sarw_ctx* c, uint32_t phase, void* localRec, const void* allRec, bool readBack)
 {
 	if (!c->initiateCalled) return fail(c, "sarw_initiate must be called before the multi-rank rounds");
+	if (c->slab) return fail(c, "slab contexts grow with sarw_mr_grow_peer (the exchange runs inside the kernel)");
 	cudaSetDevice(c->device);
 	if (phase != 2u && fresh(c)) return 1;   // phase 2 follows phase 1 of the same round: the round number in the mirror is still right
 	Control& h = *c->hctl;
 	if (h.round >= c->roundCap && ensure_rounds(c, h.round + 1)) return 1;
 	CU(c, cudaEventRecord(c->ev0, c->stream));
 	CU(c, launch_grow_mr(c->g, c->T, c->chains, c->resTrial, c->origTrial, c->resPos, c->prev, c->ctl, c->roundAcc, c->roundProg, c->dirtyCount, c->dirtyList,
-		h.round + 1, grow_blocks(c, c->g.nChains), c->mrRank, c->mrRanks, phase, localRec, allRec, nullptr, nullptr, nullptr, 0u, c->stream));
+		h.round + 1, grow_blocks(c, c->g.nChains), c->mrRank, c->mrRanks, phase, localRec, allRec, nullptr, nullptr, nullptr, 0u, nullptr, c->stream));
 	CU(c, cudaEventRecord(c->ev1, c->stream));
 	c->growLaunches += 1; c->mirrorStale = true;
 	if (readBack) {
@@ -863,11 +991,23 @@ int sarw_mr_peer_export(sarw_ctx* c, void* handle64)
 	if (c->mrRanks < 2 || c->mrRanks > 8) return fail(c, "sarw_mr_peer_export: call sarw_mr_setup with 2..8 ranks first");
 	cudaSetDevice(c->device);
 	const size_t K = ((size_t)c->g.nChains + c->mrRanks - 1) / c->mrRanks;
-	c->xbufRecBytes = 2 * (size_t)c->mrRanks * K * 32;
+	c->xbufRecBytes = c->slab ? 2 * (size_t)c->g.nChains * 32 : 2 * (size_t)c->mrRanks * K * 32;   // slab mode: one record slot per chain
 	const size_t dirtyBytes = 2 * (size_t)c->mrRanks * (1 + K) * sizeof(uint32_t);   // conflict-list inboxes
+	c->xbufDirtyBytes = (dirtyBytes + 15) & ~(size_t)15;
+	size_t cleanBytes = 0;
+	if (c->slab) {
+		c->sb.cleanCap = (uint32_t)std::min<uint64_t>(65536, std::max<uint64_t>(1024, c->g.nChains / 16));
+		cleanBytes = 2 * (size_t)c->mrRanks * clean_msg_bytes(c->sb.cleanCap);
+		if (!c->sb.ownList) {
+			CU(c, dev_alloc(c, &c->sb.ownList, (size_t)c->g.nChains * sizeof(uint32_t)));
+			CU(c, dev_alloc(c, &c->sb.ownerOf, (size_t)c->g.nChains));
+			CU(c, dev_alloc(c, (char**)&c->sb.cleanRes, (size_t)c->sb.cleanCap * 32));
+			CU(c, dev_alloc(c, &c->sb.cleanPush, (size_t)c->sb.cleanCap * sizeof(uint32_t)));
+		}
+	}
 	if (!c->xbuf) {
-		CU(c, cudaMalloc(&c->xbuf, c->xbufRecBytes + 256 + dirtyBytes));
-		CU(c, cudaMemset(c->xbuf, 0, c->xbufRecBytes + 256 + dirtyBytes));
+		CU(c, cudaMalloc(&c->xbuf, c->xbufRecBytes + 256 + c->xbufDirtyBytes + cleanBytes));
+		CU(c, cudaMemset(c->xbuf, 0, c->xbufRecBytes + 256 + c->xbufDirtyBytes + cleanBytes));
 	}
 	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
 	CU(c, cudaIpcGetMemHandle((cudaIpcMemHandle_t*)handle64, c->xbuf));
@@ -886,6 +1026,7 @@ int sarw_mr_peer_connect(sarw_ctx* c, const void* allHandles)
 			CU(c, cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
 		}
 		c->peerRec[p] = base; c->peerFlags[p] = (char*)base + c->xbufRecBytes; c->peerDirty[p] = (char*)base + c->xbufRecBytes + 256;
+		c->sb.peerClean[p] = (char*)base + c->xbufRecBytes + 256 + c->xbufDirtyBytes;
 	}
 	c->peersOpen = true;
 	return 0;
@@ -909,6 +1050,7 @@ int sarw_mr_peer_connect_local(sarw_ctx* c, void* const* bases)
 		char* base = (char*)(p == c->mrRank ? c->xbuf : bases[p]);
 		if (!base) return fail(c, "sarw_mr_peer_connect_local: no buffer for rank %u", p);
 		c->peerRec[p] = base; c->peerFlags[p] = base + c->xbufRecBytes; c->peerDirty[p] = base + c->xbufRecBytes + 256;
+		c->sb.peerClean[p] = base + c->xbufRecBytes + 256 + c->xbufDirtyBytes;
 	}
 	c->peersOpen = true; c->peersLocal = true;
 	return 0;
@@ -929,18 +1071,87 @@ int sarw_mr_grow_peer(sarw_ctx* c, int64_t maxRounds, sarw_stats* stats)
 		if ((int64_t)(roundEnd - h.round) > roundsLeft) roundEnd = h.round + (uint32_t)roundsLeft;
 		CU(c, cudaEventRecord(c->ev0, c->stream));
 		CU(c, launch_grow_mr(c->g, c->T, c->chains, c->resTrial, c->origTrial, c->resPos, c->prev, c->ctl, c->roundAcc, c->roundProg, c->dirtyCount, c->dirtyList,
-			roundEnd, grow_blocks(c, (int64_t)c->g.nChains / c->mrRanks), c->mrRank, c->mrRanks, 4u, nullptr, nullptr, c->peerRec, c->peerFlags, c->peerDirty,
-			(c->p.launchMode & 2) ? 0u : 1u, c->stream));   // launchMode bit 1: keep the verification replicated (diagnostics)
+			roundEnd, grow_blocks(c, (int64_t)c->g.nChains / c->mrRanks), c->mrRank, c->mrRanks, c->slab ? 5u : 4u, nullptr, nullptr, c->peerRec, c->peerFlags, c->peerDirty,
+			(c->p.launchMode & 2) ? 0u : 1u, c->slab ? &c->sb : nullptr, c->stream));   // launchMode bit 1: keep the verification replicated (diagnostics)
 		CU(c, cudaEventRecord(c->ev1, c->stream));
 		c->mirrorStale = true; c->growTimed = false; c->growLaunches += 1;
 		const uint32_t before = h.round;
-		if (read_control(c, nullptr)) return 1;
+		if (read_control(c, nullptr)) {
+			if (unsigned* t = g_traceHost[c->mrRank & 7]) c->err += " [trace: round " + std::to_string(t[0] >> 8) + ", stage " + std::to_string(t[0] & 255u) + "]";
+			return 1;
+		}
 		roundsLeft -= (int64_t)(h.round - before);
+		if (h.abort == 2u || h.abort == 3u) return fail(c, "multi-rank growth aborted: more same-round conflicts than the exchange buffers hold (round %u)", h.round);
 		if (h.abort) return fail(c, "multi-rank growth aborted: a peer stopped answering (round %u)", h.round);
+		if (h.oowCount) return fail(c, "slab decomposition: %u cell probes fell outside this rank's window of layers (halo too small: raise slabHalo)", h.oowCount);
 		if (check_overflow(c)) return 1;
 		if (h.round == before) break;
 	}
 	if (stats) fill_stats(c, h, stats);
+	return 0;
+}
+
+int32_t sarw_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+	return n;
+}
+
+int sarw_mr_grow_local(sarw_ctx* const* ctxs, int32_t n, int64_t maxRounds, sarw_stats* stats)
+{
+	if (!ctxs || n < 1 || n > 8) return 1;
+	for (int32_t r = 0; r < n; r++) if (!ctxs[r]) return 1;
+	sarw_ctx* c0 = ctxs[0];
+	if (n == 1) return sarw_grow(c0, 0, maxRounds, stats);
+	// contexts that share a device must fit it together: the cooperative grids of all ranks have to be resident at the same time
+	for (int32_t r = 0; r < n; r++) {
+		int sharing = 0;
+		for (int32_t q = 0; q < n; q++) sharing += ctxs[q]->device == ctxs[r]->device;
+		if (sharing > 1) {
+			const int cap = std::max(1, ctxs[r]->growBlocksMax / sharing);
+			if (ctxs[r]->p.maxBlocks <= 0 || ctxs[r]->p.maxBlocks > cap) ctxs[r]->p.maxBlocks = cap;
+		}
+	}
+	for (int32_t a = 0; a < n; a++)
+		for (int32_t b = 0; b < n; b++) {
+			if (ctxs[a]->device == ctxs[b]->device) continue;
+			int can = 0;
+			cudaDeviceCanAccessPeer(&can, ctxs[a]->device, ctxs[b]->device);
+			if (!can) return fail(c0, "sarw_mr_grow_local: device %d cannot access the memory of device %d", ctxs[a]->device, ctxs[b]->device);
+			cudaSetDevice(ctxs[a]->device);
+			cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[b]->device, 0);
+			if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(c0, "cudaDeviceEnablePeerAccess(%d -> %d): %s", ctxs[a]->device, ctxs[b]->device, cudaGetErrorString(e));
+			cudaGetLastError();
+		}
+	// every rank's persistent kernel must run at the same time: contexts that still share a stream (the device's home stream) get their own
+	for (int32_t r = 1; r < n; r++) {
+		bool shared = false;
+		for (int32_t q = 0; q < r; q++) shared = shared || ctxs[q]->stream == ctxs[r]->stream;
+		if (!shared) continue;
+		cudaSetDevice(ctxs[r]->device);
+		cudaStreamSynchronize(ctxs[r]->stream);
+		cudaStream_t s = nullptr;
+		if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return fail(c0, "cudaStreamCreate failed");
+		ctxs[r]->stream = s; ctxs[r]->ownStream = true;
+	}
+	void* bases[8] = {};
+	for (int32_t r = 0; r < n; r++) {
+		unsigned char handle[64];
+		if (sarw_mr_setup(ctxs[r], r, n, nullptr, nullptr) || sarw_mr_peer_export(ctxs[r], handle) || sarw_mr_peer_local_base(ctxs[r], &bases[r])) {
+			if (r) c0->err = ctxs[r]->err;
+			return 1;
+		}
+	}
+	for (int32_t r = 0; r < n; r++)
+		if (sarw_mr_peer_connect_local(ctxs[r], bases)) { if (r) c0->err = ctxs[r]->err; return 1; }
+	for (int32_t r = 0; r < n; r++) { cudaSetDevice(ctxs[r]->device); cudaStreamSynchronize(ctxs[r]->stream); }
+	int rc[8] = {}; sarw_stats st[8];
+	std::vector<std::thread> th;
+	for (int32_t r = 0; r < n; r++) th.emplace_back([&, r] { rc[r] = sarw_mr_grow_peer(ctxs[r], maxRounds, &st[r]); });
+	for (auto& t : th) t.join();
+	for (int32_t r = 0; r < n; r++) if (rc[r]) { if (r) c0->err = "rank " + std::to_string(r) + ": " + ctxs[r]->err; return 1; }
+	if (stats) *stats = st[0];
 	return 0;
 }
 
@@ -1139,7 +1350,8 @@ int sarw_release_lookup(sarw_ctx* c)
 	cudaSetDevice(c->device);
 	if (fresh(c)) return 1;
 	if (c->stream) cudaStreamSynchronize(c->stream);
-	dev_free(c, c->T.cells); dev_free(c, c->T.ovf);
+	if (c->cellsVm) vm_free_cells(c); else dev_free(c, c->T.cells);
+	dev_free(c, c->T.ovf);
 	c->T.cells = nullptr; c->T.ovf = nullptr; c->lookupReleased = true;
 	cudaStreamSynchronize(c->allocStream);
 	return 0;

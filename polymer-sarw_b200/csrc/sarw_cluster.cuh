@@ -215,7 +215,7 @@ __device__ __forceinline__ void prepare_chain(const Geom& g, const ChainState& c
 		rp.base[k] = (float)((double)rp.lo[k] * g.a[k] - lw);
 	}
 	rp.tile = g.useTmap && rp.nn[0] <= REGION_BOX && rp.nn[1] <= REGION_BOX && rp.nn[2] <= REGION_BOX
-		&& rp.lo[0] >= 0 && rp.lo[1] >= 0 && rp.lo[2] >= 0 && rp.lo[0] + rp.nn[0] <= g.S[0] && rp.lo[1] + rp.nn[1] <= g.S[1] && rp.lo[2] + rp.nn[2] <= g.S[2];
+		&& rp.lo[0] >= 0 && rp.lo[1] >= 0 && rp.lo[2] >= g.tmapZ0 && rp.lo[0] + rp.nn[0] <= g.S[0] && rp.lo[1] + rp.nn[1] <= g.S[1] && rp.lo[2] + rp.nn[2] <= g.tmapZ0 + g.tmapZn;
 }
 
 // one lane per x-row: bulk-copy its nn0 cells (split in two when the row crosses the periodic boundary)
@@ -226,7 +226,7 @@ __device__ __forceinline__ void region_issue_tma(const Geom& g, const Tables& T,
 	if (rp.tile) {   // the usual case: one tensor copy of the 4 x 4 x 4 box (cells beyond the table edge arrive as zeros and are never read)
 		if (lane == 0) {
 			mbar_expect_tx(mbar, (unsigned)(REGION_BOX * REGION_BOX * REGION_BOX) * (unsigned)sizeof(Cell));
-			tma_load_box3d(raw, tmap, rp.lo[0] * (int)(sizeof(Cell) / 4), rp.lo[1], rp.lo[2], mbar);
+			tma_load_box3d(raw, tmap, rp.lo[0] * (int)(sizeof(Cell) / 4), rp.lo[1], rp.lo[2] - g.tmapZ0, mbar);
 		}
 		__syncwarp();
 		return;

@@ -73,6 +73,12 @@ struct Geom {
 	uint32_t seedIgnoreId;    // nObstacles-1 or ID_NONE: the reference's "ignoreIndex=-1 + nObstacles" quirk (sarw.cpp:198,353)
 	int64_t target;
 	int64_t nGraftAtoms;      // threshold of sarw.cpp:232
+	// Slab decomposition of ONE melt over several GPUs: this context holds the cell layers (z) [winLo, winLo + winLen)
+	// (mod S[2]) = its own slab plus a halo on either side; winLen == S[2] means the whole table (every single-GPU context).
+	int winLo, winLen;
+	int slabRank, slabRanks;  // slabRanks <= 1: no decomposition
+	int tmapZ0, tmapZn;       // cell layers the tensor map of the cell table covers: [tmapZ0, tmapZ0 + tmapZn) (the whole table unless this is an inner slab)
+	int winStrict;            // growth launches: a probe outside the window is a protocol error and is counted (seeding and obstacles use the hash table there)
 };
 
 struct Tables {
@@ -83,6 +89,7 @@ struct Tables {
 	uint32_t* ovfCount;       // entries ever claimed (monotonic)
 	uint32_t ovfMask;         // table size - 1 (power of two)
 	uint32_t ovfLimit;        // at most this many entries are claimed (half the table): probing always terminates; beyond it the host fails the call
+	unsigned* oowCount;       // probes / removals that fell outside the window of a slab context during growth (must stay 0)
 	const void* tmapHost;     // HOST pointer to the 128-byte CUtensorMap of the cell table (launch wrappers copy it into the kernel parameters), or nullptr
 };
 
@@ -272,6 +279,21 @@ __device__ __forceinline__ int64_t cell_index(const Geom& g, int wx, int wy, int
 {	return wx + (int64_t)g.S[0] * (wy + (int64_t)g.S[1] * wz);
 }
 
+// ------------------------------------------------------------------ slab decomposition: which cell layers this context holds, who owns a layer
+__device__ __forceinline__ bool windowed(const Geom& g) { return g.winLen < g.S[2]; }
+__device__ __forceinline__ bool in_window(const Geom& g, int wz)
+{	int d = wz - g.winLo;
+	d += d < 0 ? g.S[2] : 0;
+	return d < g.winLen;
+}
+__host__ __device__ __forceinline__ int slab_lo(int S2, int ranks, int r) { return (int)(((long long)r * S2) / ranks); }   // slab r = layers [slab_lo(r), slab_lo(r + 1))
+__device__ __forceinline__ int slab_owner(const Geom& g, int wz)
+{	int r = (int)(((long long)wz * g.slabRanks) / g.S[2]);
+	while (r > 0 && wz < slab_lo(g.S[2], g.slabRanks, r)) --r;
+	while (r + 1 < g.slabRanks && wz >= slab_lo(g.S[2], g.slabRanks, r + 1)) ++r;
+	return r;
+}
+
 // cell + quantised in-cell offset of a bead from its fractional coordinates
 __device__ __forceinline__ int64_t bead_cell(const Geom& g, const double v[3], uint32_t q16[3], int c[3])
 {
@@ -377,10 +399,20 @@ __device__ __forceinline__ bool probe_cells(const Geom& g, const Tables& T, cons
 	for (int ci = sub; ci < total && !hit; ci += GROUP) {
 		const int ix = ci % n[0], rest = ci / n[0];
 		const int iy = rest % n[1], iz = rest / n[1];
-		const int64_t cidx = cell_index(g, wrap_cell(c0[0] + ix, g.S[0]), wrap_cell(c0[1] + iy, g.S[1]), wrap_cell(c0[2] + iz, g.S[2]));
+		const int wz = wrap_cell(c0[2] + iz, g.S[2]);
+		const int64_t cidx = cell_index(g, wrap_cell(c0[0] + ix, g.S[0]), wrap_cell(c0[1] + iy, g.S[1]), wz);
+		const float qx = q[0][ix], qy = q[1][iy], qz = q[2][iz];
+		if (windowed(g) && !in_window(g, wz)) {   // slab context, layer held by another rank: only seeds / obstacles are known here (hash table)
+			if (g.winStrict) atomicAdd(T.oowCount, 1u);
+			ovf_for_cell(T, cidx, [&](uint32_t id, uint32_t o0, uint32_t o1, uint32_t o2) {
+				if (id < idLo || id >= idHi || id == ignoreId) return false;
+				hit = pair_hits(g, T, v, qx + dec_off(g, o0, 0), qy + dec_off(g, o1, 1), qz + dec_off(g, o2, 2), id);
+				return hit;
+			});
+			continue;
+		}
 		uint32_t w[CELL_WORDS];
 		ld_cell(T.cells + cidx, w);
-		const float qx = q[0][ix], qy = q[1][iy], qz = q[2][iz];
 #pragma unroll
 		for (int s = 0; s < MAX_CAP; ++s) {
 			const uint32_t id = w[s];
@@ -424,6 +456,12 @@ __device__ __forceinline__ void insert_bead(const Geom& g, const Tables& T, cons
 	const int64_t ci = bead_cell(g, v, q16);
 	double* lp = T.lpos + 3 * (size_t)id;
 	lp[0] = pos[0]; lp[1] = pos[1]; lp[2] = pos[2];
+	if (windowed(g) && !in_window(g, (int)(ci / ((int64_t)g.S[0] * g.S[1])))) {
+		// slab context, layer held by another rank: growth beads are only recorded in lpos (replicated); seeds and obstacles, which every
+		// rank places and checks on its own, are kept in the hash table
+		if (!g.winStrict) ovf_insert(T, ci, id, q16);
+		return;
+	}
 	Cell* cell = T.cells + ci;
 	for (int k = 0; k < g.cap; ++k)
 		if (atomicCAS(&cell->id[k], ID_NONE, id) == ID_NONE) { st_off16(cell, k, q16); fence_cells_for_tma(); return; }
@@ -440,11 +478,15 @@ __device__ inline void remove_bead(const Geom& g, const Tables& T, uint32_t id)
 	double v[3]; uint32_t q16[3];
 	to_frac(g, pos, v);
 	const int64_t ci = bead_cell(g, v, q16);
-	Cell* cell = T.cells + ci;
-	bool found = false;
-	for (int k = 0; k < MAX_CAP && !found; ++k)
-		if (__ldcg(&cell->id[k]) == id) { atomicExch(&cell->id[k], ID_NONE); found = true; }   // the slot is free for the next insert
-	if (!found) ovf_remove(T, ci, id);
+	if (windowed(g) && !in_window(g, (int)(ci / ((int64_t)g.S[0] * g.S[1])))) {
+		if (!g.winStrict) ovf_remove(T, ci, id);
+	} else {
+		Cell* cell = T.cells + ci;
+		bool found = false;
+		for (int k = 0; k < MAX_CAP && !found; ++k)
+			if (__ldcg(&cell->id[k]) == id) { atomicExch(&cell->id[k], ID_NONE); found = true; }   // the slot is free for the next insert
+		if (!found) ovf_remove(T, ci, id);
+	}
 	unsigned long long ones = ~0ull;
 	lp[0] = __longlong_as_double((long long)ones); lp[1] = lp[0]; lp[2] = lp[0];
 	__threadfence();
@@ -455,20 +497,17 @@ __device__ inline void remove_bead(const Geom& g, const Tables& T, uint32_t id)
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p)
 {	unsigned v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
 }
-__device__ __forceinline__ void grid_barrier(unsigned* count, unsigned* gen, unsigned nBlocks)
+// One arrival counter that only ever grows (the launch wrapper zeroes it): barrier k of a launch is passed when the counter reaches
+// k * nBlocks. Per CTA one release-reduction and an acquire spin; the CTA barrier before it makes the release cover the stores of the whole
+// CTA (cumulativity), the one after it hands the acquired view to the other threads. The first version (arrival counter reset by the
+// last CTA + a generation word, three fences) cost ~5k cycles per barrier: a third of a C3 round with its 3-6 barriers.
+__device__ __forceinline__ void grid_barrier(unsigned* count, unsigned& target, unsigned nBlocks)
 {
 	__syncthreads();
 	if (threadIdx.x == 0) {
-		unsigned my = ld_acquire_u32(gen);
-		__threadfence();
-		if (atomicAdd(count, 1u) == nBlocks - 1u) {
-			atomicExch(count, 0u);
-			__threadfence();
-			atomicAdd(gen, 1u);
-		} else {
-			while (ld_acquire_u32(gen) == my) { }
-		}
-		__threadfence();
+		target += nBlocks;
+		asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(count) : "memory");
+		while ((int)(ld_acquire_u32(count) - target) < 0) { }
 	}
 	__syncthreads();
 }

@@ -24,7 +24,21 @@ struct Control {
 	unsigned long long cycSub[8];       // finer split of the propose phase of block 0 / warp 0 (diagnostics)
 	unsigned int needOrdered[2];        // by round parity: the parallel clean-up left work for the ordered pass (else that pass and its barrier are skipped)
 	unsigned long long pathCyc[4], pathCnt[4];   // cluster kernel: propose cycles / chain-rounds by path: dead, fast, fast->hard, hard (diagnostics)
+	// slab mode (one melt decomposed over several GPUs)
+	unsigned oowCount;                  // probes outside the window of this slab during growth: a protocol error, must stay 0
+	unsigned ownCount[2];               // by round parity: chains whose tip lies in this rank's slab
+	unsigned cleanResCount, cleanPushCount;   // re-resolutions / pushes of the running clean-up iteration
+	unsigned cleanOpen;                 // open entries of the conflict list after the last exchange
+	unsigned xseq;                      // clean-up exchanges made so far (tag of the flag handshake)
+	unsigned pad1;
 	unsigned long long busy[256];       // cluster kernel: per-warp cycles from round start to the first barrier arrive, summed (diagnostics)
+};
+
+// slab mode: one message of the clean-up exchange = {nRes, nPush, -, -}, cap 32-byte results, cap chain indices
+__host__ __device__ constexpr size_t clean_msg_bytes(uint32_t cap) { return (16 + (size_t)cap * (32 + sizeof(uint32_t)) + 15) & ~(size_t)15; }
+// device buffers of a slab context (phase 5 of launch_grow_mr); nullptr for the other multi-rank modes
+struct SlabBuffers {
+	uint32_t* ownList; uint8_t* ownerOf; void* cleanRes; uint32_t* cleanPush; uint32_t cleanCap; void* peerClean[8];
 };
 
 cudaError_t launch_find_batch(const Geom& g, const Tables& T, const double* xyz, const int64_t* ignore, int64_t n, uint8_t* hit, int numSMs,
@@ -47,7 +61,8 @@ int grow_cluster_max_chains();
 cudaError_t launch_grow_mr(const Geom& g, const Tables& T, ChainState* chains, uint32_t* resTrial, uint32_t* origTrial, double* resPos, uint32_t* prev, Control* ctl,
 	uint32_t* roundAcc, uint32_t* roundProg, uint32_t* dirtyCount, uint32_t* dirtyList, uint32_t roundEnd, int blocks,
 	uint32_t rank, uint32_t ranks, uint32_t phase, void* localRec, const void* allRec, void* const* peerRec, void* const* peerFlags,
-	void* const* peerDirty, uint32_t splitVerify, cudaStream_t st);
+	void* const* peerDirty, uint32_t splitVerify, const SlabBuffers* slab, cudaStream_t st);
+extern unsigned* g_traceHost[8];   // diagnostics: see launch_grow_mr
 cudaError_t download_scan_bytes(uint64_t nSlots, size_t* bytes);
 cudaError_t launch_download(const Geom& g, const Tables& T, const uint32_t* prev, const ChainState* chains, uint64_t nSlots, uint32_t nSeeded,
 	int terminated, uint32_t* flags, uint32_t* scan, void* cubTemp, size_t cubBytes,

@@ -238,10 +238,19 @@ __device__ void enumerate_hits(const Geom& g, const Tables& T, const double v[3]
 	for (int ci = sub; ci < total; ci += GROUP) {
 		const int ix = ci % n[0], rest = ci / n[0];
 		const int iy = rest % n[1], iz = rest / n[1];
-		const int64_t cidx = cell_index(g, wrap_cell(c0[0] + ix, g.S[0]), wrap_cell(c0[1] + iy, g.S[1]), wrap_cell(c0[2] + iz, g.S[2]));
+		const int wz = wrap_cell(c0[2] + iz, g.S[2]);
+		const int64_t cidx = cell_index(g, wrap_cell(c0[0] + ix, g.S[0]), wrap_cell(c0[1] + iy, g.S[1]), wz);
+		const float qx = q[0][ix], qy = q[1][iy], qz = q[2][iz];
+		if (windowed(g) && !in_window(g, wz)) {   // slab context: see probe_cells
+			if (g.winStrict) atomicAdd(T.oowCount, 1u);
+			ovf_for_cell(T, cidx, [&](uint32_t id, uint32_t o0, uint32_t o1, uint32_t o2) {
+				if (id > idLoExcl && id < idHi && pair_hits(g, T, v, qx + dec_off(g, o0, 0), qy + dec_off(g, o1, 1), qz + dec_off(g, o2, 2), id)) fn(id);
+				return false;
+			});
+			continue;
+		}
 		uint32_t w[CELL_WORDS];
 		ld_cell(T.cells + cidx, w);
-		const float qx = q[0][ix], qy = q[1][iy], qz = q[2][iz];
 #pragma unroll
 		for (int s = 0; s < MAX_CAP; ++s) {
 			const uint32_t id = w[s];
@@ -456,6 +465,16 @@ struct GrowArgs {
 	uint32_t* peerFlags[8];       // [r]: rank r's arrival flags: 2 parities x 8 words for the records, then 2 x 8 for the conflict lists
 	uint32_t* peerDirty[8];       // [r]: rank r's conflict-list inbox, 2 parities x mrRanks x (1 + mrK) words (count, chains...)
 	uint32_t mrSplitVerify;       // phase 4: each rank verifies only the chains it proposed and the conflict lists are exchanged
+	// phase 5: slab decomposition. Every rank holds the cell layers of its z-slab plus a halo; a chain is proposed,
+	// verified and re-resolved by the rank whose slab holds its tip; records (one slot per chain), conflict lists and re-resolution
+	// results travel through peer memory; chain states and bead positions (lpos) stay replicated.
+	uint32_t* ownList;            // chains whose tip lies in this rank's slab this round (any order)
+	uint8_t* ownerOf;             // per chain: the rank that owns it this round
+	MrRecord* cleanRes;           // re-resolutions this rank made in the running clean-up iteration: {x, y, z, trial, pad = chain}
+	uint32_t* cleanPush;          // chains those re-resolutions put in conflict
+	uint32_t cleanCap;            // capacity of both
+	unsigned char* peerClean[8];  // [r]: rank r's clean-up inbox, 2 parities x mrRanks messages of clean_msg_bytes(cleanCap)
+	volatile unsigned* trace;     // diagnostics (SARW_TRACE_MAPPED=1): mapped host memory, block 0 / thread 0 stores round << 8 | stage before every phase
 	alignas(64) unsigned char tmap[128];   // CUtensorMap of the cell table (valid when g.useTmap); read by TMA straight from the kernel parameters
 };
 
@@ -500,7 +519,10 @@ __device__ __forceinline__ bool eval_trial_coop(const Geom& g, const Tables& T, 
 // publish one chain's record: phases 1/2 into the local staging buffer, phase 4 into every rank's buffer (peer stores)
 __device__ __forceinline__ void mr_publish(const GrowArgs& A, uint32_t i, uint32_t round, const MrRecord& r)
 {
-	if (A.mrPhase == 4u) {
+	if (A.mrPhase == 5u) {   // slab mode: one slot per chain (ownership moves with the tip)
+		const size_t at = (size_t)(round & 1u) * A.g.nChains + i;
+		for (uint32_t p = 0; p < A.mrRanks; ++p) A.peerRec[p][at] = r;
+	} else if (A.mrPhase == 4u) {
 		const size_t at = (size_t)(round & 1u) * A.mrRanks * A.mrK + (size_t)A.mrRank * A.mrK + i / A.mrRanks;
 		for (uint32_t p = 0; p < A.mrRanks; ++p) A.peerRec[p][at] = r;
 	} else A.mrLocal[i / A.mrRanks] = r;
@@ -513,9 +535,9 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
 
 // one thread per GPU: tell every peer that this rank's records of `round` are complete, wait until all peers said so.
 // Returns false after ~3 s without progress (a peer died): the caller aborts the launch instead of hanging the GPU.
-__device__ bool mr_peer_meet(const GrowArgs& A, uint32_t round, uint32_t which = 0u)
+__device__ bool mr_peer_meet_tag(const GrowArgs& A, uint32_t par, uint32_t tag, uint32_t which)
 {
-	const uint32_t par = round & 1u, tag = round + 1u, off = which * 16u + par * 8u;
+	const uint32_t off = which * 16u + par * 8u;
 	__threadfence_system();
 	for (uint32_t p = 0; p < A.mrRanks; ++p) if (p != A.mrRank) st_release_sys(A.peerFlags[p] + off + A.mrRank, tag);
 	const long long t0 = clock64();
@@ -526,6 +548,7 @@ __device__ bool mr_peer_meet(const GrowArgs& A, uint32_t round, uint32_t which =
 	}
 	return true;
 }
+__device__ __forceinline__ bool mr_peer_meet(const GrowArgs& A, uint32_t round, uint32_t which = 0u) { return mr_peer_meet_tag(A, round & 1u, round + 1u, which); }
 
 // apply the result of the previous round to the chain state (sarw.cpp:270-273); all lanes compute, lane 0 stores
 __device__ __forceinline__ void commit_pending(const GrowArgs& A, uint32_t i, uint32_t pendingRound, ChainState& cs, int lane)
@@ -753,18 +776,165 @@ __device__ void cleanup_round(const GrowArgs& A, uint32_t round, int lane)
 	}
 }
 
+// ------------------------------------------------------------------ slab mode: exchange of one clean-up iteration (block 0 of every rank)
+// message of one rank and iteration (clean_msg_bytes, sarw_host.h): {nRes, nPush, -, -}, nRes re-resolutions {x, y, z, trial, chain}, nPush chains put in conflict
+
+// what resolve_dirty_chain did on the owner's side, repeated on a rank that only learns the result: the bead leaves / enters this window's
+// cells (if its layer is held here), lpos, the chain's pending result and the replicated counters change exactly as on the owner
+__device__ void slab_apply_remote_result(const GrowArgs& A, uint32_t round, const MrRecord& r)
+{
+	const Geom& g = A.g;
+	const uint32_t T_ = (uint32_t)g.maxTrials, chain = r.pad, found = r.trial <= T_ ? r.trial : 0u;
+	const uint32_t myId = round_id_base(g, round) + chain;
+	const uint32_t cur = __ldcg(&A.resTrial[chain]), t0 = __ldcg(&A.origTrial[chain]);
+	if (cur <= T_) remove_bead(g, A.T, myId);
+	atomicAdd(&A.ctl->conflicts, 1ull);
+	const long long before = cur <= T_ ? cur : T_, after = found ? found : T_;
+	atomicAdd(&A.ctl->trials, (unsigned long long)(after - before));
+	atomicAdd(&A.ctl->queries, (unsigned long long)(after - (long long)t0 + 1));
+	const int hadBead = cur <= T_, hasBead = found != 0u, hadProg = cur < T_, hasProg = found != 0u && found < T_;
+	if (hadBead != hasBead) atomicAdd(&A.roundAcc[round], (uint32_t)(hasBead - hadBead));
+	if (hadProg != hasProg) atomicAdd(&A.roundProg[round], (uint32_t)(hasProg - hadProg));
+	A.resTrial[chain] = found ? found : T_ + 1u;
+	if (found) {
+		const double p[3] = { r.x, r.y, r.z };
+		for (int k = 0; k < 3; k++) A.resPos[3 * (size_t)chain + k] = p[k];
+		insert_bead(g, A.T, p, myId);
+	}
+}
+
+// Block 0: publish this rank's results and pushes to every rank, meet, apply the other ranks' results, update the conflict list.
+// `scratch`: the block's dynamic shared memory (nothing else uses it during the clean-up).
+__device__ void slab_clean_exchange(const GrowArgs& A, uint32_t round, uint32_t xseq, unsigned char* scratch)
+{
+	const uint32_t par = xseq & 1u, R = A.mrRanks, me = A.mrRank, cap = A.cleanCap;
+	const size_t msgBytes = clean_msg_bytes(cap);
+	const uint32_t nResRaw = __ldcg(&A.ctl->cleanResCount), nPushRaw = __ldcg(&A.ctl->cleanPushCount);
+	const uint32_t nRes = min(nResRaw, cap), nPush = min(nPushRaw, cap);
+	if (threadIdx.x == 0 && (nResRaw > cap || nPushRaw > cap)) atomicExch(&A.ctl->abort, 3u);   // more conflicts in one iteration than the message holds
+	for (uint32_t p = 0; p < R; ++p) {
+		unsigned char* msg = A.peerClean[p] + ((size_t)par * R + me) * msgBytes;
+		uint4* dst = reinterpret_cast<uint4*>(msg + 16);
+		const uint4* src = reinterpret_cast<const uint4*>(A.cleanRes);
+		for (uint32_t j = threadIdx.x; j < 2u * nRes; j += blockDim.x) dst[j] = __ldcg(src + j);
+		uint32_t* pd = reinterpret_cast<uint32_t*>(msg + 16 + (size_t)cap * sizeof(MrRecord));
+		for (uint32_t j = threadIdx.x; j < nPush; j += blockDim.x) pd[j] = __ldcg(A.cleanPush + j);
+		if (threadIdx.x == 0) *reinterpret_cast<uint4*>(msg) = make_uint4(nRes, nPush, 0u, 0u);
+	}
+	__threadfence_system();
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		if (!mr_peer_meet_tag(A, par, xseq + 1u, 2u)) atomicExch(&A.ctl->abort, 1u);
+		A.ctl->cleanResCount = 0u; A.ctl->cleanPushCount = 0u;
+	}
+	__syncthreads();
+	const unsigned char* inbox = A.peerClean[me] + (size_t)par * R * msgBytes;
+	// the other ranks' results: one thread each
+	for (uint32_t p = 0; p < R; ++p) {
+		if (p == me) continue;
+		const unsigned char* msg = inbox + (size_t)p * msgBytes;
+		const uint32_t n = min(__ldcg(reinterpret_cast<const uint32_t*>(msg)), cap);
+		const uint4* rs = reinterpret_cast<const uint4*>(msg + 16);
+		for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) {
+			const uint4 a = __ldcg(rs + 2 * j), b = __ldcg(rs + 2 * j + 1);
+			MrRecord r;
+			r.x = __hiloint2double((int)a.y, (int)a.x); r.y = __hiloint2double((int)a.w, (int)a.z); r.z = __hiloint2double((int)b.y, (int)b.x); r.trial = b.z; r.pad = b.w;
+			slab_apply_remote_result(A, round, r);
+		}
+	}
+	__syncthreads();
+	// list update, identical on every rank. Pass 1 (parallel over the list): close what was just resolved, re-open closed entries of
+	// higher chains near a re-resolved chain. The re-resolved chains of all ranks are staged in shared memory in chunks.
+	struct ResTip { double x, y, z; uint32_t chain, pad; };
+	ResTip* tips = reinterpret_cast<ResTip*>(scratch);
+	constexpr uint32_t CHUNK = 1024;
+	uint32_t* openCount = reinterpret_cast<uint32_t*>(tips + CHUNK);
+	if (threadIdx.x == 0) *openCount = 0u;
+	const uint32_t total = __ldcg(&A.dirtyCount[round]);
+	const double R2 = independence_radius(A.g) * independence_radius(A.g);
+	uint32_t allRes = 0;
+	for (uint32_t p = 0; p < R; ++p) allRes += min(__ldcg(reinterpret_cast<const uint32_t*>(inbox + (size_t)p * msgBytes)), cap);
+	// per-thread state of the entries this thread looks after (entry e = threadIdx.x + k * blockDim.x): bit k of `closeMask` / `openMask`
+	for (uint32_t e0 = 0; e0 < total; e0 += blockDim.x) {
+		const uint32_t e = e0 + threadIdx.x;
+		uint32_t ent = e < total ? __ldcg(&A.dirtyList[e]) : 0u;
+		const uint32_t chain = ent & ~DONE_BIT;
+		double tip[3] = { 0, 0, 0 };
+		if (e < total) for (int k = 0; k < 3; k++) tip[k] = __ldcg(&A.chains[chain].last[k]);
+		bool resolvedNow = false, reopen = false;
+		for (uint32_t c0 = 0; c0 < allRes; c0 += CHUNK) {
+			__syncthreads();
+			{	// stage re-resolved chains [c0, c0 + CHUNK) of the concatenated messages
+				uint32_t skip = c0, off = 0;
+				for (uint32_t p = 0; p < R; ++p) {
+					const unsigned char* msg = inbox + (size_t)p * msgBytes;
+					const uint32_t n = min(__ldcg(reinterpret_cast<const uint32_t*>(msg)), cap);
+					if (skip >= n) { skip -= n; continue; }
+					const uint4* rs = reinterpret_cast<const uint4*>(msg + 16);
+					for (uint32_t j = skip + threadIdx.x; j < n && off + (j - skip) < CHUNK; j += blockDim.x) {
+						const uint32_t ch = __ldcg(rs + 2 * j + 1).w;
+						ResTip t; t.chain = ch; t.pad = 0;
+						t.x = __ldcg(&A.chains[ch].last[0]); t.y = __ldcg(&A.chains[ch].last[1]); t.z = __ldcg(&A.chains[ch].last[2]);
+						tips[off + (j - skip)] = t;
+					}
+					off += n - skip; skip = 0;
+					if (off >= CHUNK) break;
+				}
+			}
+			__syncthreads();
+			const uint32_t m = min(CHUNK, allRes - c0);
+			if (e < total)
+				for (uint32_t j = 0; j < m; ++j) {
+					const ResTip t = tips[j];
+					if (t.chain == chain) { resolvedNow = true; continue; }
+					if (t.chain < chain) {
+						double d2 = 0;
+						const double dd[3] = { tip[0] - t.x, tip[1] - t.y, tip[2] - t.z };
+						for (int k = 0; k < 3; k++) { double d = dd[k]; d -= A.g.L[k] * rint(d * A.g.Linv[k]); d2 += d * d; }
+						if (d2 <= R2) reopen = true;
+					}
+				}
+		}
+		if (e < total) {
+			const bool done = ((ent & DONE_BIT) != 0u || resolvedNow) && !reopen;
+			A.dirtyList[e] = chain | (done ? DONE_BIT : 0u);
+			if (!done) atomicAdd(openCount, 1u);
+		}
+	}
+	__syncthreads();
+	// pass 2 (one thread): chains put in conflict by the re-resolutions, in rank order; a listed chain is opened again, a new one appended
+	if (threadIdx.x == 0) {
+		uint32_t open = *openCount, n = total;
+		for (uint32_t p = 0; p < R; ++p) {
+			const unsigned char* msg = inbox + (size_t)p * msgBytes;
+			const uint32_t np = min(__ldcg(reinterpret_cast<const uint32_t*>(msg) + 1), cap);
+			const uint32_t* pd = reinterpret_cast<const uint32_t*>(msg + 16 + (size_t)cap * sizeof(MrRecord));
+			for (uint32_t j = 0; j < np; ++j) {
+				const uint32_t c = __ldcg(pd + j);
+				uint32_t at = n;
+				for (uint32_t k = 0; k < n; ++k) if ((A.dirtyList[k] & ~DONE_BIT) == c) { at = k; break; }
+				if (at == n) { if (n < A.g.nChains) { A.dirtyList[n++] = c; open++; } }
+				else if (A.dirtyList[at] & DONE_BIT) { A.dirtyList[at] = c; open++; }
+			}
+		}
+		A.dirtyCount[round] = n;
+		A.ctl->cleanOpen = open;
+	}
+	__syncthreads();
+}
+
 #include "sarw_cluster.cuh"
 
 // barrier across every CTA taking part in a round: the hardware cluster barrier when the whole launch is ONE
 // thread-block cluster (small chain counts: a few hundred cycles), else the software grid barrier (cooperative launch)
 template <bool CLUSTER>
-__device__ __forceinline__ void round_barrier(Control* ctl)
+__device__ __forceinline__ void round_barrier(Control* ctl, unsigned& barTarget)
 {
 	if (CLUSTER) {
 		asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
 		asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 	} else {
-		grid_barrier(&ctl->barCount, &ctl->barGen, gridDim.x);
+		grid_barrier(&ctl->barCount, barTarget, gridDim.x);
 	}
 }
 
@@ -793,6 +963,8 @@ __global__ void __launch_bounds__(WARPS * 32, SARW_GROW_MINBLOCKS) grow_kernel(c
 	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	__syncwarp();
 	const uint32_t T_ = (uint32_t)g.maxTrials;
+	__shared__ unsigned barTarget;   // grid barrier: arrivals needed for the next barrier of this launch (the wrapper zeroes the counter); thread 0 only
+	if (threadIdx.x == 0) barTarget = 0;
 
 	uint32_t round = __ldcg(&A.ctl->round);
 	unsigned long long nBeads = __ldcg(&A.ctl->nBeads);
@@ -802,6 +974,8 @@ __global__ void __launch_bounds__(WARPS * 32, SARW_GROW_MINBLOCKS) grow_kernel(c
 	const uint32_t phase = MR ? A.mrPhase : 0u;
 	bool pendingValid = (phase == 1u);   // is there a round whose results are not yet committed? (always possible between phase-1/2 launches)
 	const bool mr = MR && phase != 0u;
+	const bool slab = MR && phase == 5u;   // slab decomposition: ownership by the tip's cell layer (see GrowArgs)
+	uint32_t xseq = slab ? __ldcg(&A.ctl->xseq) : 0u;   // clean-up exchanges made so far (the same on every rank)
 	if (phase == 3u) {       // multi-rank: commit the last round, nothing else
 		for (uint32_t i = gw; i < g.nChains; i += nW) { ChainState cs = load_chain(A.chains + i); commit_pending(A, i, round - 1, cs, lane); }
 		return;
@@ -811,6 +985,7 @@ __global__ void __launch_bounds__(WARPS * 32, SARW_GROW_MINBLOCKS) grow_kernel(c
 	long long cycA = 0, cycV = 0, cycC = 0; uint32_t cleanRounds = 0;
 	long long sub[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }, ts0 = 0, ts1 = 0;
 #define SUBT(k) do { ts1 = clock64(); sub[k] += ts1 - ts0; ts0 = ts1; } while (0)
+#define TRACE(stage) do { if (MR && A.trace && timer) { A.trace[0] = (round << 8) | (unsigned)(stage); __threadfence_system(); } } while (0)
 	while (go && round < A.roundEnd && (long long)nBeads < g.target && lastProg) {
 		const long long tk0 = clock64();
 		ts0 = tk0;
@@ -819,9 +994,40 @@ __global__ void __launch_bounds__(WARPS * 32, SARW_GROW_MINBLOCKS) grow_kernel(c
 		const uint32_t idRound = round_id_base(g, round);
 
 		// ---------------- phase A: commit last round, then propose + tentatively insert
-		if (mr && phase != 2u && pendingValid)                   // chains proposed by other ranks: commit only, one thread each
+		if (mr && !slab && phase != 2u && pendingValid)          // chains proposed by other ranks: commit only, one thread each
 			for (uint32_t i = (gw * 32 + lane); i < g.nChains; i += nW * 32)
 				if ((i % A.mrRanks) != A.mrRank) commit_pending_thread(A, i, round - 1);
+		uint32_t nOwnSlab = 0;
+		TRACE(1);
+		if (slab) {
+			// slab mode: every chain is committed here, one thread each (the state is replicated), and goes to the rank whose slab holds the
+			// cell layer of its new tip - computed from replicated data, so every rank arrives at the same assignment without a message
+			for (uint32_t base = gw * 32; base < g.nChains; base += nW * 32) {
+				const uint32_t i = base + lane;
+				bool mine = false;
+				if (i < g.nChains) {
+					if (pendingValid) commit_pending_thread(A, i, round - 1);
+					const double z = *reinterpret_cast<volatile const double*>(&A.chains[i].last[2]);
+					const double tz = z * g.Linv[2];
+					int cz = (int)floor((tz - floor(tz)) * g.sOverL[2]);   // the layer bead_cell puts the tip bead in
+					cz = cz >= g.S[2] ? g.S[2] - 1 : (cz < 0 ? 0 : cz);
+					const int o = slab_owner(g, cz);
+					A.ownerOf[i] = (uint8_t)o;
+					mine = (uint32_t)o == A.mrRank;
+				}
+				const unsigned m = __ballot_sync(FULL, mine);
+				if (m) {
+					uint32_t at = 0;
+					if (lane == 0) at = atomicAdd(&A.ctl->ownCount[round & 1u], (uint32_t)__popc(m));
+					at = __shfl_sync(FULL, at, 0);
+					if (mine) A.ownList[at + (uint32_t)__popc(m & ((1u << lane) - 1u))] = i;
+				}
+			}
+			pendingValid = false;
+			round_barrier<false>(A.ctl, barTarget);
+			nOwnSlab = __ldcg(&A.ctl->ownCount[round & 1u]);
+		}
+		TRACE(2);
 		if (phase != 2u)
 		{
 #if defined(SARW_NO_QUAD) || defined(SARW_PROF)
@@ -875,10 +1081,10 @@ __global__ void __launch_bounds__(WARPS * 32, SARW_GROW_MINBLOCKS) grow_kernel(c
 		{
 		const int sub = lane & 7, grp = lane >> 3, gbase = lane & 24;
 		const uint32_t unit = mr ? A.mrRanks : 1u, first0 = mr ? A.mrRank : 0u;
-		const uint32_t nOwn = g.nChains > first0 ? (g.nChains - first0 + unit - 1u) / unit : 0u;   // chains this rank proposes
+		const uint32_t nOwn = slab ? nOwnSlab : (g.nChains > first0 ? (g.nChains - first0 + unit - 1u) / unit : 0u);   // chains this rank proposes
 		Cell* rawq = raw + grp * CL_REGION_CELLS;
 		float4* nbq = nb + grp * QUAD_NB_CAP;
-		auto own_chain = [&](uint32_t q) { return first0 + (4u * q + (uint32_t)grp) * unit; };
+		auto own_chain = [&](uint32_t q) { const uint32_t k = 4u * q + (uint32_t)grp; return slab ? __ldcg(A.ownList + k) : first0 + k * unit; };
 		// prefetch of a chain's state: three 32-bit words per lane (words 0-15 the chain state, 16-21 last round's position, 22 its trial)
 		auto prefetch = [&](uint32_t q, uint32_t& w0, uint32_t& w1, uint32_t& w2) {
 			w0 = w1 = w2 = 0u;
@@ -941,7 +1147,7 @@ __global__ void __launch_bounds__(WARPS * 32, SARW_GROW_MINBLOCKS) grow_kernel(c
 			if (stageMask) {
 				if (lane == 0) mbar_expect_tx(mbar, (unsigned)__popc(stageMask) * (unsigned)(CL_REGION_CELLS * sizeof(Cell)));
 				__syncwarp();
-				if (stage && sub == 0) tma_load_box3d(rawq, A.tmap, rp.lo[0] * (int)(sizeof(Cell) / 4), rp.lo[1], rp.lo[2], mbar);
+				if (stage && sub == 0) tma_load_box3d(rawq, A.tmap, rp.lo[0] * (int)(sizeof(Cell) / 4), rp.lo[1], rp.lo[2] - g.tmapZ0, mbar);
 			}
 			// ---- while the copies fly: the exact candidate of trial sub + 1 (reference arithmetic)
 			double candL[3] = { 0, 0, 0 }, vL[3] = { 0, 0, 0 }; float rel[3] = { 0, 0, 0 }; bool okL = false;
@@ -1115,17 +1321,34 @@ __global__ void __launch_bounds__(WARPS * 32, SARW_GROW_MINBLOCKS) grow_kernel(c
 #endif
 		}
 		SUBT(0);
+		TRACE(3);
 		if (phase == 1u) break;                                  // the host all-gathers the records, then launches phase 2
 		const MrRecord* allRec = A.mrAll;
-		if (phase == 4u) {                                       // exchange inside the kernel: peer stores + flag handshake
-			round_barrier<false>(A.ctl);                            // every record store of this GPU has been issued
+		if (phase == 4u || slab) {                               // exchange inside the kernel: peer stores + flag handshake
+			round_barrier<false>(A.ctl, barTarget);                            // every record store of this GPU has been issued
 			SUBT(1);
 			if (gw == 0 && lane == 0 && !mr_peer_meet(A, round)) atomicExch(&A.ctl->abort, 1u);
 			SUBT(2);
-			round_barrier<false>(A.ctl);
+			round_barrier<false>(A.ctl, barTarget);
 			SUBT(3);
 			if (__ldcg(&A.ctl->abort)) break;
-			allRec = A.peerRec[A.mrRank] + (size_t)(round & 1u) * A.mrRanks * A.mrK;
+			allRec = A.peerRec[A.mrRank] + (slab ? (size_t)(round & 1u) * g.nChains : (size_t)(round & 1u) * A.mrRanks * A.mrK);
+		}
+		TRACE(4);
+		if (slab) {                                              // tentative beads of the chains other ranks own: the state of every chain, the beads of this window
+			if (gw == 0 && lane == 0) A.ctl->ownCount[(round + 1u) & 1u] = 0u;
+			for (uint32_t i = start + gw * 32 + lane; i < end; i += nW * 32) {
+				if ((uint32_t)A.ownerOf[i] == A.mrRank) continue;
+				const MrRecord* rp_ = allRec + i;
+				MrRecord r;
+				r.x = __ldcg(&rp_->x); r.y = __ldcg(&rp_->y); r.z = __ldcg(&rp_->z); r.trial = __ldcg(&rp_->trial); r.pad = 0;
+				A.resTrial[i] = r.trial; A.origTrial[i] = r.trial;
+				if (r.trial >= 1u && r.trial <= T_) {
+					const double p[3] = { r.x, r.y, r.z };
+					insert_bead(g, A.T, p, idRound + i);     // windowed: lpos always, the cell only if its layer is held here
+					for (int k2 = 0; k2 < 3; k2++) A.resPos[3 * (size_t)i + k2] = p[k2];
+				}
+			}
 		}
 		if (phase == 2u || phase == 4u)                     // tentative beads proposed by the other ranks
 			for (uint32_t i = start + gw * 32 + lane; i < end; i += nW * 32) {
@@ -1142,12 +1365,13 @@ __global__ void __launch_bounds__(WARPS * 32, SARW_GROW_MINBLOCKS) grow_kernel(c
 			}
 		SUBT(4);
 		pendingValid = true;
-		round_barrier<false>(A.ctl);
+		round_barrier<false>(A.ctl, barTarget);
 		SUBT(5);
 		const long long tk1 = clock64();
 
 		// ---------------- phase V: conflicts with tentative beads of lower-indexed chains of this round
-		const bool splitV = phase == 4u && A.mrSplitVerify != 0u;
+		TRACE(5);
+		const bool splitV = (phase == 4u && A.mrSplitVerify != 0u) || slab;
 		{
 			uint32_t acc = 0, prog = 0; unsigned long long tr = 0;
 			if (splitV)   // round totals from the trial numbers every rank knows; the probing below covers this rank's chains only
@@ -1162,8 +1386,11 @@ __global__ void __launch_bounds__(WARPS * 32, SARW_GROW_MINBLOCKS) grow_kernel(c
 			// eight records in flight at once - find_batch_kernel's scheme - measured 2.3x slower here: 32 chains per warp are ~80 distinct
 			// 2 MB pages of the table, and the address-translation misses of one warp are served one after the other.)
 			const int vsub = lane & 7, grp = lane >> 3;
-			for (uint32_t base = first + gw * 4 * stride; base < end; base += nW * 4 * stride) {
-				const uint32_t i = base + grp * stride;
+			// (slab mode: the chains of this rank's list, the same list positions per warp as in phase A)
+			const uint32_t vBegin = slab ? gw * 4u : first + gw * 4 * stride, vEnd = slab ? nOwnSlab : end, vStep = slab ? nW * 4u : nW * 4 * stride;
+			for (uint32_t base = vBegin; base < vEnd; base += vStep) {
+				uint32_t i = base + grp * stride;
+				if (slab) { i = base + (uint32_t)grp < nOwnSlab ? __ldcg(A.ownList + base + grp) : end; if (i < start) i = end; }
 				bool h = false; uint32_t t = 0;
 				if (i < end) {
 					t = __ldcg(&A.resTrial[i]);
@@ -1195,10 +1422,12 @@ __global__ void __launch_bounds__(WARPS * 32, SARW_GROW_MINBLOCKS) grow_kernel(c
 			}
 			SUBT(6);   // verify work of block 0 / warp 0 (the barrier that follows is in cycVerify)
 		}
+		TRACE(6);
 		if (splitV) {   // exchange the conflict lists: block 0 stores this rank's list into every rank's inbox, ranks meet, lists are merged
-			round_barrier<false>(A.ctl);
+			round_barrier<false>(A.ctl, barTarget);
 			if (blockIdx.x == 0) {
-				const uint32_t par = round & 1u, mine = __ldcg(&A.dirtyCount[round]);
+				const uint32_t par = round & 1u, mine = min(__ldcg(&A.dirtyCount[round]), A.mrK);
+				if (threadIdx.x == 0 && __ldcg(&A.dirtyCount[round]) > A.mrK) atomicExch(&A.ctl->abort, 2u);   // more conflicts than the inbox holds (cannot happen short of every chain conflicting)
 				const size_t slot = ((size_t)par * A.mrRanks + A.mrRank) * (1u + A.mrK);
 				for (uint32_t p = 0; p < A.mrRanks; ++p) {
 					for (uint32_t j = threadIdx.x; j < mine; j += blockDim.x) A.peerDirty[p][slot + 1u + j] = __ldcg(&A.dirtyList[j]);
@@ -1220,22 +1449,59 @@ __global__ void __launch_bounds__(WARPS * 32, SARW_GROW_MINBLOCKS) grow_kernel(c
 				if (threadIdx.x == 0) A.dirtyCount[round] = total;
 			}
 		}
-		round_barrier<false>(A.ctl);
+		round_barrier<false>(A.ctl, barTarget);
 		if (splitV && __ldcg(&A.ctl->abort)) break;
 
 		const long long tk2 = clock64();
+		TRACE(7);
 		// ---------------- clean-up (rare): serial re-resolution in chain order
-		if (__ldcg(&A.dirtyCount[round]) != 0u) {
+		if (slab) {
+			// slab mode: no rank holds all the cells, so conflicts are settled by fixed-point iteration instead of one ordered pass. Every open
+			// entry of the (replicated) conflict list is re-resolved by the rank that owns the chain, all at once; the results and the chains
+			// they put in conflict are exchanged; every rank applies them to its window and its replicated state and updates the list in the
+			// same way: resolved entries are closed, every closed entry of a HIGHER chain near a re-resolved one is opened again (its result
+			// assumed the old bead). Each iteration settles at least the lowest open chain for good, and the state it ends in - every chain
+			// on the first trial that passes against the old beads and the final beads of all lower chains - is the serial loop's
+			// (sarw.cpp:251-281) by induction over the chain index.
+			uint32_t total = __ldcg(&A.dirtyCount[round]), open = total;
+			while (open) {
+				for (uint32_t e = gw; e < total; e += nW) {
+					const uint32_t ent = __ldcg(&A.dirtyList[e]);
+					if ((ent & DONE_BIT) || (uint32_t)A.ownerOf[ent] != A.mrRank) continue;
+					resolve_dirty_chain(A, round, ent, lane, [&](uint32_t c) { const uint32_t at = atomicAdd(&A.ctl->cleanPushCount, 1u); if (at < A.cleanCap) A.cleanPush[at] = c; });
+					if (lane == 0) {
+						const uint32_t at = atomicAdd(&A.ctl->cleanResCount, 1u);
+						if (at < A.cleanCap) {
+							MrRecord r;
+							r.x = A.resPos[3 * (size_t)ent]; r.y = A.resPos[3 * (size_t)ent + 1]; r.z = A.resPos[3 * (size_t)ent + 2]; r.trial = A.resTrial[ent]; r.pad = ent;
+							A.cleanRes[at] = r;
+						}
+					}
+					__syncwarp();
+				}
+				TRACE(8);
+				round_barrier<false>(A.ctl, barTarget);
+				TRACE(9);
+				if (blockIdx.x == 0) slab_clean_exchange(A, round, xseq, growSmem);
+				xseq++;
+				round_barrier<false>(A.ctl, barTarget);
+				if (__ldcg(&A.ctl->abort)) break;
+				total = __ldcg(&A.dirtyCount[round]); open = __ldcg(&A.ctl->cleanOpen);
+			}
+			if (total) cleanRounds++;
+			if (__ldcg(&A.ctl->abort)) break;
+		} else if (__ldcg(&A.dirtyCount[round]) != 0u) {
 			cleanup_parallel(A, round, gw, nW, lane);          // independent conflicts, one warp each
-			round_barrier<false>(A.ctl);
+			round_barrier<false>(A.ctl, barTarget);
 			// the ordered pass and its barrier only when the parallel part left something (a flag nobody writes after the barrier)
 			if (gw == 0 && lane == 0) A.ctl->needOrdered[(round + 1u) & 1u] = 0u;
 			if (__ldcg(&A.ctl->needOrdered[round & 1u]) != 0u) {
 				if (gw == 0) cleanup_round(A, round, lane);      // the rest, in chain order
-				round_barrier<false>(A.ctl);
+				round_barrier<false>(A.ctl, barTarget);
 			}
 			cleanRounds++;
 		}
+		TRACE(10);
 		cycA += tk1 - tk0; cycV += tk2 - tk1; cycC += clock64() - tk2;
 		nBeads += __ldcg(&A.roundAcc[round]);
 		lastProg = __ldcg(&A.roundProg[round]) != 0u;
@@ -1243,7 +1509,7 @@ __global__ void __launch_bounds__(WARPS * 32, SARW_GROW_MINBLOCKS) grow_kernel(c
 	}
 
 	// commit the last round of this launch (multi-rank: the next phase-1 launch, or phase 3, commits)
-	if (pendingValid && (phase == 0u || phase == 4u))
+	if (pendingValid && (phase == 0u || phase == 4u || phase == 5u))
 		for (uint32_t i = gw; i < g.nChains; i += nW) {
 			ChainState cs = load_chain(A.chains + i);
 			commit_pending(A, i, round - 1, cs, lane);
@@ -1254,10 +1520,12 @@ __global__ void __launch_bounds__(WARPS * 32, SARW_GROW_MINBLOCKS) grow_kernel(c
 	}
 	if (gw == 0 && lane == 0) {
 		A.ctl->round = round; A.ctl->nBeads = nBeads; A.ctl->lastProgressed = lastProg ? 1u : 0u;
+		if (slab) A.ctl->xseq = xseq;
 	}
 	if (timer) { A.ctl->cycPropose += cycA; A.ctl->cycVerify += cycV; A.ctl->cycCleanup += cycC; A.ctl->cleanupRounds += cleanRounds; }
 	if (timer) for (int k2 = 0; k2 < 8; k2++) A.ctl->cycSub[k2] += sub[k2];
 #undef SUBT
+#undef TRACE
 }
 
 // ------------------------------------------------------------------ K7: compaction into acceptance order
@@ -1482,7 +1750,8 @@ int cluster_max_active(uint32_t nChains)
 cudaError_t launch_grow(const Geom& g, const Tables& T, ChainState* chains, uint32_t* resTrial, uint32_t* origTrial, double* resPos, uint32_t* prev, Control* ctl,
 	uint32_t* roundAcc, uint32_t* roundProg, uint32_t* dirtyCount, uint32_t* dirtyList, uint32_t roundEnd, int blocks, int useCluster, cudaStream_t st)
 {
-	GrowArgs A{ g, T, chains, resTrial, origTrial, resPos, prev, ctl, roundAcc, roundProg, dirtyCount, dirtyList, roundEnd, 0u, 1u, 0u, 0u, nullptr, nullptr, {}, {}, {}, 0u, {} };
+	GrowArgs A{ g, T, chains, resTrial, origTrial, resPos, prev, ctl, roundAcc, roundProg, dirtyCount, dirtyList, roundEnd, 0u, 1u, 0u, 0u, nullptr, nullptr, {}, {}, {}, 0u,
+		nullptr, nullptr, nullptr, nullptr, 0u, {}, nullptr, {} };
 	if (g.useTmap && T.tmapHost) memcpy(A.tmap, T.tmapHost, sizeof A.tmap); else A.g.useTmap = 0;
 	if (useCluster) {
 		// the whole launch is one thread-block cluster: CTAs are co-scheduled by the hardware, synchronise with
@@ -1490,25 +1759,40 @@ cudaError_t launch_grow(const Geom& g, const Tables& T, ChainState* chains, uint
 		// registers per thread) up to 128 chains, 16 warps per CTA beyond.
 		return g.nChains <= 8u * CL_MAX_CTAS ? launch_cluster<8>(A, st) : launch_cluster<16>(A, st);
 	}
+	CK(cudaMemsetAsync(&ctl->barCount, 0, sizeof(unsigned), st));   // the grid barrier counts arrivals from zero in every launch
 	void* args[] = { &A };
 	return cudaLaunchCooperativeKernel((const void*)grow_kernel<GROW_WARPS, false>, dim3((unsigned)blocks), dim3(GROW_WARPS * 32), args,
 		grow_smem_bytes(GROW_WARPS), st);
 }
 
 // one phase of a multi-rank round (grow_kernel with mrPhase != 0); always the cooperative grid kernel
+unsigned* g_traceHost[8] = {};
 cudaError_t launch_grow_mr(const Geom& g, const Tables& T, ChainState* chains, uint32_t* resTrial, uint32_t* origTrial, double* resPos, uint32_t* prev, Control* ctl,
 	uint32_t* roundAcc, uint32_t* roundProg, uint32_t* dirtyCount, uint32_t* dirtyList, uint32_t roundEnd, int blocks,
 	uint32_t rank, uint32_t ranks, uint32_t phase, void* localRec, const void* allRec, void* const* peerRec, void* const* peerFlags,
-	void* const* peerDirty, uint32_t splitVerify, cudaStream_t st)
+	void* const* peerDirty, uint32_t splitVerify, const SlabBuffers* slab, cudaStream_t st)
 {
 	const uint32_t K = (g.nChains + ranks - 1) / ranks;
 	GrowArgs A{ g, T, chains, resTrial, origTrial, resPos, prev, ctl, roundAcc, roundProg, dirtyCount, dirtyList, roundEnd, rank, ranks, phase, K,
-		(MrRecord*)localRec, (const MrRecord*)allRec, {}, {}, {}, splitVerify, {} };
+		(MrRecord*)localRec, (const MrRecord*)allRec, {}, {}, {}, splitVerify, nullptr, nullptr, nullptr, nullptr, 0u, {}, nullptr, {} };
+	if (phase == 5u) {
+		if (!slab) return cudaErrorInvalidValue;
+		A.ownList = slab->ownList; A.ownerOf = slab->ownerOf; A.cleanRes = (MrRecord*)slab->cleanRes; A.cleanPush = slab->cleanPush; A.cleanCap = slab->cleanCap;
+		for (uint32_t p = 0; p < 8; ++p) A.peerClean[p] = p < ranks ? (unsigned char*)slab->peerClean[p] : nullptr;
+	}
+	A.g.winStrict = 1;   // growth: a probe outside this rank's window is a protocol error (counted in Control::oowCount)
+	if (getenv("SARW_TRACE_MAPPED")) {   // diagnostics: where was block 0 when a launch died?
+		static unsigned* hostTrace[8] = {};
+		if (!hostTrace[rank & 7]) cudaHostAlloc((void**)&hostTrace[rank & 7], 256, cudaHostAllocMapped | cudaHostAllocPortable);
+		unsigned* d = nullptr;
+		if (hostTrace[rank & 7] && cudaHostGetDevicePointer((void**)&d, hostTrace[rank & 7], 0) == cudaSuccess) { A.trace = d; g_traceHost[rank & 7] = hostTrace[rank & 7]; }
+	}
 	if (g.useTmap && T.tmapHost) memcpy(A.tmap, T.tmapHost, sizeof A.tmap); else A.g.useTmap = 0;
 	for (uint32_t p = 0; p < 8; ++p) {
 		A.peerRec[p] = peerRec && p < ranks ? (MrRecord*)peerRec[p] : nullptr; A.peerFlags[p] = peerFlags && p < ranks ? (uint32_t*)peerFlags[p] : nullptr;
 		A.peerDirty[p] = peerDirty && p < ranks ? (uint32_t*)peerDirty[p] : nullptr;
 	}
+	CK(cudaMemsetAsync(&ctl->barCount, 0, sizeof(unsigned), st));
 	void* args[] = { &A };
 	return cudaLaunchCooperativeKernel((const void*)grow_kernel<GROW_WARPS, true>, dim3((unsigned)blocks), dim3(GROW_WARPS * 32), args,
 		grow_smem_bytes(GROW_WARPS), st);

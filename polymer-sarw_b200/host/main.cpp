@@ -18,6 +18,7 @@
 #include <ctime>
 #include <string>
 #include <unistd.h>
+#include <sys/stat.h>
 #include <vector>
 
 using namespace sarwhost;
@@ -38,13 +39,15 @@ static double seconds_since(std::chrono::steady_clock::time_point t0)
 int main(int argc, char** argv)
 {
 	std::string inputFilename, logFilename, outDir;
-	bool haveSeedOpt = false; unsigned long long seedOpt = 0; int device = -1, ioThreads = 0; bool timing = false;
+	bool haveSeedOpt = false; unsigned long long seedOpt = 0; int device = -1, ioThreads = 0, gpus = 1, slabHalo = 0; bool timing = false;
 	bool wantRdf = false; double rdfMin = 2.0, rdfDr = 0.5; int rdfBins = 20;   // scripts/rdf.py:84-85 defaults, 12 A range
 	for (int i = 1; i < argc; i++) {
 		if (!strcmp(argv[i], "-i") && i + 1 < argc) inputFilename = argv[++i];
 		else if (!strcmp(argv[i], "-o") && i + 1 < argc) logFilename = argv[++i];
 		else if (!strcmp(argv[i], "--seed") && i + 1 < argc) { seedOpt = strtoull(argv[++i], 0, 10); haveSeedOpt = true; }
 		else if (!strcmp(argv[i], "--device") && i + 1 < argc) device = atoi(argv[++i]);
+		else if (!strcmp(argv[i], "--gpus") && i + 1 < argc) gpus = atoi(argv[++i]);
+		else if (!strcmp(argv[i], "--slab-halo") && i + 1 < argc) slabHalo = atoi(argv[++i]);
 		else if (!strcmp(argv[i], "--io-threads") && i + 1 < argc) ioThreads = atoi(argv[++i]);
 		else if (!strcmp(argv[i], "--timing")) timing = true;
 		else if (!strcmp(argv[i], "--rdf")) {   // optional "rMin,dr,nBins"
@@ -52,7 +55,7 @@ int main(int argc, char** argv)
 			if (i + 1 < argc && argv[i + 1][0] != '-') { if (sscanf(argv[++i], "%lf,%lf,%d", &rdfMin, &rdfDr, &rdfBins) != 3) { fprintf(stderr, "--rdf expects rMin,dr,nBins\n"); return 1; } }
 		}
 		else if (!strcmp(argv[i], "-h") || !strcmp(argv[i], "--help")) {
-			printf("usage: sarw -i <input> [-o <log>] [--seed N] [--device D] [--io-threads T] [--timing] [--rdf [rMin,dr,nBins]]\n");
+			printf("usage: sarw -i <input> [-o <log>] [--seed N] [--device D] [--gpus N] [--io-threads T] [--timing] [--rdf [rMin,dr,nBins]]\n");
 			return 0;
 		}
 	}
@@ -132,8 +135,22 @@ int main(int argc, char** argv)
 	}
 
 	auto tAll = std::chrono::steady_clock::now();
-	sarw_ctx* ctx = nullptr;
-	if (sarw_create(&P, &ctx) != 0) die("\nsarw_create failed: %s\n", sarw_last_error(nullptr));
+	// --gpus N: ONE melt over N GPUs. The box is decomposed into N slabs along z, one context (rank) per slab on device (D + r) mod #devices;
+	// every rank gets the same parameters, grafts and obstacles; the complete walk is downloaded from rank 0.
+	if (gpus < 1 || gpus > 8) die("--gpus must be between 1 and 8\n");
+	std::vector<sarw_ctx*> ranks((size_t)gpus, nullptr);
+	for (int r = 0; r < gpus; r++) {
+		sarw_params Pr = P;
+		if (gpus > 1) {
+			const int nDev = sarw_device_count();
+			if (nDev < 1) die("\nno CUDA device available; sarw (B200) has no CPU fallback\n");
+			Pr.device = ((device < 0 ? 0 : device) + r) % nDev;
+			Pr.slabRank = r; Pr.slabRanks = gpus; Pr.slabHalo = slabHalo; Pr.launchMode = 1;
+		}
+		if (sarw_create(&Pr, &ranks[(size_t)r]) != 0) die("\nsarw_create failed: %s\n", sarw_last_error(nullptr));
+	}
+	sarw_ctx* ctx = ranks[0];
+	if (gpus > 1) notes.clear(), logPrintf("\nB200: one melt over %d GPUs, box decomposed into %d slabs along z (%.1f MB of cell list per rank)\n", gpus, gpus, (double)sarw_cell_table_bytes(ctx) / 1e6);
 
 	// sarw.cpp:59, 102-123
 	if (P.nGraftChains > 0 && graftLoc == "file") {
@@ -143,7 +160,7 @@ int main(int argc, char** argv)
 			logPrintf("\nReading grafts.dat: %d graft seeds found\n", (int)n);
 			if (n < P.nGraftChains) die("Inadequate number of seeds! Expected %d seeds.\n", (int)P.nGraftChains);   // the reference only logs, then reads out of bounds
 			if (n > P.nGraftChains) { logPrintf("Removing extra seeds!\n"); n = P.nGraftChains; }
-			if (sarw_set_grafts(ctx, grafts.data(), n) != 0) die("%s\n", sarw_last_error(ctx));
+			for (sarw_ctx* c : ranks) if (sarw_set_grafts(c, grafts.data(), n) != 0) die("%s\n", sarw_last_error(c));
 		} else die("\nFailed to open grafts.dat, needed for %d grafted chains.\n", (int)P.nGraftChains);
 	}
 	// sarw.cpp:62, 126-145
@@ -151,7 +168,7 @@ int main(int argc, char** argv)
 		std::vector<double> obst;
 		if (read_xyz_records(obstacle, obst)) {
 			logPrintf("\nReading %s: %d obstacles found\n", obstacle.c_str(), (int)(obst.size() / 3));
-			if (sarw_add_obstacles(ctx, obst.data(), (int64_t)obst.size() / 3) != 0) die("%s\n", sarw_last_error(ctx));
+			for (sarw_ctx* c : ranks) if (sarw_add_obstacles(c, obst.data(), (int64_t)obst.size() / 3) != 0) die("%s\n", sarw_last_error(c));
 		} else logPrintf("\nFailed to open %s. Assuming no obstacles.\n", obstacle.c_str());
 	}
 
@@ -160,8 +177,9 @@ int main(int argc, char** argv)
 	auto tGrow = std::chrono::steady_clock::now();
 	int32_t ok = 0;
 	sarw_stats st; memset(&st, 0, sizeof st);
-	if (sarw_initiate(ctx, &ok) != 0) die("\n%s\n", sarw_last_error(ctx));
-	if (sarw_grow(ctx, 0, -1, &st) != 0) die("\n%s\n", sarw_last_error(ctx));
+	for (sarw_ctx* c : ranks) if (sarw_initiate(c, &ok) != 0) die("\n%s\n", sarw_last_error(c));
+	if (gpus == 1) { if (sarw_grow(ctx, 0, -1, &st) != 0) die("\n%s\n", sarw_last_error(ctx)); }
+	else if (sarw_mr_grow_local(ranks.data(), gpus, -1, &st) != 0) die("\n%s\n", sarw_last_error(ctx));
 	if (sarw_terminate(ctx) != 0) die("\n%s\n", sarw_last_error(ctx));
 	const double growSeconds = seconds_since(tGrow);
 	if (logProgress) {
@@ -212,7 +230,7 @@ int main(int argc, char** argv)
 		fclose(fp);
 		logPrintf("\nExporting pair distribution and chain shapes: rdf.dat, shapes.dat\n");
 	}
-	sarw_destroy(ctx);
+	for (sarw_ctx* c : ranks) sarw_destroy(c);
 
 	// sarw.cpp:489-509
 	const long long vol = (long long)(P.boxSize[0] * P.boxSize[1] * P.boxSize[2]);
@@ -243,7 +261,11 @@ int main(int argc, char** argv)
 	const double expSeconds = seconds_since(tExp);
 	// README.md:44-46 names, as aliases
 	const char* alias[3][2] = { { "polymer.dat", "polymer.data" }, { "polymer.xyz", "polymer.XYZ" }, { "polymer.xsf", "polymer.XSF" } };
-	for (auto& a : alias) { unlink(a[1]); if (symlink(a[0], a[1]) != 0) { /* case-insensitive or read-only file systems: skip */ } }
+	for (auto& a : alias) {
+		struct stat sb;   // only an old alias is replaced: on a case-insensitive file system polymer.XYZ IS polymer.xyz, the file just written
+		if (lstat(a[1], &sb) == 0) { if (!S_ISLNK(sb.st_mode)) continue; unlink(a[1]); }
+		if (symlink(a[0], a[1]) != 0) { /* read-only or link-less file systems: skip */ }
+	}
 
 	if (timing) {
 		logPrintf("\nTIMING (B200):\n");

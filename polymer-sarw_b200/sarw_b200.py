@@ -26,7 +26,7 @@ ABI_SYMBOLS = [
     "sarw_lookup_find_batch_device", "sarw_lookup_size", "sarw_rdf", "sarw_chain_shapes", "sarw_concurrent_capacity", "sarw_release_cached_memory",
     "sarw_mr_setup", "sarw_mr_more", "sarw_mr_propose", "sarw_mr_finish", "sarw_mr_commit",
     "sarw_mr_peer_export", "sarw_mr_peer_connect", "sarw_mr_grow_peer", "sarw_mr_peer_local_base", "sarw_mr_peer_connect_local",
-    "sarw_grow_async", "sarw_wait", "sarw_walk_checksum", "sarw_download_box", "sarw_release_lookup",
+    "sarw_grow_async", "sarw_wait", "sarw_walk_checksum", "sarw_download_box", "sarw_release_lookup", "sarw_cell_table_bytes", "sarw_mr_grow_local", "sarw_device_count",
 ]
 
 
@@ -40,7 +40,8 @@ class Params(C.Structure):
                 ("graftLoc", C.c_int32), ("growthOrder", C.c_int32), ("boundary", C.c_int32),
                 ("growthBias", C.c_double * 3), ("seed", C.c_uint64), ("device", C.c_int32),
                 ("cellCapacity", C.c_int32), ("cellEdge", C.c_double), ("reserveRounds", C.c_int64),
-                ("launchMode", C.c_int32), ("maxBlocks", C.c_int32)]
+                ("launchMode", C.c_int32), ("maxBlocks", C.c_int32),
+                ("slabRank", C.c_int32), ("slabRanks", C.c_int32), ("slabHalo", C.c_int32), ("reserved0", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -93,6 +94,7 @@ def load_library(path=LIB_PATH):
     lib.sarw_lookup_find_batch.argtypes = [vp, vp, vp, C.c_int64, vp]
     lib.sarw_lookup_find_batch_device.argtypes = [vp, vp, vp, C.c_int64, vp]
     lib.sarw_lookup_size.argtypes = [vp]; lib.sarw_lookup_size.restype = C.c_int64
+    lib.sarw_cell_table_bytes.argtypes = [vp]; lib.sarw_cell_table_bytes.restype = C.c_int64
     lib.sarw_mr_setup.argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.sarw_mr_more.argtypes = [vp, C.POINTER(C.c_int32)]
     lib.sarw_mr_propose.argtypes = [vp, vp]
@@ -131,7 +133,8 @@ class Context:
 
     def __init__(self, nChains=1, boxSize=(10, 10, 10), minDist=2.0, targetMassDensity=0.92, maxTrials=100,
                  boundary="ppp", nGraftChains=0, graftLoc="file", growthOrder="roundRobin", growthBias=(0, 0, 0),
-                 seed=1, device=-1, cellCapacity=0, cellEdge=0.0, reserveRounds=0, launchMode=0, maxBlocks=0):
+                 seed=1, device=-1, cellCapacity=0, cellEdge=0.0, reserveRounds=0, launchMode=0, maxBlocks=0,
+                 slabRank=0, slabRanks=0, slabHalo=0):
         self.lib = load_library()
         p = Params()
         p.nChains = nChains; p.boxSize = (C.c_double * 3)(*boxSize); p.minDist = minDist
@@ -140,6 +143,7 @@ class Context:
         p.boundary = BOUNDARY.get(boundary, 0)   # only exact ppf/pfp/fpp act, anything else == ppp (sarw.cpp:201-203)
         p.growthBias = (C.c_double * 3)(*growthBias); p.seed = seed; p.device = device
         p.cellCapacity = cellCapacity; p.cellEdge = cellEdge; p.reserveRounds = reserveRounds; p.launchMode = launchMode; p.maxBlocks = maxBlocks
+        p.slabRank = slabRank; p.slabRanks = slabRanks; p.slabHalo = slabHalo; p.reserved0 = 0
         self.params = p
         self.nChains = nChains
         h = C.c_void_p()
@@ -187,6 +191,9 @@ class Context:
 
     def lookup_size(self):
         return self.lib.sarw_lookup_size(self.h)
+
+    def cell_table_bytes(self):
+        return self.lib.sarw_cell_table_bytes(self.h)
 
     def set_stream(self, cuda_stream_ptr):
         self._ck(self.lib.sarw_set_stream(self.h, cuda_stream_ptr))

@@ -96,12 +96,13 @@ def test_ranks_c2_full_size_matches_oracle(sarw, oracle):
 # ranks' buffers and the ranks meet on flags (st.release.sys / ld.acquire.sys). Here the R ranks are R contexts of this process
 # on ONE GPU, each on its own stream and host thread, with maxBlocks small enough that all R cooperative grids are resident at
 # the same time (sarw_mr_peer_connect_local shares the exchange buffers as plain device pointers instead of CUDA IPC handles).
-def run_ranks_peer(sarw, cfg, seed, R, split_verify=True, grafts=None, obstacles=None, maxBlocks=24):
+def run_ranks_peer(sarw, cfg, seed, R, split_verify=True, grafts=None, obstacles=None, maxBlocks=24, slab=False, halo=0, download=True):
     import torch
     streams = [torch.cuda.Stream() for _ in range(R)]
     ctxs = []
     for r in range(R):
-        c = sarw.Context(seed=seed, launchMode=1 if split_verify else 3, maxBlocks=maxBlocks, **cfg)
+        kw = dict(slabRank=r, slabRanks=R, slabHalo=halo) if slab else {}
+        c = sarw.Context(seed=seed, launchMode=1 if split_verify else 3, maxBlocks=maxBlocks, **kw, **cfg)
         c.set_stream(streams[r].cuda_stream)
         if obstacles is not None: c.add_obstacles(obstacles)
         if grafts is not None: c.set_grafts(grafts)
@@ -113,8 +114,11 @@ def run_ranks_peer(sarw, cfg, seed, R, split_verify=True, grafts=None, obstacles
     outs = []
     for c, st in zip(ctxs, stats):
         c.terminate()
-        xyz, chainID, typ, bonds = c.download()
-        outs.append((xyz, chainID, typ, bonds, c.chain_lengths(), c.stats().as_dict()))
+        if download:
+            xyz, chainID, typ, bonds = c.download()
+            outs.append((xyz, chainID, typ, bonds, c.chain_lengths(), c.stats().as_dict()))
+        else:
+            outs.append((c.walk_checksum(), c.stats().as_dict()))
         c.close()
     return outs
 
@@ -174,4 +178,71 @@ def test_peer_kernel_under_torchrun_two_gpus():
                         os.path.join(root, "scripts", "mr_run.py"), "4000", "100"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
-    assert line["nccl_identical_on_all_ranks"] and line["peer_identical_on_all_ranks"]
+    assert line["nccl_identical_on_all_ranks"] and line["peer_identical_on_all_ranks"] and line["slab_identical_on_all_ranks"]
+
+
+# ------------------------------------------------------------------ slab decomposition (sarw_params.slabRanks): the box is split along z
+# Rank r holds the cell layers of slab r plus a halo (the rest of the table has no memory behind it), chains belong to the rank whose slab
+# holds their tip, same-round conflicts are settled by a fixed-point iteration whose results are exchanged. Same R-contexts-on-one-GPU
+# set-up as above; the result must still be the single-GPU walk, bit for bit, on every rank.
+@pytest.mark.parametrize("R", [2, 3, 4])
+@pytest.mark.parametrize("name,cfg,halo", [("mid", cases.MID, 4), ("mid_wide_halo", cases.MID, 0), ("dense", cases.DENSE_TINY, 4)])
+def test_slab_ranks_give_the_single_gpu_walk_bit_for_bit(sarw, name, cfg, halo, R):
+    ref = run_single(sarw, cfg, 13)
+    outs = run_ranks_peer(sarw, cfg, 13, R, slab=True, halo=halo)
+    for o in outs:
+        for a, b in zip(o[:5], ref[:5]):
+            assert np.array_equal(a, b)
+        assert (o[5]["rounds"], o[5]["nBeads"], o[5]["trials"]) == (ref[5]["rounds"], ref[5]["nBeads"], ref[5]["trials"])
+    if name == "mid":
+        assert ref[5]["conflicts"] > 0 and all(o[5]["conflicts"] == outs[0][5]["conflicts"] for o in outs)
+
+
+def test_slab_ranks_many_chains_and_conflicts(sarw, oracle):
+    """4000 chains in a 100 A box (about 10 same-round conflicts per round, some of them next to each other): the fixed-point clean-up
+    and its exchange run on every rank, chains change owner as their tips cross slab boundaries; == oracle."""
+    cfg = dict(nChains=4000, boxSize=(100.0, 100.0, 100.0), minDist=1.0, maxTrials=300, targetMassDensity=0.92)
+    outs = run_ranks_peer(sarw, cfg, 17, 3, maxBlocks=64, slab=True, halo=4)
+    o = oracle.walk(seed=17, trig="portable", **cases.oracle_kwargs(cfg))
+    for xyz, chainID, typ, bonds, lengths, st in outs:
+        assert st["conflicts"] > 20 and st["trials"] == o.trials and st["rounds"] == o.rounds
+        assert np.array_equal(xyz, o.xyz) and np.array_equal(bonds, o.bonds) and np.array_equal(typ, o.type)
+
+
+def test_slab_ranks_with_grafts_obstacles_growth_order_and_walls(sarw):
+    cfg = dict(nChains=24, boxSize=(24.0, 24.0, 30.0), minDist=1.0, maxTrials=200, boundary="ppf", nGraftChains=12, graftLoc="file", growthOrder="grafted")
+    grafts = cases.make_grafts(12, cfg["boxSize"], seed=5)
+    obst = cases.make_obstacles(30, cfg["boxSize"], seed=2)
+    ref = run_single(sarw, cfg, 4, grafts=grafts, obstacles=obst)
+    for o in run_ranks_peer(sarw, cfg, 4, 2, grafts=grafts, obstacles=obst, slab=True, halo=4):
+        for a, b in zip(o[:5], ref[:5]):
+            assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("name,R", [("C3", 2), ("BIG", 4)])
+def test_slab_ranks_large_walk_equals_oracle_hash(sarw, name, R):
+    """BASELINE configs[2] (1e7 beads, 1 GB of cells) over 2 slabs and the 1e5-chain melt (10 GB of cells) over 4: here the windows are real -
+    most of the table's address range has no memory behind it, so a stray access would fault - and the walk is still the oracle's."""
+    import json, os
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "big_walk_hashes.json")))
+    if name not in gold:
+        pytest.skip("no golden hash")
+    gold = gold[name]
+    cfg = getattr(cases, name)
+    outs = run_ranks_peer(sarw, cfg, gold["seed"], R, maxBlocks=296 // R, slab=True)
+    for xyz, chainID, typ, bonds, lengths, st in outs:
+        assert (st["nBeads"], st["rounds"], st["trials"]) == (gold["nAtoms"], gold["rounds"], gold["trials"])
+        assert cases.walk_digest(xyz, bonds, typ) == gold["sha256"]
+
+
+def test_slab_context_refuses_what_it_cannot_do(sarw):
+    c = sarw.Context(seed=1, launchMode=1, slabRank=0, slabRanks=2, **cases.C3)
+    try:
+        with pytest.raises(sarw.SarwError):
+            c.find(np.zeros((1, 3)))
+        with pytest.raises(sarw.SarwError):
+            c.mr_setup(1, 2)          # created as slab 0 of 2
+    finally:
+        c.close()
+    with pytest.raises(sarw.SarwError):
+        sarw.Context(seed=1, slabRank=2, slabRanks=2, **cases.MID)

@@ -199,3 +199,30 @@ def test_exporters_large_multithreaded_equals_single_thread(hosttest, tmp_path):
         for f in ("polymer.dat", "polymer.xyz", "polymer.xsf"):
             (out / f).unlink()
     assert digests[0] == digests[1]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gpus", [2, 3])
+def test_cli_gpus_decomposes_the_box_and_writes_the_same_files(tmp_path, gpus):
+    """`sarw -i in --gpus N`: one melt over N slab contexts (on a box with fewer devices they share a GPU); the four output files are
+    byte-identical to the single-GPU run's, for test/pe.in (walls, checked against the reference's own files) and for a melt with
+    same-round conflicts, grafts and obstacles."""
+    exe = os.path.join(BIN, "sarw")
+    shutil.copy(os.path.join(GOLDEN, "pe.in"), tmp_path / "pe.in")
+    r = subprocess.run([exe, "-i", "pe.in", "--seed", "1", "--gpus", str(gpus), "--slab-halo", "4"], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "one melt over %d GPUs" % gpus in r.stdout
+    for name in ("polymer.dat", "polymer.xyz", "polymer.xsf", "chains.dat"):
+        assert (tmp_path / name).read_bytes() == open(os.path.join(GOLDEN, "pe_seed1", name), "rb").read(), name
+    box = (60.0, 60.0, 60.0)
+    np.savetxt(tmp_path / "grafts.dat", cases.make_grafts(40, box, seed=8), fmt="%.17g")
+    np.savetxt(tmp_path / "obs.dat", cases.make_obstacles(50, box, seed=3), fmt="%.17g")
+    (tmp_path / "m.in").write_text("nChains 400\nboxSize 60,60,60\nminDist 1.0\nmaxTrials 300\nnGraftChains 40\ngraftLoc file\nobstacle obs.dat\nseed 5\nlogProgress no\n")
+    outs = []
+    for extra in ([], ["--gpus", str(gpus), "--slab-halo", "4"]):
+        d = tmp_path / ("run%d" % len(outs)); d.mkdir()
+        for f in ("m.in", "grafts.dat", "obs.dat"): shutil.copy(tmp_path / f, d / f)
+        r = subprocess.run([exe, "-i", "m.in"] + extra, cwd=d, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs.append({n: (d / n).read_bytes() for n in ("polymer.dat", "polymer.xyz", "polymer.xsf", "chains.dat")})
+    assert outs[0] == outs[1]
