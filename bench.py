@@ -15,8 +15,9 @@ Every melt uses a fresh Philox key, so no work is cached between steps.
   workloads : the same two measurements, as full records of their own (repeated steps, roofline, e2e, clocks), for BASELINE
           configs[2] (1e4 x 1000 melt, 1e7 beads) and configs[3] (1e4-chain grafted brush); N = 1 only.
   N > 1 : one process per GPU (torchrun). The headline melts of different ranks are independent ("scaling": "weak", no data-path
-          collective). The record `one_melt` is ONE melt of 1e7*N beads grown by all N GPUs together (sarw_mr_grow_peer: proposals and
-          verification partitioned, records and conflict lists exchanged inside the persistent kernel over NVLink peer memory), with
+          collective). The record `one_melt` is ONE melt of 5e7*N beads grown by all N GPUs together (sarw_mr_grow_peer on slab contexts: the box is
+          decomposed into N slabs along z, each rank holds the cell layers of its slab + halo and owns the chains whose tip is inside; bead
+          records, conflict lists and re-resolution results are exchanged inside the persistent kernel over NVLink peer memory), with
           every rank's walk checksum compared with the others' and with the single-GPU walk. At N = 8 the record `C5` is
           BASELINE configs[4]: one melt of 1e6 chains x 1000 beads (1e9 beads).
   --impl reference : the UNMODIFIED reference (oracle/_ref, built from /root/reference) timed on the host cores.
@@ -380,6 +381,39 @@ def workload_record(env, key, warmup=2, steps=5):
 
 
 # ------------------------------------------------------------------ ONE melt over all GPUs
+def all_ranks_ok(dist, err, what, device="cuda"):
+    """Every rank reports whether a step that only IT can fail at (allocation, a launch) went through; if any rank failed, ALL ranks raise
+    here, together. Without this a rank that raises leaves the others waiting in the next collective until the NCCL watchdog (minutes)."""
+    if dist is None:
+        if err is not None:
+            raise err
+        return
+    import torch
+    t = torch.tensor([0 if err is None else 1], dtype=torch.int32, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if t.item():
+        raise RuntimeError(f"{what}: {err!r}" if err is not None else f"{what}: failed on another rank")
+
+
+def connect_peers_checked(c, dist, rank, world):
+    """sarw_b200.connect_peers with the local steps (buffer allocation, opening the IPC handles) reported to all ranks before the next
+    collective"""
+    err, mine = None, None
+    try:
+        c.mr_setup(rank, world)
+        mine = c.mr_peer_export()
+    except Exception as e:   # noqa: BLE001
+        err = e
+    all_ranks_ok(dist, err, f"rank {rank}: exchange buffers")
+    handles = [None] * world
+    dist.all_gather_object(handles, mine)
+    try:
+        c.mr_peer_connect(handles)
+    except Exception as e:   # noqa: BLE001
+        err = e
+    all_ranks_ok(dist, err, f"rank {rank}: opening the peers' buffers")
+
+
 def checksum_words(torch, dist, c):
     """this rank's walk checksum and every rank's (all-gathered as int64 bit patterns)"""
     import numpy as np
@@ -405,20 +439,43 @@ def one_melt_record(env, dist, rank, world, w, warmup, steps, single_gpu_check=T
     for s in range(warmup + steps):
         seed = 31_000 + s
         slab = dict(slabRank=rank, slabRanks=world) if world > 1 and not os.environ.get("SARW_BENCH_REPLICATED") else {}
-        c = sarw_b200.Context(device=local, launchMode=1, **slab, **ctx_kwargs(w, seed))
-        c.set_stream(stream.cuda_stream)
-        cell_bytes = c.cell_table_bytes()
-        c.initiate()
+        c, err, cell_bytes = None, None, 0
+        try:
+            c = sarw_b200.Context(device=local, launchMode=1, **slab, **ctx_kwargs(w, seed))
+            c.set_stream(stream.cuda_stream)
+            cell_bytes = c.cell_table_bytes()
+            c.initiate()
+        except Exception as e:   # noqa: BLE001
+            err = e
+        try:
+            all_ranks_ok(dist, err, f"rank {rank}: creating / seeding the context")
+        except Exception:
+            if c is not None: c.close()
+            if sampler: sampler.stop()
+            raise
         if world > 1:
-            sarw_b200.connect_peers(c, dist, rank, world)
+            try:
+                connect_peers_checked(c, dist, rank, world)
+            except Exception:
+                c.close()
+                raise
         torch.cuda.synchronize()
         if dist: dist.barrier()
         if s == warmup and rank == 0:
             sampler = ClockSampler(local).start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        st = c.mr_grow_peer(-1) if world > 1 else c.grow(0, -1)
-        e1.record(stream); e1.synchronize()
+        try:
+            st = c.mr_grow_peer(-1) if world > 1 else c.grow(0, -1)
+            e1.record(stream); e1.synchronize()
+        except Exception as e:   # noqa: BLE001  (a rank whose launch aborts makes the others time out inside their kernels: every rank lands here)
+            err = e
+        try:
+            all_ranks_ok(dist, err, f"rank {rank}: growth")
+        except Exception:
+            c.close()
+            if sampler: sampler.stop()
+            raise
         ms = e0.elapsed_time(e1) + st.seedMs
         if dist:
             t = torch.tensor([ms], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = t.item()
@@ -428,23 +485,34 @@ def one_melt_record(env, dist, rank, world, w, warmup, steps, single_gpu_check=T
             times.append(ms); beads += st.nBeads
         last = s == warmup + steps - 1
         if last and rank == 0 and (box_samples or rdf):
-            extra = verify_large_walk(c, w, box_samples, rdf)
+            try:
+                extra = verify_large_walk(c, w, box_samples, rdf)
+            except Exception as e:   # noqa: BLE001  (rank 0 only: must not skip the collectives that follow)
+                extra = {"verify_error": repr(e)}
         c.close()
     clocks = sampler.stop() if sampler else None
     single = None
     if single_gpu_check and world > 1:
         # the same melt (seed of the last step) on ONE GPU: rank 0 alone, the other ranks wait at the barrier
         if rank == 0:
-            sarw_b200.release_cached_memory(local)
-            c = sarw_b200.Context(device=local, launchMode=1, **ctx_kwargs(w, 31_000 + warmup + steps - 1))
-            c.set_stream(stream.cuda_stream)
-            c.initiate()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream); st1 = c.grow(0, -1); e1.record(stream); e1.synchronize()
-            one = np.array(c.walk_checksum(), dtype=np.uint64)
-            single = {"ms": e0.elapsed_time(e1) + st1.seedMs, "beads": st1.nBeads, "checksum_equal": bool(np.array_equal(one, sums[0])),
-                      "invariants_equal": (st1.nBeads, st1.rounds, st1.trials) == (st.nBeads, st.rounds, st.trials), "conflict_resolutions": [st1.conflicts, st.conflicts]}
-            c.close()
+            c = None
+            try:
+                sarw_b200.release_cached_memory(local)
+                c = sarw_b200.Context(device=local, launchMode=1, **ctx_kwargs(w, 31_000 + warmup + steps - 1))
+                c.set_stream(stream.cuda_stream)
+                c.initiate()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream); st1 = c.grow(0, -1); e1.record(stream); e1.synchronize()
+                one = np.array(c.walk_checksum(), dtype=np.uint64)
+                single = {"ms": e0.elapsed_time(e1) + st1.seedMs, "beads": st1.nBeads, "checksum_equal": bool(np.array_equal(one, sums[0])),
+                          "invariants_equal": (st1.nBeads, st1.rounds, st1.trials) == (st.nBeads, st.rounds, st.trials),
+                          "conflict_resolutions": [st1.conflicts, st.conflicts],
+                          "conflict_resolutions_note": "re-resolution calls: depends on the clean-up schedule (one ordered pass on one GPU, fixed-point iteration over slabs), not on the walk"}
+            except Exception as e:   # noqa: BLE001  (rank 0 only: the other ranks wait at the barrier below)
+                single = {"error": repr(e)}
+            finally:
+                if c is not None: c.close()
+                sarw_b200.release_cached_memory(local)   # the single-GPU tables (the whole box) go back to the driver before the next record
         dist.barrier()
     if rank != 0:
         return None
@@ -461,8 +529,8 @@ def one_melt_record(env, dist, rank, world, w, warmup, steps, single_gpu_check=T
            "cell_table_bytes_rank0": cell_bytes,
            "rounds": st.rounds, "trials_per_bead": st.trials / max(1, st.nBeads), "conflicts": st.conflicts, "overflow_beads": st.overflowBeads,
            "all_ranks_agree": bool(agree), "walk_checksum": [int(x) for x in sums[0]],
-           "matches_single_gpu": None if single is None else bool(single["checksum_equal"] and single["invariants_equal"]),
-           "single_gpu": single, "speedup_vs_single_gpu": None if single is None else single["ms"] / times[-1],
+           "matches_single_gpu": None if single is None or "error" in single else bool(single["checksum_equal"] and single["invariants_equal"]),
+           "single_gpu": single, "speedup_vs_single_gpu": None if single is None or "error" in single else single["ms"] / times[-1],
            "cycles_per_round_rank0": {"propose": st.cycPropose / rounds, "verify": st.cycVerify / rounds, "cleanup": st.cycCleanup / rounds,
                                       "sub": {n: st.cycSub[k] / rounds for k, n in enumerate(("propose_loop", "barrier_after_propose", "peer_handshake", "barrier_after_handshake",
                                                                                                 "apply_remote", "barrier_after_apply"))}},
@@ -525,7 +593,8 @@ def run_one_melt(args, w):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=240))
     env = Env(sarw_b200, torch, local)
     big = w["nChains"] >= 500000
     rec = one_melt_record(env, dist, rank, world, w, args.warmup, args.steps, single_gpu_check=not args.no_single_check,
@@ -577,7 +646,9 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        # a collective that one rank never joins ends after four minutes instead of the default ten
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=240))
     env = Env(sarw_b200, torch, local)
     stream = env.stream
 
@@ -644,9 +715,9 @@ def main():
                     line["workloads"][key] = {"error": repr(e)}
             line["extra"] = extra_measurements(env)
         else:
-            # ONE melt of 1e7*N beads over all N GPUs, checked against the other ranks and against the single-GPU walk
+            # ONE melt of 5e7*N beads over all N GPUs, checked against the other ranks and against the single-GPU walk
             try:
-                rec = one_melt_record(env, dist, rank, world, melt_workload(10000 * world, "grown by all N GPUs together"), 1, 3)
+                rec = one_melt_record(env, dist, rank, world, melt_workload(50000 * world, "grown by all N GPUs together"), 1, 3)
             except Exception as e:
                 rec = {"error": repr(e)}
             if rank == 0: line["one_melt"] = rec

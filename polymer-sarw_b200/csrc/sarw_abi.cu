@@ -82,6 +82,8 @@ int fail(sarw_ctx* c, const char* fmt, ...)
 }
 #define CU(c, x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(c, "%s: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
 
+static void cache_flush(sarw_ctx* c);
+
 // CUDA virtual memory management through the runtime's driver entry points (no link dependency on libcuda)
 struct VmApi {
 	CUresult (*getGranularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) = nullptr;
@@ -152,6 +154,13 @@ int vm_alloc_cells_window(sarw_ctx* c, size_t nCells, size_t layerBytes, int win
 		const size_t size = hi[k] - lo[k];
 		CUmemGenericAllocationHandle h;
 		CUresult r = vm.create(&h, size, &prop, 0);
+		if (r == CUDA_ERROR_OUT_OF_MEMORY) {   // memory parked for reuse or kept by the stream-ordered pool is given back first
+			cache_flush(c);
+			cudaDeviceSynchronize();
+			cudaMemPool_t pool;
+			if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0); else cudaGetLastError();
+			r = vm.create(&h, size, &prop, 0);
+		}
 		if (r != CUDA_SUCCESS) return fail(c, "cuMemCreate of %zu bytes for the cell layers of this slab failed (%d)", size, (int)r);
 		if (vm.map(c->vmBase + lo[k], size, 0, h, 0) != CUDA_SUCCESS) { vm.release(h); return fail(c, "cuMemMap failed"); }
 		c->vmRanges[c->nVmRanges++] = { lo[k], size, h };
@@ -783,10 +792,16 @@ int sarw_release_cached_memory(int32_t device)
 		if (device >= 0 && d != (device & 63)) continue;
 		BlockCache& bc = g_blocks[d];
 		std::lock_guard<std::mutex> lk(bc.m);
-		if (bc.parked.empty()) continue;
+		if (bc.parked.empty() && device < 0) continue;
 		cudaSetDevice(d);
 		for (auto& kv : bc.parked) cudaFree(kv.second);   // parked blocks are idle: the synchronous free is safe on any stream
 		bc.parked.clear(); bc.parkedBytes = 0;
+		// the stream-ordered pool keeps what was freed into it (release threshold: everything); hand that back as well, or a later
+		// allocation that does not come from the pool - the cuMemCreate of a slab's cell layers - finds the device full
+		// (measured on 8 GPUs: rank 0, which had just grown a 4e8-bead melt on its own, could not back 13 GB of cell layers)
+		cudaDeviceSynchronize();
+		cudaMemPool_t pool;
+		if (cudaDeviceGetDefaultMemPool(&pool, d) == cudaSuccess) cudaMemPoolTrimTo(pool, 0); else cudaGetLastError();
 	}
 	cudaSetDevice(cur);
 	return 0;
