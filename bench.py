@@ -70,7 +70,8 @@ ONE_MELT = {
     "C5": melt_workload(1000000, "BASELINE configs[4], grown by all N GPUs together"),
 }
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full captures
-NCU_TRAFFIC = {"C2": (36.86e6, "profiles/r1_grow_cluster_kernel_C2_raw.csv (128-byte cells; not re-captured for the 32-byte format)")}
+NCU_TRAFFIC = {"C2": (9.88e6 + 0.02e6, "profiles/r2_grow_cluster_kernel_C2_raw.csv (one melt; round 1 with 128-byte cells: 36.9 MB)"),
+               "C3": (5.646e9 + 0.761e9, "profiles/r2_grow_kernel_C3_raw.csv (one melt; round 1 with 128-byte cells: 13.2 GB)")}
 # algorithmic bytes per overlap query and per accepted bead
 B_QUERY = 121.0
 B_BEAD = 108.0

@@ -106,3 +106,42 @@ def test_committed_bench_line_has_every_contract_key():
     assert line["gpu_launches"] > 0 and line["e2e"]["value"] != line["value"]
     ref = json.loads(open(os.path.join(root, "profiles", "r1_bench_reference_arm.json")).read().strip().splitlines()[-1])
     assert ref["impl"] == "reference" and ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["cpu_baseline"]["kind"] == "reference"
+
+
+WORKER3 = textwrap.dedent("""
+    import os, sys, json
+    sys.path.insert(0, %r)
+    import torch, torch.distributed as dist
+    import bench
+    dist.init_process_group("gloo")
+    r = dist.get_rank()
+    out = {}
+    # nobody failed: nobody raises
+    bench.all_ranks_ok(dist, None, "step 1", device="cpu"); out["clean"] = True
+    # rank 1 fails locally (an allocation, a launch): BOTH ranks raise, at the same point, so the next collective still matches
+    try:
+        bench.all_ranks_ok(dist, MemoryError("no room") if r == 1 else None, f"rank {r}: step 2", device="cpu")
+        out["raised"] = False
+    except RuntimeError as e:
+        out["raised"] = True; out["text"] = str(e)
+    t = torch.tensor([r + 1]); dist.all_reduce(t)         # the collective after the failure: must not hang or mismatch
+    out["sum"] = int(t.item())
+    gathered = [None, None]
+    dist.all_gather_object(gathered, out)
+    if r == 0: print(json.dumps(gathered))
+    dist.barrier(); dist.destroy_process_group()
+""") % ROOT
+
+
+def test_a_local_failure_is_raised_on_every_rank_with_gloo(tmp_path):
+    """bench.py's multi-GPU records: a rank that fails on its own (round 2: rank 0 could not allocate its slab of the 1e9-bead melt while
+    the other seven went on into the next all-gather and waited ten minutes for it) must take all ranks out of the record together."""
+    w = tmp_path / "worker3.py"
+    w.write_text(WORKER3)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29619", str(w)], capture_output=True, text=True, env=env, timeout=240)
+    assert r.returncode == 0, r.stderr[-2000:]
+    a, b = json.loads([l for l in r.stdout.splitlines() if l.startswith("[")][-1])
+    assert a["clean"] and b["clean"] and a["raised"] and b["raised"] and a["sum"] == b["sum"] == 3
+    assert "failed on another rank" in a["text"] and "no room" in b["text"]
