@@ -831,6 +831,7 @@ static int grow_blocks(const sarw_ctx* c, int64_t chains)
 static int grow_enqueue(sarw_ctx* c, const Geom& g, uint32_t roundNow, int64_t roundsLeft)
 {
 	if (c->lookupReleased) return fail(c, "the lookup was released (sarw_release_lookup): no more growth on this context");
+	if (c->slab) return fail(c, "this context holds one slab of a decomposed box: grow it with sarw_mr_grow_peer / sarw_mr_grow_local together with the other slabs");
 	if (roundNow >= c->roundCap && ensure_rounds(c, roundNow + 1)) return 1;
 	uint32_t roundEnd = c->roundCap;
 	if ((int64_t)(roundEnd - roundNow) > roundsLeft) roundEnd = roundNow + (uint32_t)roundsLeft;

@@ -4,7 +4,8 @@
 //   K2-K4 grow_kernel     SARW::propagateChain / randomConePos / checkCollision sarw.cpp:220-283, 159-214
 //                         + PeriodicLookup::find / addPoint                     PeriodicLookup.h:37-75
 //                         + main()'s while loop                                 sarw.cpp:67-78
-//         <8,false> one GPU, cooperative grid; <8,true> the phases of one melt over several GPUs;
+//         <8,false> one GPU, cooperative grid; <8,true> the phases of one melt over several GPUs: replicated tables (phases 1-4)
+//         or the box decomposed into z-slabs, one per GPU, each holding its layers of the cell list (phase 5);
 //         grow_cluster_kernel (sarw_cluster.cuh) for <= 256 chains: one thread-block cluster, DSMEM, hardware barrier
 //   K5  find_batch_kernel PeriodicLookup::find on caller-supplied candidates    PeriodicLookup.h:51-75
 //       zbin_*            layer order for large batches (counting sort)
@@ -850,6 +851,7 @@ __device__ void slab_clean_exchange(const GrowArgs& A, uint32_t round, uint32_t 
 	constexpr uint32_t CHUNK = 1024;
 	uint32_t* openCount = reinterpret_cast<uint32_t*>(tips + CHUNK);
 	if (threadIdx.x == 0) *openCount = 0u;
+	__syncthreads();
 	const uint32_t total = __ldcg(&A.dirtyCount[round]);
 	const double R2 = independence_radius(A.g) * independence_radius(A.g);
 	uint32_t allRes = 0;
@@ -1031,6 +1033,7 @@ __global__ void __launch_bounds__(WARPS * 32, SARW_GROW_MINBLOCKS) grow_kernel(c
 		if (phase != 2u)
 		{
 #if defined(SARW_NO_QUAD) || defined(SARW_PROF)
+		// (diagnostics builds: one chain per warp, static chain -> warp mapping; whole-box contexts only, no slab mode)
 		const uint32_t iFirst = mr ? A.mrRank + gw * A.mrRanks : gw, iStride = mr ? nW * A.mrRanks : nW;
 		uint32_t pf = iFirst < g.nChains ? chain_prefetch(A, iFirst, lane) : 0u;
 		for (uint32_t i = iFirst; i < g.nChains; i += iStride) {

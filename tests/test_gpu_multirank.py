@@ -242,6 +242,9 @@ def test_slab_context_refuses_what_it_cannot_do(sarw):
             c.find(np.zeros((1, 3)))
         with pytest.raises(sarw.SarwError):
             c.mr_setup(1, 2)          # created as slab 0 of 2
+        assert c.initiate()
+        with pytest.raises(sarw.SarwError):
+            c.grow(0, -1)             # one slab cannot grow alone
     finally:
         c.close()
     with pytest.raises(sarw.SarwError):
