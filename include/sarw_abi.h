@@ -209,6 +209,11 @@ int sarw_lookup_find_batch(sarw_ctx* ctx, const double* xyz, const int64_t* igno
 int sarw_lookup_find_batch_device(sarw_ctx* ctx, const double* d_xyz, const int64_t* d_ignore, int64_t n, uint8_t* d_hit);
 /* number of points currently in the lookup (obstacles + beads + added points) */
 int64_t sarw_lookup_size(sarw_ctx* ctx);
+/* The slab decomposition as pure functions (no device needed): out = {first layer of slab `rank`, one past its last layer, first layer of
+ * the rank's window, number of layers in the window (first + count may exceed nLayers: the window wraps around the periodic boundary;
+ * count == nLayers: the whole table)}; sarw_slab_owner = the rank whose slab holds `layer`. */
+int sarw_slab_layers(int32_t nLayers, int32_t ranks, int32_t rank, int32_t halo, int32_t out[4]);
+int32_t sarw_slab_owner(int32_t nLayers, int32_t ranks, int32_t layer);
 /* bytes of device memory behind this context's cell list (a slab context holds only its layers: about 1/slabRanks of the table plus the halo) */
 int64_t sarw_cell_table_bytes(sarw_ctx* ctx);
 

@@ -498,7 +498,7 @@ int sarw_create(const sarw_params* p, sarw_ctx** out)
 		const int halo = std::max(p->slabHalo > 0 ? p->slabHalo : 8, reach + 2);
 		const int lo = slab_lo(g.S[2], g.slabRanks, g.slabRank), hi = slab_lo(g.S[2], g.slabRanks, g.slabRank + 1);
 		if (hi - lo < 1) { fail(c, "slab decomposition: %d cell layers cannot be split over %d ranks", g.S[2], g.slabRanks); return bail(1); }
-		if (hi - lo + 2 * halo < g.S[2]) { g.winLo = ((lo - halo) % g.S[2] + g.S[2]) % g.S[2]; g.winLen = hi - lo + 2 * halo; }
+		slab_window(g.S[2], g.slabRanks, g.slabRank, halo, g.winLo, g.winLen);
 		if (g.winLen < g.S[2]) {
 			if (vm_alloc_cells_window(c, nCells, (size_t)g.S[0] * g.S[1] * sizeof(Cell), g.winLo, g.winLen, g.S[2])) return bail(1);
 			tableCells = c->windowBytes / sizeof(Cell);
@@ -644,6 +644,21 @@ int64_t sarw_lookup_size(sarw_ctx* c)
 	if (fresh(c)) return -1;
 	Control& h = *c->hctl;
 	return (int64_t)c->g.idAtomBase + (int64_t)h.nBeads;
+}
+
+int sarw_slab_layers(int32_t nLayers, int32_t ranks, int32_t rank, int32_t halo, int32_t out[4])
+{
+	if (!out || nLayers < 1 || ranks < 1 || rank < 0 || rank >= ranks || halo < 0) return 1;
+	int winLo = 0, winLen = nLayers;
+	slab_window(nLayers, ranks, rank, halo, winLo, winLen);
+	out[0] = slab_lo(nLayers, ranks, rank); out[1] = slab_lo(nLayers, ranks, rank + 1); out[2] = winLo; out[3] = winLen;
+	return 0;
+}
+
+int32_t sarw_slab_owner(int32_t nLayers, int32_t ranks, int32_t layer)
+{
+	if (nLayers < 1 || ranks < 1 || layer < 0 || layer >= nLayers) return -1;
+	return slab_owner_of(nLayers, ranks, layer);
 }
 
 int64_t sarw_cell_table_bytes(sarw_ctx* c)

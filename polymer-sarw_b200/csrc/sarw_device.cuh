@@ -287,11 +287,19 @@ __device__ __forceinline__ bool in_window(const Geom& g, int wz)
 	return d < g.winLen;
 }
 __host__ __device__ __forceinline__ int slab_lo(int S2, int ranks, int r) { return (int)(((long long)r * S2) / ranks); }   // slab r = layers [slab_lo(r), slab_lo(r + 1))
-__device__ __forceinline__ int slab_owner(const Geom& g, int wz)
-{	int r = (int)(((long long)wz * g.slabRanks) / g.S[2]);
-	while (r > 0 && wz < slab_lo(g.S[2], g.slabRanks, r)) --r;
-	while (r + 1 < g.slabRanks && wz >= slab_lo(g.S[2], g.slabRanks, r + 1)) ++r;
+__host__ __device__ __forceinline__ int slab_owner_of(int S2, int ranks, int wz)
+{	int r = (int)(((long long)wz * ranks) / S2);
+	while (r > 0 && wz < slab_lo(S2, ranks, r)) --r;
+	while (r + 1 < ranks && wz >= slab_lo(S2, ranks, r + 1)) ++r;
 	return r;
+}
+__device__ __forceinline__ int slab_owner(const Geom& g, int wz) { return slab_owner_of(g.S[2], g.slabRanks, wz); }
+// window of rank r: its slab plus `halo` layers on either side, as (first layer, number of layers), first + count may exceed S2 (wraps);
+// the whole table when the window would cover it anyway
+__host__ __device__ __forceinline__ void slab_window(int S2, int ranks, int r, int halo, int& winLo, int& winLen)
+{	const int lo = slab_lo(S2, ranks, r), hi = slab_lo(S2, ranks, r + 1);
+	if (hi - lo + 2 * halo < S2) { winLo = ((lo - halo) % S2 + S2) % S2; winLen = hi - lo + 2 * halo; }
+	else { winLo = 0; winLen = S2; }
 }
 
 // cell + quantised in-cell offset of a bead from its fractional coordinates

@@ -26,7 +26,7 @@ ABI_SYMBOLS = [
     "sarw_lookup_find_batch_device", "sarw_lookup_size", "sarw_rdf", "sarw_chain_shapes", "sarw_concurrent_capacity", "sarw_release_cached_memory",
     "sarw_mr_setup", "sarw_mr_more", "sarw_mr_propose", "sarw_mr_finish", "sarw_mr_commit",
     "sarw_mr_peer_export", "sarw_mr_peer_connect", "sarw_mr_grow_peer", "sarw_mr_peer_local_base", "sarw_mr_peer_connect_local",
-    "sarw_grow_async", "sarw_wait", "sarw_walk_checksum", "sarw_download_box", "sarw_release_lookup", "sarw_cell_table_bytes", "sarw_mr_grow_local", "sarw_device_count",
+    "sarw_grow_async", "sarw_wait", "sarw_walk_checksum", "sarw_download_box", "sarw_release_lookup", "sarw_cell_table_bytes", "sarw_mr_grow_local", "sarw_device_count", "sarw_slab_layers", "sarw_slab_owner",
 ]
 
 
@@ -95,6 +95,8 @@ def load_library(path=LIB_PATH):
     lib.sarw_lookup_find_batch_device.argtypes = [vp, vp, vp, C.c_int64, vp]
     lib.sarw_lookup_size.argtypes = [vp]; lib.sarw_lookup_size.restype = C.c_int64
     lib.sarw_cell_table_bytes.argtypes = [vp]; lib.sarw_cell_table_bytes.restype = C.c_int64
+    lib.sarw_slab_layers.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]; lib.sarw_slab_layers.restype = C.c_int
+    lib.sarw_slab_owner.argtypes = [C.c_int32, C.c_int32, C.c_int32]; lib.sarw_slab_owner.restype = C.c_int32
     lib.sarw_mr_setup.argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.sarw_mr_more.argtypes = [vp, C.POINTER(C.c_int32)]
     lib.sarw_mr_propose.argtypes = [vp, vp]
@@ -418,6 +420,18 @@ def grow_multirank(ctx, dist, rank, nranks, device="cuda"):
 def mr_chain_slot(i, nranks, K):
     """Where chain i's record sits after the all-gather (rank-major): (i % nranks) * K + i // nranks."""
     return (i % nranks) * K + i // nranks
+
+
+def slab_layers(nLayers, ranks, rank, halo):
+    """(slab first layer, slab end, window first layer, window layers) of one rank of a decomposed box; needs no GPU"""
+    out = (C.c_int32 * 4)()
+    if load_library().sarw_slab_layers(nLayers, ranks, rank, halo, out) != 0:
+        raise SarwError("sarw_slab_layers: bad arguments")
+    return tuple(out)
+
+
+def slab_owner(nLayers, ranks, layer):
+    return load_library().sarw_slab_owner(nLayers, ranks, layer)
 
 
 def connect_peers(ctx, dist, rank, nranks):
