@@ -1,6 +1,6 @@
 """Large one-melt run over N GPUs (peer-memory exchange) vs the single-GPU kernel, statistics only (no host download):
-   torchrun --nproc-per-node N scripts/mr_big.py [nChains] [beadsPerChain]
-Agreement is checked on the walk's invariants (beads, rounds, trials in reference terms, conflicts), which every rank computes."""
+   torchrun --nproc-per-node N scripts/mr_big.py [nChains] [beadsPerChain] [nosingle|-] [slab|replicated]
+Agreement is checked on the walk checksum (every coordinate and bond) and on the invariants (beads, rounds, trials in reference terms)."""
 import os, sys, time, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "polymer-sarw_b200"))
@@ -13,13 +13,16 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 200000
 per = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
 skip_single = len(sys.argv) > 3 and sys.argv[3] == "nosingle"
+slab = not (len(sys.argv) > 4 and sys.argv[4] == "replicated")      # default: the box decomposed into z-slabs, one per rank
 L = (n * per / 0.03957) ** (1.0 / 3.0)
 cfg = dict(nChains=n, boxSize=(L, L, L), minDist=1.0, maxTrials=1000, seed=7, device=local)
 stream = torch.cuda.current_stream()
 
 def run(multi):
     t0 = time.time()
-    c = sarw_b200.Context(launchMode=1, **cfg); c.set_stream(stream.cuda_stream)
+    kw = dict(slabRank=rank, slabRanks=world) if multi and slab else {}
+    c = sarw_b200.Context(launchMode=1, **kw, **cfg); c.set_stream(stream.cuda_stream)
+    cells = c.cell_table_bytes()
     c.initiate()
     if multi: sarw_b200.connect_peers(c, dist, rank, world)
     torch.cuda.synchronize(); dist.barrier()
@@ -28,7 +31,7 @@ def run(multi):
     if multi: c.mr_grow_peer(-1)
     else: c.grow(0, -1)
     e1.record(stream); e1.synchronize()
-    st = c.stats().as_dict(); c.close()
+    st = c.stats().as_dict(); st["checksum"] = c.walk_checksum(); st["cellBytes"] = cells; c.close()
     return st, e0.elapsed_time(e1), time.time() - t0
 
 res = {}
@@ -38,7 +41,7 @@ if not skip_single:
                single_cyc=[round(st1[k] / max(1, st1["rounds"])) for k in ("cycPropose", "cycVerify", "cycCleanup")])
 stN, msN, wN = run(True)
 t = torch.tensor([msN], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
-inv = torch.tensor([float(stN[k]) for k in ("nBeads", "rounds", "trials", "conflicts")], dtype=torch.float64, device="cuda")
+inv = torch.tensor([float(stN[k]) for k in ("nBeads", "rounds", "trials")] + [float(x & 0xFFFFFFFF) for x in stN["checksum"]] + [float(x >> 32) for x in stN["checksum"]], dtype=torch.float64, device="cuda")
 lo, hi = inv.clone(), inv.clone(); dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
 if rank == 0:
     res.update(n_gpus=world, nChains=n, box=L, beads=stN["nBeads"], target=stN["target"], rounds=stN["rounds"], trials_per_bead=stN["trials"] / stN["nBeads"],
@@ -47,6 +50,7 @@ if rank == 0:
                peer=[stN[k] for k in ("nBeads", "rounds", "trials", "conflicts")], all_ranks_agree=bool(torch.equal(lo, hi)),
                peer_cyc=[round(stN[k] / max(1, stN["rounds"])) for k in ("cycPropose", "cycVerify", "cycCleanup")],
                peer_sub=[round(x / max(1, stN["rounds"])) for x in stN["cycSub"]], setup_wall_s=wN)
-    if not skip_single: res["matches_single_gpu"] = res["single"] == res["peer"]
+    res.update(mode="slab" if slab else "replicated", cell_bytes_rank0=stN["cellBytes"], checksum=list(stN["checksum"]))
+    if not skip_single: res["matches_single_gpu"] = res["single"][:3] == res["peer"][:3] and list(st1["checksum"]) == list(stN["checksum"])
     print(json.dumps(res))
 dist.barrier(); dist.destroy_process_group()
