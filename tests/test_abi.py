@@ -35,10 +35,15 @@ def test_parameter_validation_and_no_cpu_fallback(sarw):
         sarw.Context(nChains=0)
     with pytest.raises(sarw.SarwError):
         sarw.Context(nChains=1, boxSize=(1.5, 10, 10), minDist=1.0)   # the reference needs floor(L/minDist) >= 2
+    for bad in (dict(slabRank=2, slabRanks=2), dict(slabRank=-1, slabRanks=3), dict(slabRank=0, slabRanks=9), dict(slabRank=0, slabRanks=2, slabHalo=-1)):
+        with pytest.raises(sarw.SarwError, match="slab"):          # checked before any device is touched
+            sarw.Context(nChains=4, boxSize=(10, 10, 10), minDist=1.0, **bad)
     import torch
     if not torch.cuda.is_available():
         with pytest.raises(sarw.SarwError, match="no CUDA device|CUDA"):
             sarw.Context(nChains=4, boxSize=(10, 10, 10), minDist=1.0)
+        with pytest.raises(sarw.SarwError, match="no CUDA device|CUDA"):   # a slab context has no CPU fallback either
+            sarw.Context(nChains=4, boxSize=(10, 10, 10), minDist=1.0, slabRank=0, slabRanks=2)
 
 
 def test_product_never_imports_oracle():
