@@ -382,12 +382,82 @@ def workload_record(env, key, warmup=2, steps=5):
 
 
 # ------------------------------------------------------------------ ONE melt over all GPUs
+class HostAgreement:
+    """The ranks agree on "did that step work everywhere?" through a TCP key-value store on the HOST, not through NCCL: a rank whose CUDA
+    context died (a faulting kernel) can still say so, and the healthy ranks do not sit in a device collective waiting for it until the
+    NCCL watchdog kills them. `poisoned` = some rank lost its context (or stopped answering): no device collective after that."""
+
+    def __init__(self, rank, world, port=None, timeout_s=60):
+        import datetime
+        import torch.distributed as dist
+        self.rank, self.world, self.n, self.poisoned = rank, world, 0, False
+        port = port or int(os.environ.get("MASTER_PORT", "29500")) + 29
+        self.store = dist.TCPStore(os.environ.get("MASTER_ADDR", "127.0.0.1"), port, world, rank == 0,
+                                   timeout=datetime.timedelta(seconds=timeout_s), wait_for_workers=False)
+
+    def _round(self, mine, timeout_s):
+        import datetime
+        self.n += 1
+        self.store.set(f"k{self.n}/{self.rank}", mine)
+        keys = [f"k{self.n}/{r}" for r in range(self.world)]
+        try:
+            self.store.wait(keys, datetime.timedelta(seconds=timeout_s))
+        except Exception as e:   # noqa: BLE001  (a rank that never answers: its process is gone or stuck)
+            self.poisoned = True
+            raise RuntimeError(f"a rank did not answer within {timeout_s} s ({e!r})")
+        return [self.store.get(k).decode(errors="replace") for k in keys]
+
+    def agree(self, err, what, hard=False, timeout_s=200):
+        """every rank passes its local exception (or None); raises on ALL ranks if any rank had one"""
+        mine = "" if err is None else ("HARD " if hard else "SOFT ") + repr(err)[:400]
+        answers = self._round(mine, timeout_s)
+        bad = [(r, a) for r, a in enumerate(answers) if a]
+        if any(a.startswith("HARD ") for _, a in bad):
+            self.poisoned = True
+        if bad:
+            raise RuntimeError(f"{what}: " + "; ".join(f"rank {r}: {a[5:]}" for r, a in bad))
+
+    def barrier(self, timeout_s=60):
+        self._round("", timeout_s)
+
+
+_AGREE = None   # set by setup_host_agreement when the ranks of a multi-GPU bench run can all reach the store
+
+
+def cuda_context_alive():
+    try:
+        import torch
+        torch.cuda.synchronize()
+        return True
+    except Exception:   # noqa: BLE001
+        return False
+
+
+def setup_host_agreement(dist, rank, world, device="cuda"):
+    """create the store on every rank and make sure, with one (still safe) collective, that ALL ranks have it; else nobody uses it"""
+    global _AGREE
+    import torch
+    ag = None
+    try:
+        ag = HostAgreement(rank, world)
+    except Exception:   # noqa: BLE001
+        ag = None
+    t = torch.tensor([1 if ag is not None else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    _AGREE = ag if t.item() == 1 else None
+    return _AGREE
+
+
 def all_ranks_ok(dist, err, what, device="cuda"):
     """Every rank reports whether a step that only IT can fail at (allocation, a launch) went through; if any rank failed, ALL ranks raise
-    here, together. Without this a rank that raises leaves the others waiting in the next collective until the NCCL watchdog (minutes)."""
+    here, together. Without this a rank that raises leaves the others waiting in the next collective until the NCCL watchdog (minutes).
+    Over the host store when there is one (see HostAgreement), else over the process group."""
     if dist is None:
         if err is not None:
             raise err
+        return
+    if _AGREE is not None:
+        _AGREE.agree(err, what, hard=err is not None and not cuda_context_alive())
         return
     import torch
     t = torch.tensor([0 if err is None else 1], dtype=torch.int32, device=device)
@@ -716,12 +786,9 @@ def main():
                     line["workloads"][key] = {"error": repr(e)}
             line["extra"] = extra_measurements(env)
         else:
-            # ONE melt of 5e7*N beads over all N GPUs, checked against the other ranks and against the single-GPU walk
-            try:
-                rec = one_melt_record(env, dist, rank, world, melt_workload(50000 * world, "grown by all N GPUs together"), 1, 3)
-            except Exception as e:
-                rec = {"error": repr(e)}
-            if rank == 0: line["one_melt"] = rec
+            setup_host_agreement(dist, rank, world)
+            # At N = 8 first BASELINE configs[4], ONE melt of 1e9 beads (13.7 GB of cell layers per rank), while no rank carries anything
+            # from an earlier record: in round 2's run it came after rank 0's single-GPU comparison melt and rank 0 could not back its slab.
             if world == 8 and not os.environ.get("SARW_BENCH_NO_C5"):
                 sarw_b200.release_cached_memory(local)
                 try:
@@ -729,6 +796,15 @@ def main():
                 except Exception as e:
                     rec = {"error": repr(e)}
                 if rank == 0: line["C5"] = rec
+                sarw_b200.release_cached_memory(local)
+            # ONE melt of 5e7*N beads over all N GPUs, checked against the other ranks and against the single-GPU walk
+            try:
+                if _AGREE is not None and _AGREE.poisoned:
+                    raise RuntimeError("skipped: a rank lost its CUDA context in the record before")
+                rec = one_melt_record(env, dist, rank, world, melt_workload(50000 * world, "grown by all N GPUs together"), 1, 3)
+            except Exception as e:
+                rec = {"error": repr(e)}
+            if rank == 0: line["one_melt"] = rec
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
             cores = host_cores()
@@ -754,6 +830,14 @@ def main():
                 line["cpu_baseline"] = {"value": None, "unit": "beads/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
         print(json.dumps(line))
     if dist:
+        if _AGREE is not None and _AGREE.poisoned:
+            # a rank's CUDA context is gone: no device collective would return; meet on the host and leave without tearing NCCL down
+            sys.stdout.flush()
+            try:
+                _AGREE.barrier(30)
+            except Exception:   # noqa: BLE001
+                pass
+            os._exit(0)
         dist.barrier(); dist.destroy_process_group()
 
 

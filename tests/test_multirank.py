@@ -145,3 +145,55 @@ def test_a_local_failure_is_raised_on_every_rank_with_gloo(tmp_path):
     a, b = json.loads([l for l in r.stdout.splitlines() if l.startswith("[")][-1])
     assert a["clean"] and b["clean"] and a["raised"] and b["raised"] and a["sum"] == b["sum"] == 3
     assert "failed on another rank" in a["text"] and "no room" in b["text"]
+
+
+WORKER4 = textwrap.dedent("""
+    import os, sys, json, time
+    sys.path.insert(0, %r)
+    import bench
+    r, port = int(sys.argv[1]), int(sys.argv[2])
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    ag = bench.HostAgreement(r, 2, port=port, timeout_s=30)
+    out = {}
+    ag.agree(None, "step 1"); out["clean"] = not ag.poisoned
+    try:
+        ag.agree(MemoryError("no room") if r == 1 else None, "step 2")          # a failure that leaves the device usable
+        out["soft"] = "not raised"
+    except RuntimeError as e:
+        out["soft"] = str(e); out["poisoned_after_soft"] = ag.poisoned
+    try:
+        ag.agree(RuntimeError("illegal memory access") if r == 0 else None, "step 3", hard=(r == 0))   # rank 0 lost its CUDA context
+        out["hard"] = "not raised"
+    except RuntimeError as e:
+        out["hard"] = str(e); out["poisoned_after_hard"] = ag.poisoned
+    ag.barrier(20)
+    if r == 0:                                                                   # rank 1 is gone: rank 0 must not wait for ever
+        t0 = time.time()
+        try:
+            ag.agree(None, "step 4", timeout_s=3); out["gone"] = "not raised"
+        except RuntimeError as e:
+            out["gone"] = str(e); out["waited"] = time.time() - t0
+    print(json.dumps(out))
+""") % ROOT
+
+
+def test_host_agreement_between_ranks_without_the_device(tmp_path):
+    """bench.py's multi-GPU records agree on failures over a TCP store on the host (HostAgreement): soft failures are raised on every rank,
+    a rank that lost its CUDA context poisons the run on every rank (no device collective afterwards), a rank that is gone costs a
+    bounded wait."""
+    import socket
+    w = tmp_path / "worker4.py"
+    w.write_text(WORKER4)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]
+    ps = [subprocess.Popen([sys.executable, str(w), str(r), str(port)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for r in range(2)]
+    outs = []
+    for p in ps:
+        o, e = p.communicate(timeout=180)
+        assert p.returncode == 0, e[-2000:]
+        outs.append(json.loads([l for l in o.splitlines() if l.startswith("{")][-1]))
+    a, b = outs
+    for o in outs:
+        assert o["clean"] and "no room" in o["soft"] and "rank 1" in o["soft"] and o["poisoned_after_soft"] is False
+        assert "illegal memory access" in o["hard"] and "rank 0" in o["hard"] and o["poisoned_after_hard"] is True
+    assert "did not answer" in a["gone"] and a["waited"] < 20
