@@ -498,10 +498,12 @@ def checksum_words(torch, dist, c):
 
 
 def one_melt_record(env, dist, rank, world, w, warmup, steps, single_gpu_check=True, box_samples=0, rdf=False):
-    """Strong scaling: every step grows ONE melt with all N GPUs (replicated state, partitioned proposals and verification, records and
-    conflict lists exchanged inside the persistent kernel over NVLink peer memory). N = 1 runs the single-GPU kernel. Every rank's walk
-    checksum (sarw_walk_checksum: every coordinate and bond) is compared with the others'; rank 0 then grows the melt of the last step
-    once more on its own and compares that checksum too. Returns the record on rank 0, None elsewhere."""
+    """Strong scaling: every step grows ONE melt with all N GPUs: the box is decomposed into N slabs along z, each rank holds the cell layers
+    of its slab + halo and proposes / verifies / re-resolves the chains whose tip is inside; bead records, conflict lists and re-resolution
+    results are exchanged inside the persistent kernel over NVLink peer memory (SARW_BENCH_REPLICATED=1: round 1's mode with every table
+    on every rank). N = 1 runs the single-GPU kernel. Every rank's walk checksum (sarw_walk_checksum: every coordinate and bond) is compared
+    with the others'; rank 0 then grows the melt of the last step once more on its own and compares that checksum too. Steps that only
+    one rank can fail at are followed by all_ranks_ok, so the ranks leave a failed record together. Returns the record on rank 0."""
     torch, sarw_b200, stream, local = env.torch, env.sarw, env.stream, env.local
     import numpy as np
     times, beads, st, agree, sums = [], 0, None, True, None
