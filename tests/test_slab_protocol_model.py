@@ -1,8 +1,8 @@
 """A CPU model of the slab-mode round against the serial loop of sarw.cpp:251-281. TEST INFRASTRUCTURE, no product code.
 
 The GPU kernels settle same-round conflicts of a decomposed box by a fixed-point iteration: all open conflicts are re-resolved at once by
-their owners, each seeing for every other chain either its old or its new bead (whatever the interleaving of warps and ranks happens to
-be), results are exchanged, closed entries of higher chains near a re-resolved chain are re-opened, chains that now collide are added.
+their owners, each seeing for every other chain that is being re-resolved its old bead, its new bead or neither (whatever the
+interleaving of warps and ranks happens to be), results are exchanged, closed entries of higher chains near a re-resolved chain are re-opened, chains that now collide are added.
 The claim: whatever the interleaving, the iteration ends in the state the serial loop produces. Here the round is modelled in numpy
 with the oracle's own Philox stream and cone arithmetic, the interleaving is drawn at random, and every round of a crowded melt is
 compared with the serial round; the serial model itself is pinned to the oracle's walk.
@@ -103,10 +103,15 @@ class Melt:
             before = list(tent)
             results, pushes = {}, set()
             todo = [x for x, o in state.items() if o]
+            busy = set(todo)
             rng.shuffle(todo)                                                        # any order: they run at the same time
             for x in todo:
-                def seen(j):                                                         # the other chain's bead as this resolver happens to see it
-                    return results[j] if j in results and rng.random() < 0.5 else before[j]
+                def seen(j):                                                         # the other chain's bead as this resolver happens to see it:
+                    if j not in busy: return before[j]                               # untouched in this pass
+                    r = rng.random()                                                 # being re-resolved right now: its old bead, its new one,
+                    if r < 0.35: return before[j]                                    # or neither (removed, not yet re-inserted)
+                    if r < 0.7 and j in results: return results[j]
+                    return (self.T + 1, None)
                 lower = [q for q in (seen(j)[1] for j in range(x)) if q is not None]
                 t, p = self.first_passing(x, rnd, orig[x], old, np.array(lower).reshape(-1, 3))
                 results[x] = (t, p)
