@@ -90,10 +90,15 @@ def test_c_example_compiles_and_links_against_the_library(tmp_path):
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     lib = os.path.join(root, "polymer-sarw_b200", "lib")
-    exe = tmp_path / "minimal"
-    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "minimal.c"),
-                    "-L", lib, "-lsarw_b200", "-Wl,-rpath," + lib, "-o", str(exe)], check=True)
-    assert exe.exists()
+    for name in ("minimal", "slabs"):      # slabs.c: one melt over N slab contexts (sarw_mr_grow_local)
+        exe = tmp_path / name
+        subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"), os.path.join(root, "examples", name + ".c"),
+                        "-L", lib, "-lsarw_b200", "-Wl,-rpath," + lib, "-o", str(exe)], check=True)
+        assert exe.exists()
+    import torch
+    if not torch.cuda.is_available():       # without a device the example says so and fails: no CPU fallback
+        r = subprocess.run([str(tmp_path / "slabs"), "2"], capture_output=True, text=True)
+        assert r.returncode == 1 and "no CUDA device" in r.stderr
 
 
 @pytest.mark.gpu
