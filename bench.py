@@ -497,7 +497,7 @@ def checksum_words(torch, dist, c):
     return mine, [o.cpu().numpy().view(np.uint64) for o in out]
 
 
-def one_melt_record(env, dist, rank, world, w, warmup, steps, single_gpu_check=True, box_samples=0, rdf=False):
+def one_melt_record(env, dist, rank, world, w, warmup, steps, single_gpu_check=True, box_samples=0, rdf=False, replicated=False):
     """Strong scaling: every step grows ONE melt with all N GPUs: the box is decomposed into N slabs along z, each rank holds the cell layers
     of its slab + halo and proposes / verifies / re-resolves the chains whose tip is inside; bead records, conflict lists and re-resolution
     results are exchanged inside the persistent kernel over NVLink peer memory (SARW_BENCH_REPLICATED=1: round 1's mode with every table
@@ -511,7 +511,7 @@ def one_melt_record(env, dist, rank, world, w, warmup, steps, single_gpu_check=T
     extra = {}
     for s in range(warmup + steps):
         seed = 31_000 + s
-        slab = dict(slabRank=rank, slabRanks=world) if world > 1 and not os.environ.get("SARW_BENCH_REPLICATED") else {}
+        slab = dict(slabRank=rank, slabRanks=world) if world > 1 and not replicated and not os.environ.get("SARW_BENCH_REPLICATED") else {}
         c, err, cell_bytes = None, None, 0
         try:
             c = sarw_b200.Context(device=local, launchMode=1, **slab, **ctx_kwargs(w, seed))
@@ -807,6 +807,18 @@ def main():
             except Exception as e:
                 rec = {"error": repr(e)}
             if rank == 0: line["one_melt"] = rec
+            # the same melt with round 1's scheme for comparison: every table on every rank (so it only fits smaller boxes), chain i proposed
+            # by rank i % N, every rank applies every bead; same seeds, so the walk must be the one of the record above
+            try:
+                if _AGREE is not None and _AGREE.poisoned:
+                    raise RuntimeError("skipped: a rank lost its CUDA context in a record before")
+                sarw_b200.release_cached_memory(local)
+                rec2 = one_melt_record(env, dist, rank, world, melt_workload(50000 * world, "grown by all N GPUs together"), 1, 3, single_gpu_check=False, replicated=True)
+                if rank == 0 and isinstance(rec, dict) and "walk_checksum" in rec:
+                    rec2["same_walk_as_one_melt"] = rec2["walk_checksum"] == rec["walk_checksum"]
+            except Exception as e:
+                rec2 = {"error": repr(e)}
+            if rank == 0: line["one_melt_replicated_tables"] = rec2
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
             cores = host_cores()
